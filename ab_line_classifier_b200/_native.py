@@ -1,0 +1,70 @@
+"""ctypes binding of libabl_b200.so (the C ABI declared in include/abl_b200.h).
+
+This is the reference-side FFI shim: plain pointers and sizes, no torch types.  There is NO
+fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libabl_b200.so")
+
+EPI_BIAS_RELU = 1
+EPI_RELU_MASK = 2
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_u, _ull = C.c_uint, C.c_ulonglong
+
+# name -> (restype, argtypes); must list EVERY symbol of include/abl_b200.h (tests check this).
+SIGNATURES = {
+    "abl_abi_version": (_i, []),
+    "abl_last_error": (C.c_char_p, []),
+    "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "abl_conv3x3_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
+    "abl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "abl_bias_grad": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "abl_conv_first_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_conv_first_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_prep_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "abl_maxpool_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_gap_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "abl_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _ull, _u, _u,
+                          _i, _i, _i, _vp]),
+    "abl_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "abl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
+    "abl_rmsprop_flat": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+    "abl_gradcam": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and attach signatures.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m ab_line_classifier_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.abl_abi_version() != 1:
+        raise RuntimeError("libabl_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; non-zero -> RuntimeError with abl_last_error()."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.abl_last_error().decode(errors="replace")
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+    return rc

@@ -1,0 +1,49 @@
+"""Build libabl_b200.so (hand-written sm_100a CUDA + the C ABI of include/abl_b200.h) in-tree with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libabl_b200.so")
+SOURCES = ["host_util.cu", "conv3x3_tc.cu", "wgrad_tc.cu", "conv_first.cu", "pointwise.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(HERE, "..", "include", "abl_b200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a and link the shared library.  Returns its path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode != 0:
+            sys.stderr.write(out)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-o", LIB, *objs])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,472 @@
+// HBM-bound kernels of the cutoffvgg16 path: weight re-layout, max-pool/ReLU backward, global
+// average pool (+backward), Dense/softmax/cross-entropy head, Adam / RMSprop, Grad-CAM.
+// All are grid-stride / vectorised (16-byte) kernels sized in multiples of the SM count.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace abl {
+
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ------------------------------------------------------------------ weight re-layout
+__global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_fwd,
+                                         __nv_bfloat16* __restrict__ w_dgrad, int Cin, int Cout) {
+    const int total = 9 * Cin * Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % Cout;
+        const int ci = (i / Cout) % Cin;
+        const int t = i / (Cout * Cin);
+        const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+        if (w_fwd) w_fwd[(static_cast<size_t>(t) * Cout + co) * Cin + ci] = v;
+        if (w_dgrad) w_dgrad[(static_cast<size_t>(8 - t) * Cin + ci) * Cout + co] = v;
+    }
+}
+
+// ------------------------------------------------------------------ MaxPoolGrad + ReluGrad
+// One thread per (pooled pixel, 8-channel chunk): 16-byte loads of the 4 window activations, the
+// pooled value and dP; writes the 4 dZ chunks.  First maximum in window scan order wins.
+__global__ void maxpool_bwd_relu_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ a,
+                                        const uint4* __restrict__ pooled, uint4* __restrict__ dz, int B, int H,
+                                        int W, int C8) {
+    const int PH = H >> 1, PW = W >> 1;
+    const long long total = static_cast<long long>(B) * PH * PW * C8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C8);
+        long long r = i / C8;
+        const int pw = static_cast<int>(r % PW);
+        r /= PW;
+        const int ph = static_cast<int>(r % PH);
+        const int n = static_cast<int>(r / PH);
+        const uint4 g = dp[i];
+        const uint4 pm = pooled[i];
+        const long long base = ((static_cast<long long>(n) * H + 2 * ph) * W + 2 * pw) * C8 + c;
+        const long long offs[4] = {base, base + C8, base + static_cast<long long>(W) * C8,
+                                   base + static_cast<long long>(W) * C8 + C8};
+        uint4 av[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) av[k] = a[offs[k]];
+        const uint32_t gv[4] = {g.x, g.y, g.z, g.w};
+        const uint32_t pv[4] = {pm.x, pm.y, pm.z, pm.w};
+        uint32_t out[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t taken_lo = 0, taken_hi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = (j == 0 ? av[k].x : j == 1 ? av[k].y : j == 2 ? av[k].z : av[k].w);
+                // activations are post-ReLU (>= 0, never -0 from fmaxf(.,0)): bit equality == value equality
+                const bool lo = !taken_lo && ((x & 0xFFFFu) == (pv[j] & 0xFFFFu)) && ((x & 0x7FFFu) != 0);
+                const bool hi = !taken_hi && ((x >> 16) == (pv[j] >> 16)) && ((x & 0x7FFF0000u) != 0);
+                const bool lo_eq = ((x & 0xFFFFu) == (pv[j] & 0xFFFFu));
+                const bool hi_eq = ((x >> 16) == (pv[j] >> 16));
+                out[k][j] = (lo ? (gv[j] & 0xFFFFu) : 0u) | (hi ? (gv[j] & 0xFFFF0000u) : 0u);
+                taken_lo |= lo_eq;   // the first maximum claims the window even if it is 0 (then masked)
+                taken_hi |= hi_eq;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dz[offs[k]] = make_uint4(out[k][0], out[k][1], out[k][2], out[k][3]);
+    }
+}
+
+// ------------------------------------------------------------------ global average pool
+// grid = (B, C/64): each block reduces HW rows x 64 channels (128 B per row) of one frame.
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const uint4* __restrict__ a, float* __restrict__ gap,
+                                                      int HW, int C) {
+    __shared__ float red[32][65];
+    const int n = blockIdx.x, cb = blockIdx.y;
+    const int chunk = threadIdx.x & 7;        // 8 x 16 B = 64 channels
+    const int rg = threadIdx.x >> 3;          // 32 row groups
+    const int C8 = C >> 3;
+    const uint4* base = a + static_cast<size_t>(n) * HW * C8 + cb * 8 + chunk;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = rg; r < HW; r += 32) {
+        const uint4 v = __ldg(base + static_cast<size_t>(r) * C8);
+        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x);
+        acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z);
+        acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rg][chunk * 8 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+        gap[static_cast<size_t>(n) * C + cb * 64 + threadIdx.x] = s / static_cast<float>(HW);
+    }
+}
+
+__global__ void gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4* __restrict__ a,
+                                    uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw) {
+    const long long total = static_cast<long long>(B) * HW * C8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C8);
+        const int n = static_cast<int>(i / (static_cast<long long>(HW) * C8));
+        const uint4 v = a[i];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8) + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint32_t av[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = bf16_lo(av[j]) > 0.f ? g[2 * j] * inv_hw : 0.f;
+            const float hi = bf16_hi(av[j]) > 0.f ? g[2 * j + 1] * inv_hw : 0.f;
+            o[j] = pack_bf16x2(lo, hi);
+        }
+        dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------ head
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+    // splitmix64 finaliser -> 32 uniform bits (counter-based: reproducible across ranks/steps)
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<uint32_t>(z >> 32);
+}
+
+constexpr int kMaxClasses = 8;
+
+// One warp per frame: lanes stride over channels, shuffle-reduce the n logits.
+__global__ void __launch_bounds__(128)
+head_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ logits, float* __restrict__ probs, const float* __restrict__ y,
+                const float* __restrict__ cw, float inv_batch, float* __restrict__ loss_sum,
+                float* __restrict__ dlogits, unsigned char* __restrict__ keep_mask, int keep_mask_in, int training,
+                float dropout, unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n) {
+    const int lane = threadIdx.x & 31;
+    const int frame = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (frame >= B) return;
+    const float keep_scale = 1.f / (1.f - dropout);
+    const uint32_t thresh = static_cast<uint32_t>(fminf(dropout, 0.99999994f) * 4294967296.0);
+    float z[kMaxClasses];
+#pragma unroll
+    for (int j = 0; j < kMaxClasses; ++j) z[j] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float h = gap[static_cast<size_t>(frame) * C + c];
+        if (training) {
+            unsigned char keep;
+            const size_t mi = static_cast<size_t>(frame) * C + c;
+            if (keep_mask_in) {
+                keep = keep_mask[mi];
+            } else {
+                const uint64_t ctr = (static_cast<uint64_t>(step) << 40) ^ (static_cast<uint64_t>(rank) << 32) ^ mi;
+                keep = mix32(seed ^ (ctr * 0xD1342543DE82EF95ull)) >= thresh ? 1 : 0;
+                keep_mask[mi] = keep;
+            }
+            h = keep ? h * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxClasses; ++j)
+            if (j < n) z[j] += h * __ldg(w + c * n + j);
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxClasses; ++j)
+        if (j < n) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) z[j] += __shfl_xor_sync(0xffffffffu, z[j], o);
+            z[j] += b[j];
+        }
+    if (lane == 0) {
+        float mx = z[0];
+        for (int j = 1; j < n; ++j) mx = fmaxf(mx, z[j]);
+        float e[kMaxClasses], s = 0.f;
+        for (int j = 0; j < n; ++j) { e[j] = expf(z[j] - mx); s += e[j]; }
+        const float inv = 1.f / s;
+        float wi = 0.f, zy = 0.f;
+        for (int j = 0; j < n; ++j) {
+            logits[frame * n + j] = z[j];
+            probs[frame * n + j] = e[j] * inv;
+            if (y) {
+                const float yj = y[frame * n + j];
+                wi += yj * (cw ? cw[j] : 1.f);
+                zy += yj * z[j];
+            }
+        }
+        if (y) {
+            const float lse = mx + logf(s);
+            if (loss_sum) atomicAdd(loss_sum, wi * (lse - zy) * inv_batch);
+            if (dlogits)
+                for (int j = 0; j < n; ++j) dlogits[frame * n + j] = wi * inv_batch * (e[j] * inv - y[frame * n + j]);
+        }
+    }
+}
+
+// grid = (C / 32 channel groups... ) simple: one block per slice of frames; thread = channel.
+__global__ void head_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ w,
+                                const float* __restrict__ dlogits, const unsigned char* __restrict__ keep_mask,
+                                float dropout, float* __restrict__ dw, float* __restrict__ db,
+                                float* __restrict__ dgap, int B, int C, int n, int frames_per_block) {
+    const float keep_scale = 1.f / (1.f - dropout);
+    const int f0 = blockIdx.x * frames_per_block;
+    const int f1 = min(B, f0 + frames_per_block);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float wrow[kMaxClasses], acc[kMaxClasses];
+#pragma unroll
+        for (int j = 0; j < kMaxClasses; ++j) { wrow[j] = j < n ? w[c * n + j] : 0.f; acc[j] = 0.f; }
+        for (int f = f0; f < f1; ++f) {
+            const size_t idx = static_cast<size_t>(f) * C + c;
+            const float scale = keep_mask ? (keep_mask[idx] ? keep_scale : 0.f) : 1.f;
+            const float h = gap[idx] * scale;
+            float dg = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMaxClasses; ++j)
+                if (j < n) {
+                    const float d = dlogits[f * n + j];
+                    acc[j] += h * d;
+                    dg += d * wrow[j];
+                }
+            dgap[idx] = dg * scale;
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxClasses; ++j)
+            if (j < n) atomicAdd(dw + c * n + j, acc[j]);
+    }
+    if (threadIdx.x < n) {
+        float s = 0.f;
+        for (int f = f0; f < f1; ++f) s += dlogits[f * n + threadIdx.x];
+        atomicAdd(db + threadIdx.x, s);
+    }
+}
+
+// ------------------------------------------------------------------ optimizers (28 / 20 B per param)
+__global__ void adam_flat_kernel(float4* __restrict__ theta, const float4* __restrict__ g, float4* __restrict__ m,
+                                 float4* __restrict__ v, long long n4, float* theta_tail, const float* g_tail,
+                                 float* m_tail, float* v_tail, int tail, float alpha, float b1, float b2, float eps) {
+    const float ob1 = 1.f - b1, ob2 = 1.f - b2;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 gg = g[i];
+        float4 mm = m[i], vv = v[i], tt = theta[i];
+        mm.x = b1 * mm.x + ob1 * gg.x; mm.y = b1 * mm.y + ob1 * gg.y;
+        mm.z = b1 * mm.z + ob1 * gg.z; mm.w = b1 * mm.w + ob1 * gg.w;
+        vv.x = b2 * vv.x + ob2 * gg.x * gg.x; vv.y = b2 * vv.y + ob2 * gg.y * gg.y;
+        vv.z = b2 * vv.z + ob2 * gg.z * gg.z; vv.w = b2 * vv.w + ob2 * gg.w * gg.w;
+        tt.x -= alpha * mm.x / (sqrtf(vv.x) + eps); tt.y -= alpha * mm.y / (sqrtf(vv.y) + eps);
+        tt.z -= alpha * mm.z / (sqrtf(vv.z) + eps); tt.w -= alpha * mm.w / (sqrtf(vv.w) + eps);
+        m[i] = mm; v[i] = vv; theta[i] = tt;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        const int i = threadIdx.x;
+        const float gg = g_tail[i];
+        const float mm = b1 * m_tail[i] + ob1 * gg;
+        const float vv = b2 * v_tail[i] + ob2 * gg * gg;
+        theta_tail[i] -= alpha * mm / (sqrtf(vv) + eps);
+        m_tail[i] = mm; v_tail[i] = vv;
+    }
+}
+
+__global__ void rmsprop_flat_kernel(float4* __restrict__ theta, const float4* __restrict__ g,
+                                    float4* __restrict__ rms, long long n4, float* theta_tail, const float* g_tail,
+                                    float* rms_tail, int tail, float lr, float rho, float eps) {
+    const float orho = 1.f - rho;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 gg = g[i];
+        float4 rr = rms[i], tt = theta[i];
+        rr.x = rho * rr.x + orho * gg.x * gg.x; rr.y = rho * rr.y + orho * gg.y * gg.y;
+        rr.z = rho * rr.z + orho * gg.z * gg.z; rr.w = rho * rr.w + orho * gg.w * gg.w;
+        tt.x -= lr * gg.x / (sqrtf(rr.x) + eps); tt.y -= lr * gg.y / (sqrtf(rr.y) + eps);
+        tt.z -= lr * gg.z / (sqrtf(rr.z) + eps); tt.w -= lr * gg.w / (sqrtf(rr.w) + eps);
+        rms[i] = rr; theta[i] = tt;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        const int i = threadIdx.x;
+        const float gg = g_tail[i];
+        const float rr = rho * rms_tail[i] + orho * gg * gg;
+        theta_tail[i] -= lr * gg / (sqrtf(rr) + eps);
+        rms_tail[i] = rr;
+    }
+}
+
+// ------------------------------------------------------------------ Grad-CAM
+// One block (256 threads) per frame.  heat (H*W floats) lives in dynamic shared memory.
+__global__ void __launch_bounds__(256)
+gradcam_kernel(const uint4* __restrict__ a, const float* __restrict__ probs, const float* __restrict__ w,
+               float* __restrict__ heat_out, int H, int W, int C, int n, int out_h, int out_w) {
+    extern __shared__ float sm[];
+    float* alpha = sm;            // [C]
+    float* heat = sm + C;         // [H*W]
+    __shared__ float wmax[8];
+    const int frame = blockIdx.x;
+    const int HW = H * W, C8 = C >> 3;
+    const float* p = probs + static_cast<size_t>(frame) * n;
+    int cls = 0;
+    float pc = p[0];
+    for (int j = 1; j < n; ++j)
+        if (p[j] > pc) { pc = p[j]; cls = j; }
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) s += pc * ((j == cls ? 1.f : 0.f) - p[j]) * w[k * n + j];
+        alpha[k] = s / static_cast<float>(HW);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4* base = a + static_cast<size_t>(frame) * HW * C8;
+    float lmax = 0.f;
+    for (int px = warp; px < HW; px += 8) {
+        float s = 0.f;
+        for (int c = lane; c < C8; c += 32) {
+            const uint4 v = __ldg(base + static_cast<size_t>(px) * C8 + c);
+            const float* al = alpha + c * 8;
+            s += al[0] * bf16_lo(v.x) + al[1] * bf16_hi(v.x) + al[2] * bf16_lo(v.y) + al[3] * bf16_hi(v.y) +
+                 al[4] * bf16_lo(v.z) + al[5] * bf16_hi(v.z) + al[6] * bf16_lo(v.w) + al[7] * bf16_hi(v.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s = fmaxf(s / static_cast<float>(C), 0.f);
+        if (lane == 0) heat[px] = s;
+        lmax = fmaxf(lmax, s);
+    }
+    if (lane == 0) wmax[warp] = lmax;
+    __syncthreads();
+    float mx = wmax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, wmax[i]);
+    const float inv = mx > 0.f ? 1.f / mx : 0.f;
+    float* out = heat_out + static_cast<size_t>(frame) * out_h * out_w;
+    const float sy = static_cast<float>(H) / out_h, sx = static_cast<float>(W) / out_w;
+    for (int i = threadIdx.x; i < out_h * out_w; i += blockDim.x) {
+        const int oy = i / out_w, ox = i - oy * out_w;
+        // cv2.resize INTER_LINEAR: half-pixel centres, edge replicate
+        const float fy = (oy + 0.5f) * sy - 0.5f, fx = (ox + 0.5f) * sx - 0.5f;
+        const int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
+        const float wy = fy - y0, wx = fx - x0;
+        const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1);
+        const int x0c = min(max(x0, 0), W - 1), x1c = min(max(x0 + 1, 0), W - 1);
+        const float top = heat[y0c * W + x0c] * (1.f - wx) + heat[y0c * W + x1c] * wx;
+        const float bot = heat[y1c * W + x0c] * (1.f - wx) + heat[y1c * W + x1c] * wx;
+        out[i] = (top * (1.f - wy) + bot * wy) * inv;
+    }
+}
+
+static inline int grid_for(long long work_items, int threads, int waves) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = static_cast<long long>(sm_count()) * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+}  // namespace abl
+
+using namespace abl;
+
+extern "C" int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_dgrad, int Cin, int Cout,
+                                     void* stream) {
+    if (!w_hwio || (!w_fwd && !w_dgrad)) { set_error("abl_prep_conv_weights: null pointer"); return ABL_ERR_NULL; }
+    if (Cin <= 0 || Cout <= 0) { set_error("abl_prep_conv_weights: bad shape"); return ABL_ERR_SHAPE; }
+    prep_conv_weights_kernel<<<grid_for(9LL * Cin * Cout, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_hwio, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cout);
+    return check_launch();
+}
+
+extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, int B, int H,
+                                    int W, int C, void* stream) {
+    if (!dp || !a || !pooled || !dz) { set_error("abl_maxpool_bwd_relu: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_relu: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    maxpool_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(dp), static_cast<const uint4*>(a), static_cast<const uint4*>(pooled),
+        static_cast<uint4*>(dz), B, H, W, C / 8);
+    return check_launch();
+}
+
+extern "C" int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream) {
+    if (!a || !gap) { set_error("abl_gap_fwd: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || HW <= 0 || (C % 64) != 0) { set_error("abl_gap_fwd: need C % 64 == 0"); return ABL_ERR_SHAPE; }
+    gap_fwd_kernel<<<dim3(B, C / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(a), gap,
+                                                                                  HW, C);
+    return check_launch();
+}
+
+extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, int B, int HW, int C, void* stream) {
+    if (!dgap || !a || !dz) { set_error("abl_gap_bwd_relu: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || HW <= 0 || (C & 7)) { set_error("abl_gap_bwd_relu: need C % 8 == 0"); return ABL_ERR_SHAPE; }
+    const long long total = static_cast<long long>(B) * HW * (C / 8);
+    gap_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dgap, static_cast<const uint4*>(a), static_cast<uint4*>(dz), B, HW, C / 8, 1.f / static_cast<float>(HW));
+    return check_launch();
+}
+
+extern "C" int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
+                            const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
+                            float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
+                            unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
+                            void* stream) {
+    if (!gap || !w || !b || !logits || !probs) { set_error("abl_head_fwd: null pointer"); return ABL_ERR_NULL; }
+    if (training && !keep_mask) { set_error("abl_head_fwd: training needs a keep_mask buffer"); return ABL_ERR_NULL; }
+    if (B <= 0 || C <= 0 || n <= 0 || n > kMaxClasses) { set_error("abl_head_fwd: need 1 <= n <= 8"); return ABL_ERR_SHAPE; }
+    if (training && !(dropout >= 0.f && dropout < 1.f)) { set_error("abl_head_fwd: dropout must be in [0,1)"); return ABL_ERR_SHAPE; }
+    head_fwd_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, keep_mask_in,
+        training, training ? dropout : 0.f, seed, step, rank, B, C, n);
+    return check_launch();
+}
+
+extern "C" int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,
+                            float dropout, float* dw, float* db, float* dgap, int B, int C, int n, void* stream) {
+    if (!gap || !w || !dlogits || !dw || !db || !dgap) { set_error("abl_head_bwd: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || C <= 0 || n <= 0 || n > kMaxClasses) { set_error("abl_head_bwd: need 1 <= n <= 8"); return ABL_ERR_SHAPE; }
+    const int fpb = 16;
+    head_bwd_kernel<<<(B + fpb - 1) / fpb, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gap, w, dlogits, keep_mask, keep_mask ? dropout : 0.f, dw, db, dgap, B, C, n, fpb);
+    return check_launch();
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n, float alpha_t, float b1,
+                             float b2, float eps, void* stream) {
+    if (!theta || !g || !m || !v) { set_error("abl_adam_flat: null pointer"); return ABL_ERR_NULL; }
+    if (n <= 0) return ABL_OK;
+    if (!aligned16(theta) || !aligned16(g) || !aligned16(m) || !aligned16(v)) {
+        set_error("abl_adam_flat: buffers must be 16-byte aligned"); return ABL_ERR_ALIGN;
+    }
+    const long long n4 = n / 4;
+    const int tail = static_cast<int>(n - n4 * 4);
+    adam_flat_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+        reinterpret_cast<float4*>(v), n4, theta + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, tail, alpha_t, b1, b2, eps);
+    return check_launch();
+}
+
+extern "C" int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, float lr, float rho, float eps,
+                                void* stream) {
+    if (!theta || !g || !rms) { set_error("abl_rmsprop_flat: null pointer"); return ABL_ERR_NULL; }
+    if (n <= 0) return ABL_OK;
+    if (!aligned16(theta) || !aligned16(g) || !aligned16(rms)) {
+        set_error("abl_rmsprop_flat: buffers must be 16-byte aligned"); return ABL_ERR_ALIGN;
+    }
+    const long long n4 = n / 4;
+    const int tail = static_cast<int>(n - n4 * 4);
+    rmsprop_flat_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(rms), n4,
+        theta + n4 * 4, g + n4 * 4, rms + n4 * 4, tail, lr, rho, eps);
+    return check_launch();
+}
+
+extern "C" int abl_gradcam(const void* a, const float* probs, const float* w, float* heat, int B, int H, int W, int C,
+                           int n, int out_h, int out_w, void* stream) {
+    if (!a || !probs || !w || !heat) { set_error("abl_gradcam: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || H <= 0 || W <= 0 || (C & 7) || n <= 0 || n > kMaxClasses || out_h <= 0 || out_w <= 0) {
+        set_error("abl_gradcam: bad shape (need C % 8 == 0, 1 <= n <= 8)"); return ABL_ERR_SHAPE;
+    }
+    const size_t smem = (static_cast<size_t>(C) + static_cast<size_t>(H) * W) * sizeof(float);
+    if (smem > 200 * 1024) { set_error("abl_gradcam: activation map too large for shared memory"); return ABL_ERR_SHAPE; }
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(gradcam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch();
+    }
+    gradcam_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(a), probs, w, heat, H,
+                                                                       W, C, n, out_h, out_w);
+    return check_launch();
+}

@@ -1,0 +1,153 @@
+"""Launch shims: torch tensors (device memory + streams only) -> the C ABI of libabl_b200.so.
+
+No torch math happens here; every function forwards raw device pointers and sizes to a
+hand-written sm_100a kernel.  Missing library or non-CUDA tensors raise -- there is no fallback.
+"""
+import torch
+
+from . import _native
+from ._native import EPI_BIAS_RELU, EPI_RELU_MASK  # noqa: F401
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("ab_line_classifier_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("ab_line_classifier_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if t is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool=None, flags=0):
+    """x bf16 [B,H,W,Cin]; w_kmajor bf16 [9,Cout,Cin]; see include/abl_b200.h abl_conv3x3_igemm."""
+    for t, n in ((x, "x"), (w_kmajor, "w"), (mask_src, "mask_src"), (out_full, "out_full"), (out_pool, "out_pool")):
+        _chk(t, torch.bfloat16, n)
+    _chk(bias, torch.float32, "bias")
+    B, H, W, Cin = x.shape
+    Cout = w_kmajor.shape[1]
+    assert w_kmajor.shape == (9, Cout, Cin), w_kmajor.shape
+    if out_full is not None:
+        assert out_full.shape == (B, H, W, Cout)
+    if out_pool is not None:
+        assert out_pool.shape == (B, H // 2, W // 2, Cout)
+    if mask_src is not None:
+        assert mask_src.shape == (B, H, W, Cout)
+    _native.call("abl_conv3x3_igemm", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(mask_src), _ptr(out_full),
+                 _ptr(out_pool), B, H, W, Cin, Cout, flags, _stream())
+
+
+def wgrad_workspace_bytes(B, H, W, Cin, Cout):
+    n = _native.load().abl_conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)
+    if n < 0:
+        raise RuntimeError(f"abl_conv3x3_wgrad: unsupported shape B={B} H={H} W={W} Cin={Cin} Cout={Cout}")
+    return n
+
+
+def conv3x3_wgrad(x, dz, dw, db, workspace, accumulate=False):
+    """dw fp32 [3,3,Cin,Cout] (+)= x (*) dz; db fp32 [Cout] += sum dz (if given)."""
+    _chk(x, torch.bfloat16, "x"); _chk(dz, torch.bfloat16, "dz")
+    _chk(dw, torch.float32, "dw"); _chk(db, torch.float32, "db")
+    B, H, W, Cin = x.shape
+    Cout = dz.shape[3]
+    assert dz.shape == (B, H, W, Cout) and dw.numel() == 9 * Cin * Cout
+    _native.call("abl_conv3x3_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), _ptr(workspace),
+                 workspace.numel() * workspace.element_size(), int(bool(accumulate)), B, H, W, Cin, Cout, _stream())
+
+
+def bias_grad(dz, db):
+    _chk(dz, torch.bfloat16, "dz"); _chk(db, torch.float32, "db")
+    C = dz.shape[-1]
+    _native.call("abl_bias_grad", _ptr(dz), _ptr(db), dz.numel() // C, C, _stream())
+
+
+def conv_first_fwd(x, w_hwio, bias, out):
+    _chk(x, torch.float32, "x"); _chk(w_hwio, torch.float32, "w"); _chk(bias, torch.float32, "bias")
+    _chk(out, torch.bfloat16, "out")
+    B, H, W, c = x.shape
+    assert c == 3 and w_hwio.numel() == 27 * out.shape[3]
+    _native.call("abl_conv_first_fwd", _ptr(x), _ptr(w_hwio), _ptr(bias), _ptr(out), B, H, W, out.shape[3], _stream())
+
+
+def conv_first_wgrad(x, dz, dw, db):
+    _chk(x, torch.float32, "x"); _chk(dz, torch.bfloat16, "dz"); _chk(dw, torch.float32, "dw")
+    B, H, W, c = x.shape
+    assert c == 3
+    _native.call("abl_conv_first_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), B, H, W, dz.shape[3], _stream())
+
+
+def prep_conv_weights(w_hwio, w_fwd=None, w_dgrad=None):
+    _chk(w_hwio, torch.float32, "w"); _chk(w_fwd, torch.bfloat16, "w_fwd"); _chk(w_dgrad, torch.bfloat16, "w_dgrad")
+    Cin, Cout = w_hwio.shape[-2], w_hwio.shape[-1]
+    _native.call("abl_prep_conv_weights", _ptr(w_hwio), _ptr(w_fwd), _ptr(w_dgrad), Cin, Cout, _stream())
+
+
+def maxpool_bwd_relu(dp, a, pooled, dz):
+    for t in (dp, a, pooled, dz):
+        _chk(t, torch.bfloat16, "tensor")
+    B, H, W, Cc = a.shape
+    _native.call("abl_maxpool_bwd_relu", _ptr(dp), _ptr(a), _ptr(pooled), _ptr(dz), B, H, W, Cc, _stream())
+
+
+def gap_fwd(a, gap):
+    _chk(a, torch.bfloat16, "a"); _chk(gap, torch.float32, "gap")
+    B, H, W, Cc = a.shape
+    _native.call("abl_gap_fwd", _ptr(a), _ptr(gap), B, H * W, Cc, _stream())
+
+
+def gap_bwd_relu(dgap, a, dz):
+    _chk(dgap, torch.float32, "dgap"); _chk(a, torch.bfloat16, "a"); _chk(dz, torch.bfloat16, "dz")
+    B, H, W, Cc = a.shape
+    _native.call("abl_gap_bwd_relu", _ptr(dgap), _ptr(a), _ptr(dz), B, H * W, Cc, _stream())
+
+
+def head_fwd(gap, w, b, logits, probs, y=None, class_weight=None, inv_batch=1.0, loss_sum=None, dlogits=None,
+             keep_mask=None, keep_mask_in=False, training=False, dropout=0.0, seed=0, step=0, rank=0):
+    for t in (gap, w, b, logits, probs, y, class_weight, loss_sum, dlogits):
+        _chk(t, torch.float32, "tensor")
+    _chk(keep_mask, torch.uint8, "keep_mask")
+    B, Cc = gap.shape
+    n = w.shape[1]
+    _native.call("abl_head_fwd", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
+                 _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
+                 int(bool(keep_mask_in)), int(bool(training)), float(dropout), int(seed), int(step), int(rank),
+                 B, Cc, n, _stream())
+
+
+def head_bwd(gap, w, dlogits, keep_mask, dropout, dw, db, dgap):
+    for t in (gap, w, dlogits, dw, db, dgap):
+        _chk(t, torch.float32, "tensor")
+    B, Cc = gap.shape
+    _native.call("abl_head_bwd", _ptr(gap), _ptr(w), _ptr(dlogits), _ptr(keep_mask), float(dropout), _ptr(dw),
+                 _ptr(db), _ptr(dgap), B, Cc, w.shape[1], _stream())
+
+
+def adam_flat(theta, g, m, v, alpha_t, b1=0.9, b2=0.999, eps=1e-7):
+    for t in (theta, g, m, v):
+        _chk(t, torch.float32, "tensor")
+    _native.call("abl_adam_flat", _ptr(theta), _ptr(g), _ptr(m), _ptr(v), theta.numel(), float(alpha_t), float(b1),
+                 float(b2), float(eps), _stream())
+
+
+def rmsprop_flat(theta, g, rms, lr, rho=0.9, eps=1e-7):
+    for t in (theta, g, rms):
+        _chk(t, torch.float32, "tensor")
+    _native.call("abl_rmsprop_flat", _ptr(theta), _ptr(g), _ptr(rms), theta.numel(), float(lr), float(rho),
+                 float(eps), _stream())
+
+
+def gradcam(a, probs, w, heat):
+    _chk(a, torch.bfloat16, "a"); _chk(probs, torch.float32, "probs"); _chk(w, torch.float32, "w")
+    _chk(heat, torch.float32, "heat")
+    B, H, W, Cc = a.shape
+    _native.call("abl_gradcam", _ptr(a), _ptr(probs), _ptr(w), _ptr(heat), B, H, W, Cc, w.shape[1],
+                 heat.shape[1], heat.shape[2], _stream())

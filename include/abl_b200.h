@@ -1,0 +1,128 @@
+/* abl_b200.h -- C ABI of libabl_b200.so: the B200-native (sm_100a) numerics of the cutoffvgg16
+ * hot path of gchetty/ab-line-classifier.
+ *
+ * The reference has NO native code: every numeric op on this path is a TensorFlow 2.9 / Keras
+ * library call made from Python.  Each entry point below therefore cites the
+ * reference call site whose Keras op(s) it replaces; the binding a maintainer adds is a ctypes stub
+ * (INTEGRATION.md), mirrored by ab_line_classifier_b200/_native.py.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller; nothing here allocates or frees.
+ *   - Activations are NHWC, bf16 unless stated; master weights/gradients are fp32 in Keras layout
+ *     (conv kernels HWIO [3][3][Cin][Cout], dense (in,out)).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered.
+ *   - Return value: 0 on success, negative ABL_ERR_* otherwise; abl_last_error() (thread-local)
+ *     describes the failure.  No exceptions cross this boundary.
+ *   - Re-entrant; no global mutable state besides per-device one-time kernel attributes.
+ */
+#ifndef ABL_B200_H_
+#define ABL_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABL_ABI_VERSION 1
+
+#define ABL_OK 0
+#define ABL_ERR_SHAPE (-1)
+#define ABL_ERR_ALIGN (-2)
+#define ABL_ERR_NULL (-3)
+#define ABL_ERR_DRIVER (-4)
+#define ABL_ERR_CUDA (-5)
+
+/* epilogue flags of abl_conv3x3_igemm */
+#define ABL_EPI_BIAS_RELU 1 /* y = relu(acc + bias[co])                  (forward)              */
+#define ABL_EPI_RELU_MASK 2 /* y = mask_src[n,h,w,co] > 0 ? acc : 0      (dgrad -> dZ of layer below) */
+
+int abl_abi_version(void);
+const char* abl_last_error(void);
+
+/* Conv2D 3x3/s1/SAME as a tcgen05 implicit GEMM.  Replaces Keras Conv2D+BiasAdd+Relu(+MaxPool2D)
+ * of the VGG16 layers reused at src/models/models.py:409-413 (forward) and, with the tap-flipped
+ * transposed filter and ABL_EPI_RELU_MASK, TF's Conv2DBackpropInput+ReluGrad that model.fit's
+ * GradientTape runs (models.py:427,432).
+ *   x        bf16 [B,H,W,Cin]
+ *   w_kmajor bf16 [9][Cout][Cin]   (from abl_prep_conv_weights: w_fwd for forward, w_dgrad for dgrad)
+ *   bias     fp32 [Cout]           (ABL_EPI_BIAS_RELU)
+ *   mask_src bf16 [B,H,W,Cout]     (ABL_EPI_RELU_MASK; post-ReLU activation of the layer below)
+ *   out_full bf16 [B,H,W,Cout] or NULL;  out_pool bf16 [B,H/2,W/2,Cout] (2x2/s2 max) or NULL
+ * Requires Cin, Cout multiples of 64 (<= 512), H*W tileable into 128-pixel rectangles. */
+int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
+                      void* out_full, void* out_pool, int B, int H, int W, int Cin, int Cout, int flags,
+                      void* stream);
+
+/* Conv2DBackpropFilter (+BiasAddGrad) of model.fit's tape (models.py:427,432) as a tcgen05 GEMM with
+ * MN-major operands read straight from the NHWC tensors, split over pixel slices into `workspace`
+ * and reduced in a fixed order (deterministic), fp32 accumulation:
+ *   dw[kh][kw][ci][co] (+)= sum_{n,h,w} x[n,h+kh-1,w+kw-1,ci] * dz[n,h,w,co]   (HWIO fp32)
+ *   db[co]              += sum_{n,h,w} dz[n,h,w,co]                            (if db != NULL; always accumulates)
+ * x bf16 [B,H,W,Cin], dz bf16 [B,H,W,Cout]; accumulate != 0 adds to dw, else overwrites it.
+ * workspace: >= abl_conv3x3_wgrad_workspace_bytes(...) bytes, 16-byte aligned, caller-owned. */
+long long abl_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float* db, void* workspace,
+                      long long workspace_bytes, int accumulate, int B, int H, int W, int Cin, int Cout,
+                      void* stream);
+/* BiasAddGrad alone: db[c] += sum_r dz[r][c], dz bf16 [rows][C]. */
+int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
+
+/* block1_conv1 (Cin=3, K=27: HBM-bound, not tensor-core shaped).  Forward reads the caller's fp32
+ * NHWC frame (already BGR / mean-subtracted, preprocessor.py:60-63) and writes bf16 relu(conv+b). */
+int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H, int W,
+                       int Cout, void* stream);
+/* dw[3][3][3][Cout] += ..., db[Cout] += ... for block1_conv1 (x fp32 [B,H,W,3], dz bf16 [B,H,W,Cout]). */
+int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W, int Cout,
+                         void* stream);
+
+/* fp32 HWIO master kernel -> the two bf16 GEMM operand layouts:
+ *   w_fwd[t][co][ci] = w[t][ci][co];   w_dgrad[t][ci][co] = w[8-t][ci][co]   (either may be NULL) */
+int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
+
+/* MaxPoolGrad + ReluGrad: dz[n,h,w,c] = dp[n,h/2,w/2,c] if a[n,h,w,c] is the first maximum of its 2x2
+ * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16. */
+int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, int B, int H, int W,
+                         int C, void* stream);
+
+/* GlobalAveragePooling2D (models.py:414): gap[n][c] = mean_{hw} a[n,hw,c]; a bf16, gap fp32. */
+int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream);
+/* its gradient fused with ReluGrad of the last conv: dz = a > 0 ? dgap[n][c] / HW : 0 (bf16). */
+int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, int B, int HW, int C, void* stream);
+
+/* Dropout -> Dense(n_classes) -> softmax (models.py:415-416) [+ categorical_crossentropy with
+ * class_weight, models.py:426 / train.py:135-136].
+ *   gap fp32 [B,C]; w fp32 [C,n]; b fp32 [n]; n <= 8.
+ *   training != 0: keep-mask from the counter hash (seed, step, rank, frame, channel) with
+ *     P(drop) = dropout, kept values scaled 1/(1-dropout); mask bytes written to keep_mask [B,C]
+ *     (if keep_mask_in != 0 the mask is READ from keep_mask instead -- test hook).
+ *   y_onehot fp32 [B,n] or NULL (no loss).  class_weight fp32 [n] or NULL.
+ *   loss_sum += sum_i w_i * (logsumexp(z_i) - z_i[y_i]) * inv_batch     (fp32 scalar, ACCUMULATES)
+ *   dlogits[i][j] = w_i * inv_batch * (p_ij - y_ij)                      (if dlogits != NULL) */
+int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
+                 const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
+                 float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
+                 unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
+                 void* stream);
+/* dw[C][n] += h^T dlogits, db[n] += sum_i dlogits, dgap[i][c] = scale_ic * sum_j dlogits[i][j] w[c][j]
+ * with h = gap * scale, scale_ic = keep_mask ? mask/(1-dropout) : 1. */
+int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,
+                 float dropout, float* dw, float* db, float* dgap, int B, int C, int n, void* stream);
+
+/* Keras 2.9 Adam (models.py:397): m,v update; theta -= alpha_t * m / (sqrt(v) + eps), where the caller
+ * passes alpha_t = lr * sqrt(1-b2^t) / (1-b1^t).  Flat fp32 buffers of n elements. */
+int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n, float alpha_t, float b1,
+                  float b2, float eps, void* stream);
+/* Keras 2.9 RMSprop (models.py:398), momentum 0, not centered. */
+int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, float lr, float rho, float eps,
+                     void* stream);
+
+/* Grad-CAM of the predicted class for a GAP->Dense->softmax head (src/explainability/gradcam.py:68-81),
+ * per frame: alpha_k = (1/HW) sum_j p_c (delta_cj - p_j) w[k][j]; heat = relu(mean_k alpha_k a[h,w,k]);
+ * heat /= max(heat) (all-zero map stays zero); bilinear resize (cv2 INTER_LINEAR semantics) to
+ * out_h x out_w.  a bf16 [B,H,W,C]; probs fp32 [B,n]; w fp32 [C,n]; heat fp32 [B,out_h,out_w]. */
+int abl_gradcam(const void* a, const float* probs, const float* w, float* heat, int B, int H, int W, int C,
+                int n, int out_h, int out_w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABL_B200_H_ */
