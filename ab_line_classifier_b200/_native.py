@@ -39,6 +39,11 @@ SIGNATURES = {
 
 _lib = None
 
+# kernels launched per entry point (abl_conv3x3_wgrad: GEMM + slice reduction [+ bias grad])
+LAUNCHES_PER_CALL = {"abl_conv3x3_wgrad": 3}
+launch_count = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+timing = None             # set to a list to record (name, args, start_event, end_event) per call
+
 
 def load():
     """dlopen the in-tree library and attach signatures.  Raises if it has not been built."""
@@ -62,8 +67,18 @@ def load():
 
 def call(name, *args):
     """Invoke an int-returning entry point; non-zero -> RuntimeError with abl_last_error()."""
+    global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if timing is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        timing.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.abl_last_error().decode(errors="replace")
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")

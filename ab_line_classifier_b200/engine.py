@@ -1,0 +1,434 @@
+"""Device engine for the cutoffvgg16 hot path: owns the HBM layout and sequences the sm_100a kernels.
+
+Replaces what Keras does under ``CutoffVGG16.fit / predict`` (reference src/models/models.py:407-444):
+forward (7 conv + 2 pool + GAP/Dropout/Dense/softmax), loss, backward for the trainable suffix of
+layers, Adam / RMSprop, Grad-CAM.  torch is used for device memory, streams and (for data parallel)
+``torch.distributed``; every numeric op is a kernel of libabl_b200.so.
+
+HBM layout (per process / GPU)
+  theta, grad, m, v, rms : flat fp32 [P] in Keras order and layout (HWIO kernels, (in,out) dense),
+                           each tensor padded to 4 floats; gradients of all layers land in ONE buffer
+                           so data-parallel all-reduce buckets are plain slices (no pack copy).
+  w_fwd[l], w_dgrad[l]   : bf16 GEMM operands [9][Cout][Cin] / [9][Cin][Cout] re-cast after each update.
+  act[l] / pooled[l]     : bf16 NHWC activations (full resolution kept only when training).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+# Keras VGG16(include_top=False).layers[1:]: (name, kind, out_channels)  (third-party layer list,
+# sliced by the reference at models.py:410)
+VGG16_LAYERS = [
+    ("block1_conv1", "conv", 64), ("block1_conv2", "conv", 64), ("block1_pool", "pool", 0),
+    ("block2_conv1", "conv", 128), ("block2_conv2", "conv", 128), ("block2_pool", "pool", 0),
+    ("block3_conv1", "conv", 256), ("block3_conv2", "conv", 256), ("block3_conv3", "conv", 256),
+    ("block3_pool", "pool", 0),
+    ("block4_conv1", "conv", 512), ("block4_conv2", "conv", 512), ("block4_conv3", "conv", 512),
+    ("block4_pool", "pool", 0),
+    ("block5_conv1", "conv", 512), ("block5_conv2", "conv", 512), ("block5_conv3", "conv", 512),
+    ("block5_pool", "pool", 0),
+]
+
+
+class ConvSpec:
+    __slots__ = ("name", "cin", "cout", "h", "w", "pool", "vgg_index")
+
+    def __init__(self, name, cin, cout, h, w, vgg_index):
+        self.name, self.cin, self.cout, self.h, self.w = name, cin, cout, h, w
+        self.pool = False
+        self.vgg_index = vgg_index   # index in vgg16.layers[1:cutoff] (what FINETUNE_LAYER slices)
+
+
+def build_plan(input_shape, cutoff_layer):
+    """Conv specs for ``vgg16.layers[1:cutoff_layer]`` (models.py:410); a pool folds into the conv above it."""
+    h, w, c = input_shape
+    if c != 3:
+        raise NotImplementedError("DATA.IMG_DIM must give 3-channel frames (VGG16 input)")
+    kept = VGG16_LAYERS[: cutoff_layer - 1]
+    if not kept or kept[0][1] != "conv":
+        raise NotImplementedError("HPARAMS.CUTOFFVGG16.CUTOFF_LAYER must keep at least block1_conv1")
+    specs = []
+    for i, (name, kind, cout) in enumerate(kept):
+        if kind == "conv":
+            specs.append(ConvSpec(name, c, cout, h, w, i))
+            c = cout
+        else:
+            if h % 2 or w % 2:
+                raise NotImplementedError(f"DATA.IMG_DIM not divisible for {name}")
+            specs[-1].pool = True
+            h, w = h // 2, w // 2
+    return specs, (h, w, c)
+
+
+class CutoffVGG16Engine:
+    def __init__(self, input_shape=(128, 128, 3), n_classes=2, cutoff_layer=10, dropout=0.45, output_bias=None,
+                 seed=10001, device=None, rank=0, world_size=1, process_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ab_line_classifier_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        ops._native.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.input_shape = tuple(int(v) for v in input_shape)
+        self.n_classes = int(n_classes)
+        if not 1 <= self.n_classes <= 8:
+            raise NotImplementedError("TRAIN.N_CLASSES must be in 1..8")
+        self.cutoff_layer = int(cutoff_layer)
+        self.dropout = float(dropout)
+        self.seed, self.rank, self.world_size, self.pg = int(seed), int(rank), int(world_size), process_group
+        self.specs, self.feat_shape = build_plan(self.input_shape, self.cutoff_layer)
+        if self.specs[0].cout != 64:
+            raise NotImplementedError("first layer must be block1_conv1 (64 filters)")
+        self.step_count = 0           # dropout counter
+        self.opt_steps = {}           # optimizer name -> steps taken (Adam bias correction)
+        self._alloc_params(output_bias)
+        self._cap = 0
+        self._cap_train = False
+        self._buf = {}
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_params(self, output_bias):
+        self.segments = {}     # Keras weight name -> (offset, numel, shape)
+        off = 0
+
+        def add(name, shape):
+            nonlocal off
+            n = int(np.prod(shape))
+            self.segments[name] = (off, n, tuple(shape))
+            off += (n + 3) // 4 * 4
+
+        self.layer_ranges = {}     # layer name -> (start, end) in the flat buffer
+        for s in self.specs:
+            start = off
+            add(s.name + "/kernel", (3, 3, s.cin, s.cout))
+            add(s.name + "/bias", (s.cout,))
+            self.layer_ranges[s.name] = (start, off)
+        start = off
+        add("output/kernel", (self.feat_shape[2], self.n_classes))
+        add("output/bias", (self.n_classes,))
+        self.layer_ranges["output"] = (start, off)
+        self.n_flat = off
+        self.n_params = sum(n for _, n, _ in self.segments.values())
+        dev = self.device
+        self.theta = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.opt_state = {}
+        self.w_fwd, self.w_dgrad = {}, {}
+        for s in self.specs[1:]:
+            self.w_fwd[s.name] = torch.empty(9, s.cout, s.cin, device=dev, dtype=torch.bfloat16)
+            self.w_dgrad[s.name] = torch.empty(9, s.cin, s.cout, device=dev, dtype=torch.bfloat16)
+        self.class_weight = torch.ones(self.n_classes, device=dev, dtype=torch.float32)
+        self.init_glorot(self.seed, output_bias)
+
+    def layer_names(self):
+        return [s.name for s in self.specs] + ["output"]
+
+    def view(self, name, buf=None):
+        off, n, shape = self.segments[name]
+        return (self.theta if buf is None else buf)[off:off + n].view(shape)
+
+    def init_glorot(self, seed, output_bias=None):
+        """Keras default init (Glorot uniform kernels, zero biases), as ``VGG16(weights=None)`` + Dense
+        would give; the reference's ImageNet download (models.py:409) needs network access."""
+        rng = np.random.default_rng(seed)
+        w = {}
+        for s in self.specs:
+            lim = math.sqrt(6.0 / (9 * s.cin + 9 * s.cout))
+            w[s.name + "/kernel"] = rng.uniform(-lim, lim, size=(3, 3, s.cin, s.cout)).astype(np.float32)
+            w[s.name + "/bias"] = np.zeros(s.cout, np.float32)
+        c = self.feat_shape[2]
+        lim = math.sqrt(6.0 / (c + self.n_classes))
+        w["output/kernel"] = rng.uniform(-lim, lim, size=(c, self.n_classes)).astype(np.float32)
+        w["output/bias"] = (np.zeros(self.n_classes, np.float32) if output_bias is None
+                            else np.asarray(output_bias, np.float32).reshape(self.n_classes))
+        self.set_weights(w)
+
+    def set_weights(self, weights, strict=True):
+        """weights: dict Keras name ('block1_conv1/kernel', ..., 'output/bias') -> array in Keras layout."""
+        host = self.theta.cpu().numpy()
+        for name, (off, n, shape) in self.segments.items():
+            key = name if name in weights else name + ":0"
+            if key not in weights:
+                if strict:
+                    raise KeyError(f"missing weight {name}")
+                continue
+            a = np.asarray(weights[key], np.float32)
+            if a.shape != shape:
+                raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+            host[off:off + n] = a.reshape(-1)
+        self.theta.copy_(torch.from_numpy(host))
+        self.refresh_operands()
+
+    def get_weights(self):
+        host = self.theta.cpu().numpy()
+        return {name: host[off:off + n].reshape(shape).copy() for name, (off, n, shape) in self.segments.items()}
+
+    def refresh_operands(self, layers=None):
+        """Re-cast fp32 master kernels into the bf16 GEMM operand layouts."""
+        for s in self.specs[1:]:
+            if layers is None or s.name in layers:
+                ops.prep_conv_weights(self.view(s.name + "/kernel"), self.w_fwd[s.name], self.w_dgrad[s.name])
+
+    # ------------------------------------------------------------------ buffers
+    def _ensure(self, batch, training):
+        if batch <= self._cap and (self._cap_train or not training):
+            return
+        cap = max(batch, self._cap)
+        training = training or self._cap_train
+        dev, bf = self.device, torch.bfloat16
+        b = {}
+        H, W, _ = self.input_shape
+        b["x"] = torch.empty(cap, H, W, 3, device=dev, dtype=torch.float32)
+        max_full = 0
+        for s in self.specs:
+            if s.pool:
+                b["pool_" + s.name] = torch.empty(cap, s.h // 2, s.w // 2, s.cout, device=dev, dtype=bf)
+            if not s.pool or training:
+                b["act_" + s.name] = torch.empty(cap, s.h, s.w, s.cout, device=dev, dtype=bf)
+            max_full = max(max_full, s.h * s.w * s.cout)
+        C = self.feat_shape[2]
+        n = self.n_classes
+        b["gap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
+        b["logits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
+        b["probs"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
+        b["y"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
+        b["loss"] = torch.zeros(1, device=dev, dtype=torch.float32)
+        if training:
+            b["dlogits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
+            b["keep"] = torch.empty(cap, C, device=dev, dtype=torch.uint8)
+            b["dgap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
+            b["dz_a"] = torch.empty(cap * max_full, device=dev, dtype=bf)
+            b["dz_b"] = torch.empty(cap * max_full, device=dev, dtype=bf)
+            b["dp"] = torch.empty(cap * max_full // 4, device=dev, dtype=bf)
+            ws = 0
+            for s in self.specs[1:]:
+                ws = max(ws, ops.wgrad_workspace_bytes(cap, s.h, s.w, s.cin, s.cout))
+            b["ws"] = torch.empty(ws, device=dev, dtype=torch.uint8)
+        self._buf, self._cap, self._cap_train = b, cap, training
+
+    def _in_act(self, li, B):
+        """Input activation of conv li (bf16), li >= 1."""
+        prev = self.specs[li - 1]
+        key = ("pool_" if prev.pool else "act_") + prev.name
+        return self._buf[key][:B]
+
+    # ------------------------------------------------------------------ forward
+    def forward_device(self, B, training=False, keep_mask_in=False, y=None, inv_batch=None, loss_out=None):
+        """Runs the network on self._buf['x'][:B] (already resident).  Returns probs view [B,n].
+        training: dropout on, class-weighted loss + dlogits.  Otherwise, if y is given, the UNweighted
+        loss sum_i l_i * inv_batch is accumulated into loss_out (Keras evaluate / validation)."""
+        b = self._buf
+        for li, s in enumerate(self.specs):
+            full = b.get("act_" + s.name)
+            full = full[:B] if full is not None else None
+            pooled = b["pool_" + s.name][:B] if s.pool else None
+            if li == 0:
+                ops.conv_first_fwd(b["x"][:B], self.view(s.name + "/kernel"), self.view(s.name + "/bias"), full)
+                if s.pool:
+                    raise NotImplementedError("a pool directly after block1_conv1 is not a VGG16 prefix")
+            else:
+                ops.conv3x3_igemm(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"), None,
+                                  full, pooled, ops.EPI_BIAS_RELU)
+        last = self.specs[-1]
+        feat = b["pool_" + last.name][:B] if last.pool else b["act_" + last.name][:B]
+        ops.gap_fwd(feat, b["gap"][:B])
+        if loss_out is None:
+            loss_out = b["loss"]
+            loss_out.zero_()
+        if training:
+            ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
+                         b["probs"][:B], y, self.class_weight, inv_batch, loss_out, b["dlogits"][:B],
+                         b["keep"][:B], keep_mask_in, True, self.dropout, self.seed, self.step_count, self.rank)
+        elif y is not None:
+            ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
+                         b["probs"][:B], y, None, inv_batch, loss_out)
+        else:
+            ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
+                         b["probs"][:B])
+        return b["probs"][:B]
+
+    def load_input(self, x):
+        """Host (numpy / CPU tensor, ideally pinned) or device fp32 NHWC frames -> self._buf['x']."""
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if x.dtype != torch.float32:
+            x = x.float()
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != self.input_shape:
+            raise ValueError(f"expected frames of shape {self.input_shape}, got {tuple(x.shape[1:])}")
+        self._buf["x"][:B].copy_(x, non_blocking=True)
+        return B
+
+    def predict_batch(self, x):
+        """x: [B,H,W,3] fp32 (BGR, mean-subtracted, as vgg16_preprocess leaves it).  Returns device probs."""
+        B = x.shape[0]
+        self._ensure(B, False)
+        self.load_input(x)
+        return self.forward_device(B)
+
+    # ------------------------------------------------------------------ backward + update
+    def trainable_suffix(self, trainable):
+        names = self.layer_names()
+        tr = [n in trainable for n in names]
+        if not any(tr):
+            raise ValueError("no trainable layer")
+        return names, tr, tr.index(True)
+
+    def backward_device(self, B, trainable, reduce_hook=None):
+        """Gradients of the loss for the trainable layers into self.grad (zeroed first).
+        reduce_hook(start, end) is called as soon as grad[start:end] is final (DP buckets)."""
+        b = self._buf
+        names, tr, lowest = self.trainable_suffix(trainable)
+        self.grad.zero_()
+        keep = b["keep"][:B]
+        if tr[-1]:
+            dwk, dbk = self.view("output/kernel", self.grad), self.view("output/bias", self.grad)
+        else:   # still need dgap; dump head grads in scratch
+            dwk = torch.zeros_like(self.view("output/kernel"))
+            dbk = torch.zeros_like(self.view("output/bias"))
+        ops.head_bwd(b["gap"][:B], self.view("output/kernel"), b["dlogits"][:B], keep, self.dropout, dwk, dbk,
+                     b["dgap"][:B])
+        if reduce_hook and tr[-1]:
+            reduce_hook(*self.layer_ranges["output"])
+        nconv = len(self.specs)
+        if lowest >= nconv:
+            return
+        last = self.specs[-1]
+        if last.pool:
+            raise NotImplementedError("training with a cutoff that ends in a pool layer")
+        cur, other = b["dz_a"], b["dz_b"]
+        dz = cur[: B * last.h * last.w * last.cout].view(B, last.h, last.w, last.cout)
+        ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz)
+        for li in range(nconv - 1, lowest - 1, -1):
+            s = self.specs[li]
+            if tr[li]:
+                dw = self.view(s.name + "/kernel", self.grad)
+                db = self.view(s.name + "/bias", self.grad)
+                if li == 0:
+                    ops.conv_first_wgrad(b["x"][:B], dz, dw, db)
+                else:
+                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw, db, b["ws"], accumulate=False)
+                if reduce_hook:
+                    reduce_hook(*self.layer_ranges[s.name])
+            if li > lowest:
+                prev = self.specs[li - 1]
+                if prev.pool:
+                    dp = b["dp"][: B * s.h * s.w * s.cin].view(B, s.h, s.w, s.cin)
+                    ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, None, dp, None, 0)
+                    ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
+                    ops.maxpool_bwd_relu(dp, b["act_" + prev.name][:B], b["pool_" + prev.name][:B], ndz)
+                else:
+                    ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
+                    ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["act_" + prev.name][:B], ndz, None,
+                                      ops.EPI_RELU_MASK)
+                dz = ndz
+                cur, other = other, cur
+
+    def _runs(self, trainable):
+        """Contiguous [start,end) runs of the flat buffer covering the trainable layers."""
+        runs = []
+        for n in self.layer_names():
+            if n in trainable:
+                s, e = self.layer_ranges[n]
+                if runs and runs[-1][1] == s:
+                    runs[-1][1] = e
+                else:
+                    runs.append([s, e])
+        return runs
+
+    def apply_optimizer(self, kind, lr, trainable, beta_1=0.9, beta_2=0.999, rho=0.9, eps=1e-7):
+        """Keras 2.9 Adam / RMSprop on the trainable slices (Appendix A.5), then re-cast bf16 operands."""
+        key = kind
+        t = self.opt_steps.get(key, 0) + 1
+        self.opt_steps[key] = t
+        if kind == "adam":
+            if "m" not in self.opt_state:
+                self.opt_state["m"] = torch.zeros_like(self.theta)
+                self.opt_state["v"] = torch.zeros_like(self.theta)
+            alpha = lr * math.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+            for s, e in self._runs(trainable):
+                ops.adam_flat(self.theta[s:e], self.grad[s:e], self.opt_state["m"][s:e], self.opt_state["v"][s:e],
+                              alpha, beta_1, beta_2, eps)
+        elif kind == "rmsprop":
+            if "rms" not in self.opt_state:
+                self.opt_state["rms"] = torch.zeros_like(self.theta)
+            for s, e in self._runs(trainable):
+                ops.rmsprop_flat(self.theta[s:e], self.grad[s:e], self.opt_state["rms"][s:e], lr, rho, eps)
+        else:
+            raise ValueError(f"unknown optimizer {kind}")
+        self.refresh_operands(trainable)
+
+    def set_class_weight(self, class_weight):
+        cw = np.ones(self.n_classes, np.float32)
+        if class_weight is not None:
+            for k, v in dict(class_weight).items():
+                cw[int(k)] = float(v)
+        self.class_weight.copy_(torch.from_numpy(cw))
+
+    def eval_batch(self, x, y, loss_out=None, inv_batch=1.0):
+        """Inference forward + unweighted categorical cross-entropy sum (Keras evaluate).  Device probs."""
+        B = x.shape[0]
+        self._ensure(B, False)
+        self.load_input(x)
+        if isinstance(y, np.ndarray):
+            y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+        self._buf["y"][:B].copy_(y, non_blocking=True)
+        return self.forward_device(B, y=self._buf["y"][:B], inv_batch=inv_batch, loss_out=loss_out)
+
+    def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
+                   apply_update=True, bucket_bytes=2 << 20, loss_out=None):
+        """One step: H2D copy of (x, y), forward (dropout on), loss, backward, [DP all-reduce], update.
+        Returns the device scalar sum_i w_i*l_i / global_batch for THIS rank's frames."""
+        B = x.shape[0]
+        self._ensure(B, True)
+        b = self._buf
+        self.load_input(x)
+        if isinstance(y, np.ndarray):
+            y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+        b["y"][:B].copy_(y, non_blocking=True)
+        if keep_mask is not None:
+            if isinstance(keep_mask, np.ndarray):
+                keep_mask = torch.from_numpy(np.ascontiguousarray(keep_mask).astype(np.uint8))
+            b["keep"][:B].copy_(keep_mask, non_blocking=True)
+        gb = float(global_batch if global_batch is not None else B * self.world_size)
+        self.forward_device(B, training=True, keep_mask_in=keep_mask is not None, y=b["y"][:B], inv_batch=1.0 / gb,
+                            loss_out=loss_out)
+        self.step_count += 1
+        handles = []
+        hook = None
+        if self.world_size > 1:
+            import torch.distributed as dist
+            pending = []   # ranges finished but not yet reduced (coalesce small layers into buckets)
+
+            def flush():
+                if pending:
+                    s, e = min(p[0] for p in pending), max(p[1] for p in pending)
+                    handles.append(dist.all_reduce(self.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                    pending.clear()
+
+            def hook(s, e):
+                pending.append((s, e))
+                if sum(q[1] - q[0] for q in pending) * 4 >= bucket_bytes:
+                    flush()
+        self.backward_device(B, trainable, reduce_hook=hook)
+        if self.world_size > 1:
+            flush()
+            for h in handles:
+                h.wait()
+        if apply_update:
+            self.apply_optimizer(optimizer, lr, trainable)
+        return b["loss"] if loss_out is None else loss_out
+
+    # ------------------------------------------------------------------ Grad-CAM
+    def gradcam_batch(self, x, out_hw=None):
+        """Per-frame Grad-CAM heat-maps (gradcam.py:68-81) -> (device heat [B,oh,ow] fp32, device probs)."""
+        last = self.specs[-1]
+        if last.pool:
+            raise NotImplementedError("Grad-CAM with a cutoff that ends in a pool layer")
+        probs = self.predict_batch(x)
+        B = x.shape[0]
+        oh, ow = out_hw if out_hw is not None else self.input_shape[:2]
+        heat = torch.empty(B, oh, ow, device=self.device, dtype=torch.float32)
+        ops.gradcam(self._buf["act_" + last.name][:B], probs, self.view("output/kernel"), heat)
+        return heat, probs

@@ -9,7 +9,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GROUPS = ["fwd", "dgrad", "wgrad", "first", "pointwise", "head", "optim", "gradcam"]
+GROUPS = ["fwd", "dgrad", "wgrad", "first", "pointwise", "head", "optim", "gradcam", "e2e"]
 
 
 def _setup():
@@ -256,6 +256,46 @@ def group_gradcam():
     ops.gradcam(a, probs, w, heat32)
     ref32 = oracle.gradcam_closed_form(a.float().cpu().numpy(), probs.cpu().numpy(), w.cpu().numpy(), None)
     ok &= _report("gradcam 32x32", heat32, torch.from_numpy(ref32).cuda(), 1e-4)
+    return ok
+
+
+def group_e2e():
+    torch = _setup()
+    import numpy as np
+    from ab_line_classifier_b200.engine import CutoffVGG16Engine
+    from oracle import oracle, synth
+    ok = True
+    B = 8
+    fr, lab = synth.synth_frames(B, seed=1234)
+    x, y = synth.vgg16_preprocess(fr), synth.one_hot(lab)
+    params = synth.randomize_biases(synth.glorot_weights(10001))
+    eng = CutoffVGG16Engine()
+    eng.set_weights(params)
+    probs = eng.predict_batch(x).cpu().numpy()
+    logits = eng._buf["logits"][:B].cpu().numpy()
+    ref32 = oracle.forward(params, x)
+    refbf = oracle.forward(params, x, bf16=True)
+    print("      logits gpu :", logits[:3].round(4).tolist())
+    print("      logits fp32:", ref32["logits"][:3].round(4).tolist())
+    print("      logits bf16:", refbf["logits"][:3].round(4).tolist())
+    ok &= _report("e2e logits vs fp32 oracle", torch.from_numpy(logits), torch.from_numpy(ref32["logits"]), 2e-2)
+    ok &= _report("e2e logits vs bf16 oracle", torch.from_numpy(logits), torch.from_numpy(refbf["logits"]), 5e-3)
+    ok &= _report("e2e block3_conv3 vs bf16 oracle", eng._buf["act_block3_conv3"][:B].float().cpu(),
+                  torch.from_numpy(refbf["block3_conv3"]), 2e-2)
+    print("      argmax equal:", (probs.argmax(-1) == ref32["probs"].argmax(-1)).all())
+    # one train step, all layers trainable, explicit dropout mask, class weights
+    mask = synth.dropout_mask(B, 256, 0.45)
+    cw = {0: 0.75, 1: 1.5}
+    eng.set_class_weight(cw)
+    loss = eng.train_step(x, y, set(eng.layer_names()), keep_mask=mask, apply_update=False)
+    l_ref, g_ref, _ = oracle.loss_and_grads(params, x, y, cw, mask, bf16=True)
+    l32, g32, _ = oracle.loss_and_grads(params, x, y, cw, mask)
+    print("      loss gpu / bf16 oracle / fp32 oracle:", float(loss.item()), l_ref, l32)
+    ok &= abs(float(loss.item()) - l_ref) < 5e-3 * max(1.0, abs(l_ref))
+    for name in eng.segments:
+        g = eng.view(name, eng.grad).cpu()
+        ok &= _report(f"grad {name} vs bf16 oracle", g, torch.from_numpy(g_ref[name]), 3e-2)
+        _report(f"   (info) vs fp32 oracle", g, torch.from_numpy(g32[name]), 5e-2)
     return ok
 
 
