@@ -395,27 +395,13 @@ class CutoffVGG16Engine:
         self.forward_device(B, training=True, keep_mask_in=keep_mask is not None, y=b["y"][:B], inv_batch=1.0 / gb,
                             loss_out=loss_out)
         self.step_count += 1
-        handles = []
-        hook = None
+        reducer = None
         if self.world_size > 1:
-            import torch.distributed as dist
-            pending = []   # ranges finished but not yet reduced (coalesce small layers into buckets)
-
-            def flush():
-                if pending:
-                    s, e = min(p[0] for p in pending), max(p[1] for p in pending)
-                    handles.append(dist.all_reduce(self.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-                    pending.clear()
-
-            def hook(s, e):
-                pending.append((s, e))
-                if sum(q[1] - q[0] for q in pending) * 4 >= bucket_bytes:
-                    flush()
-        self.backward_device(B, trainable, reduce_hook=hook)
-        if self.world_size > 1:
-            flush()
-            for h in handles:
-                h.wait()
+            from .dp import GradBucketReducer
+            reducer = GradBucketReducer(self.grad, bucket_bytes, self.pg)
+        self.backward_device(B, trainable, reduce_hook=reducer.hook if reducer else None)
+        if reducer:
+            reducer.wait()
         if apply_update:
             self.apply_optimizer(optimizer, lr, trainable)
         return b["loss"] if loss_out is None else loss_out

