@@ -171,7 +171,11 @@ def test_gradcam_heatmaps_512_frame_clip_property_and_oracle(setup):
     h = heat.cpu().numpy()
     assert h.shape == (512, 128, 128) and np.isfinite(h).all() and h.min() >= 0.0
     mx = h.reshape(512, -1).max(-1)
-    assert np.all((np.abs(mx - 1.0) < 1e-3) | (mx == 0.0))          # normalised per frame (or all-zero)
+    # normalised to max 1 at 32x32, THEN bilinearly upsampled (gradcam.py:79-81): peaks shrink a little
+    assert np.all(((mx <= 1.0 + 1e-6) & (mx > 0.6)) | (mx == 0.0))
+    h32, _ = eng.gradcam_batch(x[:64], out_hw=(32, 32))
+    m32 = h32.cpu().numpy().reshape(64, -1).max(-1)
+    assert np.all((np.abs(m32 - 1.0) < 1e-6) | (m32 == 0.0))
     ref_heat, ref_probs = oracle.gradcam_autograd(params, x[:3], out_hw=(128, 128), bf16=True)
     assert np.abs(h[:3] - ref_heat).max() < 3e-2
     assert (probs.cpu().numpy()[:3].argmax(-1) == ref_probs.argmax(-1)).all()

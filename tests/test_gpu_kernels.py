@@ -197,14 +197,14 @@ def test_head_forward_loss_backward(B):
     z = h @ wt + bt
     L = oracle.loss_from_logits(z, y.numpy(), cw)          # Keras: sum_i w_i l_i / batch
     L.backward()
-    _close(logits, z.detach(), 2e-6, "logits")
-    _close(probs, torch.softmax(z.detach(), -1), 2e-6, "probs")
-    _close(loss, L.detach().reshape(1), 2e-6, "loss")
+    _close(logits, z.detach(), 1e-5, "logits")
+    _close(probs, torch.softmax(z.detach(), -1), 1e-5, "probs")
+    _close(loss, L.detach().reshape(1), 1e-5, "loss")
     dw, db, dgap = torch.zeros(C, n, device="cuda"), torch.zeros(n, device="cuda"), torch.empty(B, C, device="cuda")
     ops.head_bwd(gap.cuda(), w.cuda(), dlog, mask, 0.45, dw, db, dgap)
-    _close(dw, wt.grad, 2e-6, "dW")
-    _close(db, bt.grad, 2e-6, "db")
-    _close(dgap, h.grad * keep / 0.55, 2e-6, "dgap")
+    _close(dw, wt.grad, 1e-5, "dW")
+    _close(db, bt.grad, 1e-5, "db")
+    _close(dgap, h.grad * keep / 0.55, 1e-5, "dgap")
     # the realised mask is reproducible from (seed, step, rank) and differs across steps and ranks
     m2 = torch.empty_like(mask)
     ops.head_fwd(gap.cuda(), w.cuda(), b.cuda(), logits, probs, None, None, 1.0, None, None, m2, False, True, 0.45,
