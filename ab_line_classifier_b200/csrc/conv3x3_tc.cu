@@ -1,7 +1,7 @@
 // 3x3 / stride 1 / SAME convolution as a tcgen05 implicit GEMM (sm_100a), NHWC bf16 in, fp32
 // accumulation in TMEM.  One kernel serves
 //   * forward  (Keras Conv2D+BiasAdd+Relu [+MaxPool 2x2], reference call site models.py:412-413):
-//       Y[n,h,w,co] = relu(b[co] + sum_{kh,kw,ci} X[n,h+kh-1,w+kw-1,ci] * Wf[kh*3+kw][co][ci])
+//       Y[n,h,w,co] = relu(b[co] + sum_{kh,kw,ci} X[n,h+kh-1,w+kw-1,ci] * Wf[kw*3+kh][co][ci])
 //   * dgrad    (Conv2DBackpropInput + ReluGrad of the layer below): the same contraction with
 //       X := dZ (Cout channels) and the tap-flipped, transposed filter Wd, epilogue = ReLU mask.
 //
@@ -10,9 +10,10 @@
 //   A (K-major, 128 rows x 128 B, SWIZZLE_128B) = TMA box {64 ch, box_w, box_h, 1} of the NHWC
 //     tensor at (c0, w0+kw-1, h0+kh-1, n); the SAME zero padding is TMA out-of-bounds fill.
 //   B (K-major, NTILE rows x 128 B)             = TMA box {64 ci, NTILE co, 1 tap} of Wf.
-// Warp roles (256 threads, persistent, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer
-// (single thread), warp 2 TMEM allocator, warps 4-7 epilogue.  The accumulator is double
-// buffered in TMEM (2 x NTILE columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (384 threads, persistent, 1 CTA/SM): warp 0 TMA producer, warp 1 MMA issuer
+// (single thread), warp 2 TMEM allocator, warps 4-11 epilogue.  The accumulator is double
+// buffered in TMEM (2 x NTILE columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+// the epilogue writes full-resolution tiles with TMA stores from a swizzled staging buffer.
 #include "host_util.h"
 #include "ptx.cuh"
 #include "../../include/abl_b200.h"
@@ -22,8 +23,8 @@ namespace abl {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements per k-block row = 128 bytes
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KiB
-constexpr int kEpiThreads = 128;
-constexpr int kThreads = 256;
+constexpr int kEpiThreads = 256;                 // 8 epilogue warps
+constexpr int kThreads = 128 + kEpiThreads;      // + producer, MMA, TMEM-alloc, spare warps
 
 struct ConvArgs {
     int B, H, W, Cin, Cout;
@@ -36,28 +37,37 @@ struct ConvArgs {
     __nv_bfloat16* out_pool;        // [B,H/2,W/2,Cout] or null
 };
 
-template <int NTILE>
+// TAPS = taps consumed per pipeline stage.  TAPS == 1: stage = one tap x 64 channels (A 16 KiB + B).
+// TAPS == 3 (used for NTILE == 64, where 4 MMAs per stage cannot amortise the issuing thread's barrier wait
+// and the TMA instruction rate): tile = 4 x 32 pixels, stage = one kw x 64 channels; A is the tile plus one
+// halo row above and below (6 x 32 pixels, 24 KiB) and serves kh = 0,1,2 through descriptor start offsets of
+// kh * 32 rows (4 KiB, a multiple of the 1 KiB swizzle atom); B = the 3 kh taps of that kw (filter operand
+// is stored kw-major: tap' = kw*3 + kh).
+template <int NTILE, int TAPS>
 struct ConvCfg {
-    static constexpr int kStages = 4;
-    static constexpr int kBBytes = NTILE * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kAStage = TAPS == 3 ? 6 * 32 * 128 : kABytes;
+    static constexpr int kBTap = NTILE * kBlockK * 2;
+    static constexpr int kBStage = TAPS * kBTap;
+    static constexpr int kStageBytes = kAStage + kBStage;
     static constexpr int kEpiN = NTILE < 128 ? NTILE : 128;        // columns staged per epilogue pass
-    static constexpr int kStageRow = kEpiN * 2 + 16;               // padded staging row (bank-conflict free)
-    static constexpr int kStagingBytes = kTileM * kStageRow;
+    static constexpr int kStagingBytes = (kEpiN / 64) * kABytes;   // [kEpiN/64 boxes][128 rows][128 B], swizzled
+    static constexpr int kStgBufs = NTILE == 256 ? 1 : 2;          // double-buffered where shared memory allows
+    static constexpr int kStages = (227 * 1024 - 256 - kStgBufs * kStagingBytes) / kStageBytes > 6
+                                       ? 6 : (227 * 1024 - 256 - kStgBufs * kStagingBytes) / kStageBytes;
     static constexpr int kTmemCols = 2 * NTILE;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 128;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStgBufs * kStagingBytes + 256;
 };
 
-template <int NTILE>
+template <int NTILE, int TAPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const ConvArgs p) {
-    using Cfg = ConvCfg<NTILE>;
+                  const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
+    using Cfg = ConvCfg<NTILE, TAPS>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + Cfg::kStages * kABytes;
+    uint8_t* smem_b = smem + Cfg::kStages * Cfg::kAStage;
     uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStgBufs * Cfg::kStagingBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::kStages;
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -66,11 +76,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int kblocks = 9 * p.kchunks;
+    const int kblocks = (9 / TAPS) * p.kchunks;     // pipeline stages per tile
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < Cfg::kStages; ++s) {
@@ -104,15 +115,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int th = m_tile % p.tiles_h;
                 const int img = m_tile / p.tiles_h;
                 const int h0 = th * p.box_h, w0 = tw * p.box_w, n0 = n_tile * NTILE;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int kh = tap / 3, kw = tap - kh * 3;
+                for (int t = 0; t < 9 / TAPS; ++t) {
+                    // filter taps are stored kw-major (tap' = kw*3 + kh): TAPS == 3 -> t = kw, all kh at once
+                    const int kw = TAPS == 3 ? t : t / 3;
+                    const int kh = TAPS == 3 ? 0 : t - kw * 3;
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                        tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * kABytes, kc * kBlockK,
+                        tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * Cfg::kAStage, kc * kBlockK,
                                     w0 + kw - 1, h0 + kh - 1, img);
-                        tma_load_3d(&map_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kc * kBlockK, n0,
-                                    tap);
+                        tma_load_3d(&map_b, &full_bar[stage], smem_b + stage * Cfg::kBStage, kc * kBlockK, n0,
+                                    t * TAPS);
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -122,6 +135,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(kTileM, NTILE, 0, 0);
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a), 16);
+            const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_b), 16);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -134,13 +150,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+                    const uint32_t a_lo = a_lo0 + stage * (Cfg::kAStage >> 4);
+                    const uint32_t b_lo = b_lo0 + stage * (Cfg::kBStage >> 4);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // kh shift = 32 tile rows = 4096 B; K advance of 16 elements = 32 B (>> 4 in the lo word)
+                            umma_bf16_lohi(tmem_d, a_lo + t * (4096 >> 4) + k * 2, dhi,
+                                           b_lo + t * (Cfg::kBTap >> 4) + k * 2, dhi, idesc,
+                                           (kb | t | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -149,11 +169,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------ epilogue (128 threads)
-        const int et = threadIdx.x - (kThreads - kEpiThreads);   // 0..127 == tile row == TMEM lane
-        const int ewarp = et >> 5;
-        constexpr int kChunks16 = Cfg::kEpiN / 8;                // 16-byte chunks per staged row
+        // ------------------------------------------------------------ epilogue (8 warps, 256 threads)
+        // Warp e reads TMEM lanes 32*(e%4).. (hardware lane quarter of its warp id) and the column half
+        // e/4 of each pass; thread = one output pixel (tile row) x 32-column chunks.  Values are packed to
+        // bf16 into a 128B-swizzled staging tile ([64-ch box][128 rows][128 B], the layout of a TMA box), from
+        // which ONE elected thread issues the full-resolution TMA store while all threads compute the 2x2
+        // max-pool (if requested) out of the same staging tile.
+        const int et = threadIdx.x - 128;                 // 0..255
+        const int lane_row = ((et >> 5) & 3) * 32 + (et & 31);   // tile row == TMEM lane
+        const int hsel = et >> 7;                         // which half of the pass' columns
+        constexpr int kPasses = NTILE / Cfg::kEpiN;
+        constexpr int kColsPerWarp = Cfg::kEpiN / 2;      // 32 or 64
+        constexpr int kChunks = kColsPerWarp / 32;        // 1 or 2
         int it = 0;
+        uint32_t pass_ctr = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int n_tile = tile % p.num_n_tiles;
             int m_tile = tile / p.num_n_tiles;
@@ -164,24 +193,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int h0 = th * p.box_h, w0 = tw * p.box_w, n0 = n_tile * NTILE;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
+            const int ph_row = lane_row / p.box_w, pw_col = lane_row - ph_row * p.box_w;
+            const size_t pix_off = ((static_cast<size_t>(img) * p.H + h0 + ph_row) * p.W + w0 + pw_col) * p.Cout;
 
 #pragma unroll 1
-            for (int half = 0; half < NTILE / Cfg::kEpiN; ++half) {
-                named_bar_sync(1, kEpiThreads);   // staging buffer free
-                uint8_t* my_row = staging + et * Cfg::kStageRow;
-#pragma unroll 1
-                for (int c = 0; c < Cfg::kEpiN / 32; ++c) {
+            for (int pass = 0; pass < kPasses; ++pass, ++pass_ctr) {
+                uint8_t* stg = staging + (pass_ctr % Cfg::kStgBufs) * Cfg::kStagingBytes;
+                const int col0 = pass * Cfg::kEpiN + hsel * kColsPerWarp;     // first column of this warp in the tile
+                // ReLU-mask prefetch (dgrad): this thread's pixel, its columns -- issued before any wait
+                uint4 mk[kChunks * 4];
+                if (p.flags & ABL_EPI_RELU_MASK) {
+                    const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix_off + n0 + col0);
+#pragma unroll
+                    for (int j = 0; j < kChunks * 4; ++j) mk[j] = __ldg(mp + j);
+                }
+                if (pass == 0) {
+                    mbar_wait(&tfull_bar[as], aphase);
+                    tc_fence_after();
+                }
+                // staging buffer free: the TMA store issued kStgBufs passes ago has finished READING it
+                if (et == 0) tma_store_wait_read<Cfg::kStgBufs - 1>();
+                named_bar_sync(1, kEpiThreads);
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
                     uint32_t r[32];
-                    const uint32_t col = as * NTILE + half * Cfg::kEpiN + c * 32;
-                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + col, r);
+                    const int col = col0 + c * 32;
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lane_row & ~31) << 16) + as * NTILE + col, r);
                     tmem_ld_wait();
                     uint32_t packed[16];
                     if (p.flags & ABL_EPI_BIAS_RELU) {
                         // warp-uniform address: one broadcast transaction per load, L1-resident
-                        const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + half * Cfg::kEpiN + c * 32);
+                        const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + col);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b4 = __ldg(bs + j);
@@ -195,53 +237,58 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int j = 0; j < 16; ++j)
                             packed[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(my_row + c * 64);
+                    if (p.flags & ABL_EPI_RELU_MASK) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t mm[4] = {mk[c * 4 + j].x, mk[c * 4 + j].y, mk[c * 4 + j].z, mk[c * 4 + j].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                // post-ReLU activations are >= 0: "> 0" <=> magnitude bits set, sign clear
+                                const uint32_t lo_on = ((mm[k] & 0x7FFFu) != 0 && !(mm[k] & 0x8000u)) ? 0xFFFFu : 0u;
+                                const uint32_t hi_on =
+                                    ((mm[k] & 0x7FFF0000u) != 0 && !(mm[k] & 0x80000000u)) ? 0xFFFF0000u : 0u;
+                                packed[4 * j + k] &= (lo_on | hi_on);
+                            }
+                        }
+                    }
+                    // swizzled store: 16-byte chunk index XOR (row & 7) inside the 64-channel box
+                    const int pcol = col - pass * Cfg::kEpiN;              // column within the pass
+                    uint8_t* box = stg + (pcol >> 6) * kABytes + lane_row * 128;
+                    const int cc0 = (pcol & 63) >> 3;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(box + (((cc0 + j) ^ (lane_row & 7)) << 4)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
-                if (half == NTILE / Cfg::kEpiN - 1) {
+                if (pass == kPasses - 1) {
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[as]);   // TMEM buffer may be overwritten by the next tile
                 }
+                fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
                 named_bar_sync(1, kEpiThreads);     // staging filled
 
-                const int cbase = n0 + half * Cfg::kEpiN;
-                if (p.out_full != nullptr) {
-                    for (int q = et; q < kTileM * kChunks16; q += kEpiThreads) {
-                        const int row = q / kChunks16, cc = q - row * kChunks16;
-                        const int h = h0 + row / p.box_w, w = w0 + row % p.box_w;
-                        const size_t off = ((static_cast<size_t>(img) * p.H + h) * p.W + w) * p.Cout + cbase + cc * 8;
-                        uint4 v = *reinterpret_cast<const uint4*>(staging + row * Cfg::kStageRow + cc * 16);
-                        if (p.flags & ABL_EPI_RELU_MASK) {
-                            const uint4 m = *reinterpret_cast<const uint4*>(p.mask_src + off);
-                            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
-                            uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                const int cbase = n0 + pass * Cfg::kEpiN;
+                if (p.out_full != nullptr && et == 0) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                // post-ReLU activations are >= 0: "> 0" <=> any magnitude bit set, sign clear
-                                const uint32_t lo_on = ((mm[j] & 0x7FFFu) != 0 && !(mm[j] & 0x8000u)) ? 0xFFFFu : 0u;
-                                const uint32_t hi_on =
-                                    ((mm[j] & 0x7FFF0000u) != 0 && !(mm[j] & 0x80000000u)) ? 0xFFFF0000u : 0u;
-                                vv[j] &= (lo_on | hi_on);
-                            }
-                            v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-                        }
-                        *reinterpret_cast<uint4*>(p.out_full + off) = v;
-                    }
+                    for (int j = 0; j < Cfg::kEpiN / 64; ++j)
+                        tma_store_4d(&map_out, stg + j * kABytes, cbase + j * 64, w0, h0, img);
+                    tma_store_commit();
                 }
                 if (p.out_pool != nullptr) {
+                    constexpr int kChunks16 = Cfg::kEpiN / 8;
                     const int pw_n = p.box_w >> 1;
-                    const int pooled = (kTileM / 4) * kChunks16;
-                    for (int q = et; q < pooled; q += kEpiThreads) {
+#pragma unroll
+                    for (int q = et; q < (kTileM / 4) * kChunks16; q += kEpiThreads) {
                         const int prow = q / kChunks16, cc = q - prow * kChunks16;
                         const int ph = prow / pw_n, pw = prow - ph * pw_n;
-                        const int r00 = (2 * ph) * p.box_w + 2 * pw;
-                        const uint8_t* s = staging + cc * 16;
-                        const uint4 a = *reinterpret_cast<const uint4*>(s + r00 * Cfg::kStageRow);
-                        const uint4 b = *reinterpret_cast<const uint4*>(s + (r00 + 1) * Cfg::kStageRow);
-                        const uint4 c2 = *reinterpret_cast<const uint4*>(s + (r00 + p.box_w) * Cfg::kStageRow);
-                        const uint4 d = *reinterpret_cast<const uint4*>(s + (r00 + p.box_w + 1) * Cfg::kStageRow);
+                        const int r00 = (2 * ph) * p.box_w + 2 * pw;          // even row: r00 & 7 in {0,2,4,6}
+                        const uint8_t* bx = stg + (cc >> 3) * kABytes;
+                        const int c8 = cc & 7;
+                        const int r01 = r00 + 1, r10 = r00 + p.box_w, r11 = r10 + 1;
+                        const uint4 a = *reinterpret_cast<const uint4*>(bx + r00 * 128 + ((c8 ^ (r00 & 7)) << 4));
+                        const uint4 b = *reinterpret_cast<const uint4*>(bx + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
+                        const uint4 c2 = *reinterpret_cast<const uint4*>(bx + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
+                        const uint4 d = *reinterpret_cast<const uint4*>(bx + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
                         const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
                         const uint32_t cv[4] = {c2.x, c2.y, c2.z, c2.w}, dv[4] = {d.x, d.y, d.z, d.w};
                         uint32_t o[4];
@@ -262,6 +309,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
         }
+        if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
     }
 
     tc_fence_before();
@@ -286,21 +334,22 @@ static int pick_box(int H, int W, int* box_h, int* box_w) {
     return ABL_ERR_SHAPE;
 }
 
-template <int NTILE>
-static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvArgs& a, cudaStream_t st) {
-    using Cfg = ConvCfg<NTILE>;
+template <int NTILE, int TAPS>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const ConvArgs& a,
+                       cudaStream_t st) {
+    using Cfg = ConvCfg<NTILE, TAPS>;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(conv3x3_tc_kernel<NTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(conv3x3_tc_kernel<NTILE, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::kSmemBytes) != cudaSuccess)
             return check_launch();
         attr_done[dev & 63] = true;
     }
     const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    conv3x3_tc_kernel<NTILE><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, a);
+    conv3x3_tc_kernel<NTILE, TAPS><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
     return check_launch();
 }
 
@@ -338,6 +387,9 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     }
     if (out_pool && (a.box_h & 1)) { set_error("abl_conv3x3_igemm: pooled output needs an even tile height"); return ABL_ERR_SHAPE; }
     const int ntile = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    // 3-taps-per-stage main loop for the narrow tile: needs the 4 x 32 pixel rectangle
+    const bool taps3 = ntile == 64 && (W % 32 == 0) && (H % 4 == 0);
+    if (taps3) { a.box_w = 32; a.box_h = 4; }
     a.tiles_h = H / a.box_h; a.tiles_w = W / a.box_w;
     a.num_m_tiles = B * a.tiles_h * a.tiles_w;
     a.num_n_tiles = Cout / ntile;
@@ -352,21 +404,29 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.box_w, (uint32_t)a.box_h, 1};
+        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.box_w, (uint32_t)(a.box_h + (taps3 ? 2 : 0)), 1};
         int r = encode_tiled(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r != ABL_OK) return r;
     }
     {
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
         const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-        const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)ntile, 1};
+        const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)ntile, taps3 ? 3u : 1u};
         int r = encode_tiled(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_kmajor, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r != ABL_OK) return r;
+    }
+    CUtensorMap mo = ma;   // valid placeholder when only the pooled output is requested (never dereferenced)
+    if (out_full) {
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        const uint32_t box[4] = {64, (uint32_t)a.box_w, (uint32_t)a.box_h, 1};
+        int r = encode_tiled(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out_full, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r != ABL_OK) return r;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (ntile) {
-        case 256: return launch_conv<256>(ma, mb, a, st);
-        case 128: return launch_conv<128>(ma, mb, a, st);
-        default: return launch_conv<64>(ma, mb, a, st);
+        case 256: return launch_conv<256, 1>(ma, mb, mo, a, st);
+        case 128: return launch_conv<128, 1>(ma, mb, mo, a, st);
+        default: return taps3 ? launch_conv<64, 3>(ma, mb, mo, a, st) : launch_conv<64, 1>(ma, mb, mo, a, st);
     }
 }

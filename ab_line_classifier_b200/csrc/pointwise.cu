@@ -18,8 +18,10 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
         const int ci = (i / Cout) % Cin;
         const int t = i / (Cout * Cin);
         const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
-        if (w_fwd) w_fwd[(static_cast<size_t>(t) * Cout + co) * Cin + ci] = v;
-        if (w_dgrad) w_dgrad[(static_cast<size_t>(8 - t) * Cin + ci) * Cout + co] = v;
+        const int kh = t / 3, kw = t - kh * 3;
+        // GEMM operands are tap-indexed kw-major (tap' = kw*3 + kh); dgrad uses the 180-degree rotated filter
+        if (w_fwd) w_fwd[(static_cast<size_t>(kw * 3 + kh) * Cout + co) * Cin + ci] = v;
+        if (w_dgrad) w_dgrad[(static_cast<size_t>((2 - kw) * 3 + (2 - kh)) * Cin + ci) * Cout + co] = v;
     }
 }
 

@@ -113,21 +113,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);   // both operands MN-major
+            // MN-major SWIZZLE_128B: 8-row (pixel) groups 1024 B apart (SBO), 64-channel blocks one box apart (LBO)
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            const uint32_t lo0 = desc_lo_sw128(smem_u32(smem), kWgBoxBytes);
             int stage = 0;
             uint32_t phase = 0;
             for (int pt = pt0; pt < pt1; ++pt) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint32_t a_lo = lo0 + stage * (p.stage_bytes >> 4);
+                const uint32_t b_lo = a_lo + (a_bytes >> 4);
+                const uint32_t acc_flag = pt > pt0 ? 1u : 0u;
                 for (int a = 0; a < npair_here; ++a) {
 #pragma unroll
                     for (int k = 0; k < kWgKPix / 16; ++k) {
-                        // K advance of 16 pixel rows = 2048 B; 8-row groups 1024 B apart (SBO);
-                        // 64-channel blocks one box apart (LBO).
-                        const uint64_t da = make_smem_desc_sw128(sa + a * 2 * kWgBoxBytes + k * 2048, kWgBoxBytes, 1024);
-                        const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kWgBoxBytes, 1024);
-                        umma_bf16(tmem_base + a * NT, da, db, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+                        // K advance of 16 pixel rows = 2048 B
+                        umma_bf16_lohi(tmem_base + a * NT, a_lo + a * (2 * kWgBoxBytes >> 4) + k * (2048 >> 4), dhi,
+                                       b_lo + k * (2048 >> 4), dhi, idesc, k > 0 ? 1u : acc_flag);
                     }
                 }
                 umma_commit(&empty_bar[stage]);

@@ -43,7 +43,8 @@ const char* abl_last_error(void);
  * transposed filter and ABL_EPI_RELU_MASK, TF's Conv2DBackpropInput+ReluGrad that model.fit's
  * GradientTape runs (models.py:427,432).
  *   x        bf16 [B,H,W,Cin]
- *   w_kmajor bf16 [9][Cout][Cin]   (from abl_prep_conv_weights: w_fwd for forward, w_dgrad for dgrad)
+ *   w_kmajor bf16 [9][Cout][Cin]   (from abl_prep_conv_weights: w_fwd for forward, w_dgrad for dgrad;
+ *                                   taps kw-major)
  *   bias     fp32 [Cout]           (ABL_EPI_BIAS_RELU)
  *   mask_src bf16 [B,H,W,Cout]     (ABL_EPI_RELU_MASK; post-ReLU activation of the layer below)
  *   out_full bf16 [B,H,W,Cout] or NULL;  out_pool bf16 [B,H/2,W/2,Cout] (2x2/s2 max) or NULL
@@ -74,8 +75,9 @@ int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, v
 int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W, int Cout,
                          void* stream);
 
-/* fp32 HWIO master kernel -> the two bf16 GEMM operand layouts:
- *   w_fwd[t][co][ci] = w[t][ci][co];   w_dgrad[t][ci][co] = w[8-t][ci][co]   (either may be NULL) */
+/* fp32 HWIO master kernel -> the two bf16 GEMM operand layouts, taps indexed kw-major (t' = kw*3 + kh):
+ *   w_fwd  [kw*3+kh][co][ci]         = w[kh][kw][ci][co]
+ *   w_dgrad[(2-kw)*3+(2-kh)][ci][co] = w[kh][kw][ci][co]   (180-degree rotated)      (either may be NULL) */
 int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
 
 /* MaxPoolGrad + ReluGrad: dz[n,h,w,c] = dp[n,h/2,w/2,c] if a[n,h,w,c] is the first maximum of its 2x2

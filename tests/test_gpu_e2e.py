@@ -156,7 +156,7 @@ def test_adam_update_through_engine(setup):
         ref, _, _ = oracle.adam_step(params[name], gr, 0.0, 0.0, 1)
         np.testing.assert_allclose(eng.view(name).cpu().numpy(), ref, atol=2e-6)
     # the bf16 operand copies follow the fp32 master weights
-    k = eng.view("block3_conv3/kernel").reshape(9, 256, 256).permute(0, 2, 1).to(torch.bfloat16)
+    k = eng.view("block3_conv3/kernel").permute(1, 0, 3, 2).reshape(9, 256, 256).to(torch.bfloat16)
     assert torch.equal(eng.w_fwd["block3_conv3"], k)
     eng.opt_state.clear(); eng.opt_steps.clear()
     eng.set_weights(params)

@@ -51,7 +51,7 @@ def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B):
     b = torch.randn(cout, generator=g) * 0.1
     wf = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
     ops.prep_conv_weights(w.cuda(), wf, None)
-    assert torch.equal(wf.cpu(), w.reshape(9, cin, cout).permute(0, 2, 1).to(torch.bfloat16))   # bit-exact re-layout
+    assert torch.equal(wf.cpu(), w.permute(1, 0, 3, 2).reshape(9, cout, cin).to(torch.bfloat16))   # bit-exact re-layout
     full = torch.full((B, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     pl = torch.full((B, H // 2, W // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16) if pool else None
     ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, full, pl, ops.EPI_BIAS_RELU)

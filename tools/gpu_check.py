@@ -65,7 +65,7 @@ def group_fwd():
             b = torch.randn(cout, device="cuda") * 0.1
             wf = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
             ops.prep_conv_weights(w, wf, None)
-            ref_wf = w.reshape(9, cin, cout).permute(0, 2, 1).to(torch.bfloat16)
+            ref_wf = w.permute(1, 0, 3, 2).reshape(9, cout, cin).to(torch.bfloat16)
             ok &= _report(f"prep w_fwd {cin}->{cout}", wf, ref_wf, 0.0)
             full = torch.full((B, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
             pl = torch.full((B, H // 2, W // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16) if pool else None
