@@ -1,0 +1,405 @@
+// block1_conv1 (Cin = 3, K = 27) forward and filter gradient on tcgen05 via an in-kernel im2col.
+// Replaces Keras Conv2D+BiasAdd+Relu of the first VGG16 layer (reference src/models/models.py:409-413)
+// and its Conv2DBackpropFilter/BiasAddGrad under model.fit.
+//
+// The layer is HBM-bound (0.2 MB in, 2 MB out per frame) and K = 27 is far too small for a TMA-fed
+// implicit GEMM, so producer warps build the A operand themselves: one thread per output pixel gathers
+// its 3x3x3 fp32 patch and writes ONE 128-byte K-major row (64 bf16 "K slots", SWIZZLE_128B) per k-block:
+//     k-block 0: slots  0..26 = hi(x)   slots 27..53 = lo(x)   slot 54 = 1   slots 55..63 = 0
+//     k-block 1: slots  0..26 = hi(x)   rest 0                                   (forward only)
+// with hi(x) = bf16(x), lo(x) = bf16(x - hi(x)).  The forward B operand pairs them with hi(W) / lo(W):
+//     y = hi(x)*hi(W) + lo(x)*hi(W) + hi(x)*lo(W) + b        (error ~2^-16: fp32-like, fp32 accumulate)
+// so the +-150-range input is NOT rounded to bf16.  The same A tile, read MN-major (K = pixels), is the
+// A operand of the filter gradient: D[slot][co] = sum_pix A[pix][slot] * dZ[pix][co], rows 0..26 + 27..53
+// give dW, row 54 (the ones slot) gives the bias gradient.
+// A tile = 128 consecutive pixels of the flattened (n,h,w) raster (contiguous 16 KiB of NHWC output).
+#include <stdio.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace abl {
+
+constexpr int kF_Cout = 64;
+constexpr int kF_TileM = 128;
+constexpr int kF_ABlock = kF_TileM * 128;     // 16 KiB: [128 px][64 slots] bf16
+constexpr int kF_Threads = 512;               // warps 0-3 control, 4-11 im2col producers (2 groups), 12-15 epilogue
+constexpr int kF_Stages = 4;
+constexpr int kF_ProdGroups = 2;              // producer group g builds the CTA's tiles g, g+2, g+4, ...
+
+struct FirstArgs {
+    const float* x;        // [B,H,W,3] fp32
+    const float* w;        // [27][64] fp32 (HWIO flattened)
+    const float* bias;     // [64]
+    float* dw;             // [27][64]  (wgrad)
+    float* db;             // [64] or null
+    int H, W;
+    long long total_pix;   // B*H*W
+    int num_tiles;         // total_pix / 128
+};
+
+// One thread = one pixel: gather the 27-value patch (zero padded) and write the swizzled K-major row(s).
+template <bool kFwd>
+__device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, int row, uint8_t* a_stage) {
+    const int wq = static_cast<int>(pix % p.W);
+    const int hq = static_cast<int>((pix / p.W) % p.H);
+    const float* base = p.x + pix * 3;
+    float v[27];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const bool hok = (hq + kh - 1) >= 0 && (hq + kh - 1) < p.H;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const bool ok = hok && (wq + kw - 1) >= 0 && (wq + kw - 1) < p.W;
+            const float* px = base + ((kh - 1) * p.W + (kw - 1)) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(kh * 3 + kw) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+        }
+    }
+    // 64 slots of k-block 0 as 32 packed bf16x2 words
+    uint32_t s0[32];
+    __nv_bfloat16 hi[27], lo[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        hi[k] = __float2bfloat16_rn(v[k]);
+        lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+    }
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int k0 = 2 * j, k1 = 2 * j + 1;
+        const __nv_bfloat16 e0 = k0 < 27 ? hi[k0] : (k0 < 54 ? lo[k0 - 27] : (k0 == 54 ? one : zero));
+        const __nv_bfloat16 e1 = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : (k1 == 54 ? one : zero));
+        s0[j] = static_cast<uint32_t>(__bfloat16_as_ushort(e0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(e1)) << 16);
+    }
+    uint8_t* r0 = a_stage + row * 128;
+    const int sw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
+    if (kFwd) {   // k-block 1: hi(x) in slots 0..26 (chunks 0..3), zeros elsewhere
+        uint8_t* r1 = r0 + kF_ABlock;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (c < 3) q = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
+            if (c == 3) q = make_uint4(s0[12], s0[13] & 0xFFFFu, 0, 0);   // slots 24,25,26 then zeros
+            *reinterpret_cast<uint4*>(r1 + ((c ^ sw) << 4)) = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kF_Threads, 1)
+conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const FirstArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;                                       // kF_Stages x 2 k-blocks x 16 KiB
+    uint8_t* smem_b = smem + kF_Stages * 2 * kF_ABlock;           // 2 k-blocks x [64 co][64 slots] = 16 KiB
+    uint8_t* staging = smem_b + 2 * 64 * 128;                     // 2 x 16 KiB swizzled output tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kF_ABlock);
+    uint64_t* afull = bars;
+    uint64_t* aempty = bars + kF_Stages;
+    uint64_t* tfull = bars + 2 * kF_Stages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5;
+
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < kF_Stages; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+        fence_barrier_init();
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 2) tmem_alloc<128>(tmem_slot);
+    // B operand, built once per CTA: row = co (128 B, swizzled), slot k of block 0 = hi(W[k%27]) for k < 54,
+    // block 1 = lo(W[k]) for k < 27.
+    for (int i = threadIdx.x; i < 2 * 64 * 64; i += blockDim.x) {
+        const int blk = i >> 12, co = (i >> 6) & 63, slot = i & 63;
+        float val = 0.f;
+        if (blk == 0 && slot < 54) {
+            val = __bfloat162float(__float2bfloat16_rn(p.w[(slot % 27) * kF_Cout + co]));
+        } else if (blk == 1 && slot < 27) {
+            const float wv = p.w[slot * kF_Cout + co];
+            val = wv - __bfloat162float(__float2bfloat16_rn(wv));
+        }
+        uint8_t* rowp = smem_b + blk * (64 * 128) + co * 128;
+        *reinterpret_cast<__nv_bfloat16*>(rowp + ((((slot >> 3) ^ (co & 7)) << 4) | ((slot & 7) << 1))) =
+            __float2bfloat16_rn(val);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a), 16);
+            const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_b), 16);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&afull[stage], phase);
+                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + stage * ((2 * kF_ABlock) >> 4);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_lohi(tmem_base + as * 64, a_lo + kb * (kF_ABlock >> 4) + k * 2, dhi,
+                                       b_lo0 + kb * ((64 * 128) >> 4) + k * 2, dhi, idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&aempty[stage]);
+                umma_commit(&tfull[as]);
+                if (++stage == kF_Stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ---------------------------------------------------------------- im2col producers (2 x 128 threads)
+        const int row = (threadIdx.x - 128) & 127;
+        const int grp = (threadIdx.x - 128) >> 7;
+        for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int stage = it % kF_Stages;
+            mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
+            im2col_row<true>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * 2 * kF_ABlock);
+            fence_proxy_async_smem();
+            mbar_arrive(&afull[stage]);
+        }
+    } else if (warp >= 12) {
+        // ---------------------------------------------------------------- epilogue (128 threads)
+        const int row = threadIdx.x - 384;       // TMEM lane
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            uint8_t* stg = staging + (it & 1) * kF_ABlock;
+            mbar_wait(&tfull[as], (it >> 1) & 1);
+            tc_fence_after();
+            if (row == 0) tma_store_wait_read<1>();
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + as * 64 + c * 32, r);
+                tmem_ld_wait();
+                const float4* bs = reinterpret_cast<const float4*>(p.bias + c * 32);
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(bs + j);
+                    packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
+                                                fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
+                    packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
+                                                    fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(stg + row * 128 + (((c * 4 + j) ^ (row & 7)) << 4)) =
+                        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (row == 0) {
+                tma_store_2d(&map_out, stg, 0, tile * kF_TileM);
+                tma_store_commit();
+            }
+        }
+        if (row == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<128>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+// Persistent CTAs; each accumulates D[slot][co] over its tiles in TMEM, then adds rows 0..54 to dw / db.
+__global__ void __launch_bounds__(kF_Threads, 1)
+conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const FirstArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;                                   // kF_Stages x 16 KiB (k-block 0 rows)
+    uint8_t* smem_z = smem + kF_Stages * kF_ABlock;           // 16 KiB of zeros: M rows 64..127
+    uint8_t* smem_b = smem_z + kF_ABlock;                     // kF_Stages x 16 KiB dZ tiles [128 px][64 co]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kF_Stages * kF_ABlock);
+    uint64_t* afull = bars;                 // 128 producer arrivals + 1 expect_tx arrival (TMA bytes)
+    uint64_t* aempty = bars + kF_Stages;
+    uint64_t* done = bars + 2 * kF_Stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5;
+
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < kF_Stages; ++s) { mbar_init(&afull[s], 129); mbar_init(&aempty[s], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&map_dz);
+    }
+    if (warp == 2) tmem_alloc<64>(tmem_slot);
+    for (int i = threadIdx.x; i < kF_ABlock / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem_z)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ntiles_here = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        if (elect_one()) {      // dZ tile loader
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&aempty[stage], phase ^ 1);
+                mbar_expect_tx(&afull[stage], kF_ABlock);
+                tma_load_2d(&map_dz, &afull[stage], smem_b + stage * kF_ABlock, 0, tile * kF_TileM);
+                if (++stage == kF_Stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);      // both operands MN-major (K = pixels)
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            int stage = 0;
+            uint32_t phase = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&afull[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem_a + stage * kF_ABlock);
+                // M block 0 = this stage's im2col rows, M block 1 (LBO away) = the shared zero block
+                const uint32_t a_lo = desc_lo_sw128(a_addr, smem_u32(smem_z) - a_addr);
+                const uint32_t b_lo = desc_lo_sw128(smem_u32(smem_b + stage * kF_ABlock), 0);
+#pragma unroll
+                for (int k = 0; k < kF_TileM / 16; ++k)
+                    umma_bf16_lohi(tmem_base, a_lo + k * (2048 >> 4), dhi, b_lo + k * (2048 >> 4), dhi, idesc,
+                                   (first && k == 0) ? 0u : 1u);
+                first = false;
+                umma_commit(&aempty[stage]);
+                if (++stage == kF_Stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(done);
+        }
+    } else if (warp >= 4 && warp < 12) {
+        const int row = (threadIdx.x - 128) & 127;
+        const int grp = (threadIdx.x - 128) >> 7;
+        for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int stage = it % kF_Stages;
+            mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
+            im2col_row<false>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kF_ABlock);
+            fence_proxy_async_smem();
+            mbar_arrive(&afull[stage]);
+        }
+    } else if (warp >= 12 && warp < 14) {
+        // D rows 0..63 live in TMEM lanes 0..63: warps 12 and 13 (lane quarters 0 and 1)
+        const int row = threadIdx.x - 384;
+        if (ntiles_here > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + c * 32, r);
+                tmem_ld_wait();
+                if (row < 54) {
+                    float* dst = p.dw + (row % 27) * kF_Cout + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+                } else if (row == 54 && p.db != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(p.db + c * 32 + j, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<64>(tmem_base);
+    }
+}
+
+static int first_args(FirstArgs* a, const float* x, int B, int H, int W, int Cout, const char* who) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cout != kF_Cout || (static_cast<long long>(B) * H * W) % kF_TileM != 0) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "%s: need Cout == 64 and B*H*W a multiple of 128", who);
+        set_error(buf);
+        return ABL_ERR_SHAPE;
+    }
+    a->x = x; a->H = H; a->W = W;
+    a->total_pix = static_cast<long long>(B) * H * W;
+    a->num_tiles = static_cast<int>(a->total_pix / kF_TileM);
+    a->w = nullptr; a->bias = nullptr; a->dw = nullptr; a->db = nullptr;
+    return ABL_OK;
+}
+
+static int pixel_map(CUtensorMap* m, const void* base, long long total_pix) {
+    const uint64_t dims[2] = {64, (uint64_t)total_pix};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, (uint32_t)kF_TileM};
+    return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace abl
+
+using namespace abl;
+
+extern "C" int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H,
+                                  int W, int Cout, void* stream) {
+    if (!x || !w_hwio || !bias || !out) { set_error("abl_conv_first_fwd: null pointer"); return ABL_ERR_NULL; }
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) {
+        set_error("abl_conv_first_fwd: out and bias must be 16-byte aligned"); return ABL_ERR_ALIGN;
+    }
+    FirstArgs a;
+    int r = first_args(&a, x, B, H, W, Cout, "abl_conv_first_fwd");
+    if (r != ABL_OK) return r;
+    a.w = w_hwio; a.bias = bias;
+    CUtensorMap mo;
+    r = pixel_map(&mo, out, a.total_pix);
+    if (r != ABL_OK) return r;
+    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + 2 * kF_ABlock + 256;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        if (cudaFuncSetAttribute(conv_first_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+            return check_launch();
+        attr_done[dev & 63] = true;
+    }
+    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+    conv_first_fwd_tc_kernel<<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mo, a);
+    return check_launch();
+}
+
+extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W,
+                                    int Cout, void* stream) {
+    if (!x || !dz || !dw) { set_error("abl_conv_first_wgrad: null pointer"); return ABL_ERR_NULL; }
+    if (reinterpret_cast<uintptr_t>(dz) & 15) { set_error("abl_conv_first_wgrad: dz must be 16-byte aligned"); return ABL_ERR_ALIGN; }
+    FirstArgs a;
+    int r = first_args(&a, x, B, H, W, Cout, "abl_conv_first_wgrad");
+    if (r != ABL_OK) return r;
+    a.dw = dw; a.db = db;
+    CUtensorMap mz;
+    r = pixel_map(&mz, dz, a.total_pix);
+    if (r != ABL_OK) return r;
+    constexpr int smem_bytes = (2 * kF_Stages + 1) * kF_ABlock + 256;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        if (cudaFuncSetAttribute(conv_first_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+            return check_launch();
+        attr_done[dev & 63] = true;
+    }
+    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+    conv_first_wgrad_tc_kernel<<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mz, a);
+    return check_launch();
+}
