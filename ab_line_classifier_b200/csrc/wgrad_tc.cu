@@ -1,41 +1,40 @@
 // Filter gradient of a 3x3/s1/SAME convolution (TF Conv2DBackpropFilter run by model.fit's tape,
 // reference call site src/models/models.py:427,432) as a tcgen05 GEMM whose REDUCTION dimension is
 // the pixel index:
-//     dW[tap][ci][co] = sum_{n,h,w} X[n,h+kh-1,w+kw-1,ci] * dZ[n,h,w,co]
-// Both operands are read straight from the NHWC tensors with TMA boxes {64 ch, box_w, box_h, 1}
-// (SWIZZLE_128B): in shared memory a box is "pixels x 64 channels", i.e. the MN-major canonical
-// layout with K = pixel rows of 128 B, so no transpose pass is needed:
-//     A = shifted X box  (M = 64 ci per box, two boxes stacked -> UMMA M = 128, LBO = box bytes)
-//     B = dZ boxes       (N = NT co = NT/64 boxes, LBO = box bytes)
-// A CTA owns one "unit" = up to ACC accumulators (A box pairs = (tap, ci-chunk) pairs) x one co
-// block of NT columns, all fed by the SAME dZ tile, and one slice of the pixel range.  Partial
-// sums go to a workspace with plain vector stores; a second kernel reduces the slices in a fixed
-// order (deterministic) into the fp32 HWIO gradient.
+//     dW[kh][kw][ci][co] = sum_{n,h,w} X[n,h+kh-1,w+kw-1,ci] * dZ[n,h,w,co]
+// Both operands are read straight from the NHWC tensors by TMA (SWIZZLE_128B boxes of 64 channels):
+// in shared memory a box is "pixel rows x 128 B", i.e. the MN-major canonical layout with K = pixel
+// rows, so no transpose pass exists anywhere.
+//
+// Work decomposition.  A CTA owns one UNIT and one slice of the pixel tiles (4 rows x 16 pixels each):
+//   unit = (kw, 128 input channels, NT output channels)            [Cin >= 128]
+//        = ({kw0,kw1} or {kw2,-}, 64 input channels, NT)           [Cin == 64: two kw share UMMA M = 128]
+// Per pipeline stage ONE 5-D TMA box brings the X tile with a one-row halo above and below
+// (6 x 16 pixels x 128 channels, 24 KiB) and ONE box brings the dZ tile (4 x 16 pixels x NT, <= 16 KiB).
+// The three kh taps are three TMEM accumulators fed from the SAME X tile through descriptor start
+// offsets of kh*16 rows (2 KiB, a multiple of the 1 KiB swizzle atom): 12 MMAs per two TMA instructions.
+// Partial sums of each pixel slice go to a workspace with plain vector stores; a second kernel reduces
+// the slices in a fixed order (deterministic) into the fp32 HWIO gradient.
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace abl {
 
-constexpr int kWgKPix = 32;                       // pixels (GEMM K) per pipeline stage
-constexpr int kWgBoxBytes = kWgKPix * 128;        // 4 KiB: one {64 ch x 32 px} box
+constexpr int kWgBw = 16, kWgBh = 4;                       // pixel tile (GEMM K = 64 per stage)
+constexpr int kWgARows = (kWgBh + 2) * kWgBw;              // 96 haloed pixel rows
+constexpr int kWgABox = kWgARows * 128;                    // 12 KiB per 64-channel block
+constexpr int kWgBBox = kWgBh * kWgBw * 128;               // 8 KiB per 64-channel block
 constexpr int kWgThreads = 256;
 constexpr int kWgMaxStages = 8;
 
 struct WgradArgs {
     int B, H, W, Cin, Cout;
-    int box_h, box_w, tiles_h, tiles_w;   // pixel-tile geometry (box_h*box_w == kWgKPix)
-    int num_ptiles;                       // B*tiles_h*tiles_w
-    int chunks;                           // Cin/64
-    int nboxes;                           // 9*chunks
-    int npairs;                           // ceil(nboxes/2)
-    int acc;                              // accumulators (pairs) per unit
-    int pair_groups;                      // ceil(npairs/acc)
-    int co_blocks;                        // Cout/NT
-    int units;                            // pair_groups*co_blocks
-    int splits;                           // pixel slices per unit; grid = units*splits
-    int stages;
-    int stage_bytes;
-    float* partial;                       // [splits][9][Cin][Cout] fp32
+    int tiles_h, tiles_w, num_ptiles;
+    int mode;            // 0: Cin >= 128 (M = 2 channel blocks of one kw); 1: Cin == 64 (M = 2 kw of one block)
+    int ci_blocks;       // mode 0: Cin/128
+    int co_blocks;       // Cout/NT
+    int units, splits, stages, stage_bytes;
+    float* partial;      // [splits][9][Cin][Cout] fp32
 };
 
 template <int NT>
@@ -43,7 +42,10 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                 const WgradArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+    constexpr int kABytes = 2 * kWgABox;                   // M = 128 = two 64-wide blocks
+    constexpr int kBBytes = (NT / 64) * kWgBBox;
+    uint8_t* zero_blk = smem + p.stages * p.stage_bytes;   // mode 1, unit {kw2,-}: the missing M block
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + kWgABox);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgMaxStages;
     uint64_t* done_bar = bars + 2 * kWgMaxStages;
@@ -52,16 +54,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int unit = blockIdx.x % p.units;
     const int split = blockIdx.x / p.units;
-    const int co_blk = unit % p.co_blocks;
-    const int pgroup = unit / p.co_blocks;
-    const int pair0 = pgroup * p.acc;
-    const int npair_here = min(p.acc, p.npairs - pair0);
-    const int co0 = co_blk * NT;
-    // contiguous slice of pixel tiles for this split
+    int kw0, kw1, ci0, co0;          // kw of M block 0 / 1 (kw1 < 0: zero block), first input / output channel
+    if (p.mode == 0) {
+        kw0 = kw1 = unit % 3;
+        ci0 = ((unit / 3) % p.ci_blocks) * 128;
+        co0 = (unit / (3 * p.ci_blocks)) * NT;
+    } else {
+        const int pair = unit & 1;
+        kw0 = pair * 2;
+        kw1 = pair == 0 ? 1 : -1;
+        ci0 = 0;
+        co0 = (unit >> 1) * NT;
+    }
     const int per = (p.num_ptiles + p.splits - 1) / p.splits;
     const int pt0 = split * per;
     const int pt1 = min(p.num_ptiles, pt0 + per);
-    const int a_bytes = 2 * p.acc * kWgBoxBytes;   // A region of a stage (fixed stride, even if fewer pairs)
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_x);
@@ -76,6 +83,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (p.mode == 1)
+        for (int i = threadIdx.x; i < kWgABox / 16; i += blockDim.x) reinterpret_cast<uint4*>(zero_blk)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -85,27 +95,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            const int nbox_here = min(2 * npair_here, p.nboxes - 2 * pair0);
-            const uint32_t tx = static_cast<uint32_t>(nbox_here + NT / 64) * kWgBoxBytes;
+            const uint32_t tx = (p.mode == 0 || kw1 >= 0 ? kABytes : kWgABox) + kBBytes;
             for (int pt = pt0; pt < pt1; ++pt) {
                 int t = pt;
                 const int tw = t % p.tiles_w;
                 t /= p.tiles_w;
                 const int th = t % p.tiles_h;
                 const int img = t / p.tiles_h;
-                const int h0 = th * p.box_h, w0 = tw * p.box_w;
+                const int h0 = th * kWgBh, w0 = tw * kWgBw;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_bar[stage], tx);
                 uint8_t* sa = smem + stage * p.stage_bytes;
-                uint8_t* sb = sa + a_bytes;
-                for (int j = 0; j < NT / 64; ++j)
-                    tma_load_4d(&map_dz, &full_bar[stage], sb + j * kWgBoxBytes, co0 + j * 64, w0, h0, img);
-                for (int b = 0; b < nbox_here; ++b) {
-                    const int box = 2 * pair0 + b;
-                    const int tap = box / p.chunks, chunk = box - tap * p.chunks;
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    tma_load_4d(&map_x, &full_bar[stage], sa + b * kWgBoxBytes, chunk * 64, w0 + kw - 1, h0 + kh - 1,
-                                img);
+                tma_load_5d(&map_dz, &full_bar[stage], sa + kABytes, 0, w0, h0, co0 / 64, img);
+                if (p.mode == 0) {
+                    tma_load_5d(&map_x, &full_bar[stage], sa, 0, w0 + kw0 - 1, h0 - 1, ci0 / 64, img);
+                } else {
+                    tma_load_5d(&map_x, &full_bar[stage], sa, 0, w0 + kw0 - 1, h0 - 1, 0, img);
+                    if (kw1 >= 0) tma_load_5d(&map_x, &full_bar[stage], sa + kWgABox, 0, w0 + kw1 - 1, h0 - 1, 0, img);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -113,23 +119,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);   // both operands MN-major
-            // MN-major SWIZZLE_128B: 8-row (pixel) groups 1024 B apart (SBO), 64-channel blocks one box apart (LBO)
+            // MN-major SWIZZLE_128B: 8-row (pixel) groups 1024 B apart (SBO), 64-channel blocks LBO apart
             constexpr uint32_t dhi = desc_hi_sw128(1024);
-            const uint32_t lo0 = desc_lo_sw128(smem_u32(smem), kWgBoxBytes);
+            const uint32_t smem0 = smem_u32(smem);
+            const uint32_t zero_addr = smem_u32(zero_blk);
             int stage = 0;
             uint32_t phase = 0;
             for (int pt = pt0; pt < pt1; ++pt) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t a_lo = lo0 + stage * (p.stage_bytes >> 4);
-                const uint32_t b_lo = a_lo + (a_bytes >> 4);
+                const uint32_t a_addr = smem0 + stage * p.stage_bytes;
+                const uint32_t a_lbo = (p.mode == 1 && kw1 < 0) ? (zero_addr - a_addr) : kWgABox;
+                const uint32_t a_lo = desc_lo_sw128(a_addr, a_lbo);
+                const uint32_t b_lo = desc_lo_sw128(a_addr + kABytes, kWgBBox);
                 const uint32_t acc_flag = pt > pt0 ? 1u : 0u;
-                for (int a = 0; a < npair_here; ++a) {
 #pragma unroll
-                    for (int k = 0; k < kWgKPix / 16; ++k) {
-                        // K advance of 16 pixel rows = 2048 B
-                        umma_bf16_lohi(tmem_base + a * NT, a_lo + a * (2 * kWgBoxBytes >> 4) + k * (2048 >> 4), dhi,
-                                       b_lo + k * (2048 >> 4), dhi, idesc, k > 0 ? 1u : acc_flag);
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int k = 0; k < (kWgBh * kWgBw) / 16; ++k) {
+                        // kh shift = 16 pixel rows = 2048 B; K advance of 16 pixel rows = 2048 B
+                        umma_bf16_lohi(tmem_base + kh * NT, a_lo + (kh + k) * (2048 >> 4), dhi, b_lo + k * (2048 >> 4),
+                                       dhi, idesc, k > 0 ? 1u : acc_flag);
                     }
                 }
                 umma_commit(&empty_bar[stage]);
@@ -139,25 +149,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
     } else if (warp >= 4) {
         const int row = threadIdx.x - 128;        // TMEM lane = D row
-        const int ewarp = row >> 5;
+        const int half = row >> 6;
         float* part = p.partial + static_cast<size_t>(split) * 9 * p.Cin * p.Cout;
         const bool have_work = pt1 > pt0;
         if (have_work) {
             mbar_wait(done_bar, 0);
             tc_fence_after();
         }
-        for (int a = 0; a < npair_here; ++a) {
-            const int box = 2 * (pair0 + a) + (row >> 6);
-            const bool valid = box < p.nboxes;
-            const int tap = valid ? box / p.chunks : 0;
-            const int chunk = valid ? box - tap * p.chunks : 0;
-            const int ci = chunk * 64 + (row & 63);
-            float* dst = part + (static_cast<size_t>(tap) * p.Cin + ci) * p.Cout + co0;
+        const int kw = half == 0 ? kw0 : kw1;
+        const int ci = p.mode == 0 ? ci0 + row : (row & 63);
+        const bool valid = kw >= 0;
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {
+            float* dst = part + (static_cast<size_t>(kh * 3 + (valid ? kw : 0)) * p.Cin + ci) * p.Cout + co0;
 #pragma unroll 1
             for (int c = 0; c < NT / 32; ++c) {
                 uint32_t r[32];
                 if (have_work) {
-                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + a * NT + c * 32, r);
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + kh * NT + c * 32, r);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
@@ -212,10 +221,8 @@ bias_grad_kernel(const uint4* __restrict__ dz, float* __restrict__ db, long long
         acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xFFFF0000u);
     }
     const int C = C8 * 8;
-    if (rg < rgs) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[rg * C + chunk * 8 + j] = acc[j];
-    }
+    for (int j = 0; j < 8; ++j) red[rg * C + chunk * 8 + j] = acc[j];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
@@ -224,35 +231,24 @@ bias_grad_kernel(const uint4* __restrict__ dz, float* __restrict__ db, long long
     }
 }
 
-static int pick_kbox(int H, int W, int* bh, int* bw) {
-    for (int w = kWgKPix; w >= 8; w >>= 1) {
-        const int h = kWgKPix / w;
-        if (W % w == 0 && H % h == 0) { *bw = w; *bh = h; return ABL_OK; }
-    }
-    return ABL_ERR_SHAPE;
-}
-
 static int wgrad_plan(int B, int H, int W, int Cin, int Cout, WgradArgs* a, int* nt_out) {
     if (B <= 0 || Cin % 64 != 0 || Cout % 64 != 0 || Cin > 512 || Cout > 512) return ABL_ERR_SHAPE;
+    if (Cin != 64 && Cin % 128 != 0) return ABL_ERR_SHAPE;
+    if (W % kWgBw != 0 || H % kWgBh != 0) return ABL_ERR_SHAPE;
     a->B = B; a->H = H; a->W = W; a->Cin = Cin; a->Cout = Cout;
-    if (pick_kbox(H, W, &a->box_h, &a->box_w) != ABL_OK) return ABL_ERR_SHAPE;
-    const int nt = (Cout % 128 == 0) ? 128 : 64;
-    a->tiles_h = H / a->box_h; a->tiles_w = W / a->box_w;
+    const int nt = (Cout % 128 == 0) ? 128 : 64;            // 3 accumulators x NT <= 512 TMEM columns
+    a->tiles_h = H / kWgBh; a->tiles_w = W / kWgBw;
     a->num_ptiles = B * a->tiles_h * a->tiles_w;
-    a->chunks = Cin / 64;
-    a->nboxes = 9 * a->chunks;
-    a->npairs = (a->nboxes + 1) / 2;
-    const int max_acc = 512 / nt;                                   // TMEM columns
-    a->pair_groups = (a->npairs + max_acc - 1) / max_acc;
-    a->acc = (a->npairs + a->pair_groups - 1) / a->pair_groups;     // balance pairs over groups
+    a->mode = Cin == 64 ? 1 : 0;
+    a->ci_blocks = Cin == 64 ? 1 : Cin / 128;
     a->co_blocks = Cout / nt;
-    a->units = a->pair_groups * a->co_blocks;
+    a->units = (a->mode == 0 ? 3 * a->ci_blocks : 2) * a->co_blocks;
     int splits = sm_count() / a->units;
     if (splits < 1) splits = 1;
     if (splits > a->num_ptiles) splits = a->num_ptiles;
     a->splits = splits;
-    a->stage_bytes = (2 * a->acc + nt / 64) * kWgBoxBytes;
-    int stages = (227 * 1024 - 1024) / a->stage_bytes;
+    a->stage_bytes = 2 * kWgABox + (nt / 64) * kWgBBox;
+    int stages = (227 * 1024 - 512 - kWgABox) / a->stage_bytes;
     if (stages > kWgMaxStages) stages = kWgMaxStages;
     if (stages < 2) return ABL_ERR_SHAPE;
     a->stages = stages;
@@ -262,18 +258,26 @@ static int wgrad_plan(int B, int H, int W, int Cin, int Cout, WgradArgs* a, int*
 
 template <int NT>
 static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdz, const WgradArgs& a, cudaStream_t st) {
-    const int smem_bytes = a.stages * a.stage_bytes + 256;
-    static int attr_bytes[64] = {0};
+    const int smem_bytes = a.stages * a.stage_bytes + kWgABox + 512;
+    static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (attr_bytes[dev & 63] < smem_bytes) {
+    if (!attr_done[dev & 63]) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess)
             return check_launch();
-        attr_bytes[dev & 63] = 227 * 1024;
+        attr_done[dev & 63] = true;
     }
     wgrad_tc_kernel<NT><<<a.units * a.splits, kWgThreads, smem_bytes, st>>>(mx, mdz, a);
     return check_launch();
+}
+
+// 5-D view of an NHWC bf16 tensor: (64 ch, W, H, C/64, N); the box stacks `blocks` 64-channel blocks.
+static int nhwc_block_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_h, int blocks) {
+    const uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)(C / 64), (uint64_t)B};
+    const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, 128, (uint64_t)H * W * C * 2};
+    const uint32_t box[5] = {64, (uint32_t)kWgBw, (uint32_t)box_h, (uint32_t)blocks, 1};
+    return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace abl
@@ -308,7 +312,8 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
     WgradArgs a;
     int nt = 0;
     if (wgrad_plan(B, H, W, Cin, Cout, &a, &nt) != ABL_OK) {
-        set_error("abl_conv3x3_wgrad: unsupported shape (Cin, Cout multiples of 64 <= 512; W % 8 == 0)");
+        set_error("abl_conv3x3_wgrad: unsupported shape (Cin 64 or a multiple of 128, Cout a multiple of 64, both <= 512; "
+                  "W % 16 == 0, H % 4 == 0)");
         return ABL_ERR_SHAPE;
     }
     const long long need = static_cast<long long>(a.splits) * 9 * Cin * Cout * 4;
@@ -319,22 +324,12 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
     }
     a.partial = static_cast<float*>(workspace);
     CUtensorMap mx, mdz;
-    {
-        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-        const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-        const uint32_t box[4] = {64, (uint32_t)a.box_w, (uint32_t)a.box_h, 1};
-        int r = encode_tiled(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (r != ABL_OK) return r;
-    }
-    {
-        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-        const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-        const uint32_t box[4] = {64, (uint32_t)a.box_w, (uint32_t)a.box_h, 1};
-        int r = encode_tiled(&mdz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dz, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (r != ABL_OK) return r;
-    }
+    int r = nhwc_block_map(&mx, x, B, H, W, Cin, kWgBh + 2, a.mode == 0 ? 2 : 1);
+    if (r != ABL_OK) return r;
+    r = nhwc_block_map(&mdz, dz, B, H, W, Cout, kWgBh, nt / 64);
+    if (r != ABL_OK) return r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int r = (nt == 128) ? launch_wgrad<128>(mx, mdz, a, st) : launch_wgrad<64>(mx, mdz, a, st);
+    r = (nt == 128) ? launch_wgrad<128>(mx, mdz, a, st) : launch_wgrad<64>(mx, mdz, a, st);
     if (r != ABL_OK) return r;
     const long long n4 = 9LL * Cin * Cout / 4;
     long long blocks = (n4 + 255) / 256;
