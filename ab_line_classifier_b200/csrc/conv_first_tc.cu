@@ -28,7 +28,8 @@ constexpr int kF_Stages = 4;
 constexpr int kF_ProdGroups = 2;              // producer group g builds the CTA's tiles g, g+2, g+4, ...
 
 struct FirstArgs {
-    const float* x;        // [B,H,W,3] fp32
+    const float* x;        // [B,H,W,3] fp32 (already BGR / mean-subtracted), or
+    const uint8_t* x8;     // [B,H,W,3] uint8 RGB: preprocessing fused into the gather (kU8 kernels)
     const float* w;        // [27][64] fp32 (HWIO flattened)
     const float* bias;     // [64]
     float* dw;             // [27][64]  (wgrad)
@@ -39,11 +40,13 @@ struct FirstArgs {
 };
 
 // One thread = one pixel: gather the 27-value patch (zero padded) and write the swizzled K-major row(s).
-template <bool kFwd>
+// kU8: the frame is raw uint8 RGB and Keras' vgg16 preprocess_input (caffe mode: RGB->BGR, subtract the
+// ImageNet BGR means; reference preprocessor.py:60-63 / models.py:13) is applied on the fly; the SAME zero
+// padding applies to the PREPROCESSED tensor, so out-of-frame taps stay exactly 0.
+template <bool kFwd, bool kU8>
 __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, int row, uint8_t* a_stage) {
     const int wq = static_cast<int>(pix % p.W);
     const int hq = static_cast<int>((pix / p.W) % p.H);
-    const float* base = p.x + pix * 3;
     float v[27];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -51,9 +54,16 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
             const bool ok = hok && (wq + kw - 1) >= 0 && (wq + kw - 1) < p.W;
-            const float* px = base + ((kh - 1) * p.W + (kw - 1)) * 3;
+            const long long off = (pix + (kh - 1) * p.W + (kw - 1)) * 3;
+            if (kU8) {
+                const float mean_bgr[3] = {103.939f, 116.779f, 123.68f};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[(kh * 3 + kw) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+                for (int c = 0; c < 3; ++c)
+                    v[(kh * 3 + kw) * 3 + c] = ok ? static_cast<float>(__ldg(p.x8 + off + (2 - c))) - mean_bgr[c] : 0.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(kh * 3 + kw) * 3 + c] = ok ? __ldg(p.x + off + c) : 0.f;
+            }
         }
     }
     // 64 slots of k-block 0 as 32 packed bf16x2 words
@@ -90,6 +100,7 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
 }
 
 // ------------------------------------------------------------------------------------------ forward
+template <bool kU8>
 __global__ void __launch_bounds__(kF_Threads, 1)
 conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const FirstArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -166,7 +177,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
             const int tile = blockIdx.x + it * gridDim.x;
             const int stage = it % kF_Stages;
             mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
-            im2col_row<true>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * 2 * kF_ABlock);
+            im2col_row<true, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * 2 * kF_ABlock);
             fence_proxy_async_smem();
             mbar_arrive(&afull[stage]);
         }
@@ -222,6 +233,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
 
 // ------------------------------------------------------------------------------------------ wgrad
 // Persistent CTAs; each accumulates D[slot][co] over its tiles in TMEM, then adds rows 0..54 to dw / db.
+template <bool kU8>
 __global__ void __launch_bounds__(kF_Threads, 1)
 conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const FirstArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -293,7 +305,7 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
             const int tile = blockIdx.x + it * gridDim.x;
             const int stage = it % kF_Stages;
             mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
-            im2col_row<false>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kF_ABlock);
+            im2col_row<false, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kF_ABlock);
             fence_proxy_async_smem();
             mbar_arrive(&afull[stage]);
         }
@@ -327,14 +339,16 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
     }
 }
 
-static int first_args(FirstArgs* a, const float* x, int B, int H, int W, int Cout, const char* who) {
+static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W, int Cout, const char* who) {
     if (B <= 0 || H <= 0 || W <= 0 || Cout != kF_Cout || (static_cast<long long>(B) * H * W) % kF_TileM != 0) {
         char buf[160];
         snprintf(buf, sizeof(buf), "%s: need Cout == 64 and B*H*W a multiple of 128", who);
         set_error(buf);
         return ABL_ERR_SHAPE;
     }
-    a->x = x; a->H = H; a->W = W;
+    a->x = u8 ? nullptr : static_cast<const float*>(x);
+    a->x8 = u8 ? static_cast<const uint8_t*>(x) : nullptr;
+    a->H = H; a->W = W;
     a->total_pix = static_cast<long long>(B) * H * W;
     a->num_tiles = static_cast<int>(a->total_pix / kF_TileM);
     a->w = nullptr; a->bias = nullptr; a->dw = nullptr; a->db = nullptr;
@@ -348,18 +362,15 @@ static int pixel_map(CUtensorMap* m, const void* base, long long total_pix) {
     return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-}  // namespace abl
-
-using namespace abl;
-
-extern "C" int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H,
-                                  int W, int Cout, void* stream) {
+template <bool kU8>
+static int first_fwd(const void* x, const float* w_hwio, const float* bias, void* out, int B, int H, int W, int Cout,
+                     void* stream, const char* who) {
     if (!x || !w_hwio || !bias || !out) { set_error("abl_conv_first_fwd: null pointer"); return ABL_ERR_NULL; }
     if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) {
         set_error("abl_conv_first_fwd: out and bias must be 16-byte aligned"); return ABL_ERR_ALIGN;
     }
     FirstArgs a;
-    int r = first_args(&a, x, B, H, W, Cout, "abl_conv_first_fwd");
+    int r = first_args(&a, x, kU8, B, H, W, Cout, who);
     if (r != ABL_OK) return r;
     a.w = w_hwio; a.bias = bias;
     CUtensorMap mo;
@@ -370,21 +381,22 @@ extern "C" int abl_conv_first_fwd(const float* x, const float* w_hwio, const flo
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(conv_first_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_first_fwd_tc_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
             return check_launch();
         attr_done[dev & 63] = true;
     }
     const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
-    conv_first_fwd_tc_kernel<<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mo, a);
+    conv_first_fwd_tc_kernel<kU8><<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mo, a);
     return check_launch();
 }
 
-extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W,
-                                    int Cout, void* stream) {
+template <bool kU8>
+static int first_wgrad(const void* x, const void* dz, float* dw, float* db, int B, int H, int W, int Cout, void* stream,
+                       const char* who) {
     if (!x || !dz || !dw) { set_error("abl_conv_first_wgrad: null pointer"); return ABL_ERR_NULL; }
     if (reinterpret_cast<uintptr_t>(dz) & 15) { set_error("abl_conv_first_wgrad: dz must be 16-byte aligned"); return ABL_ERR_ALIGN; }
     FirstArgs a;
-    int r = first_args(&a, x, B, H, W, Cout, "abl_conv_first_wgrad");
+    int r = first_args(&a, x, kU8, B, H, W, Cout, who);
     if (r != ABL_OK) return r;
     a.dw = dw; a.db = db;
     CUtensorMap mz;
@@ -395,11 +407,32 @@ extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, f
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(conv_first_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_first_wgrad_tc_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
             return check_launch();
         attr_done[dev & 63] = true;
     }
     const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
-    conv_first_wgrad_tc_kernel<<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mz, a);
+    conv_first_wgrad_tc_kernel<kU8><<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mz, a);
     return check_launch();
+}
+
+}  // namespace abl
+
+using namespace abl;
+
+extern "C" int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H,
+                                  int W, int Cout, void* stream) {
+    return first_fwd<false>(x, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd");
+}
+extern "C" int abl_conv_first_fwd_u8(const unsigned char* frames_rgb, const float* w_hwio, const float* bias, void* out,
+                                     int B, int H, int W, int Cout, void* stream) {
+    return first_fwd<true>(frames_rgb, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd_u8");
+}
+extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W,
+                                    int Cout, void* stream) {
+    return first_wgrad<false>(x, dz, dw, db, B, H, W, Cout, stream, "abl_conv_first_wgrad");
+}
+extern "C" int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db, int B,
+                                       int H, int W, int Cout, void* stream) {
+    return first_wgrad<true>(frames_rgb, dz, dw, db, B, H, W, Cout, stream, "abl_conv_first_wgrad_u8");
 }

@@ -86,6 +86,13 @@ class CutoffVGG16Engine:
         self._cap = 0
         self._cap_train = False
         self._buf = {}
+        # input ring: two (frames, labels) slots filled on a copy stream so the H2D copy of batch i+1
+        # overlaps the kernels of batch i
+        self._slot = 0
+        self._slot_u8 = [False, False]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._slot_ready = [None, None]      # event: H2D into the slot finished (recorded on the copy stream)
+        self._slot_free = [None, None]       # event: last kernel reading the slot finished (compute stream)
 
     # ------------------------------------------------------------------ parameters
     def _alloc_params(self, output_bias):
@@ -179,7 +186,8 @@ class CutoffVGG16Engine:
         dev, bf = self.device, torch.bfloat16
         b = {}
         H, W, _ = self.input_shape
-        b["x"] = torch.empty(cap, H, W, 3, device=dev, dtype=torch.float32)
+        b["x"] = [torch.empty(cap, H, W, 3, device=dev, dtype=torch.float32) for _ in range(2)]
+        b["x8"] = [torch.empty(cap, H, W, 3, device=dev, dtype=torch.uint8) for _ in range(2)]
         max_full = 0
         for s in self.specs:
             if s.pool:
@@ -192,7 +200,7 @@ class CutoffVGG16Engine:
         b["gap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
         b["logits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["probs"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
-        b["y"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
+        b["y"] = [torch.empty(cap, n, device=dev, dtype=torch.float32) for _ in range(2)]
         b["loss"] = torch.zeros(1, device=dev, dtype=torch.float32)
         if training:
             b["dlogits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
@@ -206,6 +214,11 @@ class CutoffVGG16Engine:
                 ws = max(ws, ops.wgrad_workspace_bytes(cap, s.h, s.w, s.cin, s.cout))
             b["ws"] = torch.empty(ws, device=dev, dtype=torch.uint8)
         self._buf, self._cap, self._cap_train = b, cap, training
+        self._slot_ready, self._slot_free = [None, None], [None, None]
+
+    def _x(self, B):
+        """Current slot's frames: fp32 preprocessed, or raw uint8 RGB (preprocessing fused into block1_conv1)."""
+        return (self._buf["x8"] if self._slot_u8[self._slot] else self._buf["x"])[self._slot][:B]
 
     def _in_act(self, li, B):
         """Input activation of conv li (bf16), li >= 1."""
@@ -224,7 +237,7 @@ class CutoffVGG16Engine:
             full = full[:B] if full is not None else None
             pooled = b["pool_" + s.name][:B] if s.pool else None
             if li == 0:
-                ops.conv_first_fwd(b["x"][:B], self.view(s.name + "/kernel"), self.view(s.name + "/bias"), full)
+                ops.conv_first_fwd(self._x(B), self.view(s.name + "/kernel"), self.view(s.name + "/bias"), full)
                 if s.pool:
                     raise NotImplementedError("a pool directly after block1_conv1 is not a VGG16 prefix")
             else:
@@ -248,24 +261,70 @@ class CutoffVGG16Engine:
                          b["probs"][:B])
         return b["probs"][:B]
 
-    def load_input(self, x):
-        """Host (numpy / CPU tensor, ideally pinned) or device fp32 NHWC frames -> self._buf['x']."""
-        if isinstance(x, np.ndarray):
-            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        if x.dtype != torch.float32:
-            x = x.float()
+    def reserve(self, batch, training=False):
+        """Allocate (or grow) activation / input buffers; call before stage() when the batch size or the
+        training mode is about to grow, since growing re-allocates the input slots."""
+        self._ensure(int(batch), bool(training))
+
+    @staticmethod
+    def _as_tensor(a, dtype=None):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None and a.dtype != dtype:
+            a = a.to(dtype)
+        return a
+
+    def stage(self, x, y=None, slot=None):
+        """Asynchronously copy a batch into an input slot on the copy stream and return the slot index.
+        x: fp32 [B,H,W,3] frames as ``vgg16_preprocess`` leaves them, or RAW uint8 RGB frames (then the
+        preprocessing runs inside block1_conv1).  Host tensors should be pinned for a truly async copy."""
+        x = self._as_tensor(x)
+        if x.dtype != torch.uint8:
+            x = self._as_tensor(x, torch.float32)
         B = x.shape[0]
         if tuple(x.shape[1:]) != self.input_shape:
             raise ValueError(f"expected frames of shape {self.input_shape}, got {tuple(x.shape[1:])}")
-        self._buf["x"][:B].copy_(x, non_blocking=True)
-        return B
+        self._ensure(B, self._cap_train)
+        slot = (self._slot ^ 1) if slot is None else slot
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_stream(cur) if self._slot_free[slot] is None else self._copy_stream.wait_event(
+                self._slot_free[slot])
+            u8 = x.dtype == torch.uint8
+            (self._buf["x8"] if u8 else self._buf["x"])[slot][:B].copy_(x, non_blocking=True)
+            if y is not None:
+                self._buf["y"][slot][:B].copy_(self._as_tensor(y, torch.float32), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._slot_u8[slot] = u8
+        self._slot_ready[slot] = ev
+        return slot
+
+    def use_slot(self, slot):
+        """Make ``slot`` the current input: the compute stream waits for its H2D copy."""
+        self._slot = slot
+        if self._slot_ready[slot] is not None:
+            torch.cuda.current_stream().wait_event(self._slot_ready[slot])
+
+    def release_slot(self):
+        """Record that every kernel reading the current slot has been enqueued (the slot may be refilled after it)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._slot_free[self._slot] = ev
+
+    def load_input(self, x, y=None):
+        """Synchronous-order variant: stage into the other slot and switch to it.  Returns the batch size."""
+        self.use_slot(self.stage(x, y))
+        return x.shape[0]
 
     def predict_batch(self, x):
         """x: [B,H,W,3] fp32 (BGR, mean-subtracted, as vgg16_preprocess leaves it).  Returns device probs."""
         B = x.shape[0]
         self._ensure(B, False)
         self.load_input(x)
-        return self.forward_device(B)
+        probs = self.forward_device(B)
+        self.release_slot()
+        return probs
 
     # ------------------------------------------------------------------ backward + update
     def trainable_suffix(self, trainable):
@@ -306,7 +365,7 @@ class CutoffVGG16Engine:
                 dw = self.view(s.name + "/kernel", self.grad)
                 db = self.view(s.name + "/bias", self.grad)
                 if li == 0:
-                    ops.conv_first_wgrad(b["x"][:B], dz, dw, db)
+                    ops.conv_first_wgrad(self._x(B), dz, dw, db)
                 else:
                     ops.conv3x3_wgrad(self._in_act(li, B), dz, dw, db, b["ws"], accumulate=False)
                 if reduce_hook:
@@ -370,30 +429,32 @@ class CutoffVGG16Engine:
         """Inference forward + unweighted categorical cross-entropy sum (Keras evaluate).  Device probs."""
         B = x.shape[0]
         self._ensure(B, False)
-        self.load_input(x)
-        if isinstance(y, np.ndarray):
-            y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
-        self._buf["y"][:B].copy_(y, non_blocking=True)
-        return self.forward_device(B, y=self._buf["y"][:B], inv_batch=inv_batch, loss_out=loss_out)
+        self.load_input(x, y)
+        probs = self.forward_device(B, y=self._buf["y"][self._slot][:B], inv_batch=inv_batch, loss_out=loss_out)
+        self.release_slot()
+        return probs
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
-                   apply_update=True, bucket_bytes=2 << 20, loss_out=None):
-        """One step: H2D copy of (x, y), forward (dropout on), loss, backward, [DP all-reduce], update.
-        Returns the device scalar sum_i w_i*l_i / global_batch for THIS rank's frames."""
-        B = x.shape[0]
+                   apply_update=True, bucket_bytes=2 << 20, loss_out=None, slot=None, batch=None):
+        """One step: H2D copy of (x, y) [or a slot pre-filled by stage()], forward (dropout on), loss,
+        backward, [DP all-reduce], update.  Returns the device scalar sum_i w_i*l_i / global_batch for THIS
+        rank's frames."""
+        B = batch if slot is not None else x.shape[0]
+        if slot is not None and (B > self._cap or not self._cap_train):
+            raise RuntimeError("engine.reserve(batch, training=True) must be called before staging a training batch")
         self._ensure(B, True)
         b = self._buf
-        self.load_input(x)
-        if isinstance(y, np.ndarray):
-            y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
-        b["y"][:B].copy_(y, non_blocking=True)
+        if slot is None:
+            self.load_input(x, y)
+        else:
+            self.use_slot(slot)
         if keep_mask is not None:
             if isinstance(keep_mask, np.ndarray):
                 keep_mask = torch.from_numpy(np.ascontiguousarray(keep_mask).astype(np.uint8))
             b["keep"][:B].copy_(keep_mask, non_blocking=True)
         gb = float(global_batch if global_batch is not None else B * self.world_size)
-        self.forward_device(B, training=True, keep_mask_in=keep_mask is not None, y=b["y"][:B], inv_batch=1.0 / gb,
-                            loss_out=loss_out)
+        self.forward_device(B, training=True, keep_mask_in=keep_mask is not None, y=b["y"][self._slot][:B],
+                            inv_batch=1.0 / gb, loss_out=loss_out)
         self.step_count += 1
         reducer = None
         if self.world_size > 1:
@@ -402,6 +463,7 @@ class CutoffVGG16Engine:
         self.backward_device(B, trainable, reduce_hook=reducer.hook if reducer else None)
         if reducer:
             reducer.wait()
+        self.release_slot()
         if apply_update:
             self.apply_optimizer(optimizer, lr, trainable)
         return b["loss"] if loss_out is None else loss_out

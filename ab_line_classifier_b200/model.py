@@ -214,8 +214,10 @@ class B200Model:
         if isinstance(test_data, np.ndarray) or torch.is_tensor(test_data):
             test_data = [(test_data[i:i + batch_size], None) for i in range(0, len(test_data), batch_size)]
         for x, _ in _iter_batches(test_data):
-            outs.append(self.engine.predict_batch(x).cpu().numpy())
-        return np.concatenate(outs, 0) if outs else np.zeros((0, self.n_classes), np.float32)
+            outs.append(self.engine.predict_batch(x).clone())      # stays on device: one D2H at the end
+        if not outs:
+            return np.zeros((0, self.n_classes), np.float32)
+        return torch.cat(outs).cpu().numpy()
 
     def _run_eval(self, data):
         eng = self.engine
@@ -276,32 +278,43 @@ class B200Model:
             for cb in callbacks:
                 cb.on_epoch_begin(epoch) if hasattr(cb, "on_epoch_begin") else None
             opt = self.optimizer
-            tot_loss, n_seen, slot = 0.0, 0, 0
+            tot_loss, n_seen, slot_i = 0.0, 0, 0
             sizes, probs, ys = [], [], []
             ring.zero_()
 
             def drain():
-                nonlocal tot_loss, slot
-                if slot:
-                    vals = ring[:slot].cpu().numpy()
-                    tot_loss += float(np.dot(vals, np.asarray(sizes[-slot:], np.float64)))
+                nonlocal tot_loss, slot_i
+                if slot_i:
+                    vals = ring[:slot_i].cpu().numpy()
+                    tot_loss += float(np.dot(vals, np.asarray(sizes[-slot_i:], np.float64)))
                     ring.zero_()
-                    slot = 0
+                    slot_i = 0
 
-            for x, y in _iter_batches(train_data):
+            kw = ({"beta_1": opt.beta_1, "beta_2": opt.beta_2, "eps": opt.epsilon} if opt.kind == "adam"
+                  else {"rho": opt.rho, "eps": opt.epsilon})
+            # software pipeline: the H2D copy of batch i+1 (copy stream) overlaps the kernels of batch i
+            batches = _iter_batches(train_data)
+            nxt = next(batches, None)
+            if nxt is not None:
+                eng.reserve(len(nxt[0]), True)
+                nslot = eng.stage(nxt[0], nxt[1])
+            while nxt is not None:
+                (x, y), slot = nxt, nslot
                 B = len(x)
-                kw = ({"beta_1": opt.beta_1, "beta_2": opt.beta_2, "eps": opt.epsilon} if opt.kind == "adam"
-                      else {"rho": opt.rho, "eps": opt.epsilon})
-                eng.train_step(x, y, trainable, apply_update=False, loss_out=ring[slot:slot + 1],
-                               global_batch=B * eng.world_size)
+                nxt = next(batches, None)
+                if nxt is not None:
+                    eng.reserve(len(nxt[0]), True)
+                    nslot = eng.stage(nxt[0], nxt[1], slot=slot ^ 1)
+                eng.train_step(None, None, trainable, apply_update=False, loss_out=ring[slot_i:slot_i + 1],
+                               global_batch=B * eng.world_size, slot=slot, batch=B)
                 eng.apply_optimizer(opt.kind, opt.learning_rate, trainable, **kw)
                 if self.metric_objs:
                     probs.append(eng._buf["probs"][:B].clone())
                     ys.append(np.asarray(y, np.float32))
                 sizes.append(B)
                 n_seen += B
-                slot += 1
-                if slot == ring.numel():
+                slot_i += 1
+                if slot_i == ring.numel():
                     drain()
             drain()
             logs = {"loss": tot_loss / max(n_seen, 1)}

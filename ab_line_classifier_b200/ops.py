@@ -70,19 +70,28 @@ def bias_grad(dz, db):
     _native.call("abl_bias_grad", _ptr(dz), _ptr(db), dz.numel() // C, C, _stream())
 
 
+def _first_suffix(x):
+    if x.dtype == torch.uint8:
+        return "_u8"          # raw RGB frame: vgg16 preprocessing fused into the kernel
+    _chk(x, torch.float32, "x")
+    return ""
+
+
 def conv_first_fwd(x, w_hwio, bias, out):
-    _chk(x, torch.float32, "x"); _chk(w_hwio, torch.float32, "w"); _chk(bias, torch.float32, "bias")
-    _chk(out, torch.bfloat16, "out")
+    """x fp32 [B,H,W,3] (preprocessed) or uint8 [B,H,W,3] (raw RGB)."""
+    _chk(w_hwio, torch.float32, "w"); _chk(bias, torch.float32, "bias"); _chk(out, torch.bfloat16, "out")
     B, H, W, c = x.shape
     assert c == 3 and w_hwio.numel() == 27 * out.shape[3]
-    _native.call("abl_conv_first_fwd", _ptr(x), _ptr(w_hwio), _ptr(bias), _ptr(out), B, H, W, out.shape[3], _stream())
+    _native.call("abl_conv_first_fwd" + _first_suffix(x), _ptr(x), _ptr(w_hwio), _ptr(bias), _ptr(out), B, H, W,
+                 out.shape[3], _stream())
 
 
 def conv_first_wgrad(x, dz, dw, db):
-    _chk(x, torch.float32, "x"); _chk(dz, torch.bfloat16, "dz"); _chk(dw, torch.float32, "dw")
+    _chk(dz, torch.bfloat16, "dz"); _chk(dw, torch.float32, "dw")
     B, H, W, c = x.shape
     assert c == 3
-    _native.call("abl_conv_first_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), B, H, W, dz.shape[3], _stream())
+    _native.call("abl_conv_first_wgrad" + _first_suffix(x), _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), B, H, W,
+                 dz.shape[3], _stream())
 
 
 def prep_conv_weights(w_hwio, w_fwd=None, w_dgrad=None):

@@ -43,45 +43,59 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons streamed every 100 ms DURING the timed regions (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.samples, self.stop_flag = gpu_index, [], False
+        self.gpu_index, self.samples, self.stop_flag, self.proc = gpu_index, [], False, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [v.strip() for v in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [v.strip() for v in line.strip().split(",")]
                 if len(f) >= 7:
                     self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+        finally:
+            if self.proc is not None:
+                self.proc.terminate()
 
     def summary(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(sm), "reasons": reasons}
+        try:
+            load = [s for s in self.samples if float(s[2]) > 300.0] or self.samples     # samples under load
+            sm = sorted(float(s[0]) for s in load)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                    "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
+                    "samples_under_load": len(load), "reasons": reasons}
+        except Exception as e:  # malformed nvidia-smi output must not kill the bench line
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"parse error: {e}"]}
 
 
 def synth_batches(n_batches, batch, seed):
     from ab_line_classifier_b200 import synth
-    xs, ys = [], []
+    xs, ys, raw = [], [], []
     for i in range(n_batches):
         fr, lab = synth.synth_frames(batch, seed=seed + i)
+        raw.append(fr)
         xs.append(synth.vgg16_preprocess(fr))
         ys.append(synth.one_hot(lab))
-    return xs, ys
+    return xs, ys, raw
 
 
 def cpu_train_frames_per_s(batch, iters, threads):
@@ -182,7 +196,7 @@ def main():
     inner.compile(optimizer=Adam(HPARAMS["LR_EXTRACT"]), loss="categorical_crossentropy", metrics=["accuracy"])
 
     n_rot = 4
-    xs, ys = synth_batches(n_rot, B, seed=1234 + 100 * rank)
+    xs, ys, raw_frames = synth_batches(n_rot, B, seed=1234 + 100 * rank)
     xs_pin = [torch.from_numpy(x).pin_memory() for x in xs]
     ys_pin = [torch.from_numpy(y).pin_memory() for y in ys]
     eng._ensure(B, True)
@@ -224,20 +238,52 @@ def main():
     ms_per_step = ms / args.steps
     value = B * world * args.steps / (ms / 1e3)
 
-    # ---- e2e: public API, pinned host inputs, H2D inside, loss read back (D2H) every step
-    def api_step(i):
-        inner.train_on_batch(xs_pin[i % n_rot], ys_pin[i % n_rot])
-    for i in range(3):
-        api_step(i)
-    e2e_steps = max(5, args.steps // 2)
-    ms_e2e = timed(api_step, e2e_steps)
-    sampler.stop_flag = True
+    # ---- e2e: public engine API from pinned HOST buffers.  Every step: H2D copy of that step's frames + labels
+    # (staged on the copy stream while the previous step computes), the full train step, and a D2H read of the
+    # step's loss into pinned memory.
+    ring = torch.zeros(64, device="cuda")
+    loss_host = torch.zeros(64).pin_memory()
+
+    def run_e2e(frames_host, steps):
+        def body(_):
+            pass
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        slot = eng.stage(frames_host[0], ys_pin[0])
+        for i in range(steps):
+            nslot = eng.stage(frames_host[(i + 1) % n_rot], ys_pin[(i + 1) % n_rot], slot=slot ^ 1) if i + 1 < steps else slot
+            r = i % 64
+            ring[r:r + 1].zero_()
+            eng.train_step(None, None, trainable, "adam", HPARAMS["LR_EXTRACT"], global_batch=B * world, slot=slot,
+                           batch=B, loss_out=ring[r:r + 1])
+            loss_host[r:r + 1].copy_(ring[r:r + 1], non_blocking=True)
+            slot = nslot
+        e1.record()
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        assert torch.isfinite(loss_host[: min(steps, 64)]).all()
+        return ms_
+
+    e2e_steps = args.steps
+    run_e2e(xs_pin, 3)
+    ms_e2e = run_e2e(xs_pin, e2e_steps)
     e2e_value = B * world * e2e_steps / (ms_e2e / 1e3)
+    # same, feeding RAW uint8 RGB frames (vgg16 preprocessing fused into block1_conv1: SURVEY 8 f1)
+    frames_u8 = [torch.from_numpy(f).pin_memory() for f in raw_frames]
+    run_e2e(frames_u8, 3)
+    ms_e2e_u8 = run_e2e(frames_u8, e2e_steps)
+    sampler.stop_flag = True
 
     # ---- inference throughput (extra): forward only, resident inputs
     def infer_step(i):
-        eng._buf["x"][:B].copy_(xs_dev[i % n_rot], non_blocking=True)
+        eng.load_input(xs_dev[i % n_rot])
         eng.forward_device(B)
+        eng.release_slot()
     for i in range(3):
         infer_step(i)
     ms_inf = timed(infer_step, args.steps)
@@ -298,13 +344,17 @@ def main():
             "config": workload_config(world), "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
                     "h2d_bytes_per_step": int(xs_pin[0].numel() * 4 + ys_pin[0].numel() * 4) * world,
-                    "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 4)},
+                    "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 4),
+                    "api": "engine.stage(pinned fp32 frames, labels) + engine.train_step(slot) + D2H loss, every step"},
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu,
             "extra": {"train_tflops_per_gpu": round(value / world * TRAIN_GFLOP / 1e3, 1),
                       "frac_of_sustained_peak": round(value / world * TRAIN_GFLOP / 1e3 / pk.get("bf16_tflops_sustained", 1400.0), 4),
                       "infer_frames_per_s": round(infer_fps, 1), "infer_ms_per_step": round(ms_inf / args.steps, 4),
                       "infer_tflops_per_gpu": round(infer_fps / world * FWD_GFLOP / 1e3, 1),
+                      "e2e_uint8_frames": {"value": round(B * world * e2e_steps / (ms_e2e_u8 / 1e3), 1), "unit": "frames/s",
+                                           "h2d_bytes_per_step": int(frames_u8[0].numel() + ys_pin[0].numel() * 4) * world,
+                                           "note": "raw uint8 RGB frames in, vgg16 preprocessing fused into block1_conv1"},
                       "trainable": args.trainable, "kernels_one_step": kernels},
         }
         print(json.dumps(line), flush=True)

@@ -75,6 +75,15 @@ int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, v
 int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W, int Cout,
                          void* stream);
 
+/* Same two kernels fed by the RAW uint8 RGB frame [B,H,W,3] (what decode_jpeg + nearest resize leave,
+ * reference preprocessor.py:76-80): Keras vgg16 preprocess_input (RGB->BGR, subtract 103.939/116.779/123.68;
+ * models.py:13, preprocessor.py:60-63) is fused into the gather, so the fp32 tensor never exists and the
+ * host->device copy is 4x smaller. */
+int abl_conv_first_fwd_u8(const unsigned char* frames_rgb, const float* w_hwio, const float* bias, void* out, int B,
+                          int H, int W, int Cout, void* stream);
+int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db, int B, int H,
+                            int W, int Cout, void* stream);
+
 /* fp32 HWIO master kernel -> the two bf16 GEMM operand layouts, taps indexed kw-major (t' = kw*3 + kh):
  *   w_fwd  [kw*3+kh][co][ci]         = w[kh][kw][ci][co]
  *   w_dgrad[(2-kw)*3+(2-kh)][ci][co] = w[kh][kw][ci][co]   (180-degree rotated)      (either may be NULL) */

@@ -64,9 +64,10 @@ def test_forward_matches_golden_fixture(setup):
 def test_intermediate_activations_vs_bf16_oracle(setup):
     eng, params = setup
     x, y, _ = _frames(4, seed=7)
-    eng._ensure(4, True)
+    eng.reserve(4, True)
     eng.load_input(x)
     eng.forward_device(4)
+    eng.release_slot()
     ref = oracle.forward(params, x, bf16=True)
     for name, key in [("block1_conv1", "act_block1_conv1"), ("block1_pool", "pool_block1_conv2"),
                       ("block2_pool", "pool_block2_conv2"), ("block3_conv3", "act_block3_conv3")]:
@@ -84,6 +85,41 @@ def test_ragged_batches_equal_per_frame_results(setup, B):
     all_logits = eng._buf["logits"][:33].clone()
     eng.predict_batch(x[:B])
     assert torch.equal(eng._buf["logits"][:B], all_logits[:B])
+
+
+def test_raw_uint8_frames_give_identical_logits(setup):
+    eng, _ = setup
+    x, _, frames = _frames(16, seed=5)
+    eng.predict_batch(x)
+    ref = eng._buf["logits"][:16].clone()
+    eng.predict_batch(frames)                     # uint8 RGB: preprocessing fused into block1_conv1
+    assert torch.equal(eng._buf["logits"][:16], ref)
+
+
+def test_staged_prefetch_pipeline_matches_unpipelined_training(setup):
+    """stage(next batch) on the copy stream while the current step runs == plain train_step, bit for bit
+    (wgrad is deterministic; conv1_1's atomics are excluded by freezing it)."""
+    eng, params = setup
+    x, y, _ = _frames(24, seed=13)
+    tr = set(eng.layer_names()) - {"block1_conv1"}
+    outs = []
+    for mode in ("plain", "staged"):
+        eng.set_weights(params)
+        eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+        eng.reserve(8, True)
+        if mode == "plain":
+            for i in range(3):
+                eng.train_step(x[8 * i:8 * i + 8], y[8 * i:8 * i + 8], tr)
+        else:
+            slot = eng.stage(x[:8], y[:8])
+            for i in range(3):
+                nslot = eng.stage(x[8 * i + 8:8 * i + 16], y[8 * i + 8:8 * i + 16], slot=slot ^ 1) if i < 2 else slot
+                eng.train_step(None, None, tr, slot=slot, batch=8)
+                slot = nslot
+        outs.append(eng.theta.clone())
+    assert torch.equal(outs[0], outs[1])
+    eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+    eng.set_weights(params)
 
 
 def test_full_size_batch_256_chunk_invariance_and_determinism(setup):

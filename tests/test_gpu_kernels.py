@@ -140,6 +140,30 @@ def test_conv_first_forward_and_wgrad_fp32():
     _close(db, dz.sum(dim=(0, 1, 2)), 1e-4, "conv_first bias grad")
 
 
+def test_conv_first_uint8_path_fuses_vgg16_preprocessing_bit_exactly():
+    """f1: raw uint8 RGB frames in, caffe-mode preprocess_input (preprocessor.py:60-63) inside the kernel."""
+    ops = _ops()
+    from oracle import synth
+    frames, _ = synth.synth_frames(3, seed=9)
+    frames[0, :4, :4] = 255                  # exercise the borders / saturation
+    x = synth.vgg16_preprocess(frames)
+    g = torch.Generator().manual_seed(1)
+    w = (torch.randn(3, 3, 3, 64, generator=g) * 0.1).cuda()
+    b = (torch.randn(64, generator=g) * 0.1).cuda()
+    o32 = torch.empty(3, 128, 128, 64, device="cuda", dtype=torch.bfloat16)
+    o8 = torch.empty_like(o32)
+    ops.conv_first_fwd(torch.from_numpy(x).cuda(), w, b, o32)
+    ops.conv_first_fwd(torch.from_numpy(frames).cuda(), w, b, o8)
+    assert torch.equal(o32, o8)
+    dz = (torch.randn(3, 128, 128, 64, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dw32, db32 = torch.zeros(3, 3, 3, 64, device="cuda"), torch.zeros(64, device="cuda")
+    dw8, db8 = torch.zeros_like(dw32), torch.zeros_like(db32)
+    ops.conv_first_wgrad(torch.from_numpy(x).cuda(), dz, dw32, db32)
+    ops.conv_first_wgrad(torch.from_numpy(frames).cuda(), dz, dw8, db8)
+    _close(dw8, dw32, 1e-5, "u8 wgrad")      # atomics: summation order differs between launches
+    _close(db8, db32, 1e-5, "u8 bias grad")
+
+
 def test_maxpool_backward_routes_to_first_max_and_relu_masks():
     ops = _ops()
     g = torch.Generator().manual_seed(2)
