@@ -27,6 +27,13 @@ class FakeEngine:
         return [s.name for s in self.specs] + ["output"]
 
     def _ensure(self, b, t): pass
+    def reserve(self, b, training=False): pass
+
+    def stage(self, x, y=None, slot=None):
+        self._slots = getattr(self, "_slots", {})
+        slot = 0 if slot is None else slot
+        self._slots[slot] = (x, y)
+        return slot
     def refresh_operands(self, layers=None): pass
     def get_weights(self): return {k: v.copy() for k, v in self.params.items()}
 
@@ -53,7 +60,9 @@ class FakeEngine:
         return out["probs"].detach()
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
-                   apply_update=True, bucket_bytes=0, loss_out=None):
+                   apply_update=True, bucket_bytes=0, loss_out=None, slot=None, batch=None):
+        if slot is not None:
+            x, y = self._slots[slot]
         x, y = self._np(x), self._np(y)
         mask = synth.dropout_mask(len(x), self.feat_shape[2], self.dropout, step=self.step_count)
         self.step_count += 1
