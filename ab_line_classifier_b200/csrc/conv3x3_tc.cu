@@ -14,6 +14,8 @@
 // (single thread), warp 2 TMEM allocator, warps 4-11 epilogue.  The accumulator is double
 // buffered in TMEM (2 x NTILE columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
 // the epilogue writes full-resolution tiles with TMA stores from a swizzled staging buffer.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 #include "../../include/abl_b200.h"
@@ -36,6 +38,145 @@ struct ConvArgs {
     __nv_bfloat16* out_full;        // [B,H,W,Cout] or null
     __nv_bfloat16* out_pool;        // [B,H/2,W/2,Cout] or null
 };
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of ONE 128-pixel x NTILE accumulator (shared by both main-loop variants), run by the 8
+// epilogue warps (256 threads).  Warp e reads TMEM lanes 32*(e%4).. (hardware lane quarter of its warp id)
+// and the column half e/4 of each pass; thread = one output pixel (tile row) x 32-column chunks.  Values are
+// packed to bf16 into a 128B-swizzled staging tile ([64-ch box][128 rows][128 B], the layout of a TMA box),
+// from which ONE elected thread issues the full-resolution TMA store while all threads compute the 2x2
+// max-pool (if requested) out of the same staging tile.
+//   tmem_acc : TMEM address (lane 0) of the accumulator's first column
+//   (img,h0,w0): origin of the box_h x box_w pixel rectangle; n0 = first output channel
+//   wait_bar : accumulator-full barrier to wait on before the first TMEM read (nullptr: already waited)
+//   arrive_bar: accumulator-empty barrier to arrive on after the last TMEM read (nullptr: none)
+template <int NTILE, int kEpiN, int kStgBufs>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorMap* map_out, uint8_t* staging,
+                                              uint32_t tmem_acc, int img, int h0, int w0, int n0, int box_w,
+                                              int et, uint32_t& pass_ctr, uint64_t* wait_bar, uint32_t wait_phase,
+                                              uint64_t* arrive_bar) {
+    constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
+    constexpr int kPasses = NTILE / kEpiN;
+    constexpr int kColsPerWarp = kEpiN / 2;      // 32 or 64
+    constexpr int kChunks = kColsPerWarp / 32;   // 1 or 2
+    const int lane_row = ((et >> 5) & 3) * 32 + (et & 31);   // tile row == TMEM lane
+    const int hsel = et >> 7;                                // which half of the pass' columns
+    const int ph_row = lane_row / box_w, pw_col = lane_row - ph_row * box_w;
+    const size_t pix_off = ((static_cast<size_t>(img) * p.H + h0 + ph_row) * p.W + w0 + pw_col) * p.Cout;
+
+#pragma unroll 1
+    for (int pass = 0; pass < kPasses; ++pass, ++pass_ctr) {
+        uint8_t* stg = staging + (pass_ctr % kStgBufs) * kStagingBytes;
+        const int col0 = pass * kEpiN + hsel * kColsPerWarp;     // first column of this warp in the tile
+        // ReLU-mask prefetch (dgrad): this thread's pixel, its columns -- issued before any wait
+        uint4 mk[kChunks * 4];
+        if (p.flags & ABL_EPI_RELU_MASK) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix_off + n0 + col0);
+#pragma unroll
+            for (int j = 0; j < kChunks * 4; ++j) mk[j] = __ldg(mp + j);
+        }
+        if (pass == 0 && wait_bar != nullptr) {
+            mbar_wait(wait_bar, wait_phase);
+            tc_fence_after();
+        }
+        // staging buffer free: the TMA store issued kStgBufs passes ago has finished READING it
+        if (et == 0) tma_store_wait_read<kStgBufs - 1>();
+        named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            uint32_t r[32];
+            const int col = col0 + c * 32;
+            tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(lane_row & ~31) << 16) + col, r);
+            tmem_ld_wait();
+            uint32_t packed[16];
+            if (p.flags & ABL_EPI_BIAS_RELU) {
+                // warp-uniform address: one broadcast transaction per load, L1-resident
+                const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(bs + j);
+                    packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
+                                                fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
+                    packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
+                                                    fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    packed[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            }
+            if (p.flags & ABL_EPI_RELU_MASK) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t mm[4] = {mk[c * 4 + j].x, mk[c * 4 + j].y, mk[c * 4 + j].z, mk[c * 4 + j].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // post-ReLU activations are >= 0: "> 0" <=> magnitude bits set, sign clear
+                        const uint32_t lo_on = ((mm[k] & 0x7FFFu) != 0 && !(mm[k] & 0x8000u)) ? 0xFFFFu : 0u;
+                        const uint32_t hi_on =
+                            ((mm[k] & 0x7FFF0000u) != 0 && !(mm[k] & 0x80000000u)) ? 0xFFFF0000u : 0u;
+                        packed[4 * j + k] &= (lo_on | hi_on);
+                    }
+                }
+            }
+            // swizzled store: 16-byte chunk index XOR (row & 7) inside the 64-channel box
+            const int pcol = col - pass * kEpiN;              // column within the pass
+            uint8_t* box = stg + (pcol >> 6) * kABytes + lane_row * 128;
+            const int cc0 = (pcol & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(box + (((cc0 + j) ^ (lane_row & 7)) << 4)) =
+                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (pass == kPasses - 1 && arrive_bar != nullptr) {
+            tc_fence_before();
+            mbar_arrive(arrive_bar);   // TMEM buffer may be overwritten by the next tile
+        }
+        fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
+        named_bar_sync(1, kEpiThreads);     // staging filled
+
+        const int cbase = n0 + pass * kEpiN;
+        if (p.out_full != nullptr && et == 0) {
+#pragma unroll
+            for (int j = 0; j < kEpiN / 64; ++j)
+                tma_store_4d(map_out, stg + j * kABytes, cbase + j * 64, w0, h0, img);
+            tma_store_commit();
+        }
+        if (p.out_pool != nullptr) {
+            constexpr int kChunks16 = kEpiN / 8;
+            const int pw_n = box_w >> 1;
+#pragma unroll
+            for (int q = et; q < (kTileM / 4) * kChunks16; q += kEpiThreads) {
+                const int prow = q / kChunks16, cc = q - prow * kChunks16;
+                const int ph = prow / pw_n, pw = prow - ph * pw_n;
+                const int r00 = (2 * ph) * box_w + 2 * pw;          // even row: r00 & 7 in {0,2,4,6}
+                const uint8_t* bx = stg + (cc >> 3) * kABytes;
+                const int c8 = cc & 7;
+                const int r01 = r00 + 1, r10 = r00 + box_w, r11 = r10 + 1;
+                const uint4 a = *reinterpret_cast<const uint4*>(bx + r00 * 128 + ((c8 ^ (r00 & 7)) << 4));
+                const uint4 b = *reinterpret_cast<const uint4*>(bx + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
+                const uint4 c2 = *reinterpret_cast<const uint4*>(bx + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
+                const uint4 d = *reinterpret_cast<const uint4*>(bx + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
+                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                const uint32_t cv[4] = {c2.x, c2.y, c2.z, c2.w}, dv[4] = {d.x, d.y, d.z, d.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]),
+                                                      *reinterpret_cast<const __nv_bfloat162*>(&bv[j]));
+                    const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]),
+                                                      *reinterpret_cast<const __nv_bfloat162*>(&dv[j]));
+                    const __nv_bfloat162 m2 = __hmax2(m0, m1);
+                    o[j] = *reinterpret_cast<const uint32_t*>(&m2);
+                }
+                const int h = (h0 >> 1) + ph, w = (w0 >> 1) + pw;
+                const size_t off =
+                    ((static_cast<size_t>(img) * (p.H >> 1) + h) * (p.W >> 1) + w) * p.Cout + cbase + cc * 8;
+                *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
 
 // TAPS = taps consumed per pipeline stage.  TAPS == 1: stage = one tap x 64 channels (A 16 KiB + B).
 // TAPS == 3 (used for NTILE == 64, where 4 MMAs per stage cannot amortise the issuing thread's barrier wait
@@ -170,17 +311,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (8 warps, 256 threads)
-        // Warp e reads TMEM lanes 32*(e%4).. (hardware lane quarter of its warp id) and the column half
-        // e/4 of each pass; thread = one output pixel (tile row) x 32-column chunks.  Values are packed to
-        // bf16 into a 128B-swizzled staging tile ([64-ch box][128 rows][128 B], the layout of a TMA box), from
-        // which ONE elected thread issues the full-resolution TMA store while all threads compute the 2x2
-        // max-pool (if requested) out of the same staging tile.
         const int et = threadIdx.x - 128;                 // 0..255
-        const int lane_row = ((et >> 5) & 3) * 32 + (et & 31);   // tile row == TMEM lane
-        const int hsel = et >> 7;                         // which half of the pass' columns
-        constexpr int kPasses = NTILE / Cfg::kEpiN;
-        constexpr int kColsPerWarp = Cfg::kEpiN / 2;      // 32 or 64
-        constexpr int kChunks = kColsPerWarp / 32;        // 1 or 2
         int it = 0;
         uint32_t pass_ctr = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -190,123 +321,217 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             m_tile /= p.tiles_w;
             const int th = m_tile % p.tiles_h;
             const int img = m_tile / p.tiles_h;
-            const int h0 = th * p.box_h, w0 = tw * p.box_w, n0 = n_tile * NTILE;
             const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int ph_row = lane_row / p.box_w, pw_col = lane_row - ph_row * p.box_w;
-            const size_t pix_off = ((static_cast<size_t>(img) * p.H + h0 + ph_row) * p.W + w0 + pw_col) * p.Cout;
+            epilogue_tile<NTILE, Cfg::kEpiN, Cfg::kStgBufs>(p, &map_out, staging, tmem_base + as * NTILE, img,
+                                                            th * p.box_h, tw * p.box_w, n_tile * NTILE, p.box_w, et,
+                                                            pass_ctr, &tfull_bar[as], (it >> 1) & 1, &tempty_bar[as]);
+        }
+        if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
+    }
 
-#pragma unroll 1
-            for (int pass = 0; pass < kPasses; ++pass, ++pass_ctr) {
-                uint8_t* stg = staging + (pass_ctr % Cfg::kStgBufs) * Cfg::kStagingBytes;
-                const int col0 = pass * Cfg::kEpiN + hsel * kColsPerWarp;     // first column of this warp in the tile
-                // ReLU-mask prefetch (dgrad): this thread's pixel, its columns -- issued before any wait
-                uint4 mk[kChunks * 4];
-                if (p.flags & ABL_EPI_RELU_MASK) {
-                    const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix_off + n0 + col0);
-#pragma unroll
-                    for (int j = 0; j < kChunks * 4; ++j) mk[j] = __ldg(mp + j);
-                }
-                if (pass == 0) {
-                    mbar_wait(&tfull_bar[as], aphase);
-                    tc_fence_after();
-                }
-                // staging buffer free: the TMA store issued kStgBufs passes ago has finished READING it
-                if (et == 0) tma_store_wait_read<Cfg::kStgBufs - 1>();
-                named_bar_sync(1, kEpiThreads);
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    uint32_t r[32];
-                    const int col = col0 + c * 32;
-                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lane_row & ~31) << 16) + as * NTILE + col, r);
-                    tmem_ld_wait();
-                    uint32_t packed[16];
-                    if (p.flags & ABL_EPI_BIAS_RELU) {
-                        // warp-uniform address: one broadcast transaction per load, L1-resident
-                        const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + col);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = __ldg(bs + j);
-                            packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
-                                                        fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
-                            packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
-                                                            fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            packed[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// "Halo" main loop (v2).  ncu on the v1 kernel above showed every variant saturating the L2 -> SM
+// fabric (l1tex__m_xbar2l1tex_read_bytes ~17 TB/s) with the tensor pipe 50-85 % busy: each CTA re-fetched
+// its activation tile once per tap (9x) and the filter slab once per 128 pixels.  This variant cuts both:
+//   * CTA tile = MSUB vertically stacked sub-tiles of 8 rows x 16 pixels (M = 128 each) that share every
+//     filter slab, accumulated in MSUB TMEM accumulators (x2 buffers: 2*MSUB*NTILE <= 512 columns);
+//   * per (kw, 64-channel chunk) ONE TMA box brings the tile plus a one-row halo above and below
+//     ((8*MSUB+2) x 16 pixels); the three kh taps of every sub-tile are descriptor start offsets of
+//     (8*sub + kh) image rows = multiples of 2 KiB (two 1 KiB swizzle atoms), so A is fetched 3x, not 9x;
+//   * A and B travel through separate rings with separate producer threads (warp 0: A, warp 3: B), so the
+//     small filter slabs prefetch deep while few big A stages are in flight.
+// L2 -> SM bytes per MMA clock: 96 -> 75 (N=256), 128 -> 55 (N=128, MSUB=2), 128 -> 78 (N=64, MSUB=2).
+template <int NTILE, int MSUB>
+struct HaloCfg {
+    static constexpr int kSubH = 8, kTileW = 16;
+    static constexpr int kARows = (kSubH * MSUB + 2) * kTileW;          // haloed pixel rows of one A stage
+    static constexpr int kAStage = kARows * 128;
+    static constexpr int kTPB = NTILE == 64 ? 3 : 1;                    // taps per B stage
+    static constexpr int kBTap = NTILE * kBlockK * 2;
+    static constexpr int kBStage = kTPB * kBTap;
+    static constexpr int kEpiN = NTILE < 128 ? NTILE : 128;
+    static constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
+    static constexpr int kStgBufs = NTILE == 64 ? 2 : 1;
+    static constexpr int kAStages = 3;
+    static constexpr int kBarBytes = 512;
+    static constexpr int kBRoom = (227 * 1024 - kBarBytes - kStgBufs * kStagingBytes - kAStages * kAStage) / kBStage;
+    static constexpr int kBStages = kBRoom > 8 ? 8 : kBRoom;
+    static constexpr int kTmemCols = 2 * MSUB * NTILE;
+    static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStgBufs * kStagingBytes + kBarBytes;
+    static_assert(kBStages >= 3, "filter ring too shallow");
+    static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns must be a power of two");
+};
+
+template <int NTILE, int MSUB>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
+    using Cfg = HaloCfg<NTILE, MSUB>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kAStages * Cfg::kAStage;
+    uint8_t* staging = smem_b + Cfg::kBStages * Cfg::kBStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStgBufs * Cfg::kStagingBytes);
+    uint64_t* afull_bar = bars;
+    uint64_t* aempty_bar = afull_bar + Cfg::kAStages;
+    uint64_t* bfull_bar = aempty_bar + Cfg::kAStages;
+    uint64_t* bempty_bar = bfull_bar + Cfg::kBStages;
+    uint64_t* tfull_bar = bempty_bar + Cfg::kBStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int kwkc = 3 * p.kchunks;                 // A stages per tile: (kw, 64-channel chunk)
+    constexpr int kTileH = Cfg::kSubH * MSUB;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < Cfg::kAStages; ++s) {
+            mbar_init(&afull_bar[s], 1);
+            mbar_init(&aempty_bar[s], 1);
+        }
+        for (int s = 0; s < Cfg::kBStages; ++s) {
+            mbar_init(&bfull_bar[s], 1);
+            mbar_init(&bempty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], kEpiThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ A producer (haloed activation tiles)
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_tile = tile / p.num_n_tiles;
+                const int tw = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th = m_tile % p.tiles_h;
+                const int img = m_tile / p.tiles_h;
+                const int h0 = th * kTileH, w0 = tw * Cfg::kTileW;
+                for (int kw = 0; kw < 3; ++kw) {
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&aempty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&afull_bar[stage], Cfg::kAStage);
+                        tma_load_4d(&map_a, &afull_bar[stage], smem_a + stage * Cfg::kAStage, kc * kBlockK,
+                                    w0 + kw - 1, h0 - 1, img);
+                        if (++stage == Cfg::kAStages) { stage = 0; phase ^= 1; }
                     }
-                    if (p.flags & ABL_EPI_RELU_MASK) {
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ B producer (filter slabs, kw-major taps)
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.num_n_tiles) * NTILE;
+                for (int kw = 0; kw < 3; ++kw) {
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t mm[4] = {mk[c * 4 + j].x, mk[c * 4 + j].y, mk[c * 4 + j].z, mk[c * 4 + j].w};
+                        for (int g = 0; g < 3 / Cfg::kTPB; ++g) {
+                            mbar_wait(&bempty_bar[stage], phase ^ 1);
+                            mbar_expect_tx(&bfull_bar[stage], Cfg::kBStage);
+                            tma_load_3d(&map_b, &bfull_bar[stage], smem_b + stage * Cfg::kBStage, kc * kBlockK, n0,
+                                        kw * 3 + g * Cfg::kTPB);
+                            if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(kTileM, NTILE, 0, 0);
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a), 16);
+            const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_b), 16);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * (MSUB * NTILE);
+                for (int s = 0; s < kwkc; ++s) {
+                    mbar_wait(&afull_bar[sa], pa);
+                    const uint32_t a_lo = a_lo0 + sa * (Cfg::kAStage >> 4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                // post-ReLU activations are >= 0: "> 0" <=> magnitude bits set, sign clear
-                                const uint32_t lo_on = ((mm[k] & 0x7FFFu) != 0 && !(mm[k] & 0x8000u)) ? 0xFFFFu : 0u;
-                                const uint32_t hi_on =
-                                    ((mm[k] & 0x7FFF0000u) != 0 && !(mm[k] & 0x80000000u)) ? 0xFFFF0000u : 0u;
-                                packed[4 * j + k] &= (lo_on | hi_on);
+                    for (int g = 0; g < 3 / Cfg::kTPB; ++g) {
+                        mbar_wait(&bfull_bar[sb], pb);
+                        tc_fence_after();
+                        const uint32_t b_lo = b_lo0 + sb * (Cfg::kBStage >> 4);
+#pragma unroll
+                        for (int t = 0; t < Cfg::kTPB; ++t) {
+                            const int kh = g * Cfg::kTPB + t;
+#pragma unroll
+                            for (int sub = 0; sub < MSUB; ++sub) {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k) {
+                                    // (8*sub + kh) image rows of 16 pixels = 2048 B each; K advance of 16 elements = 32 B
+                                    umma_bf16_lohi(tmem_d + sub * NTILE,
+                                                   a_lo + (Cfg::kSubH * sub + kh) * (2048 >> 4) + k * 2, dhi,
+                                                   b_lo + t * (Cfg::kBTap >> 4) + k * 2, dhi, idesc,
+                                                   (s | kh | k) != 0 ? 1u : 0u);
+                                }
                             }
                         }
+                        umma_commit(&bempty_bar[sb]);     // filter slab free when these MMAs retire
+                        if (++sb == Cfg::kBStages) { sb = 0; pb ^= 1; }
                     }
-                    // swizzled store: 16-byte chunk index XOR (row & 7) inside the 64-channel box
-                    const int pcol = col - pass * Cfg::kEpiN;              // column within the pass
-                    uint8_t* box = stg + (pcol >> 6) * kABytes + lane_row * 128;
-                    const int cc0 = (pcol & 63) >> 3;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4*>(box + (((cc0 + j) ^ (lane_row & 7)) << 4)) =
-                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    umma_commit(&aempty_bar[sa]);         // haloed activation tile free
+                    if (++sa == Cfg::kAStages) { sa = 0; pa ^= 1; }
                 }
-                if (pass == kPasses - 1) {
-                    tc_fence_before();
-                    mbar_arrive(&tempty_bar[as]);   // TMEM buffer may be overwritten by the next tile
-                }
-                fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
-                named_bar_sync(1, kEpiThreads);     // staging filled
-
-                const int cbase = n0 + pass * Cfg::kEpiN;
-                if (p.out_full != nullptr && et == 0) {
-#pragma unroll
-                    for (int j = 0; j < Cfg::kEpiN / 64; ++j)
-                        tma_store_4d(&map_out, stg + j * kABytes, cbase + j * 64, w0, h0, img);
-                    tma_store_commit();
-                }
-                if (p.out_pool != nullptr) {
-                    constexpr int kChunks16 = Cfg::kEpiN / 8;
-                    const int pw_n = p.box_w >> 1;
-#pragma unroll
-                    for (int q = et; q < (kTileM / 4) * kChunks16; q += kEpiThreads) {
-                        const int prow = q / kChunks16, cc = q - prow * kChunks16;
-                        const int ph = prow / pw_n, pw = prow - ph * pw_n;
-                        const int r00 = (2 * ph) * p.box_w + 2 * pw;          // even row: r00 & 7 in {0,2,4,6}
-                        const uint8_t* bx = stg + (cc >> 3) * kABytes;
-                        const int c8 = cc & 7;
-                        const int r01 = r00 + 1, r10 = r00 + p.box_w, r11 = r10 + 1;
-                        const uint4 a = *reinterpret_cast<const uint4*>(bx + r00 * 128 + ((c8 ^ (r00 & 7)) << 4));
-                        const uint4 b = *reinterpret_cast<const uint4*>(bx + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
-                        const uint4 c2 = *reinterpret_cast<const uint4*>(bx + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
-                        const uint4 d = *reinterpret_cast<const uint4*>(bx + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
-                        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-                        const uint32_t cv[4] = {c2.x, c2.y, c2.z, c2.w}, dv[4] = {d.x, d.y, d.z, d.w};
-                        uint32_t o[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]),
-                                                              *reinterpret_cast<const __nv_bfloat162*>(&bv[j]));
-                            const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]),
-                                                              *reinterpret_cast<const __nv_bfloat162*>(&dv[j]));
-                            const __nv_bfloat162 m2 = __hmax2(m0, m1);
-                            o[j] = *reinterpret_cast<const uint32_t*>(&m2);
-                        }
-                        const int h = (h0 >> 1) + ph, w = (w0 >> 1) + pw;
-                        const size_t off =
-                            ((static_cast<size_t>(img) * (p.H >> 1) + h) * (p.W >> 1) + w) * p.Cout + cbase + cc * 8;
-                        *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                }
+                umma_commit(&tfull_bar[as]);              // all MSUB accumulators ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (8 warps, 256 threads)
+        const int et = threadIdx.x - 128;
+        int it = 0;
+        uint32_t pass_ctr = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int n_tile = tile % p.num_n_tiles;
+            int m_tile = tile / p.num_n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int img = m_tile / p.tiles_h;
+            const int as = it & 1;
+#pragma unroll 1
+            for (int sub = 0; sub < MSUB; ++sub) {
+                epilogue_tile<NTILE, Cfg::kEpiN, Cfg::kStgBufs>(
+                    p, &map_out, staging, tmem_base + (as * MSUB + sub) * NTILE, img, th * kTileH + sub * Cfg::kSubH,
+                    tw * Cfg::kTileW, n_tile * NTILE, Cfg::kTileW, et, pass_ctr, sub == 0 ? &tfull_bar[as] : nullptr,
+                    (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr);
             }
         }
         if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
@@ -353,6 +578,25 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
     return check_launch();
 }
 
+template <int NTILE, int MSUB>
+static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const ConvArgs& a,
+                       cudaStream_t st) {
+    using Cfg = HaloCfg<NTILE, MSUB>;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        if (cudaFuncSetAttribute(conv3x3_halo_kernel<NTILE, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes) != cudaSuccess)
+            return check_launch();
+        attr_done[dev & 63] = true;
+    }
+    const int tiles = a.num_m_tiles * a.num_n_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    conv3x3_halo_kernel<NTILE, MSUB><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
+    return check_launch();
+}
+
 }  // namespace abl
 
 using namespace abl;
@@ -387,6 +631,54 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     }
     if (out_pool && (a.box_h & 1)) { set_error("abl_conv3x3_igemm: pooled output needs an even tile height"); return ABL_ERR_SHAPE; }
     const int ntile = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    // v2 "halo" main loop: tiles of (8*MSUB) rows x 16 pixels (MSUB = 1 for N = 256, else 2).  ABL_IGEMM_V1=1
+    // (environment, read per call) forces the v1 kernel for A/B measurements and its own parity tests.
+    const int msub = ntile == 256 ? 1 : 2;
+    const char* force_v1 = getenv("ABL_IGEMM_V1");
+    // N = 64 is epilogue-bound; measured on B200 the v1 4x32-pixel tile is faster for its ReLU-mask (dgrad) epilogue
+    const bool v1_better = ntile == 64 && !(flags & ABL_EPI_BIAS_RELU) && (W % 32 == 0) && (H % 4 == 0) &&
+                           !(force_v1 && force_v1[0] == '0');
+    if (W % 16 == 0 && H % (8 * msub) == 0 && !(force_v1 && force_v1[0] == '1') && !v1_better) {
+        a.box_w = 16; a.box_h = 8 * msub;
+        a.tiles_h = H / a.box_h; a.tiles_w = W / 16;
+        a.num_m_tiles = B * a.tiles_h * a.tiles_w;
+        a.num_n_tiles = Cout / ntile;
+        a.kchunks = Cin / kBlockK;
+        a.flags = flags;
+        a.bias = bias;
+        a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+        a.out_full = static_cast<__nv_bfloat16*>(out_full);
+        a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
+        CUtensorMap ma, mb;
+        {
+            const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+            const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+            const uint32_t box[4] = {(uint32_t)kBlockK, 16u, (uint32_t)(a.box_h + 2), 1};
+            int r = encode_tiled(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (r != ABL_OK) return r;
+        }
+        {
+            const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+            const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+            const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)ntile, ntile == 64 ? 3u : 1u};
+            int r = encode_tiled(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_kmajor, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (r != ABL_OK) return r;
+        }
+        CUtensorMap mo = ma;   // valid placeholder when only the pooled output is requested (never dereferenced)
+        if (out_full) {
+            const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+            const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+            const uint32_t box[4] = {64, 16u, 8u, 1};
+            int r = encode_tiled(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out_full, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (r != ABL_OK) return r;
+        }
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        switch (ntile) {
+            case 256: return launch_halo<256, 1>(ma, mb, mo, a, st);
+            case 128: return launch_halo<128, 2>(ma, mb, mo, a, st);
+            default: return launch_halo<64, 2>(ma, mb, mo, a, st);
+        }
+    }
     // 3-taps-per-stage main loop for the narrow tile: needs the 4 x 32 pixel rectangle
     const bool taps3 = ntile == 64 && (W % 32 == 0) && (H % 4 == 0);
     if (taps3) { a.box_w = 32; a.box_h = 4; }

@@ -37,13 +37,21 @@ def _close(got, ref, rel, what):
     assert err <= rel * scale, f"{what}: max|err| {err:.4g} > {rel:.3g} * {scale:.4g}"
 
 
+@pytest.fixture(params=["halo", "v1"])
+def igemm_variant(request, monkeypatch):
+    """Both main loops of abl_conv3x3_igemm: the haloed-tile kernel (default) and the v1 kernel that
+    remains the fallback for frame sizes the 16-pixel-wide tiles do not divide."""
+    monkeypatch.setenv("ABL_IGEMM_V1", "1" if request.param == "v1" else "0")
+    return request.param
+
+
 LAYERS = [(64, 64, 128, 128, True), (64, 128, 64, 64, False), (128, 128, 64, 64, True),
           (128, 256, 32, 32, False), (256, 256, 32, 32, False)]
 
 
 @pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
 @pytest.mark.parametrize("B", [1, 3])
-def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B):
+def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B, igemm_variant):
     ops = _ops()
     g = torch.Generator().manual_seed(cin * 7 + cout + B)
     x = _bf(torch.randn(B, H, W, cin, generator=g) * 0.5)
@@ -61,7 +69,7 @@ def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B):
         assert torch.equal(pl.float().cpu(), ref)
 
 
-def test_conv3x3_pool_only_output_matches_full_path():
+def test_conv3x3_pool_only_output_matches_full_path(igemm_variant):
     ops = _ops()
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(2, 64, 64, 128, generator=g) * 0.5).to(torch.bfloat16).cuda()
@@ -78,7 +86,7 @@ def test_conv3x3_pool_only_output_matches_full_path():
 
 
 @pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
-def test_conv3x3_dgrad_with_relu_mask(cin, cout, H, W, pool):
+def test_conv3x3_dgrad_with_relu_mask(cin, cout, H, W, pool, igemm_variant):
     ops = _ops()
     g = torch.Generator().manual_seed(cin + cout)
     B = 2

@@ -1,0 +1,81 @@
+"""Developer tool: data-parallel bring-up check on N GPUs (torchrun).  Prints a marker after every stage and dumps
+all Python stacks if a stage takes more than 45 s (so a hang is located instead of eating the GPU budget).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+      tools/dp_check.py
+
+Checks: NCCL init, blocking + async all-reduce, then that the DP train step (bucketed all-reduce overlapped with
+backward) produces the gradient of the single-device step on the concatenated batch."""
+import faulthandler
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+faulthandler.enable()
+T0 = time.time()
+
+
+def mark(msg):
+    faulthandler.cancel_dump_traceback_later()
+    print(f"[rank {os.environ.get('RANK', '0')} +{time.time() - T0:6.1f}s] {msg}", flush=True)
+    faulthandler.dump_traceback_later(45, exit=True)
+
+
+mark("start")
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local_rank)
+mark("torch imported")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+mark("process group up")
+t = torch.ones(4, device="cuda") * (rank + 1)
+dist.all_reduce(t)
+torch.cuda.synchronize()
+mark(f"blocking all_reduce ok: {t[0].item()}")
+big = torch.ones(1736008, device="cuda")
+hs = [dist.all_reduce(big[i * 500000:(i + 1) * 500000], async_op=True) for i in range(3)]
+for h in hs:
+    h.wait()
+torch.cuda.synchronize()
+mark(f"async all_reduce ok: {big[0].item()}")
+
+from ab_line_classifier_b200 import synth  # noqa: E402
+from ab_line_classifier_b200.engine import CutoffVGG16Engine  # noqa: E402
+
+Bl = int(sys.argv[1]) if len(sys.argv) > 1 else 8           # frames per rank
+G = Bl * world
+fr, lab = synth.synth_frames(G, seed=77)
+x, y = synth.vgg16_preprocess(fr), synth.one_hot(lab)
+keep = (np.random.default_rng(5).random((G, 256)) >= 0.45).astype(np.uint8)
+eng = CutoffVGG16Engine(rank=rank, world_size=world)
+tr = set(eng.layer_names())
+mark("engine built")
+sl = slice(rank * Bl, (rank + 1) * Bl)
+loss = eng.train_step(x[sl], y[sl], tr, keep_mask=keep[sl], apply_update=False, global_batch=G)
+torch.cuda.synchronize()
+g_dp = eng.grad.clone()
+mark(f"DP step done, local loss {loss.item():.5f}")
+# single-device reference on the concatenated batch (every rank computes it; world_size forced to 1)
+eng.world_size = 1
+loss1 = eng.train_step(x, y, tr, keep_mask=keep, apply_update=False, global_batch=G)
+torch.cuda.synchronize()
+g_1 = eng.grad.clone()
+eng.world_size = world
+ls = loss.clone()
+dist.all_reduce(ls)
+err = float((g_dp - g_1).abs().max() / g_1.abs().max())
+mark(f"single-device step done: loss {loss1.item():.5f} vs DP sum {ls.item():.5f}; max|dg|/max|g| = {err:.3e}")
+assert err < 2e-2, err                      # bf16 inter-layer gradients: batch split changes nothing but fp32 order
+assert abs(ls.item() - loss1.item()) < 1e-4
+for i in range(5):
+    eng.train_step(x[sl], y[sl], tr, global_batch=G)
+torch.cuda.synchronize()
+mark("5 DP steps with update done")
+dist.barrier()
+faulthandler.cancel_dump_traceback_later()
+dist.destroy_process_group()
+print(f"[rank {rank}] dp_check ok", flush=True)
