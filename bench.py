@@ -172,6 +172,9 @@ def main():
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    # a hung collective must not eat the GPU budget: dump every Python stack and exit after 10 minutes
+    import faulthandler
+    faulthandler.dump_traceback_later(600, exit=True)
 
     import torch
     import torch.distributed as dist
@@ -293,11 +296,12 @@ def main():
     pk, pk_src = peaks()
     roof = None
     kernels = {}
+    # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 keeps the records
+    _native.timing = []
+    device_step(0)
+    torch.cuda.synchronize()
+    recs, _native.timing = _native.timing, None
     if rank == 0:
-        _native.timing = []
-        device_step(0)
-        torch.cuda.synchronize()
-        recs, _native.timing = _native.timing, None
         tc_flops, tc_ms = 0.0, 0.0
         for name, a, e0, e1 in recs:
             t = e0.elapsed_time(e1)
@@ -336,12 +340,13 @@ def main():
                "sample": "2 timed full train steps (fwd+loss+bwd+Adam) at batch 32 after 1 warm-up, torch-CPU fp32 "
                          "restatement of the Keras path (TensorFlow 2.9 not installable in this image)"}
 
+    clocks = sampler.summary()          # also stops this rank's nvidia-smi child
     if rank == 0:
         line = {
             "metric": "cutoffvgg16 train frames/sec", "value": round(value, 1), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world), "clocks": sampler.summary(),
+            "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
                     "h2d_bytes_per_step": int(xs_pin[0].numel() * 4 + ys_pin[0].numel() * 4) * world,
                     "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": round(ms_e2e / e2e_steps, 4),
