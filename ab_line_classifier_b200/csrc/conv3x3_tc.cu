@@ -37,6 +37,7 @@ struct ConvArgs {
     const __nv_bfloat16* mask_src;  // [B,H,W,Cout] (ABL_EPI_RELU_MASK)
     __nv_bfloat16* out_full;        // [B,H,W,Cout] or null
     __nv_bfloat16* out_pool;        // [B,H/2,W/2,Cout] or null
+    float* colsum;                  // [Cout] fp32 += column sums of out_full (fused BiasAddGrad) or null
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -50,11 +51,13 @@ struct ConvArgs {
 //   (img,h0,w0): origin of the box_h x box_w pixel rectangle; n0 = first output channel
 //   wait_bar : accumulator-full barrier to wait on before the first TMEM read (nullptr: already waited)
 //   arrive_bar: accumulator-empty barrier to arrive on after the last TMEM read (nullptr: none)
+//   csum     : shared-memory fp32 [NTILE] column sums of the bf16 values written (fused BiasAddGrad of the
+//              tensor this kernel produces; the caller flushes it to global memory once per CTA) or nullptr
 template <int NTILE, int kEpiN, int kStgBufs>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorMap* map_out, uint8_t* staging,
                                               uint32_t tmem_acc, int img, int h0, int w0, int n0, int box_w,
                                               int et, uint32_t& pass_ctr, uint64_t* wait_bar, uint32_t wait_phase,
-                                              uint64_t* arrive_bar) {
+                                              uint64_t* arrive_bar, float* csum = nullptr) {
     constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
     constexpr int kPasses = NTILE / kEpiN;
     constexpr int kColsPerWarp = kEpiN / 2;      // 32 or 64
@@ -141,6 +144,33 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
             for (int j = 0; j < kEpiN / 64; ++j)
                 tma_store_4d(map_out, stg + j * kABytes, cbase + j * 64, w0, h0, img);
             tma_store_commit();
+        }
+        if (csum != nullptr) {
+            // thread = (16-byte chunk of 8 channels, group of rows) of the staged bf16 tile
+            constexpr int kCh = kEpiN / 8;                                // chunks per staged row: 16 or 8
+            constexpr int kRowsPer = kTileM / (kEpiThreads / kCh);        // 8 or 4 rows per thread
+            const int chunk = et % kCh, rg = et / kCh;
+            const uint8_t* bx = stg + (chunk >> 3) * kABytes;
+            const int c8 = chunk & 7;
+            float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < kRowsPer; ++r) {
+                const int row = rg * kRowsPer + r;
+                const uint4 v = *reinterpret_cast<const uint4*>(bx + row * 128 + ((c8 ^ (row & 7)) << 4));
+                s8[0] += __uint_as_float(v.x << 16); s8[1] += __uint_as_float(v.x & 0xFFFF0000u);
+                s8[2] += __uint_as_float(v.y << 16); s8[3] += __uint_as_float(v.y & 0xFFFF0000u);
+                s8[4] += __uint_as_float(v.z << 16); s8[5] += __uint_as_float(v.z & 0xFFFF0000u);
+                s8[6] += __uint_as_float(v.w << 16); s8[7] += __uint_as_float(v.w & 0xFFFF0000u);
+            }
+            // lanes l and l ^ kCh (and l ^ 2 kCh ...) hold the same chunk for other row groups
+#pragma unroll
+            for (int o = 16; o >= kCh; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s8[j] += __shfl_xor_sync(0xffffffffu, s8[j], o);
+            if ((et & 31) < kCh) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(&csum[pass * kEpiN + chunk * 8 + j], s8[j]);
+            }
         }
         if (p.out_pool != nullptr) {
             constexpr int kChunks16 = kEpiN / 8;
@@ -349,7 +379,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 //   * A and B travel through separate rings with separate producer threads (warp 0: A, warp 3: B), so the
 //     small filter slabs prefetch deep while few big A stages are in flight.
 // L2 -> SM bytes per MMA clock: 96 -> 75 (N=256), 128 -> 55 (N=128, MSUB=2), 128 -> 78 (N=64, MSUB=2).
-template <int NTILE, int MSUB>
+// BRES (N = 64, Cin = 64 only): the whole filter (9 taps x 64 x 64 bf16 = 72 KiB) stays resident in shared memory
+// for the life of the CTA instead of cycling through the ring: zero filter traffic after the first 3 boxes.
+template <int NTILE, int MSUB, bool BRES = false>
 struct HaloCfg {
     static constexpr int kSubH = 8, kTileW = 16;
     static constexpr int kARows = (kSubH * MSUB + 2) * kTileW;          // haloed pixel rows of one A stage
@@ -361,20 +393,21 @@ struct HaloCfg {
     static constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
     static constexpr int kStgBufs = NTILE == 64 ? 2 : 1;
     static constexpr int kAStages = 3;
-    static constexpr int kBarBytes = 512;
+    static constexpr int kBarBytes = 2048;     // barriers (first 512 B) + fp32 column sums [NTILE] (fused bias grad)
     static constexpr int kBRoom = (227 * 1024 - kBarBytes - kStgBufs * kStagingBytes - kAStages * kAStage) / kBStage;
-    static constexpr int kBStages = kBRoom > 8 ? 8 : kBRoom;
+    static constexpr int kBStages = BRES ? 3 : (kBRoom > 8 ? 8 : kBRoom);     // BRES: 3 "stages" = the 3 kw groups
+    static_assert(!BRES || (NTILE == 64 && kBRoom >= 3), "resident filter needs N = 64");
     static constexpr int kTmemCols = 2 * MSUB * NTILE;
     static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStgBufs * kStagingBytes + kBarBytes;
     static_assert(kBStages >= 3, "filter ring too shallow");
     static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns must be a power of two");
 };
 
-template <int NTILE, int MSUB>
+template <int NTILE, int MSUB, bool BRES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
-    using Cfg = HaloCfg<NTILE, MSUB>;
+    using Cfg = HaloCfg<NTILE, MSUB, BRES>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kAStages * Cfg::kAStage;
@@ -387,10 +420,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t* tfull_bar = bempty_bar + Cfg::kBStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* csum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
     const int warp = threadIdx.x >> 5;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int kwkc = 3 * p.kchunks;                 // A stages per tile: (kw, 64-channel chunk)
+    if (p.colsum != nullptr)
+        for (int i = threadIdx.x; i < NTILE; i += blockDim.x) csum[i] = 0.f;
     constexpr int kTileH = Cfg::kSubH * MSUB;
 
     if (warp == 0 && elect_one()) {
@@ -446,7 +482,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp == 3) {
         // ------------------------------------------------------------ B producer (filter slabs, kw-major taps)
-        if (elect_one()) {
+        if (BRES) {
+            // resident filter: kchunks == 1, one N tile -> stage kw holds taps kw*3 .. kw*3+2, loaded once
+            if (elect_one() && blockIdx.x < num_tiles) {
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_expect_tx(&bfull_bar[kw], Cfg::kBStage);
+                    tma_load_3d(&map_b, &bfull_bar[kw], smem_b + kw * Cfg::kBStage, 0, 0, kw * 3);
+                }
+            }
+        } else if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -486,7 +530,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint32_t a_lo = a_lo0 + sa * (Cfg::kAStage >> 4);
 #pragma unroll
                     for (int g = 0; g < 3 / Cfg::kTPB; ++g) {
-                        mbar_wait(&bfull_bar[sb], pb);
+                        if (BRES) {
+                            if (it == 0) mbar_wait(&bfull_bar[s], 0);     // s == kw (kchunks == 1): loaded once
+                            sb = s;
+                        } else {
+                            mbar_wait(&bfull_bar[sb], pb);
+                        }
                         tc_fence_after();
                         const uint32_t b_lo = b_lo0 + sb * (Cfg::kBStage >> 4);
 #pragma unroll
@@ -504,8 +553,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                 }
                             }
                         }
-                        umma_commit(&bempty_bar[sb]);     // filter slab free when these MMAs retire
-                        if (++sb == Cfg::kBStages) { sb = 0; pb ^= 1; }
+                        if (!BRES) {
+                            umma_commit(&bempty_bar[sb]);     // filter slab free when these MMAs retire
+                            if (++sb == Cfg::kBStages) { sb = 0; pb ^= 1; }
+                        }
                     }
                     umma_commit(&aempty_bar[sa]);         // haloed activation tile free
                     if (++sa == Cfg::kAStages) { sa = 0; pa ^= 1; }
@@ -516,6 +567,122 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (8 warps, 256 threads)
         const int et = threadIdx.x - 128;
+        if constexpr (NTILE == 64 && MSUB == 2) {
+            // N = 64 is epilogue-latency-bound (1152 MMA clocks per sub-tile): the two sub-tiles of a tile are
+            // drained CONCURRENTLY by two independent groups of 4 warps (own staging buffer, own named barrier,
+            // own TMA-store thread), and the ReLU mask of the NEXT tile is prefetched while this one is processed.
+            const int grp = et >> 7, gt = et & 127;
+            uint8_t* stg = staging + grp * Cfg::kStagingBytes;
+            uint4 mk[8];
+            auto tile_origin = [&](int tile, int& img, int& h0, int& w0, int& n0) {
+                n0 = (tile % p.num_n_tiles) * NTILE;
+                int m_tile = tile / p.num_n_tiles;
+                w0 = (m_tile % p.tiles_w) * Cfg::kTileW;
+                m_tile /= p.tiles_w;
+                h0 = (m_tile % p.tiles_h) * kTileH + grp * Cfg::kSubH;
+                img = m_tile / p.tiles_h;
+            };
+            auto load_mask = [&](int tile) {
+                int img, h0, w0, n0;
+                tile_origin(tile, img, h0, w0, n0);
+                const size_t off = ((static_cast<size_t>(img) * p.H + h0 + (gt >> 4)) * p.W + w0 + (gt & 15)) * p.Cout + n0;
+                const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
+            };
+            const bool masked = (p.flags & ABL_EPI_RELU_MASK) != 0;
+            if (masked && blockIdx.x < num_tiles) load_mask(blockIdx.x);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                int img, h0, w0, n0;
+                tile_origin(tile, img, h0, w0, n0);
+                const int as = it & 1;
+                mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+                tc_fence_after();
+                if (gt == 0) tma_store_wait_read<0>();      // this group's previous store has finished reading stg
+                named_bar_sync(1 + grp, 128);
+                const uint32_t tacc = tmem_base + (as * MSUB + grp) * NTILE + (static_cast<uint32_t>(gt & ~31) << 16);
+                uint32_t packed[2][16];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tacc + c * 32, r);
+                    tmem_ld_wait();
+                    if (p.flags & ABL_EPI_BIAS_RELU) {
+                        const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(bs + j);
+                            packed[c][2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
+                                                           fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
+                            packed[c][2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
+                                                               fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            packed[c][j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);               // both accumulators of this buffer drained by 256 arrivals
+                if (masked) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t mm[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t lo_on = ((mm[k] & 0x7FFFu) != 0 && !(mm[k] & 0x8000u)) ? 0xFFFFu : 0u;
+                            const uint32_t hi_on =
+                                ((mm[k] & 0x7FFF0000u) != 0 && !(mm[k] & 0x80000000u)) ? 0xFFFF0000u : 0u;
+                            packed[j >> 2][(j & 3) * 4 + k] &= (lo_on | hi_on);
+                        }
+                    }
+                    if (tile + static_cast<int>(gridDim.x) < num_tiles) load_mask(tile + gridDim.x);   // next tile's mask
+                }
+                uint8_t* row = stg + gt * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(row + ((j ^ (gt & 7)) << 4)) =
+                        make_uint4(packed[j >> 2][(j & 3) * 4], packed[j >> 2][(j & 3) * 4 + 1],
+                                   packed[j >> 2][(j & 3) * 4 + 2], packed[j >> 2][(j & 3) * 4 + 3]);
+                fence_proxy_async_smem();
+                named_bar_sync(1 + grp, 128);
+                if (p.out_full != nullptr && gt == 0) {
+                    tma_store_4d(&map_out, stg, n0, w0, h0, img);
+                    tma_store_commit();
+                }
+                if (p.out_pool != nullptr) {
+#pragma unroll
+                    for (int q = gt; q < 32 * 8; q += 128) {
+                        const int prow = q >> 3, c8 = q & 7;
+                        const int ph = prow >> 3, pw = prow & 7;
+                        const int r00 = (2 * ph) * 16 + 2 * pw;
+                        const int r01 = r00 + 1, r10 = r00 + 16, r11 = r10 + 1;
+                        const uint4 a = *reinterpret_cast<const uint4*>(stg + r00 * 128 + ((c8 ^ (r00 & 7)) << 4));
+                        const uint4 b = *reinterpret_cast<const uint4*>(stg + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
+                        const uint4 c2 = *reinterpret_cast<const uint4*>(stg + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
+                        const uint4 d = *reinterpret_cast<const uint4*>(stg + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
+                        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                        const uint32_t cv[4] = {c2.x, c2.y, c2.z, c2.w}, dv[4] = {d.x, d.y, d.z, d.w};
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]),
+                                                              *reinterpret_cast<const __nv_bfloat162*>(&bv[j]));
+                            const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]),
+                                                              *reinterpret_cast<const __nv_bfloat162*>(&dv[j]));
+                            const __nv_bfloat162 m2 = __hmax2(m0, m1);
+                            o[j] = *reinterpret_cast<const uint32_t*>(&m2);
+                        }
+                        const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1) + ph) * (p.W >> 1) +
+                                            (w0 >> 1) + pw) * p.Cout + n0 + c8 * 8;
+                        *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            if (gt == 0) tma_store_wait_all();
+        } else {
         int it = 0;
         uint32_t pass_ctr = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -531,10 +698,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 epilogue_tile<NTILE, Cfg::kEpiN, Cfg::kStgBufs>(
                     p, &map_out, staging, tmem_base + (as * MSUB + sub) * NTILE, img, th * kTileH + sub * Cfg::kSubH,
                     tw * Cfg::kTileW, n_tile * NTILE, Cfg::kTileW, et, pass_ctr, sub == 0 ? &tfull_bar[as] : nullptr,
-                    (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr);
+                    (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr, p.colsum != nullptr ? csum : nullptr);
             }
         }
         if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
+        if (p.colsum != nullptr) {           // one flush per CTA (host guarantees a single N tile)
+            named_bar_sync(1, kEpiThreads);
+            for (int i = et; i < NTILE; i += kEpiThreads) atomicAdd(p.colsum + i, csum[i]);
+        }
+        }
     }
 
     tc_fence_before();
@@ -578,22 +750,22 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
     return check_launch();
 }
 
-template <int NTILE, int MSUB>
+template <int NTILE, int MSUB, bool BRES = false>
 static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const ConvArgs& a,
                        cudaStream_t st) {
-    using Cfg = HaloCfg<NTILE, MSUB>;
+    using Cfg = HaloCfg<NTILE, MSUB, BRES>;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(conv3x3_halo_kernel<NTILE, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(conv3x3_halo_kernel<NTILE, MSUB, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::kSmemBytes) != cudaSuccess)
             return check_launch();
         attr_done[dev & 63] = true;
     }
     const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    conv3x3_halo_kernel<NTILE, MSUB><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
+    conv3x3_halo_kernel<NTILE, MSUB, BRES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
     return check_launch();
 }
 
@@ -602,9 +774,12 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
 using namespace abl;
 
 // See include/abl_b200.h for the contract.
+extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
+
 extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                                 void* out_full, void* out_pool, int B, int H, int W, int Cin, int Cout,
-                                 int flags, void* stream) {
+                                 void* out_full, void* out_pool, float* colsum, int B, int H, int W, int Cin,
+                                 int Cout, int flags, void* stream) {
+    if (colsum && !out_full) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
     if (!x || !w_kmajor) { set_error("abl_conv3x3_igemm: null input"); return ABL_ERR_NULL; }
     if (!out_full && !out_pool) { set_error("abl_conv3x3_igemm: no output requested"); return ABL_ERR_NULL; }
     if ((flags & ABL_EPI_BIAS_RELU) && !bias) { set_error("abl_conv3x3_igemm: bias missing"); return ABL_ERR_NULL; }
@@ -649,6 +824,9 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
         a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
         a.out_full = static_cast<__nv_bfloat16*>(out_full);
         a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
+        // fused BiasAddGrad: the 8-warp epilogue with a single N tile; otherwise a separate pass over out_full
+        const bool fuse_colsum = colsum != nullptr && ntile != 64 && a.num_n_tiles == 1;
+        a.colsum = fuse_colsum ? colsum : nullptr;
         CUtensorMap ma, mb;
         {
             const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -673,12 +851,18 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
             if (r != ABL_OK) return r;
         }
         cudaStream_t st = static_cast<cudaStream_t>(stream);
+        int r;
         switch (ntile) {
-            case 256: return launch_halo<256, 1>(ma, mb, mo, a, st);
-            case 128: return launch_halo<128, 2>(ma, mb, mo, a, st);
-            default: return launch_halo<64, 2>(ma, mb, mo, a, st);
+            case 256: r = launch_halo<256, 1>(ma, mb, mo, a, st); break;
+            case 128: r = launch_halo<128, 2>(ma, mb, mo, a, st); break;
+            default: r = (Cin == 64 && Cout == 64) ? launch_halo<64, 2, true>(ma, mb, mo, a, st)
+                                                    : launch_halo<64, 2, false>(ma, mb, mo, a, st);
         }
+        if (r == ABL_OK && colsum != nullptr && !fuse_colsum)
+            r = abl_bias_grad(out_full, colsum, static_cast<long long>(B) * H * W, Cout, stream);
+        return r;
     }
+    a.colsum = nullptr;
     // 3-taps-per-stage main loop for the narrow tile: needs the 4 x 32 pixel rectangle
     const bool taps3 = ntile == 64 && (W % 32 == 0) && (H % 4 == 0);
     if (taps3) { a.box_w = 32; a.box_h = 4; }
@@ -716,9 +900,12 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
         if (r != ABL_OK) return r;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int r;
     switch (ntile) {
-        case 256: return launch_conv<256, 1>(ma, mb, mo, a, st);
-        case 128: return launch_conv<128, 1>(ma, mb, mo, a, st);
-        default: return taps3 ? launch_conv<64, 3>(ma, mb, mo, a, st) : launch_conv<64, 1>(ma, mb, mo, a, st);
+        case 256: r = launch_conv<256, 1>(ma, mb, mo, a, st); break;
+        case 128: r = launch_conv<128, 1>(ma, mb, mo, a, st); break;
+        default: r = taps3 ? launch_conv<64, 3>(ma, mb, mo, a, st) : launch_conv<64, 1>(ma, mb, mo, a, st);
     }
+    if (r == ABL_OK && colsum != nullptr) r = abl_bias_grad(out_full, colsum, static_cast<long long>(B) * H * W, Cout, stream);
+    return r;
 }

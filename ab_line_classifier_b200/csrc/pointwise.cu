@@ -28,9 +28,28 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
 // ------------------------------------------------------------------ MaxPoolGrad + ReluGrad
 // One thread per (pooled pixel, 8-channel chunk): 16-byte loads of the 4 window activations, the
 // pooled value and dP; writes the 4 dZ chunks.  First maximum in window scan order wins.
-__global__ void maxpool_bwd_relu_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ a,
+// Block-level finish of a fused BiasAddGrad: every thread owns ONE 8-channel chunk for its whole grid-stride
+// walk (blockDim % C8 == 0 and the stride is a multiple of blockDim), so it arrives here with 8 partial sums;
+// they are reduced over the blockDim/C8 threads sharing the chunk in shared memory, then one atomicAdd per
+// channel and block goes to db.
+__device__ __forceinline__ void bias_partial_flush(const float (&acc)[8], float* __restrict__ db, int C8, float* red) {
+    const int chunk = threadIdx.x % C8, rg = threadIdx.x / C8, rgs = blockDim.x / C8, C = C8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rg * C + chunk * 8 + j] = acc[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < rgs; ++g) s += red[g * C + c];
+        atomicAdd(db + c, s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_relu_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ a,
                                         const uint4* __restrict__ pooled, uint4* __restrict__ dz, int B, int H,
-                                        int W, int C8) {
+                                        int W, int C8, float* __restrict__ db) {
+    extern __shared__ float red[];       // [256] x 8 floats when db != nullptr
+    float bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int PH = H >> 1, PW = W >> 1;
     const long long total = static_cast<long long>(B) * PH * PW * C8;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -70,7 +89,17 @@ __global__ void maxpool_bwd_relu_kernel(const uint4* __restrict__ dp, const uint
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) dz[offs[k]] = make_uint4(out[k][0], out[k][1], out[k][2], out[k][3]);
+        if (db != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bacc[2 * j] += bf16_lo(out[k][j]);
+                    bacc[2 * j + 1] += bf16_hi(out[k][j]);
+                }
+        }
     }
+    if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
 }
 
 // ------------------------------------------------------------------ global average pool
@@ -102,8 +131,12 @@ __global__ void __launch_bounds__(256) gap_fwd_kernel(const uint4* __restrict__ 
     }
 }
 
-__global__ void gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4* __restrict__ a,
-                                    uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw) {
+__global__ void __launch_bounds__(256)
+gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4* __restrict__ a,
+                                    uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw,
+                                    float* __restrict__ db) {
+    extern __shared__ float red[];
+    float bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long total = static_cast<long long>(B) * HW * C8;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -120,9 +153,11 @@ __global__ void gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4*
             const float lo = bf16_lo(av[j]) > 0.f ? g[2 * j] * inv_hw : 0.f;
             const float hi = bf16_hi(av[j]) > 0.f ? g[2 * j + 1] * inv_hw : 0.f;
             o[j] = pack_bf16x2(lo, hi);
+            if (db != nullptr) { bacc[2 * j] += bf16_lo(o[j]); bacc[2 * j + 1] += bf16_hi(o[j]); }   // sum of the ROUNDED dz
         }
         dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
 }
 
 // ------------------------------------------------------------------ head
@@ -371,15 +406,21 @@ extern "C" int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_d
     return check_launch();
 }
 
-extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, int B, int H,
-                                    int W, int C, void* stream) {
+extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
+
+extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db, int B,
+                                    int H, int W, int C, void* stream) {
     if (!dp || !a || !pooled || !dz) { set_error("abl_maxpool_bwd_relu: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_relu: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    maxpool_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const bool fuse = db != nullptr && (256 % (C / 8)) == 0;      // a thread keeps one channel chunk
+    maxpool_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, fuse ? 256 * 8 * sizeof(float) : 0,
+                              static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(dp), static_cast<const uint4*>(a), static_cast<const uint4*>(pooled),
-        static_cast<uint4*>(dz), B, H, W, C / 8);
-    return check_launch();
+        static_cast<uint4*>(dz), B, H, W, C / 8, fuse ? db : nullptr);
+    int r = check_launch();
+    if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, C, stream);
+    return r;
 }
 
 extern "C" int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream) {
@@ -390,13 +431,19 @@ extern "C" int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void
     return check_launch();
 }
 
-extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, int B, int HW, int C, void* stream) {
+extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db, int B, int HW, int C,
+                                void* stream) {
     if (!dgap || !a || !dz) { set_error("abl_gap_bwd_relu: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || HW <= 0 || (C & 7)) { set_error("abl_gap_bwd_relu: need C % 8 == 0"); return ABL_ERR_SHAPE; }
     const long long total = static_cast<long long>(B) * HW * (C / 8);
-    gap_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        dgap, static_cast<const uint4*>(a), static_cast<uint4*>(dz), B, HW, C / 8, 1.f / static_cast<float>(HW));
-    return check_launch();
+    const bool fuse = db != nullptr && (256 % (C / 8)) == 0;
+    gap_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, fuse ? 256 * 8 * sizeof(float) : 0,
+                          static_cast<cudaStream_t>(stream)>>>(
+        dgap, static_cast<const uint4*>(a), static_cast<uint4*>(dz), B, HW, C / 8, 1.f / static_cast<float>(HW),
+        fuse ? db : nullptr);
+    int r = check_launch();
+    if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * HW, C, stream);
+    return r;
 }
 
 extern "C" int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,

@@ -358,16 +358,21 @@ class CutoffVGG16Engine:
             raise NotImplementedError("training with a cutoff that ends in a pool layer")
         cur, other = b["dz_a"], b["dz_b"]
         dz = cur[: B * last.h * last.w * last.cout].view(B, last.h, last.w, last.cout)
-        ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz)
+        # BiasAddGrad of a layer is fused into whichever kernel PRODUCES that layer's dZ (GAP backward, max-pool
+        # backward, or the dgrad epilogue of the layer above), so dZ is never re-read for it; block1_conv1's
+        # bias gradient comes out of its own wgrad GEMM (ones column).
+        def bias_grad_of(i):
+            return self.view(self.specs[i].name + "/bias", self.grad) if (tr[i] and i > 0) else None
+
+        ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, bias_grad_of(nconv - 1))
         for li in range(nconv - 1, lowest - 1, -1):
             s = self.specs[li]
             if tr[li]:
                 dw = self.view(s.name + "/kernel", self.grad)
-                db = self.view(s.name + "/bias", self.grad)
                 if li == 0:
-                    ops.conv_first_wgrad(self._x(B), dz, dw, db)
+                    ops.conv_first_wgrad(self._x(B), dz, dw, self.view(s.name + "/bias", self.grad))
                 else:
-                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw, db, b["ws"], accumulate=False)
+                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw, None, b["ws"], accumulate=False)
                 if reduce_hook:
                     reduce_hook(*self.layer_ranges[s.name])
             if li > lowest:
@@ -376,11 +381,12 @@ class CutoffVGG16Engine:
                     dp = b["dp"][: B * s.h * s.w * s.cin].view(B, s.h, s.w, s.cin)
                     ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, None, dp, None, 0)
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
-                    ops.maxpool_bwd_relu(dp, b["act_" + prev.name][:B], b["pool_" + prev.name][:B], ndz)
+                    ops.maxpool_bwd_relu(dp, b["act_" + prev.name][:B], b["pool_" + prev.name][:B], ndz,
+                                         bias_grad_of(li - 1))
                 else:
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
                     ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["act_" + prev.name][:B], ndz, None,
-                                      ops.EPI_RELU_MASK)
+                                      ops.EPI_RELU_MASK, colsum=bias_grad_of(li - 1))
                 dz = ndz
                 cur, other = other, cur
 

@@ -28,8 +28,9 @@ def _chk(t, dtype, name):
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
-def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool=None, flags=0):
+def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool=None, flags=0, colsum=None):
     """x bf16 [B,H,W,Cin]; w_kmajor bf16 [9,Cout,Cin]; see include/abl_b200.h abl_conv3x3_igemm."""
+    _chk(colsum, torch.float32, "colsum")
     for t, n in ((x, "x"), (w_kmajor, "w"), (mask_src, "mask_src"), (out_full, "out_full"), (out_pool, "out_pool")):
         _chk(t, torch.bfloat16, n)
     _chk(bias, torch.float32, "bias")
@@ -43,7 +44,7 @@ def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool
     if mask_src is not None:
         assert mask_src.shape == (B, H, W, Cout)
     _native.call("abl_conv3x3_igemm", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(mask_src), _ptr(out_full),
-                 _ptr(out_pool), B, H, W, Cin, Cout, flags, _stream())
+                 _ptr(out_pool), _ptr(colsum), B, H, W, Cin, Cout, flags, _stream())
 
 
 def wgrad_workspace_bytes(B, H, W, Cin, Cout):
@@ -62,6 +63,8 @@ def conv3x3_wgrad(x, dz, dw, db, workspace, accumulate=False):
     assert dz.shape == (B, H, W, Cout) and dw.numel() == 9 * Cin * Cout
     _native.call("abl_conv3x3_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), _ptr(workspace),
                  workspace.numel() * workspace.element_size(), int(bool(accumulate)), B, H, W, Cin, Cout, _stream())
+    if db is None:
+        _native.launch_count -= 1      # GEMM + slice reduction only (no separate bias-grad kernel)
 
 
 def bias_grad(dz, db):
@@ -100,11 +103,12 @@ def prep_conv_weights(w_hwio, w_fwd=None, w_dgrad=None):
     _native.call("abl_prep_conv_weights", _ptr(w_hwio), _ptr(w_fwd), _ptr(w_dgrad), Cin, Cout, _stream())
 
 
-def maxpool_bwd_relu(dp, a, pooled, dz):
+def maxpool_bwd_relu(dp, a, pooled, dz, db=None):
     for t in (dp, a, pooled, dz):
         _chk(t, torch.bfloat16, "tensor")
+    _chk(db, torch.float32, "db")
     B, H, W, Cc = a.shape
-    _native.call("abl_maxpool_bwd_relu", _ptr(dp), _ptr(a), _ptr(pooled), _ptr(dz), B, H, W, Cc, _stream())
+    _native.call("abl_maxpool_bwd_relu", _ptr(dp), _ptr(a), _ptr(pooled), _ptr(dz), _ptr(db), B, H, W, Cc, _stream())
 
 
 def gap_fwd(a, gap):
@@ -113,10 +117,11 @@ def gap_fwd(a, gap):
     _native.call("abl_gap_fwd", _ptr(a), _ptr(gap), B, H * W, Cc, _stream())
 
 
-def gap_bwd_relu(dgap, a, dz):
+def gap_bwd_relu(dgap, a, dz, db=None):
     _chk(dgap, torch.float32, "dgap"); _chk(a, torch.bfloat16, "a"); _chk(dz, torch.bfloat16, "dz")
+    _chk(db, torch.float32, "db")
     B, H, W, Cc = a.shape
-    _native.call("abl_gap_bwd_relu", _ptr(dgap), _ptr(a), _ptr(dz), B, H * W, Cc, _stream())
+    _native.call("abl_gap_bwd_relu", _ptr(dgap), _ptr(a), _ptr(dz), _ptr(db), B, H * W, Cc, _stream())
 
 
 def head_fwd(gap, w, b, logits, probs, y=None, class_weight=None, inv_batch=1.0, loss_sum=None, dlogits=None,

@@ -309,7 +309,7 @@ def main():
             k["calls"] += 1
             k["ms"] += t
             if name == "abl_conv3x3_igemm":
-                fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
+                fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
             elif name == "abl_conv3x3_wgrad":
                 fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
             else:

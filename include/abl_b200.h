@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 1
+#define ABL_ABI_VERSION 2
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -48,10 +48,12 @@ const char* abl_last_error(void);
  *   bias     fp32 [Cout]           (ABL_EPI_BIAS_RELU)
  *   mask_src bf16 [B,H,W,Cout]     (ABL_EPI_RELU_MASK; post-ReLU activation of the layer below)
  *   out_full bf16 [B,H,W,Cout] or NULL;  out_pool bf16 [B,H/2,W/2,Cout] (2x2/s2 max) or NULL
+ *   colsum   fp32 [Cout] or NULL: colsum[c] += sum_{n,h,w} out_full[n,h,w,c] -- with the dgrad epilogue this is
+ *            TF's BiasAddGrad of the layer below, fused so its dZ is not read a second time (needs out_full)
  * Requires Cin, Cout multiples of 64 (<= 512), H*W tileable into 128-pixel rectangles. */
 int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                      void* out_full, void* out_pool, int B, int H, int W, int Cin, int Cout, int flags,
-                      void* stream);
+                      void* out_full, void* out_pool, float* colsum, int B, int H, int W, int Cin, int Cout,
+                      int flags, void* stream);
 
 /* Conv2DBackpropFilter (+BiasAddGrad) of model.fit's tape (models.py:427,432) as a tcgen05 GEMM with
  * MN-major operands read straight from the NHWC tensors, split over pixel slices into `workspace`
@@ -90,14 +92,16 @@ int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, flo
 int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
 
 /* MaxPoolGrad + ReluGrad: dz[n,h,w,c] = dp[n,h/2,w/2,c] if a[n,h,w,c] is the first maximum of its 2x2
- * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16. */
-int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, int B, int H, int W,
-                         int C, void* stream);
+ * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16.
+ * db fp32 [C] or NULL: db[c] += sum dz[..., c] (BiasAddGrad of the conv above the pool, fused). */
+int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db, int B, int H,
+                         int W, int C, void* stream);
 
 /* GlobalAveragePooling2D (models.py:414): gap[n][c] = mean_{hw} a[n,hw,c]; a bf16, gap fp32. */
 int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream);
-/* its gradient fused with ReluGrad of the last conv: dz = a > 0 ? dgap[n][c] / HW : 0 (bf16). */
-int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, int B, int HW, int C, void* stream);
+/* its gradient fused with ReluGrad of the last conv: dz = a > 0 ? dgap[n][c] / HW : 0 (bf16);
+ * db fp32 [C] or NULL: db[c] += sum dz[..., c] (BiasAddGrad of the last conv, fused). */
+int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db, int B, int HW, int C, void* stream);
 
 /* Dropout -> Dense(n_classes) -> softmax (models.py:415-416) [+ categorical_crossentropy with
  * class_weight, models.py:426 / train.py:135-136].

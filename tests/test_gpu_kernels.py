@@ -96,10 +96,13 @@ def test_conv3x3_dgrad_with_relu_mask(cin, cout, H, W, pool, igemm_variant):
     wd = torch.empty(9, cin, cout, device="cuda", dtype=torch.bfloat16)
     ops.prep_conv_weights(w.cuda(), None, wd)
     out = torch.full((B, H, W, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    colsum = torch.full((cin,), -1.0, device="cuda")     # fused BiasAddGrad of the layer below; accumulates
     ops.conv3x3_igemm(dz.cuda().to(torch.bfloat16), wd, None, act.cuda().to(torch.bfloat16), out, None,
-                      ops.EPI_RELU_MASK)
+                      ops.EPI_RELU_MASK, colsum=colsum)
     dx = F.conv_transpose2d(dz.permute(0, 3, 1, 2), _bf(w).permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
     _close(out, dx * (act > 0), 1.5 * BF16_ULP, "dgrad")
+    # the column sums are those of the bf16 tensor the kernel wrote (fp32 accumulation, any order)
+    _close(colsum + 1.0, out.float().sum(dim=(0, 1, 2)), 2e-5, "fused bias grad (dgrad epilogue)")
     assert torch.equal(out.float().cpu() != 0, (dx * (act > 0)).to(torch.bfloat16).float() != 0) or True
     assert (out.float().cpu()[act == 0] == 0).all()          # ReLU mask is exact
 
@@ -185,9 +188,11 @@ def test_maxpool_backward_routes_to_first_max_and_relu_masks():
     p.backward(dp.permute(0, 3, 1, 2))
     ref = an.grad.permute(0, 2, 3, 1) * (a > 0)
     dz = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    db = torch.full((C,), 0.25, device="cuda")          # fused BiasAddGrad ACCUMULATES into db
     ops.maxpool_bwd_relu(dp.cuda().to(torch.bfloat16), a.cuda().to(torch.bfloat16),
-                         p.detach().permute(0, 2, 3, 1).contiguous().cuda().to(torch.bfloat16), dz)
+                         p.detach().permute(0, 2, 3, 1).contiguous().cuda().to(torch.bfloat16), dz, db)
     assert torch.equal(dz.float().cpu(), ref)
+    _close(db - 0.25, ref.sum(dim=(0, 1, 2)), 1e-5, "fused bias grad (maxpool bwd)")
 
 
 def test_gap_forward_backward():
@@ -199,9 +204,11 @@ def test_gap_forward_backward():
     _close(gap, a.mean(dim=(1, 2)), 1e-5, "gap")
     dgap = torch.randn(3, 256, generator=g)
     dz = torch.empty(3, 32, 32, 256, device="cuda", dtype=torch.bfloat16)
-    ops.gap_bwd_relu(dgap.cuda(), a.cuda().to(torch.bfloat16), dz)
+    db = torch.zeros(256, device="cuda")
+    ops.gap_bwd_relu(dgap.cuda(), a.cuda().to(torch.bfloat16), dz, db)
     ref = ((dgap[:, None, None, :] / 1024.0) * (a > 0)).to(torch.bfloat16)
     assert torch.equal(dz.cpu(), ref)
+    _close(db, ref.float().sum(dim=(0, 1, 2)), 1e-5, "fused bias grad (gap bwd)")
 
 
 @pytest.mark.parametrize("B", [1, 37])
