@@ -28,6 +28,7 @@ SIGNATURES = {
     "abl_conv_first_fwd_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "abl_conv_first_wgrad_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "abl_prep_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "abl_prep_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "abl_maxpool_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "abl_gap_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

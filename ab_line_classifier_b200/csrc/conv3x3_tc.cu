@@ -146,10 +146,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
             tma_store_commit();
         }
         if (csum != nullptr) {
-            // thread = (16-byte chunk of 8 channels, group of rows) of the staged bf16 tile
-            constexpr int kCh = kEpiN / 8;                                // chunks per staged row: 16 or 8
-            constexpr int kRowsPer = kTileM / (kEpiThreads / kCh);        // 8 or 4 rows per thread
-            const int chunk = et % kCh, rg = et / kCh;
+            // Column sums of the staged bf16 tile.  Warp w OWNS the 16-byte chunks [w*kCh/8, (w+1)*kCh/8) (8 channels
+            // each) for the whole kernel, so after a shuffle reduction over the lanes holding other row groups one
+            // lane adds into csum with a plain read-modify-write: no shared-memory atomics (a float atomicAdd on
+            // shared memory is a CAS loop and measured 3.5 retries per add here).
+            constexpr int kCh = kEpiN / 8;                  // chunks per staged row: 16 or 8
+            constexpr int kCpw = kCh / 8;                   // chunks per warp: 2 or 1
+            constexpr int kRowsPer = kTileM / (32 / kCpw);  // rows per lane: 8 or 4
+            const int lane = et & 31, w8 = et >> 5;
+            const int chunk = w8 * kCpw + (lane & (kCpw - 1)), rg = lane / kCpw;
             const uint8_t* bx = stg + (chunk >> 3) * kABytes;
             const int c8 = chunk & 7;
             float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -162,14 +167,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
                 s8[4] += __uint_as_float(v.z << 16); s8[5] += __uint_as_float(v.z & 0xFFFF0000u);
                 s8[6] += __uint_as_float(v.w << 16); s8[7] += __uint_as_float(v.w & 0xFFFF0000u);
             }
-            // lanes l and l ^ kCh (and l ^ 2 kCh ...) hold the same chunk for other row groups
 #pragma unroll
-            for (int o = 16; o >= kCh; o >>= 1)
+            for (int o = 16; o >= kCpw; o >>= 1)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s8[j] += __shfl_xor_sync(0xffffffffu, s8[j], o);
-            if ((et & 31) < kCh) {
+            if (lane < kCpw) {
+                float* dst = csum + pass * kEpiN + chunk * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) atomicAdd(&csum[pass * kEpiN + chunk * 8 + j], s8[j]);
+                for (int j = 0; j < 8; ++j) dst[j] += s8[j];
             }
         }
         if (p.out_pool != nullptr) {

@@ -14,6 +14,7 @@
 // give dW, row 54 (the ones slot) gives the bias gradient.
 // A tile = 128 consecutive pixels of the flattened (n,h,w) raster (contiguous 16 KiB of NHWC output).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -37,7 +38,55 @@ struct FirstArgs {
     int H, W;
     long long total_pix;   // B*H*W
     int num_tiles;         // total_pix / 128
+    // staged-patch geometry (0 = tile shape not rectangular: per-thread global gather instead)
+    int wt_log2;           // tile width = min(W, 128) = 1 << wt_log2 (tile = 128/wt rows x wt pixels)
+    int patch_ok;
 };
+
+constexpr int kF_PatchRegs = 10;                               // ceil(3 * 130 * 3 / 128) elements per producer thread
+constexpr int kF_PatchFloats = kF_PatchRegs * 128;             // one group's haloed fp32 patch (5 KiB)
+
+// The input patch of a tile ((rows + 2) x (wt + 2) pixels x 3 channels, zero padded, already preprocessed) is
+// fetched with COALESCED loads one tile ahead into kF_PatchRegs registers per producer thread, parked in shared
+// memory, and the 27-tap gather then reads shared memory (lane stride 3 words: conflict-free).  The v1 gather
+// issued 27 dependent-latency global loads per pixel with only 8 producer warps per SM to hide them; ncu showed
+// the kernel at 30 % of HBM bandwidth with every pipe idle.
+struct PatchElem { int prow, pcol, ch; bool used; };
+
+__device__ __forceinline__ PatchElem patch_elem(const FirstArgs& p, int e) {
+    const int wt = 1 << p.wt_log2, pcols = wt + 2, nrows = (kF_TileM >> p.wt_log2) + 2;
+    PatchElem q;
+    q.used = e < nrows * pcols * 3;
+    q.prow = e / (pcols * 3);
+    const int rem = e - q.prow * (pcols * 3);
+    q.pcol = rem / 3;
+    q.ch = rem - q.pcol * 3;
+    return q;
+}
+
+// Issue this thread's loads of tile `tile`'s patch (values land in r[]; nothing waits here).
+template <bool kU8>
+__device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t, const int (&code)[kF_PatchRegs],
+                                            float (&r)[kF_PatchRegs]) {
+    const long long pix0 = static_cast<long long>(tile) * kF_TileM;
+    const int c0 = static_cast<int>(pix0 % p.W);
+    const long long rowlin = pix0 / p.W;                 // n * H + h of the tile's first row
+    const int h0 = static_cast<int>(rowlin % p.H);
+#pragma unroll
+    for (int k = 0; k < kF_PatchRegs; ++k) {
+        const int cd = code[k];                          // prow | pcol << 8 | ch << 16 | used << 24
+        const int prow = cd & 0xFF, pcol = (cd >> 8) & 0xFF, ch = (cd >> 16) & 3;
+        const int hh = h0 - 1 + prow, ww = c0 - 1 + pcol;
+        const bool ok = (cd >> 24) && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+        const long long off = ((rowlin - 1 + prow) * p.W + ww) * 3;
+        if (kU8) {
+            const float mean = ch == 0 ? 103.939f : (ch == 1 ? 116.779f : 123.68f);      // BGR means
+            r[k] = ok ? static_cast<float>(__ldg(p.x8 + off + (2 - ch))) - mean : 0.f;   // RGB -> BGR
+        } else {
+            r[k] = ok ? __ldg(p.x + off + ch) : 0.f;
+        }
+    }
+}
 
 // One thread = one pixel: gather the 27-value patch (zero padded) and write the swizzled K-major row(s).
 // kU8: the frame is raw uint8 RGB and Keras' vgg16 preprocess_input (caffe mode: RGB->BGR, subtract the
@@ -99,6 +148,88 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
     }
 }
 
+// hi | lo << 16 of one input value: converted ONCE per input element when the patch is parked in shared memory
+// (the v1 gather converted every element 9 times, once per tap that touches it: 54 F2F per pixel).
+__device__ __forceinline__ uint32_t split_hi_lo(float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    return static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+}
+
+// Same A rows as im2col_row, gathered from the packed shared-memory patch: 27 LDS + 27 byte-permutes per pixel.
+template <bool kFwd>
+__device__ __forceinline__ void im2col_row_patch(const uint32_t* patch, int wt_log2, int row, uint8_t* a_stage) {
+    const int pcols = (1 << wt_log2) + 2;
+    const uint32_t* base = patch + ((row >> wt_log2) * pcols + (row & ((1 << wt_log2) - 1))) * 3;
+    uint32_t u[28];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) u[kh * 9 + j] = base[kh * pcols * 3 + j];
+    u[27] = 0;
+    uint32_t s0[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j <= 12) s0[j] = __byte_perm(u[2 * j], u[2 * j + 1], 0x5410);                   // hi[2j], hi[2j+1]
+        else if (j == 13) s0[j] = __byte_perm(u[26], u[0], 0x7610);                         // hi[26], lo[0]
+        else if (j <= 26) s0[j] = __byte_perm(u[2 * j - 27], u[2 * j - 26], 0x7632);        // lo[2j-27], lo[2j-26]
+        else s0[j] = j == 27 ? 0x00003F80u : 0u;                                            // slot 54 = 1.0
+    }
+    uint8_t* r0 = a_stage + row * 128;
+    const int sw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
+    if (kFwd) {   // k-block 1: hi(x) in slots 0..26 (chunks 0..3), zeros elsewhere
+        uint8_t* r1 = r0 + kF_ABlock;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (c < 3) q = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
+            if (c == 3) q = make_uint4(s0[12], s0[13] & 0xFFFFu, 0, 0);   // slots 24,25,26 then zeros
+            *reinterpret_cast<uint4*>(r1 + ((c ^ sw) << 4)) = q;
+        }
+    }
+}
+
+// im2col producer loop of one 128-thread group (group g builds the CTA's tiles g, g+2, ...): shared by forward and
+// wgrad.  kBlocks = 16 KiB k-blocks per A stage (2 forward, 1 wgrad).
+template <bool kFwd, bool kU8>
+__device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_a, float* patch, uint64_t* afull,
+                                              uint64_t* aempty, int row, int grp) {
+    constexpr int kStageBytes = (kFwd ? 2 : 1) * kF_ABlock;
+    int code[kF_PatchRegs];
+    float nxt[kF_PatchRegs];
+    if (p.patch_ok) {
+#pragma unroll
+        for (int k = 0; k < kF_PatchRegs; ++k) {
+            const PatchElem q = patch_elem(p, row + 128 * k);
+            code[k] = q.prow | (q.pcol << 8) | (q.ch << 16) | ((q.used ? 1 : 0) << 24);
+        }
+        if (blockIdx.x + static_cast<long long>(grp) * gridDim.x < p.num_tiles)
+            patch_fetch<kU8>(p, blockIdx.x + grp * gridDim.x, row, code, nxt);
+    }
+    for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int stage = it % kF_Stages;
+        if (p.patch_ok) {
+            named_bar_sync(2 + grp, 128);                 // the previous tile's gather has finished reading the patch
+#pragma unroll
+            for (int k = 0; k < kF_PatchRegs; ++k) reinterpret_cast<uint32_t*>(patch)[row + 128 * k] = split_hi_lo(nxt[k]);
+            if (blockIdx.x + static_cast<long long>(it + kF_ProdGroups) * gridDim.x < p.num_tiles)
+                patch_fetch<kU8>(p, tile + kF_ProdGroups * gridDim.x, row, code, nxt);     // next tile: in flight
+            named_bar_sync(2 + grp, 128);                 // patch complete
+        }
+        mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
+        if (p.patch_ok)
+            im2col_row_patch<kFwd>(reinterpret_cast<const uint32_t*>(patch), p.wt_log2, row, smem_a + stage * kStageBytes);
+        else
+            im2col_row<kFwd, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kStageBytes);
+        fence_proxy_async_smem();
+        mbar_arrive(&afull[stage]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ forward
 template <bool kU8>
 __global__ void __launch_bounds__(kF_Threads, 1)
@@ -113,6 +244,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
     uint64_t* tfull = bars + 2 * kF_Stages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     const int warp = threadIdx.x >> 5;
 
     if (warp == 1 && elect_one()) {
@@ -173,14 +305,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
         // ---------------------------------------------------------------- im2col producers (2 x 128 threads)
         const int row = (threadIdx.x - 128) & 127;
         const int grp = (threadIdx.x - 128) >> 7;
-        for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int stage = it % kF_Stages;
-            mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
-            im2col_row<true, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * 2 * kF_ABlock);
-            fence_proxy_async_smem();
-            mbar_arrive(&afull[stage]);
-        }
+        producer_loop<true, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp);
     } else if (warp >= 12) {
         // ---------------------------------------------------------------- epilogue (128 threads)
         const int row = threadIdx.x - 384;       // TMEM lane
@@ -245,6 +370,7 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
     uint64_t* aempty = bars + kF_Stages;
     uint64_t* done = bars + 2 * kF_Stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     const int warp = threadIdx.x >> 5;
 
     if (warp == 1 && elect_one()) {
@@ -301,14 +427,7 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
     } else if (warp >= 4 && warp < 12) {
         const int row = (threadIdx.x - 128) & 127;
         const int grp = (threadIdx.x - 128) >> 7;
-        for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int stage = it % kF_Stages;
-            mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
-            im2col_row<false, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kF_ABlock);
-            fence_proxy_async_smem();
-            mbar_arrive(&afull[stage]);
-        }
+        producer_loop<false, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp);
     } else if (warp >= 12 && warp < 14) {
         // D rows 0..63 live in TMEM lanes 0..63: warps 12 and 13 (lane quarters 0 and 1)
         const int row = threadIdx.x - 384;
@@ -352,6 +471,13 @@ static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W,
     a->total_pix = static_cast<long long>(B) * H * W;
     a->num_tiles = static_cast<int>(a->total_pix / kF_TileM);
     a->w = nullptr; a->bias = nullptr; a->dw = nullptr; a->db = nullptr;
+    // staged patch: a tile (128 raster pixels) must be a rectangle inside one frame
+    const int wt = W < kF_TileM ? W : kF_TileM;
+    const bool pow2 = (wt & (wt - 1)) == 0;
+    a->patch_ok = (pow2 && (W <= kF_TileM || W % kF_TileM == 0) && (static_cast<long long>(H) * W) % kF_TileM == 0 &&
+                   getenv("ABL_FIRST_GATHER") == nullptr) ? 1 : 0;
+    a->wt_log2 = 0;
+    while ((1 << a->wt_log2) < wt) ++a->wt_log2;
     return ABL_OK;
 }
 
@@ -376,7 +502,7 @@ static int first_fwd(const void* x, const float* w_hwio, const float* bias, void
     CUtensorMap mo;
     r = pixel_map(&mo, out, a.total_pix);
     if (r != ABL_OK) return r;
-    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + 2 * kF_ABlock + 256;
+    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + 2 * kF_ABlock + 256 + kF_ProdGroups * kF_PatchFloats * 4;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -402,7 +528,7 @@ static int first_wgrad(const void* x, const void* dz, float* dw, float* db, int 
     CUtensorMap mz;
     r = pixel_map(&mz, dz, a.total_pix);
     if (r != ABL_OK) return r;
-    constexpr int smem_bytes = (2 * kF_Stages + 1) * kF_ABlock + 256;
+    constexpr int smem_bytes = (2 * kF_Stages + 1) * kF_ABlock + 256 + kF_ProdGroups * kF_PatchFloats * 4;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

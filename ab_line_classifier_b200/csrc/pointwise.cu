@@ -25,6 +25,32 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
     }
 }
 
+// All layers in one launch (after every optimizer step): blockIdx.y = layer.
+constexpr int kMaxPrepLayers = 16;
+struct PrepMulti {
+    const float* w[kMaxPrepLayers];
+    __nv_bfloat16* w_fwd[kMaxPrepLayers];
+    __nv_bfloat16* w_dgrad[kMaxPrepLayers];
+    int cin[kMaxPrepLayers], cout[kMaxPrepLayers];
+};
+__global__ void prep_conv_weights_multi_kernel(const __grid_constant__ PrepMulti m) {
+    const int l = blockIdx.y;
+    const float* __restrict__ w = m.w[l];
+    __nv_bfloat16* __restrict__ w_fwd = m.w_fwd[l];
+    __nv_bfloat16* __restrict__ w_dgrad = m.w_dgrad[l];
+    const int Cin = m.cin[l], Cout = m.cout[l];
+    const int total = 9 * Cin * Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % Cout;
+        const int ci = (i / Cout) % Cin;
+        const int t = i / (Cout * Cin);
+        const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+        const int kh = t / 3, kw = t - kh * 3;
+        if (w_fwd) w_fwd[(static_cast<size_t>(kw * 3 + kh) * Cout + co) * Cin + ci] = v;
+        if (w_dgrad) w_dgrad[(static_cast<size_t>((2 - kw) * 3 + (2 - kh)) * Cin + ci) * Cout + co] = v;
+    }
+}
+
 // ------------------------------------------------------------------ MaxPoolGrad + ReluGrad
 // One thread per (pooled pixel, 8-channel chunk): 16-byte loads of the 4 window activations, the
 // pooled value and dP; writes the 4 dZ chunks.  First maximum in window scan order wins.
@@ -403,6 +429,27 @@ extern "C" int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_d
     if (Cin <= 0 || Cout <= 0) { set_error("abl_prep_conv_weights: bad shape"); return ABL_ERR_SHAPE; }
     prep_conv_weights_kernel<<<grid_for(9LL * Cin * Cout, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w_hwio, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cout);
+    return check_launch();
+}
+
+extern "C" int abl_prep_conv_weights_multi(const float* const* w_hwio, void* const* w_fwd, void* const* w_dgrad,
+                                           const int* cin, const int* cout, int n_layers, void* stream) {
+    if (!w_hwio || !w_fwd || !w_dgrad || !cin || !cout) { set_error("abl_prep_conv_weights_multi: null pointer"); return ABL_ERR_NULL; }
+    if (n_layers <= 0 || n_layers > kMaxPrepLayers) { set_error("abl_prep_conv_weights_multi: 1..16 layers"); return ABL_ERR_SHAPE; }
+    PrepMulti m;
+    int max_total = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (!w_hwio[l] || (!w_fwd[l] && !w_dgrad[l]) || cin[l] <= 0 || cout[l] <= 0) {
+            set_error("abl_prep_conv_weights_multi: bad layer entry"); return ABL_ERR_NULL;
+        }
+        m.w[l] = w_hwio[l];
+        m.w_fwd[l] = static_cast<__nv_bfloat16*>(w_fwd[l]);
+        m.w_dgrad[l] = static_cast<__nv_bfloat16*>(w_dgrad[l]);
+        m.cin[l] = cin[l]; m.cout[l] = cout[l];
+        if (9 * cin[l] * cout[l] > max_total) max_total = 9 * cin[l] * cout[l];
+    }
+    const int bx = grid_for(max_total, 256, 2);
+    prep_conv_weights_multi_kernel<<<dim3(bx, n_layers), 256, 0, static_cast<cudaStream_t>(stream)>>>(m);
     return check_launch();
 }
 

@@ -173,9 +173,10 @@ class CutoffVGG16Engine:
 
     def refresh_operands(self, layers=None):
         """Re-cast fp32 master kernels into the bf16 GEMM operand layouts."""
-        for s in self.specs[1:]:
-            if layers is None or s.name in layers:
-                ops.prep_conv_weights(self.view(s.name + "/kernel"), self.w_fwd[s.name], self.w_dgrad[s.name])
+        todo = [(self.view(s.name + "/kernel"), self.w_fwd[s.name], self.w_dgrad[s.name])
+                for s in self.specs[1:] if layers is None or s.name in layers]
+        if todo:
+            ops.prep_conv_weights_multi(todo)       # one launch for all layers
 
     # ------------------------------------------------------------------ buffers
     def _ensure(self, batch, training):

@@ -103,6 +103,21 @@ def prep_conv_weights(w_hwio, w_fwd=None, w_dgrad=None):
     _native.call("abl_prep_conv_weights", _ptr(w_hwio), _ptr(w_fwd), _ptr(w_dgrad), Cin, Cout, _stream())
 
 
+def prep_conv_weights_multi(layers):
+    """layers: list of (w_hwio fp32 [3,3,Cin,Cout], w_fwd bf16 [9,Cout,Cin], w_dgrad bf16 [9,Cin,Cout]); one launch."""
+    import ctypes as C
+    n = len(layers)
+    w = (C.c_void_p * n)(*[_ptr(l[0]) for l in layers])
+    wf = (C.c_void_p * n)(*[_ptr(l[1]) for l in layers])
+    wd = (C.c_void_p * n)(*[_ptr(l[2]) for l in layers])
+    cin = (C.c_int * n)(*[int(l[0].shape[2]) for l in layers])
+    cout = (C.c_int * n)(*[int(l[0].shape[3]) for l in layers])
+    for l in layers:
+        _chk(l[0], torch.float32, "w_hwio"); _chk(l[1], torch.bfloat16, "w_fwd"); _chk(l[2], torch.bfloat16, "w_dgrad")
+    _native.call("abl_prep_conv_weights_multi", C.cast(w, C.c_void_p), C.cast(wf, C.c_void_p), C.cast(wd, C.c_void_p),
+                 C.cast(cin, C.c_void_p), C.cast(cout, C.c_void_p), n, _stream())
+
+
 def maxpool_bwd_relu(dp, a, pooled, dz, db=None):
     for t in (dp, a, pooled, dz):
         _chk(t, torch.bfloat16, "tensor")

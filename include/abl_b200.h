@@ -90,6 +90,10 @@ int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, flo
  *   w_fwd  [kw*3+kh][co][ci]         = w[kh][kw][ci][co]
  *   w_dgrad[(2-kw)*3+(2-kh)][ci][co] = w[kh][kw][ci][co]   (180-degree rotated)      (either may be NULL) */
 int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
+/* The same for n_layers (<= 16) layers in ONE launch (after each optimizer step); the five arrays are HOST
+ * arrays of n_layers entries (device pointers / channel counts). */
+int abl_prep_conv_weights_multi(const float* const* w_hwio, void* const* w_fwd, void* const* w_dgrad,
+                                const int* cin, const int* cout, int n_layers, void* stream);
 
 /* MaxPoolGrad + ReluGrad: dz[n,h,w,c] = dp[n,h/2,w/2,c] if a[n,h,w,c] is the first maximum of its 2x2
  * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16.

@@ -69,6 +69,23 @@ def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B, igemm_variant)
         assert torch.equal(pl.float().cpu(), ref)
 
 
+def test_prep_conv_weights_multi_equals_per_layer_launches():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    layers, refs = [], []
+    for cin, cout in [(64, 64), (64, 128), (256, 256)]:
+        w = torch.randn(3, 3, cin, cout, generator=g).cuda()
+        wf = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
+        wd = torch.empty(9, cin, cout, device="cuda", dtype=torch.bfloat16)
+        rf, rd = torch.empty_like(wf), torch.empty_like(wd)
+        ops.prep_conv_weights(w, rf, rd)
+        layers.append((w, wf, wd))
+        refs.append((rf, rd))
+    ops.prep_conv_weights_multi(layers)
+    for (w, wf, wd), (rf, rd) in zip(layers, refs):
+        assert torch.equal(wf, rf) and torch.equal(wd, rd)
+
+
 def test_conv3x3_pool_only_output_matches_full_path(igemm_variant):
     ops = _ops()
     g = torch.Generator().manual_seed(5)
@@ -131,10 +148,17 @@ def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B):
     assert torch.equal(dw, dw3), "wgrad must be deterministic (fixed-order slice reduction)"
 
 
-def test_conv_first_forward_and_wgrad_fp32():
+@pytest.mark.parametrize("B,H,W", [(3, 128, 128), (2, 64, 64), (1, 32, 256), (4, 16, 32), (2, 48, 96)])
+@pytest.mark.parametrize("gather", ["patch", "global"])
+def test_conv_first_forward_and_wgrad_fp32(B, H, W, gather, monkeypatch):
+    """Both im2col sources: the shared-memory patch prefetched one tile ahead (tiles that are rectangles of one frame:
+    W a power of two <= 128 or a multiple of 128) and the per-pixel global gather (any other shape, here 48x96)."""
+    if gather == "global":
+        monkeypatch.setenv("ABL_FIRST_GATHER", "1")
+    else:
+        monkeypatch.delenv("ABL_FIRST_GATHER", raising=False)
     ops = _ops()
     g = torch.Generator().manual_seed(1)
-    B, H, W = 3, 128, 128
     x = (torch.rand(B, H, W, 3, generator=g) * 255 - 115).contiguous()
     w = torch.randn(3, 3, 3, 64, generator=g) * 0.1
     b = torch.randn(64, generator=g) * 0.1
