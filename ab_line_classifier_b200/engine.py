@@ -86,6 +86,7 @@ class CutoffVGG16Engine:
         self._cap = 0
         self._cap_train = False
         self._buf = {}
+        self._graphs = {}             # (batch, uint8 input, buffer generation) -> captured forward CUDA graph
         # input ring: two (frames, labels) slots filled on a copy stream so the H2D copy of batch i+1
         # overlaps the kernels of batch i
         self._slot = 0
@@ -318,14 +319,45 @@ class CutoffVGG16Engine:
         self.use_slot(self.stage(x, y))
         return x.shape[0]
 
-    def predict_batch(self, x):
-        """x: [B,H,W,3] fp32 (BGR, mean-subtracted, as vgg16_preprocess leaves it).  Returns device probs."""
+    GRAPH_MAX_BATCH = 64     # below this the forward pass is launch-bound (9 kernels of a few microseconds each)
+
+    def predict_batch(self, x, use_graph=None):
+        """x: [B,H,W,3] fp32 (BGR, mean-subtracted, as vgg16_preprocess leaves it) or raw uint8 RGB.
+        Returns device probs.  Small batches (the reference's batch-1 loops: ``clock_avg_runtime`` predict.py:425-448,
+        ``WandbGradcamEvalCallback._inference`` train_utils.py:280-293) replay a captured CUDA graph of the 10
+        forward launches instead of launching them one by one."""
         B = x.shape[0]
         self._ensure(B, False)
-        self.load_input(x)
-        probs = self.forward_device(B)
+        if use_graph is None:
+            use_graph = B <= self.GRAPH_MAX_BATCH
+        if not use_graph:
+            self.load_input(x)
+            probs = self.forward_device(B)
+            self.release_slot()
+            return probs
+        u8 = (x.dtype == torch.uint8) if torch.is_tensor(x) else (np.asarray(x).dtype == np.uint8)
+        g = self._forward_graph(B, u8)
+        self.use_slot(self.stage(x, slot=0))
+        g.replay()
         self.release_slot()
-        return probs
+        return self._buf["probs"][:B]
+
+    def _forward_graph(self, B, u8):
+        """CUDA graph of forward_device(B) reading input slot 0 (captured once per (batch, input dtype, buffers))."""
+        key = (B, bool(u8), id(self._buf))
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        self._slot, self._slot_u8[0] = 0, bool(u8)
+        for _ in range(2):                       # warm-up outside capture: one-time kernel attributes, lazy module load
+            self.forward_device(B)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward_device(B)
+        self._graphs = {k: v for k, v in self._graphs.items() if k[2] == id(self._buf)}   # drop graphs of old buffers
+        self._graphs[key] = g
+        return g
 
     # ------------------------------------------------------------------ backward + update
     def trainable_suffix(self, trainable):

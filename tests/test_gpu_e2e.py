@@ -50,6 +50,24 @@ def test_forward_logits_and_argmax_batch32(setup):
     assert (probs.argmax(-1) == rbf["probs"].argmax(-1)).all()      # arbiter: same roundings => same labels
 
 
+@pytest.mark.parametrize("B", [1, 5, 32])
+def test_cuda_graph_forward_is_bit_identical_to_launch_by_launch(setup, B):
+    """Small batches replay a captured CUDA graph (the reference's batch-1 loops, predict.py:425-448 and
+    train_utils.py:280-293); the graph must give exactly what the individual launches give, also when the batch
+    size changes between calls and after a weight update."""
+    eng, params = setup
+    x, _, fr = _frames(B, seed=40 + B)
+    p_graph = eng.predict_batch(x, use_graph=True).clone()
+    p_plain = eng.predict_batch(x, use_graph=False).clone()
+    assert torch.equal(p_graph, p_plain)
+    p_u8 = eng.predict_batch(fr, use_graph=True).clone()            # raw uint8 frames: own graph
+    assert torch.equal(p_u8, p_plain)
+    w2 = {k: (v * 1.01).astype(np.float32) for k, v in params.items()}
+    eng.set_weights(w2)                                              # graphs read the live weight buffers
+    assert torch.equal(eng.predict_batch(x, use_graph=True), eng.predict_batch(x, use_graph=False).clone())
+    eng.set_weights(params)
+
+
 def test_forward_matches_golden_fixture(setup):
     eng, _ = setup
     g = np.load(GOLD)
