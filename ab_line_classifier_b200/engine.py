@@ -87,6 +87,13 @@ class CutoffVGG16Engine:
         self._cap_train = False
         self._buf = {}
         self._graphs = {}             # (batch, uint8 input, buffer generation) -> captured forward CUDA graph
+        # data parallel: all-reduce gradient buckets while backward still runs (True) or once after it (False).
+        # Measured at 4 x B200, batch 256/GPU: 4.91 ms/step overlapped vs 4.68 ms after backward -- the persistent
+        # conv kernels own every SM (1 CTA of ~220 KB shared memory each, static tile assignment), so a CTA whose SM
+        # is held by a concurrent NCCL kernel starts late and stretches the whole launch; the 6.9 MB all-reduce
+        # itself takes < 0.1 ms.  Default: after backward.
+        import os
+        self.dp_overlap = os.environ.get("ABL_DP_OVERLAP", "0") == "1"
         # input ring: two (frames, labels) slots filled on a copy stream so the H2D copy of batch i+1
         # overlaps the kernels of batch i
         self._slot = 0
@@ -498,6 +505,8 @@ class CutoffVGG16Engine:
         reducer = None
         if self.world_size > 1:
             from .dp import GradBucketReducer
+            if not self.dp_overlap:
+                bucket_bytes = 1 << 40            # one all-reduce of every trainable slice after backward
             reducer = GradBucketReducer(self.grad, bucket_bytes, self.pg)
         self.backward_device(B, trainable, reduce_hook=reducer.hook if reducer else None)
         if reducer:
