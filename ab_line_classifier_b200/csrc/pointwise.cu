@@ -350,6 +350,58 @@ __global__ void rmsprop_flat_kernel(float4* __restrict__ theta, const float4* __
     }
 }
 
+// ------------------------------------------------------------------ data-parallel optimizer over NVLink peer memory
+// ONE kernel = reduce-scatter(grad) -> Adam / RMSprop on this rank's shard -> all-gather(theta), all through peer
+// pointers of a symmetric allocation (every rank maps every rank's flat theta / grad buffer):
+//   g     = sum_r grad_r[i]         peer LOADS over NVLink, fixed rank order (every rank would compute the same bits)
+//   theta = update(theta, g, m, v)  optimizer state is touched for this rank's 1/world shard only
+//   theta_r[i] = theta  for all r   peer STORES: every rank ends the step with identical weights
+// so a step moves (world-1)/world x 4 bytes/param in each direction per GPU instead of a ring all-reduce plus a
+// separate optimizer pass, and no NCCL kernel competes with the persistent conv kernels for SMs.  The caller
+// brackets the launch with two device-side barriers (all gradients final / all weights delivered).
+constexpr int kMaxPeers = 8;
+struct PeerBufs {
+    float4* theta[kMaxPeers];
+    const float4* grad[kMaxPeers];
+};
+
+template <int kKind>   // 0 = Adam (p0 = alpha_t, p1 = beta1, p2 = beta2), 1 = RMSprop (p0 = lr, p1 = rho)
+__global__ void opt_flat_dp_kernel(const __grid_constant__ PeerBufs pb, float4* __restrict__ m, float4* __restrict__ v,
+                                   long long lo4, long long hi4, int world, int rank, float p0, float p1, float p2,
+                                   float eps) {
+    for (long long i = lo4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int r = 0; r < world; ++r) {
+            const float4 q = __ldcv(pb.grad[r] + i);      // not cached: written by a peer's kernels this step
+            g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+        }
+        float4 tt = pb.theta[rank][i];
+        if (kKind == 0) {
+            const float ob1 = 1.f - p1, ob2 = 1.f - p2;
+            float4 mm = m[i], vv = v[i];
+            mm.x = p1 * mm.x + ob1 * g.x; mm.y = p1 * mm.y + ob1 * g.y;
+            mm.z = p1 * mm.z + ob1 * g.z; mm.w = p1 * mm.w + ob1 * g.w;
+            vv.x = p2 * vv.x + ob2 * g.x * g.x; vv.y = p2 * vv.y + ob2 * g.y * g.y;
+            vv.z = p2 * vv.z + ob2 * g.z * g.z; vv.w = p2 * vv.w + ob2 * g.w * g.w;
+            tt.x -= p0 * mm.x / (sqrtf(vv.x) + eps); tt.y -= p0 * mm.y / (sqrtf(vv.y) + eps);
+            tt.z -= p0 * mm.z / (sqrtf(vv.z) + eps); tt.w -= p0 * mm.w / (sqrtf(vv.w) + eps);
+            m[i] = mm; v[i] = vv;
+        } else {
+            const float orho = 1.f - p1;
+            float4 rr = m[i];
+            rr.x = p1 * rr.x + orho * g.x * g.x; rr.y = p1 * rr.y + orho * g.y * g.y;
+            rr.z = p1 * rr.z + orho * g.z * g.z; rr.w = p1 * rr.w + orho * g.w * g.w;
+            tt.x -= p0 * g.x / (sqrtf(rr.x) + eps); tt.y -= p0 * g.y / (sqrtf(rr.y) + eps);
+            tt.z -= p0 * g.z / (sqrtf(rr.z) + eps); tt.w -= p0 * g.w / (sqrtf(rr.w) + eps);
+            m[i] = rr;
+        }
+#pragma unroll 1
+        for (int r = 0; r < world; ++r) pb.theta[r][i] = tt;
+    }
+}
+
 // ------------------------------------------------------------------ Grad-CAM
 // One block of up to 1024 threads per frame.  Eight lanes share a pixel (8 x 16 B = one 128-byte line per load, four
 // pixels per warp load: fully coalesced), each lane contracts its channels against alpha[] in shared memory and a
@@ -560,6 +612,37 @@ extern "C" int abl_rmsprop_flat(float* theta, const float* g, float* rms, long l
     rmsprop_flat_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(rms), n4,
         theta + n4 * 4, g + n4 * 4, rms + n4 * 4, tail, lr, rho, eps);
+    return check_launch();
+}
+
+extern "C" int abl_opt_flat_dp(int kind, float* const* theta_peers, const float* const* grad_peers, float* m_or_rms,
+                               float* v, long long offset, long long n, int rank, int world, float lr_or_alpha,
+                               float b1_or_rho, float b2, float eps, void* stream) {
+    if (!theta_peers || !grad_peers || !m_or_rms || (kind == 0 && !v)) { set_error("abl_opt_flat_dp: null pointer"); return ABL_ERR_NULL; }
+    if (kind != 0 && kind != 1) { set_error("abl_opt_flat_dp: kind must be 0 (Adam) or 1 (RMSprop)"); return ABL_ERR_SHAPE; }
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("abl_opt_flat_dp: need 1 <= world <= 8"); return ABL_ERR_SHAPE; }
+    if ((offset & 3) || (n & 3) || n < 0) { set_error("abl_opt_flat_dp: offset and n must be multiples of 4 floats"); return ABL_ERR_SHAPE; }
+    if (n == 0) return ABL_OK;
+    PeerBufs pb;
+    for (int r = 0; r < kMaxPeers; ++r) { pb.theta[r] = nullptr; pb.grad[r] = nullptr; }
+    for (int r = 0; r < world; ++r) {
+        if (!theta_peers[r] || !grad_peers[r] || !aligned16(theta_peers[r]) || !aligned16(grad_peers[r])) {
+            set_error("abl_opt_flat_dp: peer buffers must be non-null and 16-byte aligned"); return ABL_ERR_ALIGN;
+        }
+        pb.theta[r] = reinterpret_cast<float4*>(theta_peers[r] + offset);
+        pb.grad[r] = reinterpret_cast<const float4*>(grad_peers[r] + offset);
+    }
+    const long long n4 = n / 4;
+    const long long lo4 = n4 * rank / world, hi4 = n4 * (rank + 1) / world;     // this rank's shard of the run
+    if (hi4 <= lo4) return ABL_OK;
+    float4* m4 = reinterpret_cast<float4*>(m_or_rms + offset);
+    float4* v4 = v ? reinterpret_cast<float4*>(v + offset) : nullptr;
+    const int grid = grid_for(hi4 - lo4, 256, 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kind == 0)
+        opt_flat_dp_kernel<0><<<grid, 256, 0, st>>>(pb, m4, v4, lo4, hi4, world, rank, lr_or_alpha, b1_or_rho, b2, eps);
+    else
+        opt_flat_dp_kernel<1><<<grid, 256, 0, st>>>(pb, m4, v4, lo4, hi4, world, rank, lr_or_alpha, b1_or_rho, b2, eps);
     return check_launch();
 }
 

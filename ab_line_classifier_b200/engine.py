@@ -80,6 +80,10 @@ class CutoffVGG16Engine:
         self.specs, self.feat_shape = build_plan(self.input_shape, self.cutoff_layer)
         if self.specs[0].cout != 64:
             raise NotImplementedError("first layer must be block1_conv1 (64 filters)")
+        # data parallel: fused reduce-scatter + optimizer + all-gather over NVLink peer memory (default) or NCCL
+        # all-reduce + local optimizer (ABL_DP_FUSED=0, and always for apply_update=False gradient inspection)
+        import os
+        self.fused_dp = os.environ.get("ABL_DP_FUSED", "1") != "0"
         self.step_count = 0           # dropout counter
         self.opt_steps = {}           # optimizer name -> steps taken (Adam bias correction)
         self._alloc_params(output_bias)
@@ -126,8 +130,13 @@ class CutoffVGG16Engine:
         self.n_flat = off
         self.n_params = sum(n for _, n, _ in self.segments.values())
         dev = self.device
-        self.theta = torch.zeros(off, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(off, device=dev, dtype=torch.float32)
+        self._symm = None          # symmetric-memory handle (peer pointers + device barrier) when DP is fused
+        self._grad_unreduced = False
+        if self.world_size > 1 and self.fused_dp:
+            self._alloc_symmetric(off)
+        if self._symm is None:
+            self.theta = torch.zeros(off, device=dev, dtype=torch.float32)
+            self.grad = torch.zeros(off, device=dev, dtype=torch.float32)
         self.opt_state = {}
         self.w_fwd, self.w_dgrad = {}, {}
         for s in self.specs[1:]:
@@ -135,6 +144,25 @@ class CutoffVGG16Engine:
             self.w_dgrad[s.name] = torch.empty(9, s.cin, s.cout, device=dev, dtype=torch.bfloat16)
         self.class_weight = torch.ones(self.n_classes, device=dev, dtype=torch.float32)
         self.init_glorot(self.seed, output_bias)
+
+    def _alloc_symmetric(self, n_flat):
+        """theta and grad in ONE symmetric allocation: after the rendezvous every rank holds a peer pointer to every
+        rank's buffers (NVLink P2P) and a device-side barrier; abl_opt_flat_dp reads / writes through them."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if self.world_size > 8 or not dist.is_initialized():
+            return
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        buf = symm.empty(2 * n_flat, dtype=torch.float32, device=self.device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        self._symm_buf, self._symm = buf, hdl
+        self.theta, self.grad = buf[:n_flat], buf[n_flat:]
+        self._theta_peers = [int(p) for p in hdl.buffer_ptrs]
+        self._grad_peers = [int(p) + 4 * n_flat for p in hdl.buffer_ptrs]
+        self._grad_unreduced = False
+        torch.cuda.synchronize()
+        hdl.barrier()
 
     def layer_names(self):
         return [s.name for s in self.specs] + ["output"]
@@ -447,21 +475,35 @@ class CutoffVGG16Engine:
         key = kind
         t = self.opt_steps.get(key, 0) + 1
         self.opt_steps[key] = t
+        fused = self._symm is not None and self._grad_unreduced
+        if fused:
+            self._symm.barrier()             # every rank's gradients are final
         if kind == "adam":
             if "m" not in self.opt_state:
-                self.opt_state["m"] = torch.zeros_like(self.theta)
-                self.opt_state["v"] = torch.zeros_like(self.theta)
+                self.opt_state["m"] = torch.zeros(self.n_flat, device=self.device)
+                self.opt_state["v"] = torch.zeros(self.n_flat, device=self.device)
             alpha = lr * math.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
             for s, e in self._runs(trainable):
-                ops.adam_flat(self.theta[s:e], self.grad[s:e], self.opt_state["m"][s:e], self.opt_state["v"][s:e],
-                              alpha, beta_1, beta_2, eps)
+                if fused:
+                    ops.opt_flat_dp("adam", self._theta_peers, self._grad_peers, self.opt_state["m"],
+                                    self.opt_state["v"], s, e - s, self.rank, self.world_size, alpha, beta_1, beta_2, eps)
+                else:
+                    ops.adam_flat(self.theta[s:e], self.grad[s:e], self.opt_state["m"][s:e], self.opt_state["v"][s:e],
+                                  alpha, beta_1, beta_2, eps)
         elif kind == "rmsprop":
             if "rms" not in self.opt_state:
-                self.opt_state["rms"] = torch.zeros_like(self.theta)
+                self.opt_state["rms"] = torch.zeros(self.n_flat, device=self.device)
             for s, e in self._runs(trainable):
-                ops.rmsprop_flat(self.theta[s:e], self.grad[s:e], self.opt_state["rms"][s:e], lr, rho, eps)
+                if fused:
+                    ops.opt_flat_dp("rmsprop", self._theta_peers, self._grad_peers, self.opt_state["rms"], None, s,
+                                    e - s, self.rank, self.world_size, lr, rho, 0.0, eps)
+                else:
+                    ops.rmsprop_flat(self.theta[s:e], self.grad[s:e], self.opt_state["rms"][s:e], lr, rho, eps)
         else:
             raise ValueError(f"unknown optimizer {kind}")
+        if fused:
+            self._symm.barrier()             # every shard of the new weights has landed everywhere; grads may be reused
+            self._grad_unreduced = False
         self.refresh_operands(trainable)
 
     def set_class_weight(self, class_weight):
@@ -481,7 +523,7 @@ class CutoffVGG16Engine:
         return probs
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
-                   apply_update=True, bucket_bytes=2 << 20, loss_out=None, slot=None, batch=None):
+                   apply_update=True, bucket_bytes=2 << 20, loss_out=None, slot=None, batch=None, defer_reduce=False):
         """One step: H2D copy of (x, y) [or a slot pre-filled by stage()], forward (dropout on), loss,
         backward, [DP all-reduce], update.  Returns the device scalar sum_i w_i*l_i / global_batch for THIS
         rank's frames."""
@@ -503,7 +545,12 @@ class CutoffVGG16Engine:
                             inv_batch=1.0 / gb, loss_out=loss_out)
         self.step_count += 1
         reducer = None
-        if self.world_size > 1:
+        # fused DP: leave self.grad un-reduced; apply_optimizer() sums it across ranks inside the optimizer kernel.
+        # (apply_update=False without defer_reduce keeps the NCCL all-reduce so callers can inspect the full gradient.)
+        fused = self._symm is not None and (apply_update or defer_reduce)
+        if fused:
+            self._grad_unreduced = True
+        if self.world_size > 1 and not fused:
             from .dp import GradBucketReducer
             if not self.dp_overlap:
                 bucket_bytes = 1 << 40            # one all-reduce of every trainable slice after backward

@@ -253,7 +253,8 @@ class B200Model:
         trainable = self.trainable_names()
         kw = ({"beta_1": opt.beta_1, "beta_2": opt.beta_2, "eps": opt.epsilon} if opt.kind == "adam"
               else {"rho": opt.rho, "eps": opt.epsilon})
-        loss = eng.train_step(x, y, trainable, apply_update=False, global_batch=len(x) * eng.world_size)
+        loss = eng.train_step(x, y, trainable, apply_update=False, global_batch=len(x) * eng.world_size,
+                              defer_reduce=True)
         eng.apply_optimizer(opt.kind, opt.learning_rate, trainable, **kw)
         return float(loss.item())
 
@@ -306,7 +307,7 @@ class B200Model:
                     eng.reserve(len(nxt[0]), True)
                     nslot = eng.stage(nxt[0], nxt[1], slot=slot ^ 1)
                 eng.train_step(None, None, trainable, apply_update=False, loss_out=ring[slot_i:slot_i + 1],
-                               global_batch=B * eng.world_size, slot=slot, batch=B)
+                               global_batch=B * eng.world_size, slot=slot, batch=B, defer_reduce=True)
                 eng.apply_optimizer(opt.kind, opt.learning_rate, trainable, **kw)
                 if self.metric_objs:
                     probs.append(eng._buf["probs"][:B].clone())

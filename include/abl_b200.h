@@ -134,6 +134,19 @@ int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n,
 int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, float lr, float rho, float eps,
                      void* stream);
 
+/* Data-parallel optimizer step over NVLink peer memory (new: the reference is single-device).  ONE kernel does
+ * reduce-scatter(grad) -> Adam (kind 0) / RMSprop (kind 1) on this rank's 1/world shard -> all-gather(theta):
+ *   theta_peers[r], grad_peers[r] (HOST arrays of `world` DEVICE pointers) are the bases of rank r's flat fp32 theta /
+ *   grad buffers as mapped into THIS process (a symmetric allocation; entry `rank` is the local buffer); the run
+ *   [offset, offset + n) of every buffer is processed (multiples of 4 floats).
+ *   g = sum_r grad_r[i] in fixed rank order; theta updated with the local m_or_rms / v state (same offset); the new
+ *   value is stored into every rank's theta.  Arguments as abl_adam_flat (lr_or_alpha = alpha_t, b1_or_rho = beta1)
+ *   or abl_rmsprop_flat (lr, rho; b2 and v unused).
+ * The caller must place a cross-rank barrier before (all gradients final) and after (all weights delivered). */
+int abl_opt_flat_dp(int kind, float* const* theta_peers, const float* const* grad_peers, float* m_or_rms, float* v,
+                    long long offset, long long n, int rank, int world, float lr_or_alpha, float b1_or_rho, float b2,
+                    float eps, void* stream);
+
 /* Grad-CAM of the predicted class for a GAP->Dense->softmax head (src/explainability/gradcam.py:68-81),
  * per frame: alpha_k = (1/HW) sum_j p_c (delta_cj - p_j) w[k][j]; heat = relu(mean_k alpha_k a[h,w,k]);
  * heat /= max(heat) (all-zero map stays zero); bilinear resize (cv2 INTER_LINEAR semantics) to

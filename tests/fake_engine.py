@@ -60,7 +60,7 @@ class FakeEngine:
         return out["probs"].detach()
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
-                   apply_update=True, bucket_bytes=0, loss_out=None, slot=None, batch=None):
+                   apply_update=True, bucket_bytes=0, loss_out=None, slot=None, batch=None, defer_reduce=False):
         if slot is not None:
             x, y = self._slots[slot]
         x, y = self._np(x), self._np(y)
