@@ -350,6 +350,81 @@ __global__ void rmsprop_flat_kernel(float4* __restrict__ theta, const float4* __
     }
 }
 
+// ------------------------------------------------------------------ clip-level aggregation (predict.py:159-166)
+// One warp per clip over that clip's rows of the frame-probability table.  Per clip it produces everything the three
+// reference rules need: the class-wise mean ('average', predict.py:164), the longest run of frames with
+// p[b] > threshold ('contiguous', predict.py:283-308) and the highest mean of p[b] over `window` consecutive frames
+// ('sliding_window', predict.py:365-376; 0 when the clip is shorter than the window, as in the reference's loop).
+// Each lane scans a contiguous chunk of frames; chunks are combined with the run-length monoid
+// (len, all_ones, prefix_run, suffix_run, best_run) through shuffles.  Window sums use a lane-local sliding sum.
+struct RunState { int len, pre, suf, best; };
+__device__ __forceinline__ RunState run_combine(const RunState a, const RunState b) {
+    RunState r;
+    r.len = a.len + b.len;
+    r.pre = (a.pre == a.len) ? a.len + b.pre : a.pre;
+    r.suf = (b.suf == b.len) ? b.len + a.suf : b.suf;
+    r.best = max(max(a.best, b.best), a.suf + b.pre);
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+clip_aggregate_kernel(const float* __restrict__ probs, const long long* __restrict__ offsets, int n_clips, int n,
+                      int b_idx, float threshold, int window, float* __restrict__ mean_out, int* __restrict__ run_out,
+                      float* __restrict__ win_out) {
+    const int lane = threadIdx.x & 31;
+    const int clip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (clip >= n_clips) return;
+    const long long f0 = offsets[clip], f1 = offsets[clip + 1];
+    const int nf = static_cast<int>(f1 - f0);
+    const float* p = probs + f0 * n;
+    // class-wise means: lanes stride over (frame, class) pairs of each class
+    for (int j = 0; j < n; ++j) {
+        float s = 0.f;
+        for (int f = lane; f < nf; f += 32) s += p[static_cast<long long>(f) * n + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) mean_out[static_cast<long long>(clip) * n + j] = nf > 0 ? s / static_cast<float>(nf) : 0.f;
+    }
+    // longest run of positives: contiguous chunk per lane, then an ordered combine over lanes
+    const int per = (nf + 31) / 32;
+    const int c0 = min(nf, lane * per), c1 = min(nf, c0 + per);
+    RunState st = {c1 - c0, 0, 0, 0};
+    {
+        int cur = 0;
+        bool prefix = true;
+        for (int f = c0; f < c1; ++f) {
+            const bool on = p[static_cast<long long>(f) * n + b_idx] > threshold;
+            cur = on ? cur + 1 : 0;
+            if (prefix) { if (on) st.pre = cur; else prefix = false; }
+            st.best = max(st.best, cur);
+        }
+        st.suf = cur;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {      // tree combine keeping lane order: lane l absorbs lane l + o
+        RunState other;
+        other.len = __shfl_down_sync(0xffffffffu, st.len, o);
+        other.pre = __shfl_down_sync(0xffffffffu, st.pre, o);
+        other.suf = __shfl_down_sync(0xffffffffu, st.suf, o);
+        other.best = __shfl_down_sync(0xffffffffu, st.best, o);
+        if ((lane & (2 * o - 1)) == 0 && lane + o < 32) st = run_combine(st, other);
+    }
+    if (lane == 0) run_out[clip] = st.best;
+    // sliding window: windows starting at i in [0, nf - window]; lanes stride over start positions
+    float best = 0.f;
+    if (window > 0 && nf >= window) {
+        const float inv = 1.f / static_cast<float>(window);
+        for (int i = lane; i + window <= nf; i += 32) {
+            float s = 0.f;
+            for (int k = 0; k < window; ++k) s += p[static_cast<long long>(i + k) * n + b_idx];
+            best = fmaxf(best, s * inv);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) win_out[clip] = best;
+}
+
 // ------------------------------------------------------------------ data-parallel optimizer over NVLink peer memory
 // ONE kernel = reduce-scatter(grad) -> Adam / RMSprop on this rank's shard -> all-gather(theta), all through peer
 // pointers of a symmetric allocation (every rank maps every rank's flat theta / grad buffer):
@@ -612,6 +687,18 @@ extern "C" int abl_rmsprop_flat(float* theta, const float* g, float* rms, long l
     rmsprop_flat_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(rms), n4,
         theta + n4 * 4, g + n4 * 4, rms + n4 * 4, tail, lr, rho, eps);
+    return check_launch();
+}
+
+extern "C" int abl_clip_aggregate(const float* probs, const long long* clip_offsets, int n_clips, int n_classes,
+                                  int b_idx, float threshold, int window, float* mean_out, int* run_out,
+                                  float* win_out, void* stream) {
+    if (!probs || !clip_offsets || !mean_out || !run_out || !win_out) { set_error("abl_clip_aggregate: null pointer"); return ABL_ERR_NULL; }
+    if (n_clips <= 0 || n_classes <= 0 || b_idx < 0 || b_idx >= n_classes || window < 0) {
+        set_error("abl_clip_aggregate: bad arguments"); return ABL_ERR_SHAPE;
+    }
+    clip_aggregate_kernel<<<(n_clips + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        probs, clip_offsets, n_clips, n_classes, b_idx, threshold, window, mean_out, run_out, win_out);
     return check_launch();
 }
 

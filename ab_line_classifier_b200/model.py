@@ -209,15 +209,18 @@ class B200Model:
         x = np.asarray(x, np.float32) if not torch.is_tensor(x) else x
         return self.engine.predict_batch(x).cpu().numpy()
 
-    def predict(self, test_data, verbose=1, batch_size=512):
+    def predict(self, test_data, verbose=1, batch_size=512, return_device=False):
+        """Keras Model.predict: concatenated softmax probabilities [N, n_classes] (numpy; return_device=True keeps the
+        result in HBM for a following device-side step such as the clip aggregation)."""
         outs = []
         if isinstance(test_data, np.ndarray) or torch.is_tensor(test_data):
             test_data = [(test_data[i:i + batch_size], None) for i in range(0, len(test_data), batch_size)]
         for x, _ in _iter_batches(test_data):
             outs.append(self.engine.predict_batch(x).clone())      # stays on device: one D2H at the end
         if not outs:
-            return np.zeros((0, self.n_classes), np.float32)
-        return torch.cat(outs).cpu().numpy()
+            return (torch.zeros(0, self.n_classes, device=self.engine.device) if return_device
+                    else np.zeros((0, self.n_classes), np.float32))
+        return torch.cat(outs) if return_device else torch.cat(outs).cpu().numpy()
 
     def _run_eval(self, data):
         eng = self.engine

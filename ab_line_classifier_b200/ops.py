@@ -174,6 +174,19 @@ def rmsprop_flat(theta, g, rms, lr, rho=0.9, eps=1e-7):
                  float(eps), _stream())
 
 
+def clip_aggregate(probs, clip_offsets, b_idx, threshold, window):
+    """probs fp32 [N,n] (device), clip_offsets int64 [n_clips+1] (device) -> (mean [n_clips,n], run int32 [n_clips],
+    win fp32 [n_clips]); see abl_clip_aggregate."""
+    _chk(probs, torch.float32, "probs"); _chk(clip_offsets, torch.int64, "clip_offsets")
+    n_clips, n = clip_offsets.numel() - 1, probs.shape[1]
+    mean = torch.empty(n_clips, n, device=probs.device, dtype=torch.float32)
+    run = torch.empty(n_clips, device=probs.device, dtype=torch.int32)
+    win = torch.empty(n_clips, device=probs.device, dtype=torch.float32)
+    _native.call("abl_clip_aggregate", _ptr(probs), _ptr(clip_offsets), n_clips, n, int(b_idx), float(threshold),
+                 int(window), _ptr(mean), _ptr(run), _ptr(win), _stream())
+    return mean, run, win
+
+
 def opt_flat_dp(kind, theta_ptrs, grad_ptrs, m_or_rms, v, offset, n, rank, world, lr_or_alpha, b1_or_rho, b2=0.0,
                 eps=1e-7):
     """Fused reduce-scatter(grad) -> Adam/RMSprop(shard) -> all-gather(theta) over peer pointers (abl_opt_flat_dp).

@@ -134,6 +134,16 @@ int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n,
 int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, float lr, float rho, float eps,
                      void* stream);
 
+/* Clip-level aggregation of frame probabilities (src/predict.py:159-166 with the helpers at 283-308 and 365-376),
+ * all clips in one launch instead of the reference's per-clip Python loop.  probs fp32 [N_frames, n_classes] with the
+ * frames of clip c in rows clip_offsets[c] .. clip_offsets[c+1]-1 (clip_offsets: n_clips+1 int64, device).
+ *   mean_out[c][j] = mean_f probs[f][j]                                  ('average')
+ *   run_out[c]     = longest run of frames with probs[f][b_idx] > threshold   ('contiguous')
+ *   win_out[c]     = max over i of mean(probs[i:i+window, b_idx]), 0 if the clip has fewer than `window` frames
+ *                                                                        ('sliding_window') */
+int abl_clip_aggregate(const float* probs, const long long* clip_offsets, int n_clips, int n_classes, int b_idx,
+                       float threshold, int window, float* mean_out, int* run_out, float* win_out, void* stream);
+
 /* Data-parallel optimizer step over NVLink peer memory (new: the reference is single-device).  ONE kernel does
  * reduce-scatter(grad) -> Adam (kind 0) / RMSprop (kind 1) on this rank's 1/world shard -> all-gather(theta):
  *   theta_peers[r], grad_peers[r] (HOST arrays of `world` DEVICE pointers) are the bases of rank r's flat fp32 theta /

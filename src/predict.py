@@ -79,39 +79,58 @@ def max_contiguous_b_line_preds(pred_series):
     return best
 
 
-def predict_with_contiguity_threshold(pred_series, contiguity_threshold):
-    '''Clip is positive if it has >= contiguity_threshold consecutive positive frames (predict.py:299-308).'''
-    return int(max_contiguous_b_line_preds(pred_series) >= contiguity_threshold)
+def predict_with_contiguity_threshold(pred_probs, contiguity_threshold, classification_threshold):
+    '''[1 - c, c] with c = 1 if the clip has >= contiguity_threshold consecutive frames whose B-line probability
+    exceeds classification_threshold (reference predict.py:299-308).'''
+    b_preds = (np.asarray(pred_probs)[:, 1] > classification_threshold).astype(int)
+    clip_pred = int(max_contiguous_b_line_preds(b_preds) >= contiguity_threshold)
+    return np.array([1 - clip_pred, clip_pred])
 
 
 def highest_avg_contiguous_pred_prob(pred_probs, window):
-    '''Highest mean B-line probability over any `window` consecutive frames (predict.py:365-376).'''
+    '''Highest mean B-line probability over any `window` consecutive frames (predict.py:365-376); like the
+    reference's loop it is 0 when the clip has fewer than `window` frames.'''
     pred_probs = np.asarray(pred_probs, np.float64)
-    if len(pred_probs) < window:
-        return float(np.mean(pred_probs)) if len(pred_probs) else 0.0
+    if window <= 0 or len(pred_probs) < window:
+        return 0.0
     c = np.concatenate([[0.0], np.cumsum(pred_probs)])
-    return float(np.max((c[window:] - c[:-window]) / window))
+    return float(max(0.0, np.max((c[window:] - c[:-window]) / window)))
 
 
 def compute_clip_predictions(model, preprocessing_func, clips, class_thresh=0.5, clip_algorithm='contiguous'):
     '''
-    clips: list of (clip_id, frames [n,H,W,3], label or None).  Frame predictions per clip, then the clip-level
-    rule selected by CLIP_PREDICTION.ALGORITHM (reference predict.py:125-188).
+    clips: list of (clip_id, frames [n,H,W,3], label or None).  Frame predictions, then the clip-level rule selected by
+    CLIP_PREDICTION.ALGORITHM (reference predict.py:125-188).  The reference loops over clips in Python and rebuilds a
+    dataset per clip (predict.py:148-156); here the frames of ALL clips go through the network in full batches and ONE
+    kernel (abl_clip_aggregate) evaluates the rule for every clip on the device.
     '''
+    import torch
+    from ab_line_classifier_b200 import ops
+    if clip_algorithm not in ('contiguous', 'sliding_window', 'average'):
+        raise Exception('Unknown value for "clip_algorithm" argument.')
+    b = CLASS_IDX_MAP['b_lines']
+    clips = [c for c in clips]
+    if not clips:
+        return []
+    counts = [len(frames) for _, frames, _ in clips]
+    frames_all = np.concatenate([np.asarray(frames) for _, frames, _ in clips], 0)
+    x = preprocessing_func(frames_all) if preprocessing_func is not None else np.asarray(frames_all, np.float32) / 255.
+    probs = model.predict(ArrayDataset(x, None, max(cfg['TRAIN']['BATCH_SIZE'], 512)), return_device=True)
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).to(probs.device)
+    mean, run, win = ops.clip_aggregate(probs, offsets, b, class_thresh, cfg['CLIP_PREDICTION']['SLIDING_WINDOW'])
+    mean, run, win = mean.cpu().numpy(), run.cpu().numpy(), win.cpu().numpy()
     rows = []
-    for clip_id, frames, label in clips:
-        preds, probs = predict_set(model, preprocessing_func, frames, threshold=class_thresh)
-        pb = probs[:, CLASS_IDX_MAP['b_lines']]
+    for i, (clip_id, frames, label) in enumerate(clips):
         if clip_algorithm == 'contiguous':
-            clip_pred = predict_with_contiguity_threshold(preds, cfg['CLIP_PREDICTION']['CONTIGUITY_THRESHOLD'])
-            clip_prob = float(max_contiguous_b_line_preds(preds))
+            cp = float(run[i] >= cfg['CLIP_PREDICTION']['CONTIGUITY_THRESHOLD'])
+            clip_pred_prob = np.array([1. - cp, cp])
         elif clip_algorithm == 'sliding_window':
-            clip_prob = highest_avg_contiguous_pred_prob(pb, cfg['CLIP_PREDICTION']['SLIDING_WINDOW'])
-            clip_pred = int(clip_prob >= class_thresh)
+            clip_pred_prob = np.array([1. - win[i], win[i]])
         else:
-            clip_prob = float(np.mean(pb))
-            clip_pred = int(clip_prob >= class_thresh)
-        rows.append({'clip': clip_id, 'label': label, 'pred': clip_pred, 'score': clip_prob, 'n_frames': len(frames)})
+            clip_pred_prob = mean[i]
+        rows.append({'clip': clip_id, 'label': label, 'pred': int(clip_pred_prob[b] >= class_thresh),
+                     'score': float(clip_pred_prob[b]), 'probs': clip_pred_prob, 'max_contiguous': int(run[i]),
+                     'n_frames': counts[i]})
     return rows
 
 

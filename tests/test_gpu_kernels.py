@@ -321,6 +321,36 @@ def test_gradcam_matches_closed_form_oracle():
         assert heat[4].abs().max().item() == 0.0
 
 
+def test_clip_aggregate_matches_reference_rules_bit_exactly_on_runs():
+    """f2: every clip in one launch vs the loop-for-loop restatement of predict.py:283-308, 365-376, 164.  Ragged clips:
+    empty-ish (1 frame), shorter than the window, exactly the window, long; runs touching both ends."""
+    ops = _ops()
+    from oracle import clip_rules
+    rng = np.random.default_rng(5)
+    counts = [1, 2, 3, 4, 5, 31, 32, 33, 64, 257, 1000, 7]
+    probs = []
+    for i, n in enumerate(counts):
+        pb = rng.random(n).astype(np.float32)
+        if i % 3 == 0:
+            pb[: n // 2 + 1] = 0.9          # run touching the start
+        if i % 4 == 1:
+            pb[n // 2:] = 0.8               # run touching the end
+        if n == 64:
+            pb[:] = 0.99                    # all positive
+        probs.append(np.stack([1 - pb, pb], 1))
+    allp = np.concatenate(probs, 0).astype(np.float32)
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).cuda()
+    thr, window = 0.5, 4
+    mean, run, win = ops.clip_aggregate(torch.from_numpy(allp).cuda(), off, 1, thr, window)
+    mean, run, win = mean.cpu().numpy(), run.cpu().numpy(), win.cpu().numpy()
+    for i, p in enumerate(probs):
+        assert run[i] == clip_rules.max_contiguous((p[:, 1] > thr).astype(int)), f"clip {i} ({counts[i]} frames)"
+        for ct in (1, 3, 40):
+            assert int(run[i] >= ct) == clip_rules.contiguity_rule(p, ct, thr)[1]
+        assert win[i] == pytest.approx(clip_rules.sliding_window_rule(p, window)[1], abs=1e-6)
+        np.testing.assert_allclose(mean[i], clip_rules.average_rule(p.astype(np.float64)), atol=5e-6)   # fp32 sum of <= 1000 terms
+
+
 def test_error_behaviour_bad_shapes_and_alignment():
     ops = _ops()
     x = torch.zeros(1, 20, 20, 64, device="cuda", dtype=torch.bfloat16)       # 20x20 cannot be tiled

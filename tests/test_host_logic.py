@@ -137,14 +137,21 @@ def test_class_weight_and_output_bias_formulas():
 
 
 def test_clip_aggregation_rules():
+    """Host helpers kept from reference predict.py:283-308, 365-376 against the loop-for-loop restatement."""
+    from oracle import clip_rules
     from src.predict import (highest_avg_contiguous_pred_prob, max_contiguous_b_line_preds,
                              predict_with_contiguity_threshold)
     assert max_contiguous_b_line_preds([0, 1, 1, 0, 1, 1, 1, 0]) == 3
     assert max_contiguous_b_line_preds([]) == 0
-    assert predict_with_contiguity_threshold([1, 1, 0, 1], 3) == 0
-    assert predict_with_contiguity_threshold([1, 1, 1, 0], 3) == 1
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 4, 5, 17, 100):
+        pb = rng.random(n)
+        probs = np.stack([1 - pb, pb], 1)
+        np.testing.assert_array_equal(predict_with_contiguity_threshold(probs, 3, 0.5),
+                                      clip_rules.contiguity_rule(probs, 3, 0.5))
+        assert highest_avg_contiguous_pred_prob(pb, 4) == pytest.approx(clip_rules.sliding_window_rule(probs, 4)[1])
     assert highest_avg_contiguous_pred_prob([.1, .9, .8, .7, .6, .1], 4) == pytest.approx(0.75)
-    assert highest_avg_contiguous_pred_prob([.2, .4], 4) == pytest.approx(0.3)
+    assert highest_avg_contiguous_pred_prob([.2, .4], 4) == 0.0        # no full window: the reference's loop never runs
 
 
 def test_engine_plan_and_unsupported_configs():
