@@ -24,9 +24,11 @@ namespace abl {
 constexpr int kF_Cout = 64;
 constexpr int kF_TileM = 128;
 constexpr int kF_ABlock = kF_TileM * 128;     // 16 KiB: [128 px][64 slots] bf16
-constexpr int kF_Threads = 512;               // warps 0-3 control, 4-11 im2col producers (2 groups), 12-15 epilogue
+constexpr int kF_Threads = 512;               // warps 0-3 control, 4-15 = 3 worker groups of 4 warps
 constexpr int kF_Stages = 4;
-constexpr int kF_ProdGroups = 2;              // producer group g builds the CTA's tiles g, g+2, g+4, ...
+constexpr int kF_ProdGroups = 3;              // worker group g owns the CTA's tiles g, g+3, g+6, ...: it builds the im2col
+                                              // rows and (forward) drains the accumulator of its previous tile
+constexpr int kF_AccBufs = 4;                 // forward TMEM accumulators (64 columns each)
 
 struct FirstArgs {
     const float* x;        // [B,H,W,3] fp32 (already BGR / mean-subtracted), or
@@ -51,17 +53,21 @@ constexpr int kF_PatchFloats = kF_PatchRegs * 128;             // one group's ha
 // memory, and the 27-tap gather then reads shared memory (lane stride 3 words: conflict-free).  The v1 gather
 // issued 27 dependent-latency global loads per pixel with only 8 producer warps per SM to hide them; ncu showed
 // the kernel at 30 % of HBM bandwidth with every pipe idle.
-struct PatchElem { int prow, pcol, ch; bool used; };
-
-__device__ __forceinline__ PatchElem patch_elem(const FirstArgs& p, int e) {
+// Per-thread, tile-invariant description of patch element e = t + 128 k, packed into one register:
+//   bits 0-1 channel, bit 2 used, bit 3 first patch row, bit 4 last patch row, bit 5 first column, bit 6 last column,
+//   bits 8.. offset (in input elements) of the value relative to the tile's first pixel, biased by kF_RelBias.
+constexpr int kF_RelBias = 1 << 22;
+template <bool kU8>
+__device__ __forceinline__ int patch_code(const FirstArgs& p, int e) {
     const int wt = 1 << p.wt_log2, pcols = wt + 2, nrows = (kF_TileM >> p.wt_log2) + 2;
-    PatchElem q;
-    q.used = e < nrows * pcols * 3;
-    q.prow = e / (pcols * 3);
-    const int rem = e - q.prow * (pcols * 3);
-    q.pcol = rem / 3;
-    q.ch = rem - q.pcol * 3;
-    return q;
+    const bool used = e < nrows * pcols * 3;
+    const int prow = e / (pcols * 3);
+    const int rem = e - prow * (pcols * 3);
+    const int pcol = rem / 3;
+    const int ch = rem - pcol * 3;
+    const int rel = ((prow - 1) * p.W + (pcol - 1)) * 3 + (kU8 ? 2 - ch : ch);      // uint8 frames are RGB: BGR = reversed
+    return ch | (used ? 4 : 0) | (prow == 0 ? 8 : 0) | (prow == nrows - 1 ? 16 : 0) | (pcol == 0 ? 32 : 0) |
+           (pcol == pcols - 1 ? 64 : 0) | ((rel + kF_RelBias) << 8);
 }
 
 // Issue this thread's loads of tile `tile`'s patch (values land in r[]; nothing waits here).
@@ -70,21 +76,44 @@ __device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t,
                                             float (&r)[kF_PatchRegs]) {
     const long long pix0 = static_cast<long long>(tile) * kF_TileM;
     const int c0 = static_cast<int>(pix0 % p.W);
-    const long long rowlin = pix0 / p.W;                 // n * H + h of the tile's first row
-    const int h0 = static_cast<int>(rowlin % p.H);
+    const int h0 = static_cast<int>((pix0 / p.W) % p.H);
+    const int wt = 1 << p.wt_log2;
+    // which borders of the frame this tile touches: an element on the matching patch border is zero padding
+    const int edge = (h0 == 0 ? 8 : 0) | (h0 + (kF_TileM >> p.wt_log2) == p.H ? 16 : 0) | (c0 == 0 ? 32 : 0) |
+                     (c0 + wt == p.W ? 64 : 0);
+    const long long base = pix0 * 3 - kF_RelBias;
 #pragma unroll
     for (int k = 0; k < kF_PatchRegs; ++k) {
-        const int cd = code[k];                          // prow | pcol << 8 | ch << 16 | used << 24
-        const int prow = cd & 0xFF, pcol = (cd >> 8) & 0xFF, ch = (cd >> 16) & 3;
-        const int hh = h0 - 1 + prow, ww = c0 - 1 + pcol;
-        const bool ok = (cd >> 24) && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
-        const long long off = ((rowlin - 1 + prow) * p.W + ww) * 3;
+        const int cd = code[k];
+        const bool ok = (cd & 4) && !(cd & edge);
+        const long long off = base + (cd >> 8);
         if (kU8) {
+            const int ch = cd & 3;
             const float mean = ch == 0 ? 103.939f : (ch == 1 ? 116.779f : 123.68f);      // BGR means
-            r[k] = ok ? static_cast<float>(__ldg(p.x8 + off + (2 - ch))) - mean : 0.f;   // RGB -> BGR
+            r[k] = ok ? static_cast<float>(__ldg(p.x8 + off)) - mean : 0.f;
         } else {
-            r[k] = ok ? __ldg(p.x + off + ch) : 0.f;
+            r[k] = ok ? __ldg(p.x + off) : 0.f;
         }
+    }
+}
+
+// Write one pixel's A row(s).  Only chunks that can hold data are stored: k-block 0 chunks 0..6 (slots 0..55) and, in
+// forward, k-block 1 chunks 0..3 (hi(x) in slots 0..26, the constant 1 of the bias row in slot 27); every other chunk
+// of the stage was zero-filled once at kernel start and is never written again.
+template <bool kFwd>
+__device__ __forceinline__ void store_a_row(const uint32_t (&s0)[32], int row, uint8_t* a_stage) {
+    uint8_t* r0 = a_stage + row * 128;
+    const int sw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 7; ++c)
+        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
+    if (kFwd) {
+        uint8_t* r1 = r0 + kF_ABlock;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<uint4*>(r1 + ((c ^ sw) << 4)) = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
+        // slots 24, 25 | 26, 27 = hi(x[26]), 1.0 (pairs with lo(bias) in the B operand) | zeros
+        *reinterpret_cast<uint4*>(r1 + ((3 ^ sw) << 4)) = make_uint4(s0[12], (s0[13] & 0xFFFFu) | 0x3F800000u, 0, 0);
     }
 }
 
@@ -131,21 +160,7 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
         const __nv_bfloat16 e1 = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : (k1 == 54 ? one : zero));
         s0[j] = static_cast<uint32_t>(__bfloat16_as_ushort(e0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(e1)) << 16);
     }
-    uint8_t* r0 = a_stage + row * 128;
-    const int sw = row & 7;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
-    if (kFwd) {   // k-block 1: hi(x) in slots 0..26 (chunks 0..3), zeros elsewhere
-        uint8_t* r1 = r0 + kF_ABlock;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (c < 3) q = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
-            if (c == 3) q = make_uint4(s0[12], s0[13] & 0xFFFFu, 0, 0);   // slots 24,25,26 then zeros
-            *reinterpret_cast<uint4*>(r1 + ((c ^ sw) << 4)) = q;
-        }
-    }
+    store_a_row<kFwd>(s0, row, a_stage);
 }
 
 // hi | lo << 16 of one input value: converted ONCE per input element when the patch is parked in shared memory
@@ -175,37 +190,20 @@ __device__ __forceinline__ void im2col_row_patch(const uint32_t* patch, int wt_l
         else if (j <= 26) s0[j] = __byte_perm(u[2 * j - 27], u[2 * j - 26], 0x7632);        // lo[2j-27], lo[2j-26]
         else s0[j] = j == 27 ? 0x00003F80u : 0u;                                            // slot 54 = 1.0
     }
-    uint8_t* r0 = a_stage + row * 128;
-    const int sw = row & 7;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
-    if (kFwd) {   // k-block 1: hi(x) in slots 0..26 (chunks 0..3), zeros elsewhere
-        uint8_t* r1 = r0 + kF_ABlock;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (c < 3) q = make_uint4(s0[4 * c], s0[4 * c + 1], s0[4 * c + 2], s0[4 * c + 3]);
-            if (c == 3) q = make_uint4(s0[12], s0[13] & 0xFFFFu, 0, 0);   // slots 24,25,26 then zeros
-            *reinterpret_cast<uint4*>(r1 + ((c ^ sw) << 4)) = q;
-        }
-    }
+    store_a_row<kFwd>(s0, row, a_stage);
 }
 
 // im2col producer loop of one 128-thread group (group g builds the CTA's tiles g, g+2, ...): shared by forward and
 // wgrad.  kBlocks = 16 KiB k-blocks per A stage (2 forward, 1 wgrad).
-template <bool kFwd, bool kU8>
+template <bool kFwd, bool kU8, typename AfterTile>
 __device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_a, float* patch, uint64_t* afull,
-                                              uint64_t* aempty, int row, int grp) {
+                                              uint64_t* aempty, int row, int grp, AfterTile after_tile) {
     constexpr int kStageBytes = (kFwd ? 2 : 1) * kF_ABlock;
     int code[kF_PatchRegs];
     float nxt[kF_PatchRegs];
     if (p.patch_ok) {
 #pragma unroll
-        for (int k = 0; k < kF_PatchRegs; ++k) {
-            const PatchElem q = patch_elem(p, row + 128 * k);
-            code[k] = q.prow | (q.pcol << 8) | (q.ch << 16) | ((q.used ? 1 : 0) << 24);
-        }
+        for (int k = 0; k < kF_PatchRegs; ++k) code[k] = patch_code<kU8>(p, row + 128 * k);
         if (blockIdx.x + static_cast<long long>(grp) * gridDim.x < p.num_tiles)
             patch_fetch<kU8>(p, blockIdx.x + grp * gridDim.x, row, code, nxt);
     }
@@ -227,6 +225,7 @@ __device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_
             im2col_row<kFwd, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kStageBytes);
         fence_proxy_async_smem();
         mbar_arrive(&afull[stage]);
+        if (it >= kF_ProdGroups) after_tile(it - kF_ProdGroups);      // e.g. epilogue of this group's previous tile
     }
 }
 
@@ -237,25 +236,28 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;                                       // kF_Stages x 2 k-blocks x 16 KiB
     uint8_t* smem_b = smem + kF_Stages * 2 * kF_ABlock;           // 2 k-blocks x [64 co][64 slots] = 16 KiB
-    uint8_t* staging = smem_b + 2 * 64 * 128;                     // 2 x 16 KiB swizzled output tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kF_ABlock);
+    uint8_t* staging = smem_b + 2 * 64 * 128;                     // one 16 KiB swizzled output tile per worker group
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kF_ProdGroups * kF_ABlock);
     uint64_t* afull = bars;
     uint64_t* aempty = bars + kF_Stages;
     uint64_t* tfull = bars + 2 * kF_Stages;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + kF_AccBufs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kF_AccBufs);
     float* patches = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     const int warp = threadIdx.x >> 5;
 
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < kF_Stages; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+        for (int s = 0; s < kF_AccBufs; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
         fence_barrier_init();
         tma_prefetch_desc(&map_out);
     }
-    if (warp == 2) tmem_alloc<128>(tmem_slot);
+    if (warp == 2) tmem_alloc<kF_AccBufs * 64>(tmem_slot);
+    for (int i = threadIdx.x; i < kF_Stages * 2 * kF_ABlock / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);       // see store_a_row
     // B operand, built once per CTA: row = co (128 B, swizzled), slot k of block 0 = hi(W[k%27]) for k < 54,
-    // block 1 = lo(W[k]) for k < 27.
+    // block 1 = lo(W[k]) for k < 27.  The bias rides along: block 0 slot 54 (A holds 1.0 there) = hi(b[co]) and
+    // block 1 slot 27 (A: 1.0) = lo(b[co]), so the accumulator already contains conv + bias in fp32-like precision.
     for (int i = threadIdx.x; i < 2 * 64 * 64; i += blockDim.x) {
         const int blk = i >> 12, co = (i >> 6) & 63, slot = i & 63;
         float val = 0.f;
@@ -264,6 +266,10 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
         } else if (blk == 1 && slot < 27) {
             const float wv = p.w[slot * kF_Cout + co];
             val = wv - __bfloat162float(__float2bfloat16_rn(wv));
+        } else if (blk == 0 && slot == 54) {
+            val = __bfloat162float(__float2bfloat16_rn(p.bias[co]));
+        } else if (blk == 1 && slot == 27) {
+            val = p.bias[co] - __bfloat162float(__float2bfloat16_rn(p.bias[co]));
         }
         uint8_t* rowp = smem_b + blk * (64 * 128) + co * 128;
         *reinterpret_cast<__nv_bfloat16*>(rowp + ((((slot >> 3) ^ (co & 7)) << 4) | ((slot & 7) << 1))) =
@@ -285,8 +291,8 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+                const int as = it % kF_AccBufs;
+                mbar_wait(&tempty[as], ((it / kF_AccBufs) & 1) ^ 1);
                 mbar_wait(&afull[stage], phase);
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + stage * ((2 * kF_ABlock) >> 4);
@@ -301,37 +307,31 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
                 if (++stage == kF_Stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 12) {
-        // ---------------------------------------------------------------- im2col producers (2 x 128 threads)
-        const int row = (threadIdx.x - 128) & 127;
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- worker groups (3 x 128 threads)
+        // Group g: for each of its tiles, build the im2col rows, then drain the accumulator of its PREVIOUS tile
+        // (whose MMAs ran meanwhile) -> bias + ReLU -> bf16 -> swizzled staging -> TMA store.  With three groups the
+        // epilogue latency of one tile (a single warp per scheduler: ~1.8k clocks) overlaps two other tiles' work;
+        // the v1 layout had ONE epilogue group and was bound by exactly that latency (221 tiles x 1.8k clocks).
+        const int row = (threadIdx.x - 128) & 127;       // tile row == TMEM lane (group base warp is a multiple of 4)
         const int grp = (threadIdx.x - 128) >> 7;
-        producer_loop<true, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp);
-    } else if (warp >= 12) {
-        // ---------------------------------------------------------------- epilogue (128 threads)
-        const int row = threadIdx.x - 384;       // TMEM lane
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            uint8_t* stg = staging + (it & 1) * kF_ABlock;
-            mbar_wait(&tfull[as], (it >> 1) & 1);
+        uint8_t* stg = staging + grp * kF_ABlock;
+        auto epilogue = [&](int it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int as = it % kF_AccBufs;
+            mbar_wait(&tfull[as], (it / kF_AccBufs) & 1);
             tc_fence_after();
-            if (row == 0) tma_store_wait_read<1>();
-            named_bar_sync(1, 128);
+            if (row == 0) tma_store_wait_read<0>();      // this group's previous store has finished reading stg
+            named_bar_sync(2 + grp, 128);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + as * 64 + c * 32, r);
                 tmem_ld_wait();
-                const float4* bs = reinterpret_cast<const float4*>(p.bias + c * 32);
-                uint32_t packed[16];
+                uint32_t packed[16];       // the accumulator already holds conv + bias (bias row of the B operand)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = __ldg(bs + j);
-                    packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
-                                                fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
-                    packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
-                                                    fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
-                }
+                for (int j = 0; j < 16; ++j)
+                    packed[j] = pack_bf16x2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(stg + row * 128 + (((c * 4 + j) ^ (row & 7)) << 4)) =
@@ -340,19 +340,24 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
             tc_fence_before();
             mbar_arrive(&tempty[as]);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(2 + grp, 128);
             if (row == 0) {
                 tma_store_2d(&map_out, stg, 0, tile * kF_TileM);
                 tma_store_commit();
             }
-        }
+        };
+        producer_loop<true, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp, epilogue);
+        // the last tile of this group has not been drained yet
+        int n_here = 0;
+        for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) ++n_here;
+        if (n_here > 0) epilogue(grp + (n_here - 1) * kF_ProdGroups);
         if (row == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<128>(tmem_base);
+        tmem_dealloc<kF_AccBufs * 64>(tmem_base);
     }
 }
 
@@ -380,8 +385,8 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
         tma_prefetch_desc(&map_dz);
     }
     if (warp == 2) tmem_alloc<64>(tmem_slot);
-    for (int i = threadIdx.x; i < kF_ABlock / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(smem_z)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (kF_Stages + 1) * kF_ABlock / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);       // A stages (see store_a_row) + the zero block
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -424,14 +429,15 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
             }
             umma_commit(done);
         }
-    } else if (warp >= 4 && warp < 12) {
-        const int row = (threadIdx.x - 128) & 127;
-        const int grp = (threadIdx.x - 128) >> 7;
-        producer_loop<false, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp);
-    } else if (warp >= 12 && warp < 14) {
-        // D rows 0..63 live in TMEM lanes 0..63: warps 12 and 13 (lane quarters 0 and 1)
-        const int row = threadIdx.x - 384;
-        if (ntiles_here > 0) {
+    } else if (warp >= 4) {
+        {
+            const int row = (threadIdx.x - 128) & 127;
+            const int grp = (threadIdx.x - 128) >> 7;
+            producer_loop<false, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp, [](int) {});
+        }
+        // D rows 0..63 live in TMEM lanes 0..63: warps 4 and 5 (lane quarters 0 and 1) drain them at the end
+        const int row = threadIdx.x - 128;
+        if (warp < 6 && ntiles_here > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
 #pragma unroll
@@ -502,7 +508,7 @@ static int first_fwd(const void* x, const float* w_hwio, const float* bias, void
     CUtensorMap mo;
     r = pixel_map(&mo, out, a.total_pix);
     if (r != ABL_OK) return r;
-    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + 2 * kF_ABlock + 256 + kF_ProdGroups * kF_PatchFloats * 4;
+    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + kF_ProdGroups * kF_ABlock + 256 + kF_ProdGroups * kF_PatchFloats * 4;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

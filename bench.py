@@ -325,8 +325,22 @@ def main():
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
         peak = pk.get("bf16_tflops_sustained", 1400.0)
         step_ms_instr = sum(k["ms"] for k in kernels.values())
+        # DRAM traffic of the same launches from the committed `ncu --set full` capture of one train step
+        # (profiles/r1_ncu_step.json, tools/ncu_summary.py): sum over the conv-family launches of one step
+        traffic, traffic_note = None, "no ncu capture found under profiles/"
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_ncu_step.json")) as f:
+                cap = json.load(f)["launches"]
+            fam = [r for r in cap if ("conv3x3_" in r["kernel"] or "wgrad_tc_kernel" in r["kernel"])]
+            if fam and B == PER_GPU_BATCH:
+                traffic = round(sum(r.get("dram_read_bytes", 0) + r.get("dram_write_bytes", 0) for r in fam) / 1e9, 3)
+                traffic_note = (f"GB per step: dram__bytes_read.sum + dram__bytes_write.sum over the {len(fam)} conv-family "
+                                "launches of one step (profiles/r1_ncu_step.json); algorithmic activation+gradient bytes "
+                                "of the same launches: see DESIGN.md section 4")
+        except Exception:
+            pass
         roof = {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "tcgen05 implicit-GEMM conv family (conv3x3_tc_kernel fwd+dgrad, wgrad_tc_kernel): all "
                           "launches of one step, algorithmic FLOPs / summed CUDA-event durations",
                 "peak_source": pk_src + ", bf16_tflops_sustained (kernels timed inside a long step)",
