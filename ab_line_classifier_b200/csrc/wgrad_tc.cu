@@ -15,6 +15,8 @@
 // offsets of kh*16 rows (2 KiB, a multiple of the 1 KiB swizzle atom): 12 MMAs per two TMA instructions.
 // Partial sums of each pixel slice go to a workspace with plain vector stores; a second kernel reduces
 // the slices in a fixed order (deterministic) into the fp32 HWIO gradient.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -190,6 +192,154 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cin == 64 variant.  The generic kernel above pairs two kw taps on UMMA M (2 x 64 input channels) and leaves half
+// of the second unit's rows on a zero block (75 % useful MMAs), with N = Cout-block of 64..128.  For N = 64 an SS-mode
+// MMA is shared-memory-read-bound (A 4 KiB + B 2 KiB per 32 tensor clocks; ncu: tensor pipe 50 % active).  Here the
+// three kh taps move to the N side instead: the dZ tile is loaded with a one-row halo above and below and the B
+// operand is THREE overlapping row-shifted windows of it (N = 3 x 64, "leading byte offset" = one image row = 2 KiB):
+//     D[(kw, ci)][(n, co)] = sum_p X[p + (0, kw-1)][ci] * dZ[p + (n-1, 0)][co]   ==   dW[kh = 2-n][kw][ci][co]
+// (substitute q = p + (n-1, 0); rows outside the frame are TMA zero fill on both operands).  Two M128 x N192 MMAs per
+// 16 pixels cover all 9 taps (rows {kw0,kw1} and {kw2, zero}): 192 tensor clocks instead of 6 x ~58.
+constexpr int kW64XBox = kWgBh * kWgBw * 128;             // 8 KiB: 4 x 16 pixels x 64 channels (no halo)
+constexpr int kW64ZBox = (kWgBh + 2) * kWgBw * 128;       // 12 KiB: haloed dZ tile
+constexpr int kW64Stage = 3 * kW64XBox + kW64ZBox;        // 36 KiB
+constexpr int kW64Stages = 6;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
+                  const WgradArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* zero_blk = smem + kW64Stages * kW64Stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + kW64XBox);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgMaxStages;
+    uint64_t* done_bar = bars + 2 * kWgMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x % p.units;          // 64-wide block of output channels
+    const int split = blockIdx.x / p.units;
+    const int co0 = unit * 64;
+    const int per = (p.num_ptiles + p.splits - 1) / p.splits;
+    const int pt0 = split * per;
+    const int pt1 = min(p.num_ptiles, pt0 + per);
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_dz);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < kW64Stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < kW64XBox / 16; i += blockDim.x) reinterpret_cast<uint4*>(zero_blk)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pt0; pt < pt1; ++pt) {
+                int t = pt;
+                const int tw = t % p.tiles_w;
+                t /= p.tiles_w;
+                const int th = t % p.tiles_h;
+                const int img = t / p.tiles_h;
+                const int h0 = th * kWgBh, w0 = tw * kWgBw;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], kW64Stage);
+                uint8_t* sa = smem + stage * kW64Stage;
+                tma_load_5d(&map_dz, &full_bar[stage], sa + 3 * kW64XBox, 0, w0, h0 - 1, co0 / 64, img);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                    tma_load_5d(&map_x, &full_bar[stage], sa + kw * kW64XBox, 0, w0 + kw - 1, h0, 0, img);
+                if (++stage == kW64Stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);   // both operands MN-major (K = pixels)
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            const uint32_t smem0 = smem_u32(smem);
+            const uint32_t zero_addr = smem_u32(zero_blk);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pt0; pt < pt1; ++pt) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem0 + stage * kW64Stage;
+                const uint32_t a1_lo = desc_lo_sw128(sa, kW64XBox);                              // {kw0, kw1}
+                const uint32_t a2_lo = desc_lo_sw128(sa + 2 * kW64XBox, zero_addr - (sa + 2 * kW64XBox));   // {kw2, zero}
+                const uint32_t b_lo = desc_lo_sw128(sa + 3 * kW64XBox, 2048);                    // 3 windows, one image row apart
+                const uint32_t acc_flag = pt > pt0 ? 1u : 0u;
+#pragma unroll
+                for (int k = 0; k < (kWgBh * kWgBw) / 16; ++k) {
+                    // K advance of 16 pixel rows = 2048 B on both operands
+                    umma_bf16_lohi(tmem_base, a1_lo + k * (2048 >> 4), dhi, b_lo + k * (2048 >> 4), dhi, idesc,
+                                   k > 0 ? 1u : acc_flag);
+                    umma_bf16_lohi(tmem_base + 192, a2_lo + k * (2048 >> 4), dhi, b_lo + k * (2048 >> 4), dhi, idesc,
+                                   k > 0 ? 1u : acc_flag);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kW64Stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(done_bar);
+        }
+    } else if (warp >= 4) {
+        const int row = threadIdx.x - 128;        // TMEM lane = D row = (kw block, ci)
+        float* part = p.partial + static_cast<size_t>(split) * 9 * p.Cin * p.Cout;
+        const bool have_work = pt1 > pt0;
+        if (have_work) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+        }
+        const int ci = row & 63;
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+            const int kw = acc == 0 ? (row >> 6) : 2;
+            const bool valid = acc == 0 || row < 64;
+#pragma unroll 1
+            for (int n = 0; n < 3; ++n) {             // N block n <-> kh = 2 - n
+                float* dst = part + (static_cast<size_t>((2 - n) * 3 + kw) * p.Cin + ci) * p.Cout + co0;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    if (have_work) {
+                        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + acc * 192 + n * 64 + c * 32, r);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    if (valid) {
+                        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // dw[i] (+)= sum_s partial[s][i], fixed summation order.
 __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, long long n4,
                                     int splits, int accumulate) {
@@ -243,11 +393,16 @@ static int wgrad_plan(int B, int H, int W, int Cin, int Cout, WgradArgs* a, int*
     a->ci_blocks = Cin == 64 ? 1 : Cin / 128;
     a->co_blocks = Cout / nt;
     a->units = (a->mode == 0 ? 3 * a->ci_blocks : 2) * a->co_blocks;
+    const char* generic = getenv("ABL_WGRAD_GENERIC");
+    if (Cin == 64 && !(generic && generic[0] == '1')) {     // wgrad64_tc_kernel: unit = 64 output channels
+        a->mode = 2;
+        a->units = Cout / 64;
+    }
     int splits = sm_count() / a->units;
     if (splits < 1) splits = 1;
     if (splits > a->num_ptiles) splits = a->num_ptiles;
     a->splits = splits;
-    a->stage_bytes = 2 * kWgABox + (nt / 64) * kWgBBox;
+    a->stage_bytes = a->mode == 2 ? kW64Stage : 2 * kWgABox + (nt / 64) * kWgBBox;
     int stages = (227 * 1024 - 512 - kWgABox) / a->stage_bytes;
     if (stages > kWgMaxStages) stages = kWgMaxStages;
     if (stages < 2) return ABL_ERR_SHAPE;
@@ -324,12 +479,31 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
     }
     a.partial = static_cast<float*>(workspace);
     CUtensorMap mx, mdz;
-    int r = nhwc_block_map(&mx, x, B, H, W, Cin, kWgBh + 2, a.mode == 0 ? 2 : 1);
-    if (r != ABL_OK) return r;
-    r = nhwc_block_map(&mdz, dz, B, H, W, Cout, kWgBh, nt / 64);
-    if (r != ABL_OK) return r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    r = (nt == 128) ? launch_wgrad<128>(mx, mdz, a, st) : launch_wgrad<64>(mx, mdz, a, st);
+    int r;
+    if (a.mode == 2) {
+        r = nhwc_block_map(&mx, x, B, H, W, Cin, kWgBh, 1);              // plain 4 x 16 pixel tile per kw
+        if (r != ABL_OK) return r;
+        r = nhwc_block_map(&mdz, dz, B, H, W, Cout, kWgBh + 2, 1);       // haloed dZ tile, one 64-channel block
+        if (r != ABL_OK) return r;
+        constexpr int smem_bytes = kW64Stages * kW64Stage + kW64XBox + 512;
+        static bool attr_done[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_done[dev & 63]) {
+            if (cudaFuncSetAttribute(wgrad64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+                return check_launch();
+            attr_done[dev & 63] = true;
+        }
+        wgrad64_tc_kernel<<<a.units * a.splits, kWgThreads, smem_bytes, st>>>(mx, mdz, a);
+        r = check_launch();
+    } else {
+        r = nhwc_block_map(&mx, x, B, H, W, Cin, kWgBh + 2, a.mode == 0 ? 2 : 1);
+        if (r != ABL_OK) return r;
+        r = nhwc_block_map(&mdz, dz, B, H, W, Cout, kWgBh, nt / 64);
+        if (r != ABL_OK) return r;
+        r = (nt == 128) ? launch_wgrad<128>(mx, mdz, a, st) : launch_wgrad<64>(mx, mdz, a, st);
+    }
     if (r != ABL_OK) return r;
     const long long n4 = 9LL * Cin * Cout / 4;
     long long blocks = (n4 + 255) / 256;
