@@ -331,7 +331,8 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r1_ncu_step.json")) as f:
                 cap = json.load(f)["launches"]
-            fam = [r for r in cap if ("conv3x3_" in r["kernel"] or "wgrad_tc_kernel" in r["kernel"])]
+            fam = [r for r in cap if ("conv3x3_" in r["kernel"] or "wgrad_tc_kernel" in r["kernel"]
+                                     or "wgrad64_tc_kernel" in r["kernel"]) and "conv_first" not in r["kernel"]]
             if fam and B == PER_GPU_BATCH:
                 traffic = round(sum(r.get("dram_read_bytes", 0) + r.get("dram_write_bytes", 0) for r in fam) / 1e9, 3)
                 traffic_note = (f"GB per step: dram__bytes_read.sum + dram__bytes_write.sum over the {len(fam)} conv-family "
