@@ -37,6 +37,7 @@ SIGNATURES = {
     "abl_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "abl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "abl_rmsprop_flat": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+    "abl_resize_nearest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_clip_aggregate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "abl_opt_flat_dp": (_i, [_i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _f, _f, _f, _f, _vp]),
     "abl_gradcam": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

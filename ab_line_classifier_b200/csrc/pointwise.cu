@@ -350,6 +350,27 @@ __global__ void rmsprop_flat_kernel(float4* __restrict__ theta, const float4* __
     }
 }
 
+// ------------------------------------------------------------------ nearest-neighbour resize of raw uint8 frames
+// tf.image.resize(method=NEAREST_NEIGHBOR) as the reference's _parse_fn applies it (preprocessor.py:76-80): TF2 uses
+// half-pixel centres, src = min(floor((dst + 0.5) * in/out), in - 1), evaluated in fp32 like TF's kernel.  One thread
+// per output pixel (3 bytes); the result feeds block1_conv1's uint8 path, which applies vgg16.preprocess_input.
+__global__ void resize_nearest_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int B, int h,
+                                         int w, int H, int W) {
+    const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
+    const long long total = static_cast<long long>(B) * H * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % W);
+        const int oy = static_cast<int>((i / W) % H);
+        const long long n = i / (static_cast<long long>(W) * H);
+        const int iy = min(static_cast<int>(floorf((oy + 0.5f) * sy)), h - 1);
+        const int ix = min(static_cast<int>(floorf((ox + 0.5f) * sx)), w - 1);
+        const uint8_t* s = src + ((n * h + iy) * w + ix) * 3;
+        uint8_t* d = dst + i * 3;
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    }
+}
+
 // ------------------------------------------------------------------ clip-level aggregation (predict.py:159-166)
 // One warp per clip over that clip's rows of the frame-probability table.  Per clip it produces everything the three
 // reference rules need: the class-wise mean ('average', predict.py:164), the longest run of frames with
@@ -687,6 +708,15 @@ extern "C" int abl_rmsprop_flat(float* theta, const float* g, float* rms, long l
     rmsprop_flat_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(rms), n4,
         theta + n4 * 4, g + n4 * 4, rms + n4 * 4, tail, lr, rho, eps);
+    return check_launch();
+}
+
+extern "C" int abl_resize_nearest_u8(const unsigned char* src, unsigned char* dst, int B, int h, int w, int H, int W,
+                                     void* stream) {
+    if (!src || !dst) { set_error("abl_resize_nearest_u8: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) { set_error("abl_resize_nearest_u8: bad shape"); return ABL_ERR_SHAPE; }
+    const long long total = static_cast<long long>(B) * H * W;
+    resize_nearest_u8_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, B, h, w, H, W);
     return check_launch();
 }
 

@@ -102,6 +102,7 @@ class CutoffVGG16Engine:
         # overlaps the kernels of batch i
         self._slot = 0
         self._slot_u8 = [False, False]
+        self._raw = [None, None]             # device staging of raw frames that still need the resize
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._slot_ready = [None, None]      # event: H2D into the slot finished (recorded on the copy stream)
         self._slot_free = [None, None]       # event: last kernel reading the slot finished (compute stream)
@@ -319,16 +320,28 @@ class CutoffVGG16Engine:
         if x.dtype != torch.uint8:
             x = self._as_tensor(x, torch.float32)
         B = x.shape[0]
-        if tuple(x.shape[1:]) != self.input_shape:
-            raise ValueError(f"expected frames of shape {self.input_shape}, got {tuple(x.shape[1:])}")
+        u8 = x.dtype == torch.uint8
+        resize = u8 and x.dim() == 4 and x.shape[3] == 3 and tuple(x.shape[1:]) != self.input_shape
+        if tuple(x.shape[1:]) != self.input_shape and not resize:
+            raise ValueError(f"expected frames of shape {self.input_shape}, got {tuple(x.shape[1:])} "
+                             "(only raw uint8 RGB frames are resized on the device)")
         self._ensure(B, self._cap_train)
         slot = (self._slot ^ 1) if slot is None else slot
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_stream(cur) if self._slot_free[slot] is None else self._copy_stream.wait_event(
                 self._slot_free[slot])
-            u8 = x.dtype == torch.uint8
-            (self._buf["x8"] if u8 else self._buf["x"])[slot][:B].copy_(x, non_blocking=True)
+            if resize:
+                # decoded frames at their native size: nearest-neighbour resize to IMG_DIM on the device, as
+                # Preprocessor._parse_fn does on the host (preprocessor.py:76-80); the copy stream runs it
+                raw = self._raw[slot]
+                if raw is None or raw.numel() < x.numel():
+                    raw = self._raw[slot] = torch.empty(x.numel(), device=self.device, dtype=torch.uint8)
+                rv = raw[: x.numel()].view(x.shape)
+                rv.copy_(x, non_blocking=True)
+                ops.resize_nearest_u8(rv, self._buf["x8"][slot][:B])
+            else:
+                (self._buf["x8"] if u8 else self._buf["x"])[slot][:B].copy_(x, non_blocking=True)
             if y is not None:
                 self._buf["y"][slot][:B].copy_(self._as_tensor(y, torch.float32), non_blocking=True)
             ev = torch.cuda.Event()

@@ -174,6 +174,14 @@ def rmsprop_flat(theta, g, rms, lr, rho=0.9, eps=1e-7):
                  float(eps), _stream())
 
 
+def resize_nearest_u8(src, dst):
+    """src uint8 [B,h,w,3] -> dst uint8 [B,H,W,3], tf.image.resize NEAREST_NEIGHBOR semantics (abl_resize_nearest_u8)."""
+    _chk(src, torch.uint8, "src"); _chk(dst, torch.uint8, "dst")
+    B, h, w, _ = src.shape
+    assert dst.shape[0] == B and dst.shape[3] == 3 and src.shape[3] == 3
+    _native.call("abl_resize_nearest_u8", _ptr(src), _ptr(dst), B, h, w, dst.shape[1], dst.shape[2], _stream())
+
+
 def clip_aggregate(probs, clip_offsets, b_idx, threshold, window):
     """probs fp32 [N,n] (device), clip_offsets int64 [n_clips+1] (device) -> (mean [n_clips,n], run int32 [n_clips],
     win fp32 [n_clips]); see abl_clip_aggregate."""

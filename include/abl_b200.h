@@ -134,6 +134,11 @@ int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n,
 int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, float lr, float rho, float eps,
                      void* stream);
 
+/* tf.image.resize(image, IMG_DIM, method=NEAREST_NEIGHBOR) of the reference's input pipeline (src/data/preprocessor.py:
+ * 76-80) on raw uint8 RGB frames: src [B,h,w,3] -> dst [B,H,W,3], TF2 half-pixel-centre rule
+ * src_index = min(floor((dst_index + 0.5) * in / out), in - 1).  The output is what abl_conv_first_*_u8 consume. */
+int abl_resize_nearest_u8(const unsigned char* src, unsigned char* dst, int B, int h, int w, int H, int W, void* stream);
+
 /* Clip-level aggregation of frame probabilities (src/predict.py:159-166 with the helpers at 283-308 and 365-376),
  * all clips in one launch instead of the reference's per-clip Python loop.  probs fp32 [N_frames, n_classes] with the
  * frames of clip c in rows clip_offsets[c] .. clip_offsets[c+1]-1 (clip_offsets: n_clips+1 int64, device).

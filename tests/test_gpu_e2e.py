@@ -68,6 +68,19 @@ def test_cuda_graph_forward_is_bit_identical_to_launch_by_launch(setup, B):
     eng.set_weights(params)
 
 
+def test_raw_frames_of_another_size_are_resized_on_the_device(setup):
+    """Decoded frames at native resolution (uint8 RGB): nearest-neighbour resize (preprocessor.py:80) + vgg16
+    preprocessing (preprocessor.py:60-63) both happen on the GPU and give the logits of the host-prepared frames."""
+    from oracle import preprocess
+    eng, _ = setup
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 256, size=(6, 240, 320, 3), dtype=np.uint8)
+    p_dev = eng.predict_batch(raw, use_graph=False).clone()
+    x_host = preprocess.vgg16_preprocess(preprocess.nearest_resize_tf(raw, (128, 128)))
+    p_host = eng.predict_batch(x_host, use_graph=False).clone()
+    assert torch.equal(p_dev, p_host)
+
+
 def test_forward_matches_golden_fixture(setup):
     eng, _ = setup
     g = np.load(GOLD)

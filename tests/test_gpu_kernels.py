@@ -321,6 +321,18 @@ def test_gradcam_matches_closed_form_oracle():
         assert heat[4].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("h,w", [(128, 128), (300, 400), (64, 64), (97, 131), (480, 640), (1, 1)])
+def test_resize_nearest_u8_matches_tf_semantics_bit_exactly(h, w):
+    """f1: tf.image.resize(NEAREST_NEIGHBOR) of preprocessor.py:80 on raw uint8 frames (down-, up-sampling, odd sizes)."""
+    ops = _ops()
+    from oracle import preprocess
+    rng = np.random.default_rng(h * 1000 + w)
+    src = rng.integers(0, 256, size=(3, h, w, 3), dtype=np.uint8)
+    dst = torch.zeros(3, 128, 128, 3, device="cuda", dtype=torch.uint8)
+    ops.resize_nearest_u8(torch.from_numpy(src).cuda(), dst)
+    np.testing.assert_array_equal(dst.cpu().numpy(), preprocess.nearest_resize_tf(src, (128, 128)))
+
+
 def test_clip_aggregate_matches_reference_rules_bit_exactly_on_runs():
     """f2: every clip in one launch vs the loop-for-loop restatement of predict.py:283-308, 365-376, 164.  Ragged clips:
     empty-ish (1 frame), shorter than the window, exactly the window, long; runs touching both ends."""
