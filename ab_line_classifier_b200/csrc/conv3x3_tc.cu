@@ -22,6 +22,7 @@
 
 namespace abl {
 
+constexpr int ABL_MAIN_WS_PAIRS = 1 << 8;     // internal: weight-stationary MMAs in the N = 64 main loop
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements per k-block row = 128 bytes
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KiB
@@ -543,6 +544,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                         tc_fence_after();
                         const uint32_t b_lo = b_lo0 + sb * (Cfg::kBStage >> 4);
+                        if (NTILE == 64 && MSUB == 2 && (p.flags & ABL_MAIN_WS_PAIRS)) {
+                            // weight-stationary MMA pairs: the two sub-tiles share one shared-memory read of B
+#pragma unroll
+                            for (int t = 0; t < Cfg::kTPB; ++t) {
+                                const int kh = g * Cfg::kTPB + t;
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k) {
+                                    umma_bf16_lohi_ws<0>(tmem_d, a_lo + kh * (2048 >> 4) + k * 2, dhi,
+                                                         b_lo + t * (Cfg::kBTap >> 4) + k * 2, dhi, idesc,
+                                                         (s | kh | k) != 0 ? 1u : 0u);
+                                    umma_bf16_lohi_ws<1>(tmem_d + NTILE, a_lo + (Cfg::kSubH + kh) * (2048 >> 4) + k * 2, dhi,
+                                                         b_lo + t * (Cfg::kBTap >> 4) + k * 2, dhi, idesc,
+                                                         (s | kh | k) != 0 ? 1u : 0u);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int t = 0; t < Cfg::kTPB; ++t) {
                             const int kh = g * Cfg::kTPB + t;
@@ -557,6 +574,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                                    (s | kh | k) != 0 ? 1u : 0u);
                                 }
                             }
+                        }
                         }
                         if (!BRES) {
                             umma_commit(&bempty_bar[sb]);     // filter slab free when these MMAs retire
@@ -826,6 +844,12 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
         a.num_n_tiles = Cout / ntile;
         a.kchunks = Cin / kBlockK;
         a.flags = flags;
+        {
+            // N = 64: weight-stationary MMA pairs (tcgen05.mma.ws, collector b0 fill -> lastuse): the two sub-tiles of
+            // a tile share one shared-memory read of each filter slice; measured +4 % on B200.  ABL_N64_WS=0 disables.
+            const char* ws = getenv("ABL_N64_WS");
+            if (!(ws && ws[0] == '0')) a.flags |= ABL_MAIN_WS_PAIRS;
+        }
         a.bias = bias;
         a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
         a.out_full = static_cast<__nv_bfloat16*>(out_full);
