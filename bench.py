@@ -98,7 +98,7 @@ def synth_batches(n_batches, batch, seed):
     return xs, ys, raw
 
 
-def cpu_train_frames_per_s(batch, iters, threads):
+def cpu_train_frames_per_s(batch, iters, threads, warmup=1):
     """torch-CPU fp32 restatement of the Keras train step (oracle port): fwd + loss + full backward + Adam."""
     import torch
     from oracle import oracle, synth
@@ -110,13 +110,13 @@ def cpu_train_frames_per_s(batch, iters, threads):
     m = {k: np.zeros_like(v) for k, v in params.items()}
     v = {k: np.zeros_like(p) for k, p in params.items()}
     times = []
-    for it in range(iters + 1):
+    for it in range(iters + warmup):
         t0 = time.perf_counter()
         _, grads, _ = oracle.loss_and_grads(params, x, y, None, mask)
         for k in params:
             params[k], m[k], v[k] = oracle.adam_step(params[k], grads[k], m[k], v[k], it + 1)
         dt = time.perf_counter() - t0
-        if it > 0:
+        if it >= warmup:
             times.append(dt)
     return batch / (sum(times) / len(times)), sum(times) / len(times)
 
@@ -130,11 +130,12 @@ def run_reference(args):
     t_all0 = time.perf_counter()
     # warm-up + timed "steps": each step is one B=32 train step (bounded sample of the B=256 workload)
     fps_list = []
-    n_iter = max(1, min(args.steps, 8))
-    fps, sec = cpu_train_frames_per_s(batch, n_iter, threads)
+    n_iter = max(1, min(args.steps, 8))          # bounded sample: the whole arm ends within a few minutes
+    n_warm = max(1, min(args.warmup, 2))
+    fps, sec = cpu_train_frames_per_s(batch, n_iter, threads, n_warm)
     line = {
         "impl": "reference", "metric": "cutoffvgg16 train frames/sec", "value": fps, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": n_iter, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": n_iter, "warmup": n_warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus, batch_note=f"CPU sample: batch {batch} per step"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
