@@ -19,7 +19,7 @@ _u, _ull = C.c_uint, C.c_ulonglong
 SIGNATURES = {
     "abl_abi_version": (_i, []),
     "abl_last_error": (C.c_char_p, []),
-    "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "abl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "abl_bias_grad": (_i, [_vp, _vp, _ll, _i, _vp]),
@@ -30,6 +30,7 @@ SIGNATURES = {
     "abl_prep_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "abl_prep_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "abl_maxpool_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_maxpool_bwd_code": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "abl_gap_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "abl_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _ull, _u, _u,
@@ -65,7 +66,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abl_abi_version() != 2:
+    if lib.abl_abi_version() != 3:
         raise RuntimeError("libabl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -39,7 +39,35 @@ struct ConvArgs {
     __nv_bfloat16* out_full;        // [B,H,W,Cout] or null
     __nv_bfloat16* out_pool;        // [B,H/2,W/2,Cout] or null
     float* colsum;                  // [Cout] fp32 += column sums of out_full (fused BiasAddGrad) or null
+    uint16_t* pool_code;            // [B,H/2,W/2,Cout/8]: 2-bit index of the window's first maximum per channel, or null
 };
+
+// 2x2 max-pool of 8 channels (four packed bf16x2 words per window element) + optional routing code: for every
+// channel the 2-bit index (window scan order a, b, c, d) of the FIRST element equal to the maximum -- the element
+// TF's MaxPoolGrad routes the gradient to.  Channel k of the chunk occupies bits [2k, 2k+1] of the 16-bit code.
+// Values are post-ReLU (>= +0, never -0), so bit equality is value equality.
+__device__ __forceinline__ void pool8(const uint4& a, const uint4& b, const uint4& c, const uint4& d, uint32_t (&o)[4],
+                                      uint32_t& code, bool want_code) {
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    code = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]),
+                                          *reinterpret_cast<const __nv_bfloat162*>(&bv[j]));
+        const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]),
+                                          *reinterpret_cast<const __nv_bfloat162*>(&dv[j]));
+        const __nv_bfloat162 m2 = __hmax2(m0, m1);
+        o[j] = *reinterpret_cast<const uint32_t*>(&m2);
+        if (want_code) {
+            const uint32_t ea = __vcmpeq2(av[j], o[j]), eb = __vcmpeq2(bv[j], o[j]), ec = __vcmpeq2(cv[j], o[j]);
+            const uint32_t bit0 = ~ea & (eb | ~ec);      // index 1 or 3
+            const uint32_t bit1 = ~ea & ~eb;             // index 2 or 3
+            const uint32_t w = (bit0 & 0x00010001u) | (bit1 & 0x00020002u);   // lo channel: bits 0-1, hi channel: bits 16-17
+            code |= ((w & 3u) | ((w >> 14) & 0xCu)) << (4 * j);
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Epilogue of ONE 128-pixel x NTILE accumulator (shared by both main-loop variants), run by the 8
@@ -193,22 +221,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
                 const uint4 b = *reinterpret_cast<const uint4*>(bx + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
                 const uint4 c2 = *reinterpret_cast<const uint4*>(bx + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
                 const uint4 d = *reinterpret_cast<const uint4*>(bx + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
-                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-                const uint32_t cv[4] = {c2.x, c2.y, c2.z, c2.w}, dv[4] = {d.x, d.y, d.z, d.w};
-                uint32_t o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]),
-                                                      *reinterpret_cast<const __nv_bfloat162*>(&bv[j]));
-                    const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]),
-                                                      *reinterpret_cast<const __nv_bfloat162*>(&dv[j]));
-                    const __nv_bfloat162 m2 = __hmax2(m0, m1);
-                    o[j] = *reinterpret_cast<const uint32_t*>(&m2);
-                }
+                uint32_t o[4], code;
+                pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
                 const int h = (h0 >> 1) + ph, w = (w0 >> 1) + pw;
                 const size_t off =
                     ((static_cast<size_t>(img) * (p.H >> 1) + h) * (p.W >> 1) + w) * p.Cout + cbase + cc * 8;
                 *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
             }
         }
     }
@@ -686,21 +705,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint4 b = *reinterpret_cast<const uint4*>(stg + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
                         const uint4 c2 = *reinterpret_cast<const uint4*>(stg + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
                         const uint4 d = *reinterpret_cast<const uint4*>(stg + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
-                        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-                        const uint32_t cv[4] = {c2.x, c2.y, c2.z, c2.w}, dv[4] = {d.x, d.y, d.z, d.w};
-                        uint32_t o[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&av[j]),
-                                                              *reinterpret_cast<const __nv_bfloat162*>(&bv[j]));
-                            const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&cv[j]),
-                                                              *reinterpret_cast<const __nv_bfloat162*>(&dv[j]));
-                            const __nv_bfloat162 m2 = __hmax2(m0, m1);
-                            o[j] = *reinterpret_cast<const uint32_t*>(&m2);
-                        }
+                        uint32_t o[4], code;
+                        pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
                         const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1) + ph) * (p.W >> 1) +
                                             (w0 >> 1) + pw) * p.Cout + n0 + c8 * 8;
                         *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                        if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
                     }
                 }
             }
@@ -800,9 +810,10 @@ using namespace abl;
 extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
 
 extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                                 void* out_full, void* out_pool, float* colsum, int B, int H, int W, int Cin,
-                                 int Cout, int flags, void* stream) {
+                                 void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B,
+                                 int H, int W, int Cin, int Cout, int flags, void* stream) {
     if (colsum && !out_full) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
+    if (pool_code && !out_pool) { set_error("abl_conv3x3_igemm: pool_code needs out_pool"); return ABL_ERR_NULL; }
     if (!x || !w_kmajor) { set_error("abl_conv3x3_igemm: null input"); return ABL_ERR_NULL; }
     if (!out_full && !out_pool) { set_error("abl_conv3x3_igemm: no output requested"); return ABL_ERR_NULL; }
     if ((flags & ABL_EPI_BIAS_RELU) && !bias) { set_error("abl_conv3x3_igemm: bias missing"); return ABL_ERR_NULL; }
@@ -854,6 +865,7 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
         a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
         a.out_full = static_cast<__nv_bfloat16*>(out_full);
         a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
+        a.pool_code = pool_code;
         // fused BiasAddGrad: the 8-warp epilogue with a single N tile; otherwise a separate pass over out_full
         const bool fuse_colsum = colsum != nullptr && ntile != 64 && a.num_n_tiles == 1;
         a.colsum = fuse_colsum ? colsum : nullptr;
@@ -905,6 +917,7 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
     a.out_full = static_cast<__nv_bfloat16*>(out_full);
     a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
+        a.pool_code = pool_code;
 
     CUtensorMap ma, mb;
     {

@@ -128,6 +128,50 @@ maxpool_bwd_relu_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ 
     if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
 }
 
+// MaxPoolGrad from the 2-bit routing codes the forward epilogue stored (abl_conv3x3_igemm pool_code): the
+// full-resolution activation is neither kept nor re-read.  dp must already carry the ReLU mask of the pooled value
+// (the dgrad that produces it runs with ABL_EPI_RELU_MASK against the pooled tensor: relu'(max) == relu' of the
+// routed element).  Traffic per full-resolution element: 2 B written + 0.56 B read (was 2 + 3 B).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_code_kernel(const uint4* __restrict__ dp, const uint16_t* __restrict__ code, uint4* __restrict__ dz, int B,
+                        int H, int W, int C8, float* __restrict__ db) {
+    extern __shared__ float red[];
+    float bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int PH = H >> 1, PW = W >> 1;
+    const long long total = static_cast<long long>(B) * PH * PW * C8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C8);
+        long long r = i / C8;
+        const int pw = static_cast<int>(r % PW);
+        r /= PW;
+        const int ph = static_cast<int>(r % PH);
+        const int n = static_cast<int>(r / PH);
+        const uint4 g = __ldg(dp + i);
+        const uint32_t cd = __ldg(code + i);
+        const uint32_t gv[4] = {g.x, g.y, g.z, g.w};
+        const long long base = ((static_cast<long long>(n) * H + 2 * ph) * W + 2 * pw) * C8 + c;
+        const long long offs[4] = {base, base + C8, base + static_cast<long long>(W) * C8,
+                                   base + static_cast<long long>(W) * C8 + C8};
+        uint32_t out[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = (cd >> (4 * j)) & 3u, hi = (cd >> (4 * j + 2)) & 3u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                out[k][j] = (lo == static_cast<uint32_t>(k) ? (gv[j] & 0xFFFFu) : 0u) |
+                            (hi == static_cast<uint32_t>(k) ? (gv[j] & 0xFFFF0000u) : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dz[offs[k]] = make_uint4(out[k][0], out[k][1], out[k][2], out[k][3]);
+        if (db != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { bacc[2 * j] += bf16_lo(gv[j]); bacc[2 * j + 1] += bf16_hi(gv[j]); }
+        }
+    }
+    if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
+}
+
 // ------------------------------------------------------------------ global average pool
 // grid = (B, C/64): each block reduces HW rows x 64 channels (128 B per row) of one frame.
 __global__ void __launch_bounds__(256) gap_fwd_kernel(const uint4* __restrict__ a, float* __restrict__ gap,
@@ -626,6 +670,21 @@ extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* p
                               static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(dp), static_cast<const uint4*>(a), static_cast<const uint4*>(pooled),
         static_cast<uint4*>(dz), B, H, W, C / 8, fuse ? db : nullptr);
+    int r = check_launch();
+    if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, C, stream);
+    return r;
+}
+
+extern "C" int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db, int B, int H,
+                                    int W, int C, void* stream) {
+    if (!dp || !pool_code || !dz) { set_error("abl_maxpool_bwd_code: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_code: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    const bool fuse = db != nullptr && (256 % (C / 8)) == 0;
+    maxpool_bwd_code_kernel<<<grid_for(total, 256, 16), 256, fuse ? 256 * 8 * sizeof(float) : 0,
+                              static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(dp), pool_code,
+                                                                   static_cast<uint4*>(dz), B, H, W, C / 8,
+                                                                   fuse ? db : nullptr);
     int r = check_launch();
     if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, C, stream);
     return r;

@@ -84,6 +84,8 @@ class CutoffVGG16Engine:
         # all-reduce + local optimizer (ABL_DP_FUSED=0, and always for apply_update=False gradient inspection)
         import os
         self.fused_dp = os.environ.get("ABL_DP_FUSED", "1") != "0"
+        # training keeps 2-bit max-pool routing codes instead of the pre-pool activations (ABL_POOL_CODES=0: keep them)
+        self.pool_codes = os.environ.get("ABL_POOL_CODES", "1") != "0"
         self.step_count = 0           # dropout counter
         self.opt_steps = {}           # optimizer name -> steps taken (Adam bias correction)
         self._alloc_params(output_bias)
@@ -230,7 +232,15 @@ class CutoffVGG16Engine:
         for s in self.specs:
             if s.pool:
                 b["pool_" + s.name] = torch.empty(cap, s.h // 2, s.w // 2, s.cout, device=dev, dtype=bf)
-            if not s.pool or training:
+                if training:
+                    if self.pool_codes:
+                        # 2-bit routing codes of the fused max-pool (1/8 of the pooled bytes) replace the
+                        # full-resolution activation that MaxPoolGrad would otherwise have to keep and re-read
+                        b["code_" + s.name] = torch.empty(cap, s.h // 2, s.w // 2, s.cout // 8, device=dev,
+                                                          dtype=torch.int16)
+                    else:
+                        b["act_" + s.name] = torch.empty(cap, s.h, s.w, s.cout, device=dev, dtype=bf)
+            else:
                 b["act_" + s.name] = torch.empty(cap, s.h, s.w, s.cout, device=dev, dtype=bf)
             max_full = max(max_full, s.h * s.w * s.cout)
         C = self.feat_shape[2]
@@ -279,8 +289,9 @@ class CutoffVGG16Engine:
                 if s.pool:
                     raise NotImplementedError("a pool directly after block1_conv1 is not a VGG16 prefix")
             else:
+                code = b.get("code_" + s.name)
                 ops.conv3x3_igemm(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"), None,
-                                  full, pooled, ops.EPI_BIAS_RELU)
+                                  full, pooled, ops.EPI_BIAS_RELU, pool_code=code[:B] if code is not None else None)
         last = self.specs[-1]
         feat = b["pool_" + last.name][:B] if last.pool else b["act_" + last.name][:B]
         ops.gap_fwd(feat, b["gap"][:B])
@@ -460,10 +471,17 @@ class CutoffVGG16Engine:
                 prev = self.specs[li - 1]
                 if prev.pool:
                     dp = b["dp"][: B * s.h * s.w * s.cin].view(B, s.h, s.w, s.cin)
-                    ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, None, dp, None, 0)
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
-                    ops.maxpool_bwd_relu(dp, b["act_" + prev.name][:B], b["pool_" + prev.name][:B], ndz,
-                                         bias_grad_of(li - 1))
+                    code = b.get("code_" + prev.name)
+                    if code is not None:
+                        # relu'(pooled) in the dgrad epilogue, then routing by the forward's 2-bit codes
+                        ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["pool_" + prev.name][:B], dp, None,
+                                          ops.EPI_RELU_MASK)
+                        ops.maxpool_bwd_code(dp, code[:B], ndz, bias_grad_of(li - 1))
+                    else:
+                        ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, None, dp, None, 0)
+                        ops.maxpool_bwd_relu(dp, b["act_" + prev.name][:B], b["pool_" + prev.name][:B], ndz,
+                                             bias_grad_of(li - 1))
                 else:
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
                     ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["act_" + prev.name][:B], ndz, None,

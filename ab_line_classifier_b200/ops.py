@@ -28,9 +28,10 @@ def _chk(t, dtype, name):
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
-def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool=None, flags=0, colsum=None):
+def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool=None, flags=0, colsum=None,
+                  pool_code=None):
     """x bf16 [B,H,W,Cin]; w_kmajor bf16 [9,Cout,Cin]; see include/abl_b200.h abl_conv3x3_igemm."""
-    _chk(colsum, torch.float32, "colsum")
+    _chk(colsum, torch.float32, "colsum"); _chk(pool_code, torch.int16, "pool_code")
     for t, n in ((x, "x"), (w_kmajor, "w"), (mask_src, "mask_src"), (out_full, "out_full"), (out_pool, "out_pool")):
         _chk(t, torch.bfloat16, n)
     _chk(bias, torch.float32, "bias")
@@ -44,7 +45,7 @@ def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool
     if mask_src is not None:
         assert mask_src.shape == (B, H, W, Cout)
     _native.call("abl_conv3x3_igemm", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(mask_src), _ptr(out_full),
-                 _ptr(out_pool), _ptr(colsum), B, H, W, Cin, Cout, flags, _stream())
+                 _ptr(out_pool), _ptr(pool_code), _ptr(colsum), B, H, W, Cin, Cout, flags, _stream())
 
 
 def wgrad_workspace_bytes(B, H, W, Cin, Cout):
@@ -124,6 +125,14 @@ def maxpool_bwd_relu(dp, a, pooled, dz, db=None):
     _chk(db, torch.float32, "db")
     B, H, W, Cc = a.shape
     _native.call("abl_maxpool_bwd_relu", _ptr(dp), _ptr(a), _ptr(pooled), _ptr(dz), _ptr(db), B, H, W, Cc, _stream())
+
+
+def maxpool_bwd_code(dp, pool_code, dz, db=None):
+    """dz from the forward's 2-bit routing codes; dp must already carry relu'(pooled) (abl_maxpool_bwd_code)."""
+    _chk(dp, torch.bfloat16, "dp"); _chk(dz, torch.bfloat16, "dz"); _chk(pool_code, torch.int16, "pool_code")
+    _chk(db, torch.float32, "db")
+    B, H, W, Cc = dz.shape
+    _native.call("abl_maxpool_bwd_code", _ptr(dp), _ptr(pool_code), _ptr(dz), _ptr(db), B, H, W, Cc, _stream())
 
 
 def gap_fwd(a, gap):

@@ -309,9 +309,9 @@ def main():
             k = kernels.setdefault(name, {"calls": 0, "ms": 0.0, "gflop": 0.0})
             k["calls"] += 1
             k["ms"] += t
-            if name == "abl_conv3x3_igemm":
-                fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
-            elif name == "abl_conv3x3_wgrad":
+            if name == "abl_conv3x3_igemm":        # (x, w, bias, mask, full, pool, code, colsum, B, H, W, Cin, Cout, ...)
+                fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
+            elif name == "abl_conv3x3_wgrad":      # (x, dz, dw, db, ws, ws_bytes, acc, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
             else:
                 fl = 0.0

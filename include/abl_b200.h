@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 2
+#define ABL_ABI_VERSION 3
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -48,12 +48,15 @@ const char* abl_last_error(void);
  *   bias     fp32 [Cout]           (ABL_EPI_BIAS_RELU)
  *   mask_src bf16 [B,H,W,Cout]     (ABL_EPI_RELU_MASK; post-ReLU activation of the layer below)
  *   out_full bf16 [B,H,W,Cout] or NULL;  out_pool bf16 [B,H/2,W/2,Cout] (2x2/s2 max) or NULL
+ *   pool_code uint16 [B,H/2,W/2,Cout/8] or NULL (needs out_pool): per pooled element the 2-bit index (window scan
+ *            order) of the FIRST maximum, channel k of an 8-channel chunk in bits [2k,2k+1] -- what MaxPoolGrad needs,
+ *            so training keeps neither the full-resolution activation nor re-reads it (abl_maxpool_bwd_code)
  *   colsum   fp32 [Cout] or NULL: colsum[c] += sum_{n,h,w} out_full[n,h,w,c] -- with the dgrad epilogue this is
  *            TF's BiasAddGrad of the layer below, fused so its dZ is not read a second time (needs out_full)
  * Requires Cin, Cout multiples of 64 (<= 512), H*W tileable into 128-pixel rectangles. */
 int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                      void* out_full, void* out_pool, float* colsum, int B, int H, int W, int Cin, int Cout,
-                      int flags, void* stream);
+                      void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B, int H, int W,
+                      int Cin, int Cout, int flags, void* stream);
 
 /* Conv2DBackpropFilter (+BiasAddGrad) of model.fit's tape (models.py:427,432) as a tcgen05 GEMM with
  * MN-major operands read straight from the NHWC tensors, split over pixel slices into `workspace`
@@ -100,6 +103,12 @@ int abl_prep_conv_weights_multi(const float* const* w_hwio, void* const* w_fwd, 
  * db fp32 [C] or NULL: db[c] += sum dz[..., c] (BiasAddGrad of the conv above the pool, fused). */
 int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db, int B, int H,
                          int W, int C, void* stream);
+
+/* MaxPoolGrad from the routing codes of abl_conv3x3_igemm (pool_code): dz[n,h,w,c] = dp[n,h/2,w/2,c] for the window
+ * element the code names, else 0.  dp must already be masked by relu'(pooled) (run the dgrad that produces it with
+ * ABL_EPI_RELU_MASK and mask_src = the pooled activation).  db as in abl_maxpool_bwd_relu. */
+int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db, int B, int H, int W,
+                         int C, void* stream);
 
 /* GlobalAveragePooling2D (models.py:414): gap[n][c] = mean_{hw} a[n,hw,c]; a bf16, gap fp32. */
 int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream);

@@ -219,6 +219,40 @@ def test_maxpool_backward_routes_to_first_max_and_relu_masks():
     _close(db - 0.25, ref.sum(dim=(0, 1, 2)), 1e-5, "fused bias grad (maxpool bwd)")
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 64, 128, 128), (128, 128, 64, 64)])
+def test_pool_routing_codes_reproduce_maxpool_backward_bit_exactly(cin, cout, H, W, igemm_variant):
+    """Training keeps 2-bit routing codes from the fused max-pool epilogue instead of the pre-pool activation:
+    MaxPoolGrad + ReluGrad through the codes must equal the activation-based kernel bit for bit (first maximum wins,
+    zero windows give no gradient)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin + H)
+    B = 2
+    x = _bf(torch.randn(B, H, W, cin, generator=g) * 0.5)
+    x[0, :6, :6, :] = 0                                   # all-zero windows after ReLU (bias <= 0 there)
+    w = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = -torch.rand(cout, generator=g) * 0.05
+    wf = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w.cuda(), wf, None)
+    full = torch.empty(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    pooled = torch.empty(B, H // 2, W // 2, cout, device="cuda", dtype=torch.bfloat16)
+    code = torch.zeros(B, H // 2, W // 2, cout // 8, device="cuda", dtype=torch.int16)
+    ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, full, pooled, ops.EPI_BIAS_RELU, pool_code=code)
+    dp = (torch.randn(B, H // 2, W // 2, cout, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dz_ref = torch.empty_like(full)
+    db_ref = torch.zeros(cout, device="cuda")
+    ops.maxpool_bwd_relu(dp, full, pooled, dz_ref, db_ref)
+    dp_masked = torch.where(pooled > 0, dp, torch.zeros_like(dp))      # what the dgrad epilogue does (relu'(pooled))
+    dz = torch.full_like(full, float("nan"))
+    db = torch.zeros(cout, device="cuda")
+    ops.maxpool_bwd_code(dp_masked, code, dz, db)
+    assert torch.equal(dz, dz_ref)
+    _close(db, db_ref, 1e-5, "bias grad through routing codes")
+    # pooled-only (inference-style) launch writes the same codes
+    code2 = torch.zeros_like(code)
+    ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, None, pooled, ops.EPI_BIAS_RELU, pool_code=code2)
+    assert torch.equal(code, code2)
+
+
 def test_gap_forward_backward():
     ops = _ops()
     g = torch.Generator().manual_seed(3)

@@ -27,7 +27,7 @@ for r in range(reps):
     recs, _native.timing = _native.timing, None
     for i, (name, a, e0, e1) in enumerate(recs):
         if name == "abl_conv3x3_igemm":
-            shape = (a[7], a[8], a[9], a[10], a[11], a[12]); fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
+            shape = (a[8], a[9], a[10], a[11], a[12], a[13]); fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
         elif name == "abl_conv3x3_wgrad":
             shape = (a[7], a[8], a[9], a[10], a[11]); fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
         else:
