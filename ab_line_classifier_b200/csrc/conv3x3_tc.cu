@@ -80,13 +80,17 @@ __device__ __forceinline__ void pool8(const uint4& a, const uint4& b, const uint
 //   (img,h0,w0): origin of the box_h x box_w pixel rectangle; n0 = first output channel
 //   wait_bar : accumulator-full barrier to wait on before the first TMEM read (nullptr: already waited)
 //   arrive_bar: accumulator-empty barrier to arrive on after the last TMEM read (nullptr: none)
+//   next_origin: element offset in mask_src of the (h0, w0, channel 0) corner of the NEXT rectangle this thread group
+//              will process, or -1: the ReLU-mask line each thread needs for its next pass is prefetched into L2 one
+//              pass ahead (ncu: the mask load's HBM latency was ~10 % of the dgrad epilogue's stall samples)
 //   csum     : shared-memory fp32 [NTILE] column sums of the bf16 values written (fused BiasAddGrad of the
 //              tensor this kernel produces; the caller flushes it to global memory once per CTA) or nullptr
 template <int NTILE, int kEpiN, int kStgBufs>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorMap* map_out, uint8_t* staging,
                                               uint32_t tmem_acc, int img, int h0, int w0, int n0, int box_w,
                                               int et, uint32_t& pass_ctr, uint64_t* wait_bar, uint32_t wait_phase,
-                                              uint64_t* arrive_bar, float* csum = nullptr) {
+                                              uint64_t* arrive_bar, float* csum = nullptr,
+                                              long long next_origin = -1) {
     constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
     constexpr int kPasses = NTILE / kEpiN;
     constexpr int kColsPerWarp = kEpiN / 2;      // 32 or 64
@@ -106,6 +110,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
             const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix_off + n0 + col0);
 #pragma unroll
             for (int j = 0; j < kChunks * 4; ++j) mk[j] = __ldg(mp + j);
+            // next pass: same pixel, next column block; after the last pass: same thread position in the next rectangle
+            const __nv_bfloat16* nx = nullptr;
+            if (pass + 1 < kPasses) nx = p.mask_src + pix_off + n0 + col0 + kEpiN;
+            else if (next_origin >= 0)
+                nx = p.mask_src + next_origin + (static_cast<size_t>(ph_row) * p.W + pw_col) * p.Cout + n0 + hsel * kColsPerWarp;
+            if (nx != nullptr) {
+#pragma unroll
+                for (int j = 0; j < kChunks; ++j)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + j * 32));
+            }
         }
         if (pass == 0 && wait_bar != nullptr) {
             mbar_wait(wait_bar, wait_phase);
@@ -728,10 +742,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int as = it & 1;
 #pragma unroll 1
             for (int sub = 0; sub < MSUB; ++sub) {
+                long long next_origin = -1;           // where this thread's next ReLU-mask line lives (L2 prefetch)
+                if (p.flags & ABL_EPI_RELU_MASK) {
+                    if (sub + 1 < MSUB) {
+                        next_origin = ((static_cast<long long>(img) * p.H + th * kTileH + (sub + 1) * Cfg::kSubH) * p.W +
+                                       tw * Cfg::kTileW) * p.Cout;
+                    } else if (tile + static_cast<int>(gridDim.x) < num_tiles) {
+                        int m2 = (tile + gridDim.x) / p.num_n_tiles;
+                        const int tw2 = m2 % p.tiles_w;
+                        m2 /= p.tiles_w;
+                        const int th2 = m2 % p.tiles_h, img2 = m2 / p.tiles_h;
+                        next_origin = ((static_cast<long long>(img2) * p.H + th2 * kTileH) * p.W + tw2 * Cfg::kTileW) * p.Cout;
+                    }
+                }
                 epilogue_tile<NTILE, Cfg::kEpiN, Cfg::kStgBufs>(
                     p, &map_out, staging, tmem_base + (as * MSUB + sub) * NTILE, img, th * kTileH + sub * Cfg::kSubH,
                     tw * Cfg::kTileW, n_tile * NTILE, Cfg::kTileW, et, pass_ctr, sub == 0 ? &tfull_bar[as] : nullptr,
-                    (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr, p.colsum != nullptr ? csum : nullptr);
+                    (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr, p.colsum != nullptr ? csum : nullptr,
+                    next_origin);
             }
         }
         if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits

@@ -37,6 +37,7 @@ struct WgradArgs {
     int co_blocks;       // Cout/NT
     int units, splits, stages, stage_bytes;
     float* partial;      // [splits][9][Cin][Cout] fp32
+    float* db;           // wgrad64 only: bias gradient [Cout] (atomic accumulation) or null
 };
 
 template <int NT>
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                   const WgradArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* zero_blk = smem + kW64Stages * kW64Stage;
+    uint8_t* zero_blk = smem + kW64Stages * kW64Stage;      // (holds ones, see below)
     uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + kW64XBox);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgMaxStages;
@@ -238,7 +239,10 @@ wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
-    for (int i = threadIdx.x; i < kW64XBox / 16; i += blockDim.x) reinterpret_cast<uint4*>(zero_blk)[i] = make_uint4(0, 0, 0, 0);
+    // rows 64..127 of the second MMA pair with no kw tap: instead of zeros they hold bf16 1.0, so those accumulator
+    // rows become sum_pixels dZ = the bias gradient (BiasAddGrad for free: the MMAs were issued anyway)
+    for (int i = threadIdx.x; i < kW64XBox / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(zero_blk)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -327,6 +331,10 @@ wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         for (int j = 0; j < 8; ++j)
                             d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    } else if (row == 64 && n == 1 && p.db != nullptr && have_work) {
+                        // ones row x un-shifted dZ window: every pixel of this CTA's slice exactly once
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(p.db + co0 + c * 32 + j, __uint_as_float(r[j]));
                     }
                 }
             }
@@ -478,6 +486,7 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
         set_error("abl_conv3x3_wgrad: pointers must be 16-byte aligned"); return ABL_ERR_ALIGN;
     }
     a.partial = static_cast<float*>(workspace);
+    a.db = a.mode == 2 ? db : nullptr;
     CUtensorMap mx, mdz;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int r;
@@ -513,6 +522,6 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
                                                                 reinterpret_cast<float4*>(dw), n4, a.splits, accumulate);
     r = check_launch();
     if (r != ABL_OK) return r;
-    if (db) return abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, Cout, stream);
+    if (db && a.mode != 2) return abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, Cout, stream);
     return ABL_OK;
 }

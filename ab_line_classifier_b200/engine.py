@@ -453,8 +453,13 @@ class CutoffVGG16Engine:
         # BiasAddGrad of a layer is fused into whichever kernel PRODUCES that layer's dZ (GAP backward, max-pool
         # backward, or the dgrad epilogue of the layer above), so dZ is never re-read for it; block1_conv1's
         # bias gradient comes out of its own wgrad GEMM (ones column).
+        # ... except for Cin == 64 layers, whose wgrad GEMM has idle accumulator rows that a ones block turns
+        # into the bias gradient for free (wgrad64_tc_kernel).
+        def wgrad_has_bias(i):
+            return i > 0 and self.specs[i].cin == 64 and ops.wgrad_fuses_bias(self.specs[i].cin)
+
         def bias_grad_of(i):
-            return self.view(self.specs[i].name + "/bias", self.grad) if (tr[i] and i > 0) else None
+            return self.view(self.specs[i].name + "/bias", self.grad) if (tr[i] and i > 0 and not wgrad_has_bias(i)) else None
 
         ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, bias_grad_of(nconv - 1))
         for li in range(nconv - 1, lowest - 1, -1):
@@ -464,7 +469,9 @@ class CutoffVGG16Engine:
                 if li == 0:
                     ops.conv_first_wgrad(self._x(B), dz, dw, self.view(s.name + "/bias", self.grad))
                 else:
-                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw, None, b["ws"], accumulate=False)
+                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw,
+                                      self.view(s.name + "/bias", self.grad) if wgrad_has_bias(li) else None, b["ws"],
+                                      accumulate=False)
                 if reduce_hook:
                     reduce_hook(*self.layer_ranges[s.name])
             if li > lowest:

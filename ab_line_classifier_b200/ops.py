@@ -64,8 +64,14 @@ def conv3x3_wgrad(x, dz, dw, db, workspace, accumulate=False):
     assert dz.shape == (B, H, W, Cout) and dw.numel() == 9 * Cin * Cout
     _native.call("abl_conv3x3_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), _ptr(workspace),
                  workspace.numel() * workspace.element_size(), int(bool(accumulate)), B, H, W, Cin, Cout, _stream())
-    if db is None:
+    if db is None or wgrad_fuses_bias(Cin):
         _native.launch_count -= 1      # GEMM + slice reduction only (no separate bias-grad kernel)
+
+
+def wgrad_fuses_bias(cin):
+    """True when abl_conv3x3_wgrad produces db inside its GEMM (the Cin == 64 kernel, unless the generic one is forced)."""
+    import os
+    return cin == 64 and os.environ.get("ABL_WGRAD_GENERIC", "0") != "1"
 
 
 def bias_grad(dz, db):
