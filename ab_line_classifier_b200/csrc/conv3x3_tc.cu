@@ -874,7 +874,8 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     const char* force_v1 = getenv("ABL_IGEMM_V1");
     // N = 64 MMAs are shared-memory-read-bound in SS mode (ncu: tensor pipe 50 % active = one M128 N64 K16 MMA per
     // 64 clocks); with Cin = 128 the v1 4x32 tile measured 7 % faster than the haloed tile (134 vs 144 us, B = 256)
-    const bool v1_better = ntile == 64 && Cin != 64 && (W % 32 == 0) && (H % 4 == 0) &&
+    // -- without a ReLU-mask epilogue only: with one, the haloed kernel's next-tile mask prefetch wins (150 vs 157 us)
+    const bool v1_better = ntile == 64 && Cin != 64 && !(flags & ABL_EPI_RELU_MASK) && (W % 32 == 0) && (H % 4 == 0) &&
                            !(force_v1 && force_v1[0] == '0');
     if (W % 16 == 0 && H % (8 * msub) == 0 && !(force_v1 && force_v1[0] == '1') && !v1_better) {
         a.box_w = 16; a.box_h = 8 * msub;

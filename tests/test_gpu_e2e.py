@@ -248,3 +248,29 @@ def test_gradcam_heatmaps_512_frame_clip_property_and_oracle(setup):
     ref_heat, ref_probs = oracle.gradcam_autograd(params, x[:3], out_hw=(128, 128), bf16=True)
     assert np.abs(h[:3] - ref_heat).max() < 3e-2
     assert (probs.cpu().numpy()[:3].argmax(-1) == ref_probs.argmax(-1)).all()
+
+
+def test_full_size_batches_size_independent_properties(setup):
+    """BASELINE.json sizes (batch 256 training, batch 1024 inference) are beyond what the CPU oracle finishes in
+    seconds, so they are checked through properties that do not need it:
+      * forward: frames are independent -> a batch of 1024 gives bit-identical probabilities to its four 256-chunks;
+      * backward: the loss is a sum over frames -> the gradient of a batch of 256 (loss scaled by 1/256) equals the sum
+        of the gradients of its two halves (same scale), up to fp32 summation order."""
+    eng, params = setup
+    x, y, _ = _frames(1024, seed=77)
+    p_all = eng.predict_batch(x, use_graph=False).clone()
+    for i in range(0, 1024, 256):
+        assert torch.equal(eng.predict_batch(x[i:i + 256], use_graph=False), p_all[i:i + 256])
+    tr = set(eng.layer_names())
+    keep = (np.random.default_rng(9).random((256, 256)) >= 0.45).astype(np.uint8)
+    eng.train_step(x[:256], y[:256], tr, keep_mask=keep, apply_update=False, global_batch=256)
+    g_full = eng.grad.clone()
+    g_sum = torch.zeros_like(g_full)
+    for sl in (slice(0, 128), slice(128, 256)):
+        eng.train_step(x[sl], y[sl], tr, keep_mask=keep[sl], apply_update=False, global_batch=256)
+        g_sum += eng.grad
+    scale = float(g_full.abs().max())
+    assert scale > 0
+    assert float((g_full - g_sum).abs().max()) < 2e-3 * scale      # bf16 dZ is per frame: only fp32 order differs
+    eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+    eng.set_weights(params)
