@@ -8,7 +8,9 @@ import torch
 
 class ArrayDataset:
     def __init__(self, x, y=None, batch_size=64, shuffle=False, seed=0, pin=True):
-        self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        # raw uint8 RGB frames stay uint8 (4x smaller H2D copies; preprocessing / resize run on the device)
+        x = np.asarray(x)
+        self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if x.dtype == np.uint8 else np.float32))
         self.y = None if y is None else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
         if pin and torch.cuda.is_available():
             self.x = self.x.pin_memory()

@@ -215,8 +215,23 @@ class B200Model:
         outs = []
         if isinstance(test_data, np.ndarray) or torch.is_tensor(test_data):
             test_data = [(test_data[i:i + batch_size], None) for i in range(0, len(test_data), batch_size)]
-        for x, _ in _iter_batches(test_data):
-            outs.append(self.engine.predict_batch(x).clone())      # stays on device: one D2H at the end
+        eng = self.engine
+        it = _iter_batches(test_data)
+        nxt = next(it, None)
+        slot = None
+        while nxt is not None:
+            x = nxt[0]
+            B = len(x)
+            if slot is None:                                   # nothing staged ahead (first batch, or the buffers grew)
+                eng.reserve(B, False)
+                slot = eng.stage(x)
+            cur = slot
+            nxt, slot = next(it, None), None
+            if nxt is not None and len(nxt[0]) <= eng._cap:
+                slot = eng.stage(nxt[0], slot=cur ^ 1)         # H2D copy of the next batch overlaps this forward pass
+            eng.use_slot(cur)
+            outs.append(eng.forward_device(B).clone())          # stays on device: one D2H at the end
+            eng.release_slot()
         if not outs:
             return (torch.zeros(0, self.n_classes, device=self.engine.device) if return_device
                     else np.zeros((0, self.n_classes), np.float32))

@@ -34,6 +34,16 @@ class FakeEngine:
         slot = 0 if slot is None else slot
         self._slots[slot] = (x, y)
         return slot
+    _cap = 1 << 30
+
+    def use_slot(self, slot):
+        self._cur = slot
+
+    def release_slot(self): pass
+
+    def forward_device(self, B):
+        return self.predict_batch(self._slots[self._cur][0])
+
     def refresh_operands(self, layers=None): pass
     def get_weights(self): return {k: v.copy() for k, v in self.params.items()}
 

@@ -75,6 +75,28 @@ def main():
     out["inference_sweep"] = sweep
     del x_all
 
+    # ---------------------------------------------------------------- predict() through the public model API, HOST frames
+    # (reference predict.py:54-87 path: dataset of frames -> model.predict -> probabilities on the host); H2D copies of
+    # batch i+1 overlap the forward pass of batch i, one D2H of the [N,2] probabilities at the end.
+    from ab_line_classifier_b200.data import ArrayDataset
+    from ab_line_classifier_b200.model import B200Model
+    model = B200Model(eng, eng.input_shape, eng.n_classes, eng.dropout)
+    api = {}
+    for label, frames_host in (("fp32_preprocessed", synth.vgg16_preprocess(fr)), ("uint8_raw", fr)):
+        ds = ArrayDataset(frames_host, None, 512)
+        model.predict(ds)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        import time
+        w0 = time.perf_counter()
+        for _ in range(3):
+            p = model.predict(ds)
+        wall = (time.perf_counter() - w0) / 3
+        api[label] = {"frames": len(fr), "batch": 512, "ms": round(wall * 1e3, 3),
+                      "frames_per_s": round(len(fr) / wall, 1), "h2d_bytes": int(ds.x.numel() * ds.x.element_size())}
+    out["predict_api_host_frames_4096"] = api
+    del model
+
     # ---------------------------------------------------------------- C2 train-step variants at batch 256
     B = 256
     fr, lab = synth.synth_frames(B, seed=1)
