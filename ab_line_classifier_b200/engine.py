@@ -53,6 +53,12 @@ def build_plan(input_shape, cutoff_layer):
     specs = []
     for i, (name, kind, cout) in enumerate(kept):
         if kind == "conv":
+            if i > 0 and (w % 16 or h % 8):
+                # the tcgen05 kernels tile feature maps into 8 x 16 pixel rectangles (TMA boxes); other sizes would
+                # need partial tiles
+                raise NotImplementedError(
+                    f"DATA.IMG_DIM: the {h}x{w} input of {name} is not a multiple of 8x16 pixels "
+                    "(use image sides that are multiples of 64 for CUTOFF_LAYER 10)")
             specs.append(ConvSpec(name, c, cout, h, w, i))
             c = cout
         else:

@@ -274,3 +274,41 @@ def test_full_size_batches_size_independent_properties(setup):
     assert float((g_full - g_sum).abs().max()) < 2e-3 * scale      # bf16 dZ is per frame: only fp32 order differs
     eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
     eng.set_weights(params)
+
+
+@pytest.mark.parametrize("H,W,cutoff", [(64, 64, 10), (256, 128, 10), (128, 128, 7), (96, 96, 10)])
+def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
+    """config.yml DATA.IMG_DIM / HPARAMS.CUTOFFVGG16.CUTOFF_LAYER other than the graded 128x128 / 10: forward logits and
+    one training step's loss + gradients against the bf16-faithful oracle (96x96 exercises the v1 conv kernel and the
+    per-pixel gather of block1_conv1: its block-3 maps are 24x24, which 16-pixel-wide tiles do not divide)."""
+    from ab_line_classifier_b200.engine import CutoffVGG16Engine
+    params = synth.randomize_biases(synth.glorot_weights(10001, cutoff_layer=cutoff))
+    try:
+        eng = CutoffVGG16Engine(input_shape=(H, W, 3), cutoff_layer=cutoff)
+    except NotImplementedError as e:
+        pytest.skip(str(e))
+    eng.set_weights(params)
+    rng = np.random.default_rng(H + W + cutoff)
+    B = 4
+    x = synth.vgg16_preprocess(rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8))
+    y = synth.one_hot(np.arange(B) % 2)
+    try:
+        eng.predict_batch(x, use_graph=False)
+    except RuntimeError as e:          # shapes the kernels cannot tile are reported, never silently mis-computed
+        assert "abl_" in str(e)
+        pytest.skip(f"unsupported by the kernels: {e}")
+    logits = eng._buf["logits"][:B].cpu().numpy()
+    ref = oracle.forward(params, x, cutoff_layer=cutoff, bf16=True)
+    assert np.abs(logits - ref["logits"]).max() < TOL_BF16
+    C = eng.feat_shape[2]
+    if eng.specs[-1].pool:
+        return                         # training needs a cutoff that ends in a conv layer
+    keep = synth.dropout_mask(B, C, 0.45)
+    tr = set(eng.layer_names())
+    loss = float(eng.train_step(x, y, tr, keep_mask=keep, apply_update=False).item())
+    l_ref, g_ref, _ = oracle.loss_and_grads(params, x, y, None, keep, cutoff_layer=cutoff, bf16=True)
+    assert abs(loss - float(l_ref)) < 1e-3 * max(1.0, abs(float(l_ref)))
+    g = eng.grad.cpu().numpy()
+    for name, (off, n, shape) in eng.segments.items():
+        got, want = g[off:off + n].reshape(shape), g_ref[name]
+        assert np.abs(got - want).max() <= 3e-2 * (np.abs(want).max() + 1e-12), name
