@@ -42,8 +42,9 @@ class ConvSpec:
         self.vgg_index = vgg_index   # index in vgg16.layers[1:cutoff] (what FINETUNE_LAYER slices)
 
 
-def build_plan(input_shape, cutoff_layer):
-    """Conv specs for ``vgg16.layers[1:cutoff_layer]`` (models.py:410); a pool folds into the conv above it."""
+def build_plan(input_shape, cutoff_layer, check_tiling=False):
+    """Conv specs for ``vgg16.layers[1:cutoff_layer]`` (models.py:410); a pool folds into the conv above it.
+    check_tiling: also require feature-map sizes the device kernels can tile (the engine sets it)."""
     h, w, c = input_shape
     if c != 3:
         raise NotImplementedError("DATA.IMG_DIM must give 3-channel frames (VGG16 input)")
@@ -53,7 +54,7 @@ def build_plan(input_shape, cutoff_layer):
     specs = []
     for i, (name, kind, cout) in enumerate(kept):
         if kind == "conv":
-            if i > 0 and (w % 16 or h % 8):
+            if check_tiling and i > 0 and (w % 16 or h % 8):
                 # the tcgen05 kernels tile feature maps into 8 x 16 pixel rectangles (TMA boxes); other sizes would
                 # need partial tiles
                 raise NotImplementedError(
@@ -83,7 +84,7 @@ class CutoffVGG16Engine:
         self.cutoff_layer = int(cutoff_layer)
         self.dropout = float(dropout)
         self.seed, self.rank, self.world_size, self.pg = int(seed), int(rank), int(world_size), process_group
-        self.specs, self.feat_shape = build_plan(self.input_shape, self.cutoff_layer)
+        self.specs, self.feat_shape = build_plan(self.input_shape, self.cutoff_layer, check_tiling=True)
         if self.specs[0].cout != 64:
             raise NotImplementedError("first layer must be block1_conv1 (64 filters)")
         # data parallel: fused reduce-scatter + optimizer + all-gather over NVLink peer memory (default) or NCCL

@@ -157,7 +157,7 @@ def test_clip_aggregation_rules():
 def test_engine_plan_and_unsupported_configs():
     from ab_line_classifier_b200.engine import build_plan
     with pytest.raises(NotImplementedError, match="IMG_DIM"):
-        build_plan((96, 96, 3), 10)           # block3 maps would be 24x24: not tileable into 8x16 rectangles
+        build_plan((96, 96, 3), 10, check_tiling=True)           # block3 maps would be 24x24: not tileable into 8x16 rectangles
     specs, feat = build_plan((128, 128, 3), 10)
     assert [s.name for s in specs] == ["block1_conv1", "block1_conv2", "block2_conv1", "block2_conv2",
                                        "block3_conv1", "block3_conv2", "block3_conv3"]
