@@ -577,7 +577,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                         tc_fence_after();
                         const uint32_t b_lo = b_lo0 + sb * (Cfg::kBStage >> 4);
-                        if (NTILE == 64 && MSUB == 2 && (p.flags & ABL_MAIN_WS_PAIRS)) {
+                        if (NTILE <= 128 && MSUB == 2 && (p.flags & ABL_MAIN_WS_PAIRS)) {
                             // weight-stationary MMA pairs: the two sub-tiles share one shared-memory read of B
 #pragma unroll
                             for (int t = 0; t < Cfg::kTPB; ++t) {
@@ -885,10 +885,13 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
         a.kchunks = Cin / kBlockK;
         a.flags = flags;
         {
-            // N = 64: weight-stationary MMA pairs (tcgen05.mma.ws, collector b0 fill -> lastuse): the two sub-tiles of
-            // a tile share one shared-memory read of each filter slice; measured +4 % on B200.  ABL_N64_WS=0 disables.
+            // Weight-stationary MMA pairs (tcgen05.mma.ws, collector b0 fill -> lastuse): the two sub-tiles of a tile
+            // share one shared-memory read of each filter slice.  ABL_N64_WS=0 disables.
+            // Same-box A/B on B200 (batch 256): N = 64 +4 %; N = 128: block2_conv1 fwd 122 -> 114 us, block2_conv2 dgrad
+            // 226 -> 210 us, but block2_conv2 fwd 200 -> 206 us, so N = 128 uses it for Cin = 64 and masked Cin = 128.
             const char* ws = getenv("ABL_N64_WS");
-            if (!(ws && ws[0] == '0')) a.flags |= ABL_MAIN_WS_PAIRS;
+            const bool ws_shape = ntile == 64 || (ntile == 128 && (Cin == 64 || (Cin == 128 && (flags & ABL_EPI_RELU_MASK))));
+            if (ws_shape && !(ws && ws[0] == '0')) a.flags |= ABL_MAIN_WS_PAIRS;
         }
         a.bias = bias;
         a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
