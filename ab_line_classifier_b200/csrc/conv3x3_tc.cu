@@ -40,6 +40,10 @@ struct ConvArgs {
     __nv_bfloat16* out_pool;        // [B,H/2,W/2,Cout] or null
     float* colsum;                  // [Cout] fp32 += column sums of out_full (fused BiasAddGrad) or null
     uint16_t* pool_code;            // [B,H/2,W/2,Cout/8]: 2-bit index of the window's first maximum per channel, or null
+    // dgrad through a max-pool: route each output value straight to the 2x2 window element named by the forward's
+    // routing code (MaxPoolGrad fused into the epilogue; the pooled-resolution gradient never reaches HBM)
+    __nv_bfloat16* out_unpool;      // [B,2H,2W,Cout] or null
+    const uint16_t* unpool_code;    // [B,H,W,Cout/8]
 };
 
 // 2x2 max-pool of 8 channels (four packed bf16x2 words per window element) + optional routing code: for every
@@ -67,6 +71,26 @@ __device__ __forceinline__ void pool8(const uint4& a, const uint4& b, const uint
             code |= ((w & 3u) | ((w >> 14) & 0xCu)) << (4 * j);
         }
     }
+}
+
+// Inverse of pool8 for gradients: 8 channels of a pooled gradient g (already masked by relu'(pooled)) go to the window
+// element named by the 2-bit codes, zeros to the other three; writes the four full-resolution 16-byte chunks.
+__device__ __forceinline__ void unpool8_store(const uint4& g, uint32_t cd, __nv_bfloat16* base, size_t right,
+                                              size_t down) {
+    const uint32_t gv[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = (cd >> (4 * j)) & 3u, hi = (cd >> (4 * j + 2)) & 3u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k][j] = (lo == static_cast<uint32_t>(k) ? (gv[j] & 0xFFFFu) : 0u) |
+                      (hi == static_cast<uint32_t>(k) ? (gv[j] & 0xFFFF0000u) : 0u);
+    }
+    *reinterpret_cast<uint4*>(base) = make_uint4(o[0][0], o[0][1], o[0][2], o[0][3]);
+    *reinterpret_cast<uint4*>(base + right) = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
+    *reinterpret_cast<uint4*>(base + down) = make_uint4(o[2][0], o[2][1], o[2][2], o[2][3]);
+    *reinterpret_cast<uint4*>(base + down + right) = make_uint4(o[3][0], o[3][1], o[3][2], o[3][3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -187,6 +211,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
             for (int j = 0; j < kEpiN / 64; ++j)
                 tma_store_4d(map_out, stg + j * kABytes, cbase + j * 64, w0, h0, img);
             tma_store_commit();
+        }
+        if (p.out_unpool != nullptr) {
+            // thread = (tile pixel, 8-channel chunk): consecutive threads cover one pixel's channels -> coalesced
+            constexpr int kCh16 = kEpiN / 8;
+            const size_t right = p.Cout, down = static_cast<size_t>(2 * p.W) * p.Cout;
+#pragma unroll 2
+            for (int q = et; q < kTileM * kCh16; q += kEpiThreads) {
+                const int r = q / kCh16, cc = q - r * kCh16;
+                const int ph = r / box_w, pw = r - ph * box_w;
+                const uint4 g = *reinterpret_cast<const uint4*>(stg + (cc >> 3) * kABytes + r * 128 + (((cc & 7) ^ (r & 7)) << 4));
+                const size_t pix = (static_cast<size_t>(img) * p.H + h0 + ph) * p.W + w0 + pw;
+                const uint32_t cd = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((cbase >> 3) + cc));
+                __nv_bfloat16* dst = p.out_unpool +
+                    ((static_cast<size_t>(img) * 2 * p.H + 2 * (h0 + ph)) * (2 * p.W) + 2 * (w0 + pw)) * p.Cout + cbase + cc * 8;
+                unpool8_store(g, cd, dst, right, down);
+            }
         }
         if (csum != nullptr) {
             // Column sums of the staged bf16 tile.  Warp w OWNS the 16-byte chunks [w*kCh/8, (w+1)*kCh/8) (8 channels
@@ -647,6 +687,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
             };
             const bool masked = (p.flags & ABL_EPI_RELU_MASK) != 0;
+            float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // fused bias gradient of the un-pooled tensor
             if (masked && blockIdx.x < num_tiles) load_mask(blockIdx.x);
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -708,6 +749,26 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     tma_store_4d(&map_out, stg, n0, w0, h0, img);
                     tma_store_commit();
                 }
+                if (p.out_unpool != nullptr) {
+                    const size_t right = p.Cout, down = static_cast<size_t>(2 * p.W) * p.Cout;
+#pragma unroll 2
+                    for (int q = gt; q < 128 * 8; q += 128) {        // q & 7 = this thread's chunk for the whole kernel
+                        const int r = q >> 3, cc = q & 7;
+                        const uint4 g = *reinterpret_cast<const uint4*>(stg + r * 128 + ((cc ^ (r & 7)) << 4));
+                        const int hh = h0 + (r >> 4), ww = w0 + (r & 15);
+                        const size_t pix = (static_cast<size_t>(img) * p.H + hh) * p.W + ww;
+                        const uint32_t cd = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((n0 >> 3) + cc));
+                        __nv_bfloat16* dst = p.out_unpool +
+                            ((static_cast<size_t>(img) * 2 * p.H + 2 * hh) * (2 * p.W) + 2 * ww) * p.Cout + n0 + cc * 8;
+                        unpool8_store(g, cd, dst, right, down);
+                        if (p.colsum != nullptr) {
+                            bacc[0] += __uint_as_float(g.x << 16); bacc[1] += __uint_as_float(g.x & 0xFFFF0000u);
+                            bacc[2] += __uint_as_float(g.y << 16); bacc[3] += __uint_as_float(g.y & 0xFFFF0000u);
+                            bacc[4] += __uint_as_float(g.z << 16); bacc[5] += __uint_as_float(g.z & 0xFFFF0000u);
+                            bacc[6] += __uint_as_float(g.w << 16); bacc[7] += __uint_as_float(g.w & 0xFFFF0000u);
+                        }
+                    }
+                }
                 if (p.out_pool != nullptr) {
 #pragma unroll
                     for (int q = gt; q < 32 * 8; q += 128) {
@@ -729,6 +790,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
             }
             if (gt == 0) tma_store_wait_all();
+            if (p.colsum != nullptr) {        // chunk sums of all 256 threads -> csum -> one global atomic per channel
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(&csum[(gt & 7) * 8 + j], bacc[j]);
+                named_bar_sync(3, kEpiThreads);      // ids 1 and 2 belong to the two groups
+                for (int i = et; i < NTILE; i += kEpiThreads) atomicAdd(p.colsum + i, csum[i]);
+            }
         } else {
         int it = 0;
         uint32_t pass_ctr = 0;
@@ -837,15 +904,19 @@ using namespace abl;
 // See include/abl_b200.h for the contract.
 extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
 
-extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                                 void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B,
-                                 int H, int W, int Cin, int Cout, int flags, void* stream) {
-    if (colsum && !out_full) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
+static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
+                           void* out_full, void* out_pool, unsigned short* pool_code, float* colsum,
+                           void* out_unpool, const unsigned short* unpool_code, int B, int H, int W, int Cin, int Cout,
+                           int flags, void* stream) {
+    if (colsum && !out_full && !out_unpool) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
     if (pool_code && !out_pool) { set_error("abl_conv3x3_igemm: pool_code needs out_pool"); return ABL_ERR_NULL; }
+    if (out_unpool && (!unpool_code || out_full || out_pool)) {
+        set_error("abl_conv3x3_dgrad_unpool: needs routing codes and no other output"); return ABL_ERR_NULL;
+    }
     if (!x || !w_kmajor) { set_error("abl_conv3x3_igemm: null input"); return ABL_ERR_NULL; }
-    if (!out_full && !out_pool) { set_error("abl_conv3x3_igemm: no output requested"); return ABL_ERR_NULL; }
+    if (!out_full && !out_pool && !out_unpool) { set_error("abl_conv3x3_igemm: no output requested"); return ABL_ERR_NULL; }
     if ((flags & ABL_EPI_BIAS_RELU) && !bias) { set_error("abl_conv3x3_igemm: bias missing"); return ABL_ERR_NULL; }
-    if ((flags & ABL_EPI_RELU_MASK) && (!mask_src || !out_full)) {
+    if ((flags & ABL_EPI_RELU_MASK) && (!mask_src || (!out_full && !out_unpool))) {
         set_error("abl_conv3x3_igemm: relu-mask epilogue needs mask_src and out_full");
         return ABL_ERR_NULL;
     }
@@ -876,8 +947,8 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     // 64 clocks); with Cin = 128 the v1 4x32 tile measured 7 % faster than the haloed tile (134 vs 144 us, B = 256)
     // -- without a ReLU-mask epilogue only: with one, the haloed kernel's next-tile mask prefetch wins (150 vs 157 us)
     const bool v1_better = ntile == 64 && Cin != 64 && !(flags & ABL_EPI_RELU_MASK) && (W % 32 == 0) && (H % 4 == 0) &&
-                           !(force_v1 && force_v1[0] == '0');
-    if (W % 16 == 0 && H % (8 * msub) == 0 && !(force_v1 && force_v1[0] == '1') && !v1_better) {
+                           !out_unpool && !(force_v1 && force_v1[0] == '0');
+    if (W % 16 == 0 && H % (8 * msub) == 0 && (!(force_v1 && force_v1[0] == '1') || out_unpool) && !v1_better) {
         a.box_w = 16; a.box_h = 8 * msub;
         a.tiles_h = H / a.box_h; a.tiles_w = W / 16;
         a.num_m_tiles = B * a.tiles_h * a.tiles_w;
@@ -899,8 +970,13 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
         a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
         a.pool_code = pool_code;
         // fused BiasAddGrad: the 8-warp epilogue with a single N tile; otherwise a separate pass over out_full
-        const bool fuse_colsum = colsum != nullptr && ntile != 64 && a.num_n_tiles == 1;
+        const bool fuse_colsum = colsum != nullptr && a.num_n_tiles == 1 && (ntile != 64 || out_unpool != nullptr);
         a.colsum = fuse_colsum ? colsum : nullptr;
+        a.out_unpool = static_cast<__nv_bfloat16*>(out_unpool);
+        a.unpool_code = unpool_code;
+        if (out_unpool && (ntile == 256 || !fuse_colsum && colsum != nullptr)) {
+            set_error("abl_conv3x3_dgrad_unpool: supported for Cout <= 128 (single N tile)"); return ABL_ERR_SHAPE;
+        }
         CUtensorMap ma, mb;
         {
             const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -936,7 +1012,10 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
             r = abl_bias_grad(out_full, colsum, static_cast<long long>(B) * H * W, Cout, stream);
         return r;
     }
+    if (out_unpool) { set_error("abl_conv3x3_dgrad_unpool: needs W % 16 == 0 and H % 16 == 0"); return ABL_ERR_SHAPE; }
     a.colsum = nullptr;
+    a.out_unpool = nullptr;
+    a.unpool_code = nullptr;
     // 3-taps-per-stage main loop for the narrow tile: needs the 4 x 32 pixel rectangle
     const bool taps3 = ntile == 64 && (W % 32 == 0) && (H % 4 == 0);
     if (taps3) { a.box_w = 32; a.box_h = 4; }
@@ -983,4 +1062,20 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
     }
     if (r == ABL_OK && colsum != nullptr) r = abl_bias_grad(out_full, colsum, static_cast<long long>(B) * H * W, Cout, stream);
     return r;
+}
+
+extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
+                                 void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B,
+                                 int H, int W, int Cin, int Cout, int flags, void* stream) {
+    return conv_igemm_impl(x, w_kmajor, bias, mask_src, out_full, out_pool, pool_code, colsum, nullptr, nullptr, B, H, W,
+                           Cin, Cout, flags, stream);
+}
+
+// See include/abl_b200.h: dgrad through a max-pool in one kernel.
+extern "C" int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, const void* pooled,
+                                        const unsigned short* pool_code, void* dz_out, float* db, int B, int H, int W,
+                                        int Cin, int Cout, void* stream) {
+    if (!pooled || !pool_code || !dz_out) { set_error("abl_conv3x3_dgrad_unpool: null pointer"); return ABL_ERR_NULL; }
+    return conv_igemm_impl(dz, w_dgrad, nullptr, pooled, nullptr, nullptr, nullptr, db, dz_out, pool_code, B, H, W, Cin,
+                           Cout, ABL_EPI_RELU_MASK, stream);
 }

@@ -93,6 +93,7 @@ class CutoffVGG16Engine:
         self.fused_dp = os.environ.get("ABL_DP_FUSED", "1") != "0"
         # training keeps 2-bit max-pool routing codes instead of the pre-pool activations (ABL_POOL_CODES=0: keep them)
         self.pool_codes = os.environ.get("ABL_POOL_CODES", "1") != "0"
+        self.fuse_unpool = os.environ.get("ABL_FUSE_UNPOOL", "1") != "0"    # MaxPoolGrad inside the dgrad epilogue
         self.step_count = 0           # dropout counter
         self.opt_steps = {}           # optimizer name -> steps taken (Adam bias correction)
         self._alloc_params(output_bias)
@@ -487,7 +488,11 @@ class CutoffVGG16Engine:
                     dp = b["dp"][: B * s.h * s.w * s.cin].view(B, s.h, s.w, s.cin)
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
                     code = b.get("code_" + prev.name)
-                    if code is not None:
+                    if code is not None and self.fuse_unpool and ops.dgrad_unpool_supported(s.h, s.w, s.cin):
+                        # dgrad + relu'(pooled) + MaxPoolGrad (+ BiasAddGrad) in one kernel
+                        ops.conv3x3_dgrad_unpool(dz, self.w_dgrad[s.name], b["pool_" + prev.name][:B], code[:B], ndz,
+                                                 bias_grad_of(li - 1))
+                    elif code is not None:
                         # relu'(pooled) in the dgrad epilogue, then routing by the forward's 2-bit codes
                         ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["pool_" + prev.name][:B], dp, None,
                                           ops.EPI_RELU_MASK)

@@ -48,6 +48,24 @@ def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool
                  _ptr(out_pool), _ptr(pool_code), _ptr(colsum), B, H, W, Cin, Cout, flags, _stream())
 
 
+def dgrad_unpool_supported(H, W, Cout):
+    """Shapes abl_conv3x3_dgrad_unpool handles (H, W = pooled resolution, Cout = channels of the pooled tensor)."""
+    return W % 16 == 0 and H % 16 == 0 and Cout % 64 == 0 and Cout <= 128
+
+
+def conv3x3_dgrad_unpool(dz, w_dgrad, pooled, pool_code, dz_out, db=None):
+    """dgrad + relu'(pooled) + MaxPoolGrad (+ BiasAddGrad) in one kernel; see abl_conv3x3_dgrad_unpool."""
+    for t, n in ((dz, "dz"), (w_dgrad, "w_dgrad"), (pooled, "pooled"), (dz_out, "dz_out")):
+        _chk(t, torch.bfloat16, n)
+    _chk(pool_code, torch.int16, "pool_code"); _chk(db, torch.float32, "db")
+    B, H, W, Cin = dz.shape
+    Cout = w_dgrad.shape[1]
+    assert w_dgrad.shape == (9, Cout, Cin) and pooled.shape == (B, H, W, Cout)
+    assert dz_out.shape == (B, 2 * H, 2 * W, Cout) and pool_code.shape == (B, H, W, Cout // 8)
+    _native.call("abl_conv3x3_dgrad_unpool", _ptr(dz), _ptr(w_dgrad), _ptr(pooled), _ptr(pool_code), _ptr(dz_out),
+                 _ptr(db), B, H, W, Cin, Cout, _stream())
+
+
 def wgrad_workspace_bytes(B, H, W, Cin, Cout):
     n = _native.load().abl_conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)
     if n < 0:

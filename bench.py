@@ -313,6 +313,8 @@ def main():
                 fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
             elif name == "abl_conv3x3_wgrad":      # (x, dz, dw, db, ws, ws_bytes, acc, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
+            elif name == "abl_conv3x3_dgrad_unpool":   # (dz, w, pooled, code, out, db, B, H, W, Cin, Cout, stream)
+                fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
             else:
                 fl = 0.0
             k["gflop"] += fl / 1e9
@@ -343,7 +345,7 @@ def main():
             pass
         roof = {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
-                "kernel": "tcgen05 implicit-GEMM conv family (conv3x3_tc_kernel fwd+dgrad, wgrad_tc_kernel): all "
+                "kernel": "tcgen05 implicit-GEMM conv family (conv3x3_halo_kernel fwd / dgrad / dgrad+unpool, wgrad_tc_kernel, wgrad64_tc_kernel): all "
                           "launches of one step, algorithmic FLOPs / summed CUDA-event durations",
                 "peak_source": pk_src + ", bf16_tflops_sustained (kernels timed inside a long step)",
                 "share_of_step": round(tc_ms / step_ms_instr, 4) if step_ms_instr else None}

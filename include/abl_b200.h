@@ -58,6 +58,17 @@ int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, co
                       void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B, int H, int W,
                       int Cin, int Cout, int flags, void* stream);
 
+/* Conv2DBackpropInput + ReluGrad + MaxPoolGrad (+ BiasAddGrad) in ONE kernel, for a conv whose input is the output of a
+ * 2x2 max-pool: the dgrad GEMM at the pooled resolution H x W, relu'(pooled) applied in the epilogue, and every value
+ * routed straight to the window element the forward's routing code names (zeros elsewhere), so the pooled-resolution
+ * gradient never reaches HBM and no separate MaxPoolGrad pass runs.
+ *   dz bf16 [B,H,W,Cin_gemm] (gradient of this conv's output); w_dgrad bf16 [9][Cout][Cin_gemm] (abl_prep_conv_weights);
+ *   pooled bf16 [B,H,W,Cout], pool_code uint16 [B,H,W,Cout/8] (both from the forward abl_conv3x3_igemm of the layer
+ *   below); dz_out bf16 [B,2H,2W,Cout]; db fp32 [Cout] or NULL: += sum of the routed gradients (BiasAddGrad of the
+ *   layer below).  Requires Cout <= 128, W % 16 == 0, H % 16 == 0. */
+int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, const void* pooled, const unsigned short* pool_code,
+                             void* dz_out, float* db, int B, int H, int W, int Cin, int Cout, void* stream);
+
 /* Conv2DBackpropFilter (+BiasAddGrad) of model.fit's tape (models.py:427,432) as a tcgen05 GEMM with
  * MN-major operands read straight from the NHWC tensors, split over pixel slices into `workspace`
  * and reduced in a fixed order (deterministic), fp32 accumulation:

@@ -253,6 +253,32 @@ def test_pool_routing_codes_reproduce_maxpool_backward_bit_exactly(cin, cout, H,
     assert torch.equal(code, code2)
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 128, 64, 64), (128, 256, 32, 32)])
+def test_dgrad_unpool_equals_dgrad_then_maxpool_backward(cin, cout, H, W):
+    """abl_conv3x3_dgrad_unpool (dgrad + relu'(pooled) + MaxPoolGrad + BiasAddGrad in one kernel) vs the two-kernel
+    path through the routing codes: bit-identical dZ, bias gradient equal up to fp32 order.  (cin = channels of the
+    pooled tensor = GEMM N; cout = channels of the incoming gradient = GEMM K.)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin + cout)
+    B = 3
+    pooled = _bf(torch.relu(torch.randn(B, H, W, cin, generator=g))).to(torch.bfloat16).cuda()
+    code = torch.randint(0, 1 << 16, (B, H, W, cin // 8), generator=g, dtype=torch.int32).to(torch.int16).cuda()
+    dz = (torch.randn(B, H, W, cout, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    w = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    wd = torch.empty(9, cin, cout, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w.cuda(), None, wd)
+    dp = torch.empty(B, H, W, cin, device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3_igemm(dz, wd, None, pooled, dp, None, ops.EPI_RELU_MASK)
+    ref = torch.empty(B, 2 * H, 2 * W, cin, device="cuda", dtype=torch.bfloat16)
+    db_ref = torch.zeros(cin, device="cuda")
+    ops.maxpool_bwd_code(dp, code, ref, db_ref)
+    out = torch.full_like(ref, float("nan"))
+    db = torch.zeros(cin, device="cuda")
+    ops.conv3x3_dgrad_unpool(dz, wd, pooled, code, out, db)
+    assert torch.equal(out, ref)
+    _close(db, db_ref, 1e-4, "fused bias grad (dgrad + unpool)")
+
+
 def test_gap_forward_backward():
     ops = _ops()
     g = torch.Generator().manual_seed(3)
