@@ -20,6 +20,8 @@ SIGNATURES = {
     "abl_abi_version": (_i, []),
     "abl_last_error": (C.c_char_p, []),
     "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "abl_conv3x3_igemm_gap": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "abl_gap_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_dgrad_unpool": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "abl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),

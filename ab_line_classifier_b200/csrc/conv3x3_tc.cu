@@ -44,6 +44,9 @@ struct ConvArgs {
     // routing code (MaxPoolGrad fused into the epilogue; the pooled-resolution gradient never reaches HBM)
     __nv_bfloat16* out_unpool;      // [B,2H,2W,Cout] or null
     const uint16_t* unpool_code;    // [B,H,W,Cout/8]
+    // fused GlobalAveragePooling partial sums: row (8x16-pixel rectangle index) x Cout fp32, plain stores (each value
+    // has exactly one writer -> deterministic); abl_gap_reduce adds the rectangles of a frame in fixed order
+    float* gap_part;                // [B * (H/8) * (W/16)][Cout] or null
 };
 
 // 2x2 max-pool of 8 channels (four packed bf16x2 words per window element) + optional routing code: for every
@@ -107,6 +110,7 @@ __device__ __forceinline__ void unpool8_store(const uint4& g, uint32_t cd, __nv_
 //   next_origin: element offset in mask_src of the (h0, w0, channel 0) corner of the NEXT rectangle this thread group
 //              will process, or -1: the ReLU-mask line each thread needs for its next pass is prefetched into L2 one
 //              pass ahead (ncu: the mask load's HBM latency was ~10 % of the dgrad epilogue's stall samples)
+//   gap_row  : global fp32 [Cout] row receiving this rectangle's column sums (fused GAP partial sums) or nullptr
 //   csum     : shared-memory fp32 [NTILE] column sums of the bf16 values written (fused BiasAddGrad of the
 //              tensor this kernel produces; the caller flushes it to global memory once per CTA) or nullptr
 template <int NTILE, int kEpiN, int kStgBufs>
@@ -114,7 +118,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
                                               uint32_t tmem_acc, int img, int h0, int w0, int n0, int box_w,
                                               int et, uint32_t& pass_ctr, uint64_t* wait_bar, uint32_t wait_phase,
                                               uint64_t* arrive_bar, float* csum = nullptr,
-                                              long long next_origin = -1) {
+                                              long long next_origin = -1, float* gap_row = nullptr) {
     constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
     constexpr int kPasses = NTILE / kEpiN;
     constexpr int kColsPerWarp = kEpiN / 2;      // 32 or 64
@@ -228,7 +232,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
                 unpool8_store(g, cd, dst, right, down);
             }
         }
-        if (csum != nullptr) {
+        if (csum != nullptr || gap_row != nullptr) {
             // Column sums of the staged bf16 tile.  Warp w OWNS the 16-byte chunks [w*kCh/8, (w+1)*kCh/8) (8 channels
             // each) for the whole kernel, so after a shuffle reduction over the lanes holding other row groups one
             // lane adds into csum with a plain read-modify-write: no shared-memory atomics (a float atomicAdd on
@@ -255,9 +259,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s8[j] += __shfl_xor_sync(0xffffffffu, s8[j], o);
             if (lane < kCpw) {
-                float* dst = csum + pass * kEpiN + chunk * 8;
+                if (csum != nullptr) {
+                    float* dst = csum + pass * kEpiN + chunk * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] += s8[j];
+                    for (int j = 0; j < 8; ++j) dst[j] += s8[j];
+                }
+                if (gap_row != nullptr) {
+                    float4* dst = reinterpret_cast<float4*>(gap_row + cbase + chunk * 8);
+                    dst[0] = make_float4(s8[0], s8[1], s8[2], s8[3]);
+                    dst[1] = make_float4(s8[4], s8[5], s8[6], s8[7]);
+                }
             }
         }
         if (p.out_pool != nullptr) {
@@ -826,7 +837,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     p, &map_out, staging, tmem_base + (as * MSUB + sub) * NTILE, img, th * kTileH + sub * Cfg::kSubH,
                     tw * Cfg::kTileW, n_tile * NTILE, Cfg::kTileW, et, pass_ctr, sub == 0 ? &tfull_bar[as] : nullptr,
                     (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr, p.colsum != nullptr ? csum : nullptr,
-                    next_origin);
+                    next_origin,
+                    p.gap_part != nullptr
+                        ? p.gap_part + ((static_cast<size_t>(img) * (p.H >> 3) + (th * kTileH >> 3) + sub) * p.tiles_w + tw) * p.Cout
+                        : nullptr);
             }
         }
         if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
@@ -906,15 +920,15 @@ extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, v
 
 static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
                            void* out_full, void* out_pool, unsigned short* pool_code, float* colsum,
-                           void* out_unpool, const unsigned short* unpool_code, int B, int H, int W, int Cin, int Cout,
-                           int flags, void* stream) {
+                           void* out_unpool, const unsigned short* unpool_code, float* gap_part, int B, int H, int W,
+                           int Cin, int Cout, int flags, void* stream) {
     if (colsum && !out_full && !out_unpool) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
     if (pool_code && !out_pool) { set_error("abl_conv3x3_igemm: pool_code needs out_pool"); return ABL_ERR_NULL; }
     if (out_unpool && (!unpool_code || out_full || out_pool)) {
         set_error("abl_conv3x3_dgrad_unpool: needs routing codes and no other output"); return ABL_ERR_NULL;
     }
     if (!x || !w_kmajor) { set_error("abl_conv3x3_igemm: null input"); return ABL_ERR_NULL; }
-    if (!out_full && !out_pool && !out_unpool) { set_error("abl_conv3x3_igemm: no output requested"); return ABL_ERR_NULL; }
+    if (!out_full && !out_pool && !out_unpool && !gap_part) { set_error("abl_conv3x3_igemm: no output requested"); return ABL_ERR_NULL; }
     if ((flags & ABL_EPI_BIAS_RELU) && !bias) { set_error("abl_conv3x3_igemm: bias missing"); return ABL_ERR_NULL; }
     if ((flags & ABL_EPI_RELU_MASK) && (!mask_src || (!out_full && !out_unpool))) {
         set_error("abl_conv3x3_igemm: relu-mask epilogue needs mask_src and out_full");
@@ -947,8 +961,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
     // 64 clocks); with Cin = 128 the v1 4x32 tile measured 7 % faster than the haloed tile (134 vs 144 us, B = 256)
     // -- without a ReLU-mask epilogue only: with one, the haloed kernel's next-tile mask prefetch wins (150 vs 157 us)
     const bool v1_better = ntile == 64 && Cin != 64 && !(flags & ABL_EPI_RELU_MASK) && (W % 32 == 0) && (H % 4 == 0) &&
-                           !out_unpool && !(force_v1 && force_v1[0] == '0');
-    if (W % 16 == 0 && H % (8 * msub) == 0 && (!(force_v1 && force_v1[0] == '1') || out_unpool) && !v1_better) {
+                           !out_unpool && !gap_part && !(force_v1 && force_v1[0] == '0');
+    if (W % 16 == 0 && H % (8 * msub) == 0 && (!(force_v1 && force_v1[0] == '1') || out_unpool || gap_part) && !v1_better) {
         a.box_w = 16; a.box_h = 8 * msub;
         a.tiles_h = H / a.box_h; a.tiles_w = W / 16;
         a.num_m_tiles = B * a.tiles_h * a.tiles_w;
@@ -974,6 +988,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         a.colsum = fuse_colsum ? colsum : nullptr;
         a.out_unpool = static_cast<__nv_bfloat16*>(out_unpool);
         a.unpool_code = unpool_code;
+        a.gap_part = gap_part;
+        if (gap_part && ntile == 64) { set_error("abl_conv3x3_igemm_gap: needs Cout a multiple of 128"); return ABL_ERR_SHAPE; }
         if (out_unpool && (ntile == 256 || !fuse_colsum && colsum != nullptr)) {
             set_error("abl_conv3x3_dgrad_unpool: supported for Cout <= 128 (single N tile)"); return ABL_ERR_SHAPE;
         }
@@ -1013,9 +1029,11 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         return r;
     }
     if (out_unpool) { set_error("abl_conv3x3_dgrad_unpool: needs W % 16 == 0 and H % 16 == 0"); return ABL_ERR_SHAPE; }
+    if (gap_part) { set_error("abl_conv3x3_igemm_gap: needs W % 16 == 0 and H % 16 == 0 (H % 8 for Cout % 256 == 0)"); return ABL_ERR_SHAPE; }
     a.colsum = nullptr;
     a.out_unpool = nullptr;
     a.unpool_code = nullptr;
+    a.gap_part = nullptr;
     // 3-taps-per-stage main loop for the narrow tile: needs the 4 x 32 pixel rectangle
     const bool taps3 = ntile == 64 && (W % 32 == 0) && (H % 4 == 0);
     if (taps3) { a.box_w = 32; a.box_h = 4; }
@@ -1067,8 +1085,16 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
 extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
                                  void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B,
                                  int H, int W, int Cin, int Cout, int flags, void* stream) {
-    return conv_igemm_impl(x, w_kmajor, bias, mask_src, out_full, out_pool, pool_code, colsum, nullptr, nullptr, B, H, W,
-                           Cin, Cout, flags, stream);
+    return conv_igemm_impl(x, w_kmajor, bias, mask_src, out_full, out_pool, pool_code, colsum, nullptr, nullptr, nullptr, B,
+                           H, W, Cin, Cout, flags, stream);
+}
+
+// See include/abl_b200.h: forward conv + bias + ReLU with the GlobalAveragePooling partial sums fused in.
+extern "C" int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full,
+                                     float* gap_part, int B, int H, int W, int Cin, int Cout, void* stream) {
+    if (!gap_part) { set_error("abl_conv3x3_igemm_gap: gap_part is null"); return ABL_ERR_NULL; }
+    return conv_igemm_impl(x, w_kmajor, bias, nullptr, out_full, nullptr, nullptr, nullptr, nullptr, nullptr, gap_part, B, H,
+                           W, Cin, Cout, ABL_EPI_BIAS_RELU, stream);
 }
 
 // See include/abl_b200.h: dgrad through a max-pool in one kernel.
@@ -1076,6 +1102,6 @@ extern "C" int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, con
                                         const unsigned short* pool_code, void* dz_out, float* db, int B, int H, int W,
                                         int Cin, int Cout, void* stream) {
     if (!pooled || !pool_code || !dz_out) { set_error("abl_conv3x3_dgrad_unpool: null pointer"); return ABL_ERR_NULL; }
-    return conv_igemm_impl(dz, w_dgrad, nullptr, pooled, nullptr, nullptr, nullptr, db, dz_out, pool_code, B, H, W, Cin,
-                           Cout, ABL_EPI_RELU_MASK, stream);
+    return conv_igemm_impl(dz, w_dgrad, nullptr, pooled, nullptr, nullptr, nullptr, db, dz_out, pool_code, nullptr, B, H, W,
+                           Cin, Cout, ABL_EPI_RELU_MASK, stream);
 }

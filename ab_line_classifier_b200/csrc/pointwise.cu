@@ -201,6 +201,22 @@ __global__ void __launch_bounds__(256) gap_fwd_kernel(const uint4* __restrict__ 
     }
 }
 
+// gap[n][c] = (1/HW) * sum_p part[n*parts + p][c], p in fixed order: finishes the GAP partial sums that
+// abl_conv3x3_igemm_gap's epilogue wrote per 8x16-pixel rectangle (deterministic, 8 KiB read per frame).
+__global__ void gap_reduce_kernel(const float4* __restrict__ part, float4* __restrict__ gap, int B, int parts, int C4,
+                                  float inv_hw) {
+    const int total = B * C4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / C4, c = i - n * C4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < parts; ++q) {
+            const float4 v = __ldg(part + (static_cast<size_t>(n) * parts + q) * C4 + c);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        gap[i] = make_float4(s.x * inv_hw, s.y * inv_hw, s.z * inv_hw, s.w * inv_hw);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4* __restrict__ a,
                                     uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw,
@@ -695,6 +711,15 @@ extern "C" int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void
     if (B <= 0 || HW <= 0 || (C % 64) != 0) { set_error("abl_gap_fwd: need C % 64 == 0"); return ABL_ERR_SHAPE; }
     gap_fwd_kernel<<<dim3(B, C / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(a), gap,
                                                                                   HW, C);
+    return check_launch();
+}
+
+extern "C" int abl_gap_reduce(const float* gap_part, float* gap, int B, int parts, int C, int HW, void* stream) {
+    if (!gap_part || !gap) { set_error("abl_gap_reduce: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || parts <= 0 || C <= 0 || (C & 3) || HW <= 0) { set_error("abl_gap_reduce: bad shape (C % 4 == 0)"); return ABL_ERR_SHAPE; }
+    gap_reduce_kernel<<<grid_for(static_cast<long long>(B) * (C / 4), 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(gap_part), reinterpret_cast<float4*>(gap), B, parts, C / 4,
+        1.f / static_cast<float>(HW));
     return check_launch();
 }
 

@@ -94,6 +94,8 @@ class CutoffVGG16Engine:
         # training keeps 2-bit max-pool routing codes instead of the pre-pool activations (ABL_POOL_CODES=0: keep them)
         self.pool_codes = os.environ.get("ABL_POOL_CODES", "1") != "0"
         self.fuse_unpool = os.environ.get("ABL_FUSE_UNPOOL", "1") != "0"    # MaxPoolGrad inside the dgrad epilogue
+        self.fuse_gap = os.environ.get("ABL_FUSE_GAP", "1") != "0"          # GAP partial sums inside the last conv
+        self._gap_parts = 0
         self.step_count = 0           # dropout counter
         self.opt_steps = {}           # optimizer name -> steps taken (Adam bias correction)
         self._alloc_params(output_bias)
@@ -254,6 +256,10 @@ class CutoffVGG16Engine:
         C = self.feat_shape[2]
         n = self.n_classes
         b["gap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
+        last = self.specs[-1]
+        if self.fuse_gap and not last.pool and ops.igemm_gap_supported(last.h, last.w, last.cout):
+            self._gap_parts = (last.h // 8) * (last.w // 16)
+            b["gap_part"] = torch.empty(cap * self._gap_parts, C, device=dev, dtype=torch.float32)
         b["logits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["probs"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["y"] = [torch.empty(cap, n, device=dev, dtype=torch.float32) for _ in range(2)]
@@ -283,7 +289,8 @@ class CutoffVGG16Engine:
         return self._buf[key][:B]
 
     # ------------------------------------------------------------------ forward
-    def forward_device(self, B, training=False, keep_mask_in=False, y=None, inv_batch=None, loss_out=None):
+    def forward_device(self, B, training=False, keep_mask_in=False, y=None, inv_batch=None, loss_out=None,
+                       need_last_act=True):
         """Runs the network on self._buf['x'][:B] (already resident).  Returns probs view [B,n].
         training: dropout on, class-weighted loss + dlogits.  Otherwise, if y is given, the UNweighted
         loss sum_i l_i * inv_batch is accumulated into loss_out (Keras evaluate / validation)."""
@@ -296,13 +303,21 @@ class CutoffVGG16Engine:
                 ops.conv_first_fwd(self._x(B), self.view(s.name + "/kernel"), self.view(s.name + "/bias"), full)
                 if s.pool:
                     raise NotImplementedError("a pool directly after block1_conv1 is not a VGG16 prefix")
+            elif li == len(self.specs) - 1 and "gap_part" in b:
+                # last conv: GlobalAveragePooling partial sums come out of the epilogue; without Grad-CAM / training
+                # (need_last_act False) the activation itself is never written
+                ops.conv3x3_igemm_gap(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"),
+                                      full if (training or need_last_act) else None, b["gap_part"])
             else:
                 code = b.get("code_" + s.name)
                 ops.conv3x3_igemm(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"), None,
                                   full, pooled, ops.EPI_BIAS_RELU, pool_code=code[:B] if code is not None else None)
         last = self.specs[-1]
-        feat = b["pool_" + last.name][:B] if last.pool else b["act_" + last.name][:B]
-        ops.gap_fwd(feat, b["gap"][:B])
+        if "gap_part" in b:
+            ops.gap_reduce(b["gap_part"], b["gap"][:B], self._gap_parts, last.h * last.w)
+        else:
+            feat = b["pool_" + last.name][:B] if last.pool else b["act_" + last.name][:B]
+            ops.gap_fwd(feat, b["gap"][:B])
         if loss_out is None:
             loss_out = b["loss"]
             loss_out.zero_()
@@ -388,7 +403,7 @@ class CutoffVGG16Engine:
 
     GRAPH_MAX_BATCH = 64     # below this the forward pass is launch-bound (9 kernels of a few microseconds each)
 
-    def predict_batch(self, x, use_graph=None):
+    def predict_batch(self, x, use_graph=None, need_last_act=False):
         """x: [B,H,W,3] fp32 (BGR, mean-subtracted, as vgg16_preprocess leaves it) or raw uint8 RGB.
         Returns device probs.  Small batches (the reference's batch-1 loops: ``clock_avg_runtime`` predict.py:425-448,
         ``WandbGradcamEvalCallback._inference`` train_utils.py:280-293) replay a captured CUDA graph of the 10
@@ -399,29 +414,29 @@ class CutoffVGG16Engine:
             use_graph = B <= self.GRAPH_MAX_BATCH
         if not use_graph:
             self.load_input(x)
-            probs = self.forward_device(B)
+            probs = self.forward_device(B, need_last_act=need_last_act)
             self.release_slot()
             return probs
         u8 = (x.dtype == torch.uint8) if torch.is_tensor(x) else (np.asarray(x).dtype == np.uint8)
-        g = self._forward_graph(B, u8)
+        g = self._forward_graph(B, u8, need_last_act)
         self.use_slot(self.stage(x, slot=0))
         g.replay()
         self.release_slot()
         return self._buf["probs"][:B]
 
-    def _forward_graph(self, B, u8):
+    def _forward_graph(self, B, u8, need_last_act=False):
         """CUDA graph of forward_device(B) reading input slot 0 (captured once per (batch, input dtype, buffers))."""
-        key = (B, bool(u8), id(self._buf))
+        key = (B, bool(u8), id(self._buf), bool(need_last_act))
         g = self._graphs.get(key)
         if g is not None:
             return g
         self._slot, self._slot_u8[0] = 0, bool(u8)
         for _ in range(2):                       # warm-up outside capture: one-time kernel attributes, lazy module load
-            self.forward_device(B)
+            self.forward_device(B, need_last_act=need_last_act)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.forward_device(B)
+            self.forward_device(B, need_last_act=need_last_act)
         self._graphs = {k: v for k, v in self._graphs.items() if k[2] == id(self._buf)}   # drop graphs of old buffers
         self._graphs[key] = g
         return g
@@ -568,7 +583,8 @@ class CutoffVGG16Engine:
         B = x.shape[0]
         self._ensure(B, False)
         self.load_input(x, y)
-        probs = self.forward_device(B, y=self._buf["y"][self._slot][:B], inv_batch=inv_batch, loss_out=loss_out)
+        probs = self.forward_device(B, y=self._buf["y"][self._slot][:B], inv_batch=inv_batch, loss_out=loss_out,
+                                    need_last_act=False)
         self.release_slot()
         return probs
 
@@ -619,7 +635,7 @@ class CutoffVGG16Engine:
         last = self.specs[-1]
         if last.pool:
             raise NotImplementedError("Grad-CAM with a cutoff that ends in a pool layer")
-        probs = self.predict_batch(x)
+        probs = self.predict_batch(x, need_last_act=True)
         B = x.shape[0]
         oh, ow = out_hw if out_hw is not None else self.input_shape[:2]
         heat = torch.empty(B, oh, ow, device=self.device, dtype=torch.float32)

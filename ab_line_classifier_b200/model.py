@@ -230,7 +230,7 @@ class B200Model:
             if nxt is not None and len(nxt[0]) <= eng._cap:
                 slot = eng.stage(nxt[0], slot=cur ^ 1)         # H2D copy of the next batch overlaps this forward pass
             eng.use_slot(cur)
-            outs.append(eng.forward_device(B).clone())          # stays on device: one D2H at the end
+            outs.append(eng.forward_device(B, need_last_act=False).clone())   # stays on device: one D2H at the end
             eng.release_slot()
         if not outs:
             return (torch.zeros(0, self.n_classes, device=self.engine.device) if return_device

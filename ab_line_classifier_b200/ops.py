@@ -48,6 +48,28 @@ def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool
                  _ptr(out_pool), _ptr(pool_code), _ptr(colsum), B, H, W, Cin, Cout, flags, _stream())
 
 
+def igemm_gap_supported(H, W, Cout):
+    """Shapes abl_conv3x3_igemm_gap handles."""
+    return W % 16 == 0 and Cout % 128 == 0 and (H % 8 == 0 if Cout % 256 == 0 else H % 16 == 0)
+
+
+def conv3x3_igemm_gap(x, w_kmajor, bias, out_full, gap_part):
+    """Last conv forward (+bias+ReLU) with the GAP partial sums fused in; out_full may be None."""
+    _chk(x, torch.bfloat16, "x"); _chk(w_kmajor, torch.bfloat16, "w"); _chk(bias, torch.float32, "bias")
+    _chk(out_full, torch.bfloat16, "out_full"); _chk(gap_part, torch.float32, "gap_part")
+    B, H, W, Cin = x.shape
+    Cout = w_kmajor.shape[1]
+    assert gap_part.numel() >= B * (H // 8) * (W // 16) * Cout
+    _native.call("abl_conv3x3_igemm_gap", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(out_full), _ptr(gap_part), B, H, W,
+                 Cin, Cout, _stream())
+
+
+def gap_reduce(gap_part, gap, parts, hw):
+    _chk(gap_part, torch.float32, "gap_part"); _chk(gap, torch.float32, "gap")
+    B, Cc = gap.shape
+    _native.call("abl_gap_reduce", _ptr(gap_part), _ptr(gap), B, parts, Cc, hw, _stream())
+
+
 def dgrad_unpool_supported(H, W, Cout):
     """Shapes abl_conv3x3_dgrad_unpool handles (H, W = pooled resolution, Cout = channels of the pooled tensor)."""
     return W % 16 == 0 and H % 16 == 0 and Cout % 64 == 0 and Cout <= 128

@@ -58,6 +58,16 @@ int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, co
                       void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B, int H, int W,
                       int Cin, int Cout, int flags, void* stream);
 
+/* Forward conv + bias + ReLU (as abl_conv3x3_igemm with ABL_EPI_BIAS_RELU) of the LAST conv layer with Keras'
+ * GlobalAveragePooling2D (models.py:414) fused in: the epilogue also writes the per-channel sums of every 8x16-pixel
+ * rectangle it produces, gap_part fp32 [B * (H/8) * (W/16)][Cout] (one writer per value: deterministic), and
+ * abl_gap_reduce adds a frame's rectangles in fixed order.  out_full may be NULL (inference without Grad-CAM: the
+ * activation never reaches HBM).  Requires Cout % 128 == 0, W % 16 == 0, H % 16 == 0 (H % 8 if Cout % 256 == 0). */
+int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full, float* gap_part, int B,
+                          int H, int W, int Cin, int Cout, void* stream);
+/* gap[n][c] = (1/HW) * sum_{p < parts} gap_part[n*parts + p][c]   (parts = (H/8) * (W/16)) */
+int abl_gap_reduce(const float* gap_part, float* gap, int B, int parts, int C, int HW, void* stream);
+
 /* Conv2DBackpropInput + ReluGrad + MaxPoolGrad (+ BiasAddGrad) in ONE kernel, for a conv whose input is the output of a
  * 2x2 max-pool: the dgrad GEMM at the pooled resolution H x W, relu'(pooled) applied in the epilogue, and every value
  * routed straight to the window element the forward's routing code names (zeros elsewhere), so the pooled-resolution

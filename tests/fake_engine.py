@@ -41,7 +41,7 @@ class FakeEngine:
 
     def release_slot(self): pass
 
-    def forward_device(self, B):
+    def forward_device(self, B, need_last_act=True):
         return self.predict_batch(self._slots[self._cur][0])
 
     def refresh_operands(self, layers=None): pass

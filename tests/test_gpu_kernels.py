@@ -279,6 +279,33 @@ def test_dgrad_unpool_equals_dgrad_then_maxpool_backward(cin, cout, H, W):
     _close(db, db_ref, 1e-4, "fused bias grad (dgrad + unpool)")
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(256, 256, 32, 32), (128, 128, 32, 64)])
+def test_conv_with_fused_gap_partial_sums(cin, cout, H, W):
+    """abl_conv3x3_igemm_gap: same activation as the plain forward conv, and the epilogue's per-rectangle sums reduce
+    to the GlobalAveragePooling of that (bf16) activation; with out_full = NULL the sums are unchanged (inference)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cin + W)
+    B = 3
+    x = (torch.randn(B, H, W, cin, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = (torch.randn(cout, generator=g) * 0.1).cuda()
+    wf = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w.cuda(), wf, None)
+    ref = torch.empty(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3_igemm(x, wf, b, None, ref, None, ops.EPI_BIAS_RELU)
+    parts = (H // 8) * (W // 16)
+    out = torch.full_like(ref, float("nan"))
+    part = torch.full((B * parts, cout), float("nan"), device="cuda")
+    ops.conv3x3_igemm_gap(x, wf, b, out, part)
+    assert torch.equal(out, ref)
+    gap = torch.empty(B, cout, device="cuda")
+    ops.gap_reduce(part, gap, parts, H * W)
+    _close(gap, ref.float().mean(dim=(1, 2)), 1e-5, "fused GAP")
+    part2 = torch.full_like(part, float("nan"))
+    ops.conv3x3_igemm_gap(x, wf, b, None, part2)
+    assert torch.equal(part, part2)                       # deterministic, independent of the activation store
+
+
 def test_gap_forward_backward():
     ops = _ops()
     g = torch.Generator().manual_seed(3)
