@@ -315,6 +315,8 @@ def main():
                 fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
             elif name == "abl_conv3x3_dgrad_unpool":   # (dz, w, pooled, code, out, db, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
+            elif name == "abl_conv3x3_igemm_gap":      # (x, w, bias, out, gap_part, B, H, W, Cin, Cout, stream)
+                fl = 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]
             else:
                 fl = 0.0
             k["gflop"] += fl / 1e9

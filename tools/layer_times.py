@@ -28,6 +28,8 @@ for r in range(reps):
     for i, (name, a, e0, e1) in enumerate(recs):
         if name == "abl_conv3x3_igemm":
             shape = (a[8], a[9], a[10], a[11], a[12], a[13]); fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
+        elif name == "abl_conv3x3_igemm_gap":
+            shape = (a[5], a[6], a[7], a[8], a[9], "gap"); fl = 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]
         elif name == "abl_conv3x3_dgrad_unpool":
             shape = (a[6], a[7], a[8], a[9], a[10], "unpool"); fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
         elif name == "abl_conv3x3_wgrad":
