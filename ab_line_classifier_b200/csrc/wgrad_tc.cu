@@ -348,17 +348,37 @@ wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
 }
 
-// dw[i] (+)= sum_s partial[s][i], fixed summation order.
-__global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, long long n4,
-                                    int splits, int accumulate) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float4 s = accumulate ? dw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < splits; ++k) {
-            const float4 v = __ldg(partial + k * n4 + i);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+// dw[i] (+)= sum_s partial[s][i], fixed summation order (deterministic).  Block = 32 float4 columns x 8 split groups:
+// thread (c, g) adds splits g, g+8, g+16, ... (several loads in flight), then the 8 group sums are combined in group
+// order through shared memory.  (v1 gave one thread a whole column: up to 148 dependent loads in only 36 blocks,
+// 38 us for 22 MB; this form is bandwidth-bound.)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, long long n4, int splits,
+                    int accumulate) {
+    __shared__ float4 red[8][32];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    for (long long base = static_cast<long long>(blockIdx.x) * 32; base < n4; base += static_cast<long long>(gridDim.x) * 32) {
+        const long long i = base + c;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+#pragma unroll 4
+            for (int k = g; k < splits; k += 8) {
+                const float4 v = __ldg(partial + k * n4 + i);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
         }
-        dw[i] = s;
+        red[g][c] = s;
+        __syncthreads();
+        if (g == 0 && i < n4) {
+            float4 t = accumulate ? dw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = red[q][c];
+                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+            }
+            dw[i] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -515,7 +535,7 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
     }
     if (r != ABL_OK) return r;
     const long long n4 = 9LL * Cin * Cout / 4;
-    long long blocks = (n4 + 255) / 256;
+    long long blocks = (n4 + 31) / 32;
     const long long cap = static_cast<long long>(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const float4*>(workspace),
