@@ -5,6 +5,11 @@
 //   * dgrad    (Conv2DBackpropInput + ReluGrad of the layer below): the same contraction with
 //       X := dZ (Cout channels) and the tap-flipped, transposed filter Wd, epilogue = ReLU mask.
 //
+// Two main loops share one epilogue: conv3x3_halo_kernel (default: haloed activation tiles, stacked sub-tiles, split
+// A/B rings; see the comment above it) and conv3x3_tc_kernel (v1, described next: the fallback for frame sizes the
+// 16-pixel-wide tiles do not divide).  Entry points: abl_conv3x3_igemm (forward / dgrad), abl_conv3x3_igemm_gap (last
+// conv + fused GlobalAveragePooling sums), abl_conv3x3_dgrad_unpool (dgrad + ReluGrad + MaxPoolGrad in the epilogue).
+//
 // GEMM view per CTA tile: M = 128 output pixels (a box_h x box_w rectangle of one frame),
 // N = NTILE output channels, K = 9 taps x Cin.  A k-block is one tap x 64 input channels:
 //   A (K-major, 128 rows x 128 B, SWIZZLE_128B) = TMA box {64 ch, box_w, box_h, 1} of the NHWC
