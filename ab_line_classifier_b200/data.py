@@ -1,22 +1,38 @@
 """Host input pipeline stand-in for the reference's tf.data ``Preprocessor.prepare`` output
-(src/data/preprocessor.py:36-66): batches of (x fp32 [b,H,W,3] preprocessed, y one-hot fp32 [b,n]),
-reshuffled over the full dataset every epoch, last batch short (no drop_remainder).  Frames are held in
-pinned host memory so the engine's H2D copies are asynchronous."""
+(src/data/preprocessor.py:36-66): batches of (x [b,H,W,3], y one-hot fp32 [b,n]), reshuffled over the full dataset
+every epoch, last batch short (no drop_remainder).
+
+x is either fp32 frames as ``vgg16_preprocess`` leaves them or RAW uint8 RGB frames (4x smaller; preprocessing and
+resize then run on the device).  Two residencies:
+  * host (default): frames in pinned memory; every batch is gathered by index into one of a few rotating pinned
+    buffers (no per-epoch copy of the whole dataset), so the engine's H2D copies stay asynchronous;
+  * device (``device="cuda"``): the whole dataset lives in HBM (180 GB per B200: 1 M uint8 frames = 49 GB) and a batch
+    is one device-side gather -- the shuffle never touches the host.
+"""
 import numpy as np
 import torch
 
 
 class ArrayDataset:
-    def __init__(self, x, y=None, batch_size=64, shuffle=False, seed=0, pin=True):
-        # raw uint8 RGB frames stay uint8 (4x smaller H2D copies; preprocessing / resize run on the device)
-        x = np.asarray(x)
-        self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if x.dtype == np.uint8 else np.float32))
-        self.y = None if y is None else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
-        if pin and torch.cuda.is_available():
-            self.x = self.x.pin_memory()
-            self.y = None if self.y is None else self.y.pin_memory()
+    N_PINNED = 4      # rotating pinned batch buffers: a buffer is reused only after 3 later batches were staged
+
+    def __init__(self, x, y=None, batch_size=64, shuffle=False, seed=0, pin=True, device=None):
+        x = np.asarray(x) if not torch.is_tensor(x) else x
+        if not torch.is_tensor(x):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if x.dtype == np.uint8 else np.float32))
+        y = None if y is None else (y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)))
+        self.device = torch.device(device) if device is not None else None
+        if self.device is not None:
+            x = x.to(self.device)
+            y = None if y is None else y.to(self.device)
+        elif pin and torch.cuda.is_available():
+            x = x.pin_memory()
+            y = None if y is None else y.pin_memory()
+        self.x, self.y = x, y
         self.batch_size, self.shuffle = int(batch_size), shuffle
         self.rng = np.random.default_rng(seed)
+        self._pinned = pin and torch.cuda.is_available() and self.device is None
+        self._bufs, self._k = None, 0
 
     def __len__(self):
         return (len(self.x) + self.batch_size - 1) // self.batch_size
@@ -25,15 +41,35 @@ class ArrayDataset:
     def n_frames(self):
         return len(self.x)
 
+    def _gather(self, idx):
+        """Rows ``idx`` of (x, y): device gather, or host gather into the next rotating pinned buffer."""
+        if self.device is not None:
+            idx = idx.to(self.device)
+            return self.x.index_select(0, idx), (None if self.y is None else self.y.index_select(0, idx))
+        if not self._pinned:
+            return self.x[idx], (None if self.y is None else self.y[idx])
+        if self._bufs is None:
+            b = self.batch_size
+            self._bufs = [(torch.empty((b,) + tuple(self.x.shape[1:]), dtype=self.x.dtype).pin_memory(),
+                           None if self.y is None else torch.empty((b,) + tuple(self.y.shape[1:]), dtype=self.y.dtype).pin_memory())
+                          for _ in range(self.N_PINNED)]
+        bx, by = self._bufs[self._k]
+        self._k = (self._k + 1) % self.N_PINNED
+        n = len(idx)
+        torch.index_select(self.x, 0, idx, out=bx[:n])
+        if self.y is not None:
+            torch.index_select(self.y, 0, idx, out=by[:n])
+        return bx[:n], (None if self.y is None else by[:n])
+
     def __iter__(self):
         n = len(self.x)
-        if self.shuffle:
-            perm = torch.from_numpy(self.rng.permutation(n))
-            x, y = self.x[perm], (None if self.y is None else self.y[perm])
-        else:
-            x, y = self.x, self.y
+        if not self.shuffle:
+            for i in range(0, n, self.batch_size):
+                yield self.x[i:i + self.batch_size], (None if self.y is None else self.y[i:i + self.batch_size])
+            return
+        perm = torch.from_numpy(self.rng.permutation(n))
         for i in range(0, n, self.batch_size):
-            yield x[i:i + self.batch_size], (None if y is None else y[i:i + self.batch_size])
+            yield self._gather(perm[i:i + self.batch_size])
 
     def unbatch(self):
         """(frame, label) pairs, like ``tf.data.Dataset.unbatch`` (train_utils.py:285)."""

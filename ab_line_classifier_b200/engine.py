@@ -365,6 +365,8 @@ class CutoffVGG16Engine:
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_stream(cur) if self._slot_free[slot] is None else self._copy_stream.wait_event(
                 self._slot_free[slot])
+            if x.is_cuda:            # device-resident dataset: the batch was gathered on the caller's stream just now
+                self._copy_stream.wait_stream(cur)
             if resize:
                 # decoded frames at their native size: nearest-neighbour resize to IMG_DIM on the device, as
                 # Preprocessor._parse_fn does on the host (preprocessor.py:76-80); the copy stream runs it

@@ -153,6 +153,13 @@ def _iter_batches(data):
             yield item, None
 
 
+def _cat_labels(ys):
+    """Per-batch one-hot labels (numpy, pinned or device tensors) -> one float32 numpy array."""
+    if ys and torch.is_tensor(ys[0]):
+        return torch.cat([y.float() for y in ys]).cpu().numpy()
+    return np.concatenate([np.asarray(y, np.float32) for y in ys], 0)
+
+
 class B200Model:
     """Inner model (stand-in for the ``tf.keras.Model`` built at models.py:407-421)."""
 
@@ -246,11 +253,11 @@ class B200Model:
             if y is None:
                 raise ValueError("evaluate needs (x, y) batches")
             probs.append(eng.eval_batch(x, y, loss_out=loss).clone())
-            ys.append(np.asarray(y, np.float32))
+            ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled
         if not probs:
             return [0.0] + [0.0] * len(self.metric_objs)
         p = torch.cat(probs).cpu().numpy()
-        yt = np.concatenate(ys, 0)
+        yt = _cat_labels(ys)
         res = [float(loss.item()) / len(yt)]
         res += [m.result(yt, p) for m in self.metric_objs]
         return res
@@ -329,7 +336,7 @@ class B200Model:
                 eng.apply_optimizer(opt.kind, opt.learning_rate, trainable, **kw)
                 if self.metric_objs:
                     probs.append(eng._buf["probs"][:B].clone())
-                    ys.append(np.asarray(y, np.float32))
+                    ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled
                 sizes.append(B)
                 n_seen += B
                 slot_i += 1
@@ -338,7 +345,7 @@ class B200Model:
             drain()
             logs = {"loss": tot_loss / max(n_seen, 1)}
             if self.metric_objs and probs:
-                p, yt = torch.cat(probs).cpu().numpy(), np.concatenate(ys, 0)
+                p, yt = torch.cat(probs).cpu().numpy(), _cat_labels(ys)
                 for m in self.metric_objs:
                     logs[m.name] = m.result(yt, p)
             if validation_data is not None:

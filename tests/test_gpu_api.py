@@ -101,3 +101,22 @@ def test_predict_set_clip_predictions_and_gradcam_explainer():
     assert np.abs(heat[:2] - ref).max() < 3e-2
     mean_ms, _ = P.clock_avg_runtime(m.model, 3, 5)
     assert mean_ms > 0
+
+
+def test_array_dataset_host_and_device_residency_yield_the_same_batches():
+    """Shuffled batches gathered by index into rotating pinned buffers (host) or by a device-side gather (dataset resident
+    in HBM) are the same frames in the same order; buffers are recycled, so consumers must copy what they keep."""
+    from ab_line_classifier_b200.data import ArrayDataset
+    frames, labels = synth.synth_frames(70, seed=11)
+    y = synth.one_hot(labels)
+    host = ArrayDataset(frames, y, 16, shuffle=True, seed=5)
+    dev = ArrayDataset(frames, y, 16, shuffle=True, seed=5, device="cuda")
+    ref = np.random.default_rng(5).permutation(70)
+    got = 0
+    for (xh, yh), (xd, yd) in zip(host, dev):
+        n = len(xh)
+        assert xh.dtype == torch.uint8 and xh.is_pinned() and xd.is_cuda
+        np.testing.assert_array_equal(xh.numpy(), frames[ref[got:got + n]])
+        assert torch.equal(xd.cpu(), xh) and torch.equal(yd.cpu(), yh)
+        got += n
+    assert got == 70

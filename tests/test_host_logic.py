@@ -200,3 +200,20 @@ def test_product_does_not_import_the_oracle():
                     if "import oracle" in txt or "from oracle" in txt:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_array_dataset_batches_shuffle_and_short_last_batch():
+    from ab_line_classifier_b200.data import ArrayDataset
+    x = np.arange(10 * 2 * 2 * 3, dtype=np.float32).reshape(10, 2, 2, 3)
+    y = np.eye(2, dtype=np.float32)[np.arange(10) % 2]
+    ds = ArrayDataset(x, y, 4, shuffle=True, seed=3, pin=False)
+    for epoch in range(2):
+        seen = []
+        sizes = []
+        for xb, yb in ds:
+            sizes.append(len(xb))
+            seen += [int(v) for v in (xb[:, 0, 0, 0] / 12).tolist()]
+            np.testing.assert_array_equal(yb.numpy(), y[[int(v) for v in (xb[:, 0, 0, 0] / 12).tolist()]])
+        assert sizes == [4, 4, 2] and sorted(seen) == list(range(10))          # every frame once, last batch short
+    assert len(ds) == 3 and ds.n_frames == 10
+    assert [len(b[0]) for b in ArrayDataset(x, None, 4)] == [4, 4, 2]
