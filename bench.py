@@ -153,7 +153,7 @@ def workload_config(n_gpus, batch_note=None):
            "img_dim": [128, 128], "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus,
            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
            "gflop_per_frame": TRAIN_GFLOP,
-           "l2": "per-step working set ~2.9 GB >> 126 MB L2; 4 distinct resident input batches rotated"}
+           "l2": "per-step working set ~2 GB (1.05 GB kept activations + gradients) >> 126 MB L2; 4 distinct resident input batches rotated"}
     if batch_note:
         cfg["note"] = batch_note
     return cfg
