@@ -312,3 +312,23 @@ def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
     for name, (off, n, shape) in eng.segments.items():
         got, want = g[off:off + n].reshape(shape), g_ref[name]
         assert np.abs(got - want).max() <= 3e-2 * (np.abs(want).max() + 1e-12), name
+
+
+def test_ragged_single_and_empty_batches(setup):
+    """Edge cases of the data contract (preprocessor.py:53: no drop_remainder): batch sizes that are not multiples of
+    anything (37, 1) against the oracle, and an empty dataset through the public predict()."""
+    from ab_line_classifier_b200.model import B200Model
+    eng, params = setup
+    for B in (37, 1):
+        x, _, _ = _frames(B, seed=90 + B)
+        eng.predict_batch(x, use_graph=False)
+        logits = eng._buf["logits"][:B].cpu().numpy()
+        ref = oracle.forward(params, x, bf16=True)
+        assert np.abs(logits - ref["logits"]).max() < TOL_BF16
+    model = B200Model(eng, eng.input_shape, eng.n_classes, eng.dropout)
+    out = model.predict(np.zeros((0, 128, 128, 3), np.float32))
+    assert out.shape == (0, 2) and out.dtype == np.float32
+    x, y, _ = _frames(37, seed=5)
+    p = model.predict(x, batch_size=16)                       # 16 + 16 + 5
+    assert p.shape == (37, 2)
+    np.testing.assert_allclose(p, eng.predict_batch(x, use_graph=False).cpu().numpy(), rtol=0, atol=0)
