@@ -38,8 +38,10 @@ SIGNATURES = {
     "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "abl_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _ull, _u, _u,
                           _i, _i, _i, _vp]),
+    "abl_head_fwd_stepdev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _f, _ull, _vp, _u, _i, _i, _i, _vp]),
     "abl_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "abl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
+    "abl_adam_flat_tab": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _f, _f, _f, _vp]),
     "abl_rmsprop_flat": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
     "abl_resize_nearest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_clip_aggregate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
@@ -69,7 +71,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abl_abi_version() != 3:
+    if lib.abl_abi_version() != 4:
         raise RuntimeError("libabl_b200.so ABI version mismatch")
     _lib = lib
     return lib

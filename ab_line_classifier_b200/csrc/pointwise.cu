@@ -269,7 +269,9 @@ head_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, cons
                 float* __restrict__ logits, float* __restrict__ probs, const float* __restrict__ y,
                 const float* __restrict__ cw, float inv_batch, float* __restrict__ loss_sum,
                 float* __restrict__ dlogits, unsigned char* __restrict__ keep_mask, int keep_mask_in, int training,
-                float dropout, unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n) {
+                float dropout, unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
+                const unsigned int* __restrict__ step_dev) {
+    if (step_dev != nullptr) step = *step_dev;      // CUDA-graph replays: the counter lives on the device
     const int lane = threadIdx.x & 31;
     const int frame = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (frame >= B) return;
@@ -368,7 +370,11 @@ __global__ void head_bwd_kernel(const float* __restrict__ gap, const float* __re
 // ------------------------------------------------------------------ optimizers (28 / 20 B per param)
 __global__ void adam_flat_kernel(float4* __restrict__ theta, const float4* __restrict__ g, float4* __restrict__ m,
                                  float4* __restrict__ v, long long n4, float* theta_tail, const float* g_tail,
-                                 float* m_tail, float* v_tail, int tail, float alpha, float b1, float b2, float eps) {
+                                 float* m_tail, float* v_tail, int tail, float alpha, float b1, float b2, float eps,
+                                 const float* __restrict__ alpha_tab, const int* __restrict__ t_dev, int tab_len) {
+    // CUDA-graph replays: the step count lives on the device and alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) comes from a table
+    // the host computed with the same arithmetic as the eager path (entries beyond the table equal its last one)
+    if (alpha_tab != nullptr) alpha = alpha_tab[min(max(*t_dev, 1), tab_len) - 1];
     const float ob1 = 1.f - b1, ob2 = 1.f - b2;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -743,19 +749,38 @@ extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, floa
     return r;
 }
 
-extern "C" int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
-                            const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
-                            float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
-                            unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                            void* stream) {
+static int head_fwd_impl(const float* gap, const float* w, const float* b, float* logits, float* probs,
+                         const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
+                         float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
+                         unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
+                         const unsigned int* step_dev, void* stream) {
     if (!gap || !w || !b || !logits || !probs) { set_error("abl_head_fwd: null pointer"); return ABL_ERR_NULL; }
     if (training && !keep_mask) { set_error("abl_head_fwd: training needs a keep_mask buffer"); return ABL_ERR_NULL; }
     if (B <= 0 || C <= 0 || n <= 0 || n > kMaxClasses) { set_error("abl_head_fwd: need 1 <= n <= 8"); return ABL_ERR_SHAPE; }
     if (training && !(dropout >= 0.f && dropout < 1.f)) { set_error("abl_head_fwd: dropout must be in [0,1)"); return ABL_ERR_SHAPE; }
     head_fwd_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, keep_mask_in,
-        training, training ? dropout : 0.f, seed, step, rank, B, C, n);
+        training, training ? dropout : 0.f, seed, step, rank, B, C, n, step_dev);
     return check_launch();
+}
+
+extern "C" int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
+                            const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
+                            float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
+                            unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
+                            void* stream) {
+    return head_fwd_impl(gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask,
+                         keep_mask_in, training, dropout, seed, step, rank, B, C, n, nullptr, stream);
+}
+
+extern "C" int abl_head_fwd_stepdev(const float* gap, const float* w, const float* b, float* logits, float* probs,
+                                    const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
+                                    float* dlogits, unsigned char* keep_mask, int training, float dropout,
+                                    unsigned long long seed, const unsigned int* step_dev, unsigned int rank, int B,
+                                    int C, int n, void* stream) {
+    if (!step_dev) { set_error("abl_head_fwd_stepdev: step_dev is null"); return ABL_ERR_NULL; }
+    return head_fwd_impl(gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, 0,
+                         training, dropout, seed, 0u, rank, B, C, n, step_dev, stream);
 }
 
 extern "C" int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,
@@ -770,8 +795,22 @@ extern "C" int abl_head_bwd(const float* gap, const float* w, const float* dlogi
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static int adam_flat_impl(float* theta, const float* g, float* m, float* v, long long n, float alpha_t, float b1, float b2,
+                          float eps, const float* alpha_tab, const int* t_dev, int tab_len, void* stream);
+
 extern "C" int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n, float alpha_t, float b1,
                              float b2, float eps, void* stream) {
+    return adam_flat_impl(theta, g, m, v, n, alpha_t, b1, b2, eps, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int abl_adam_flat_tab(float* theta, const float* g, float* m, float* v, long long n, const float* alpha_tab,
+                                 const int* t_dev, int tab_len, float b1, float b2, float eps, void* stream) {
+    if (!alpha_tab || !t_dev || tab_len <= 0) { set_error("abl_adam_flat_tab: table / step pointer missing"); return ABL_ERR_NULL; }
+    return adam_flat_impl(theta, g, m, v, n, 0.f, b1, b2, eps, alpha_tab, t_dev, tab_len, stream);
+}
+
+static int adam_flat_impl(float* theta, const float* g, float* m, float* v, long long n, float alpha_t, float b1, float b2,
+                          float eps, const float* alpha_tab, const int* t_dev, int tab_len, void* stream) {
     if (!theta || !g || !m || !v) { set_error("abl_adam_flat: null pointer"); return ABL_ERR_NULL; }
     if (n <= 0) return ABL_OK;
     if (!aligned16(theta) || !aligned16(g) || !aligned16(m) || !aligned16(v)) {
@@ -781,7 +820,8 @@ extern "C" int abl_adam_flat(float* theta, const float* g, float* m, float* v, l
     const int tail = static_cast<int>(n - n4 * 4);
     adam_flat_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
-        reinterpret_cast<float4*>(v), n4, theta + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, tail, alpha_t, b1, b2, eps);
+        reinterpret_cast<float4*>(v), n4, theta + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, tail, alpha_t, b1, b2, eps,
+        alpha_tab, t_dev, tab_len);
     return check_launch();
 }
 

@@ -13,6 +13,7 @@ HBM layout (per process / GPU)
   act[l] / pooled[l]     : bf16 NHWC activations (full resolution kept only when training).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -103,6 +104,10 @@ class CutoffVGG16Engine:
         self._cap_train = False
         self._buf = {}
         self._graphs = {}             # (batch, uint8 input, buffer generation) -> captured forward CUDA graph
+        self._tgraphs, self._tg_seen, self._alpha_tabs = {}, {}, {}      # whole-train-step graphs (fit_step)
+        self._step_dev = self._t_dev = None
+        self._dev_counters = None
+        self.train_graphs = os.environ.get("ABL_TRAIN_GRAPHS", "1") != "0"
         # data parallel: all-reduce gradient buckets while backward still runs (True) or once after it (False).
         # Measured at 4 x B200, batch 256/GPU: 4.91 ms/step overlapped vs 4.68 ms after backward -- the persistent
         # conv kernels own every SM (1 CTA of ~220 KB shared memory each, static tile assignment), so a CTA whose SM
@@ -290,7 +295,7 @@ class CutoffVGG16Engine:
 
     # ------------------------------------------------------------------ forward
     def forward_device(self, B, training=False, keep_mask_in=False, y=None, inv_batch=None, loss_out=None,
-                       need_last_act=True):
+                       need_last_act=True, step_dev=None):
         """Runs the network on self._buf['x'][:B] (already resident).  Returns probs view [B,n].
         training: dropout on, class-weighted loss + dlogits.  Otherwise, if y is given, the UNweighted
         loss sum_i l_i * inv_batch is accumulated into loss_out (Keras evaluate / validation)."""
@@ -324,7 +329,8 @@ class CutoffVGG16Engine:
         if training:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
                          b["probs"][:B], y, self.class_weight, inv_batch, loss_out, b["dlogits"][:B],
-                         b["keep"][:B], keep_mask_in, True, self.dropout, self.seed, self.step_count, self.rank)
+                         b["keep"][:B], keep_mask_in, True, self.dropout, self.seed, self.step_count, self.rank,
+                         step_dev=step_dev)
         elif y is not None:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
                          b["probs"][:B], y, None, inv_batch, loss_out)
@@ -537,11 +543,13 @@ class CutoffVGG16Engine:
                     runs.append([s, e])
         return runs
 
-    def apply_optimizer(self, kind, lr, trainable, beta_1=0.9, beta_2=0.999, rho=0.9, eps=1e-7):
-        """Keras 2.9 Adam / RMSprop on the trainable slices (Appendix A.5), then re-cast bf16 operands."""
+    def apply_optimizer(self, kind, lr, trainable, beta_1=0.9, beta_2=0.999, rho=0.9, eps=1e-7, alpha_tab=None):
+        """Keras 2.9 Adam / RMSprop on the trainable slices (Appendix A.5), then re-cast bf16 operands.
+        alpha_tab (CUDA-graph capture): Adam's alpha_t comes from this device table indexed by the device step count."""
         key = kind
         t = self.opt_steps.get(key, 0) + 1
-        self.opt_steps[key] = t
+        if alpha_tab is None:
+            self.opt_steps[key] = t          # (graph replays mirror the counter on the host themselves)
         fused = self._symm is not None and self._grad_unreduced
         if fused:
             self._symm.barrier()             # every rank's gradients are final
@@ -554,6 +562,9 @@ class CutoffVGG16Engine:
                 if fused:
                     ops.opt_flat_dp("adam", self._theta_peers, self._grad_peers, self.opt_state["m"],
                                     self.opt_state["v"], s, e - s, self.rank, self.world_size, alpha, beta_1, beta_2, eps)
+                elif alpha_tab is not None:
+                    ops.adam_flat_tab(self.theta[s:e], self.grad[s:e], self.opt_state["m"][s:e], self.opt_state["v"][s:e],
+                                      alpha_tab, self._t_dev, beta_1, beta_2, eps)
                 else:
                     ops.adam_flat(self.theta[s:e], self.grad[s:e], self.opt_state["m"][s:e], self.opt_state["v"][s:e],
                                   alpha, beta_1, beta_2, eps)
@@ -630,6 +641,80 @@ class CutoffVGG16Engine:
         if apply_update:
             self.apply_optimizer(optimizer, lr, trainable)
         return b["loss"] if loss_out is None else loss_out
+
+    # ------------------------------------------------------------------ whole-step CUDA graph (small batches)
+    TRAIN_GRAPH_MAX_BATCH = 64    # above this the step is GPU-bound; below, ~0.7 ms of host enqueue time per step dominates
+    ALPHA_TABLE_LEN = 32768       # Adam alpha_t for t = 1..T (beyond T it equals lr to fp32 precision)
+
+    def fit_step(self, trainable, optimizer, lr, slot, batch, global_batch, loss_out=None, **kw):
+        """What fit() does per batch: train_step on a staged slot + apply_optimizer.  For small batches on one GPU the
+        ~36 launches (forward, loss, backward, optimizer, operand re-cast) are captured ONCE per configuration into a
+        CUDA graph and replayed; the dropout step and the Adam step count advance in device memory."""
+        trainable = frozenset(trainable)
+        eligible = (self.train_graphs and self.world_size == 1 and batch <= self.TRAIN_GRAPH_MAX_BATCH
+                    and batch <= self._cap and self._cap_train)
+        key = (batch, trainable, optimizer, float(lr), tuple(sorted(kw.items())), slot, self._slot_u8[slot],
+               id(self._buf), float(global_batch)) if eligible else None
+        if eligible:
+            self._tg_seen[key] = self._tg_seen.get(key, 0) + 1
+        if not eligible or self._tg_seen[key] <= 2:       # the first two steps of a configuration run eagerly
+            self.train_step(None, None, trainable, apply_update=False, loss_out=loss_out, global_batch=global_batch,
+                            slot=slot, batch=batch, defer_reduce=True)
+            self.apply_optimizer(optimizer, lr, trainable, **kw)
+            return
+        b = self._buf
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+            self._t_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+        t_host = self.opt_steps.get(optimizer, 0)
+        if self._dev_counters != (self.step_count, optimizer, t_host):      # re-sync after eager steps
+            self._step_dev.fill_(self.step_count)
+            self._t_dev.fill_(t_host)
+        g = self._tgraphs.get(key)
+        self.use_slot(slot)
+        if g is None:
+            alpha_tab = None
+            if optimizer == "adam":
+                b1, b2 = kw.get("beta_1", 0.9), kw.get("beta_2", 0.999)
+                tk = (float(lr), b1, b2)
+                if tk not in self._alpha_tabs:
+                    tt = np.arange(1, self.ALPHA_TABLE_LEN + 1, dtype=np.float64)
+                    tab = np.array([lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t) for t in tt], np.float32)
+                    self._alpha_tabs[tk] = torch.from_numpy(tab).to(self.device)
+                alpha_tab = self._alpha_tabs[tk]
+            if optimizer == "adam" and "m" not in self.opt_state or optimizer == "rmsprop" and "rms" not in self.opt_state:
+                raise RuntimeError("optimizer state must exist before capture")      # two eager steps guarantee it
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                b["loss"].zero_()
+                self.forward_device(batch, training=True, y=b["y"][slot][:batch], inv_batch=1.0 / float(global_batch),
+                                    loss_out=b["loss"], step_dev=self._step_dev)
+                self._step_dev.add_(1)
+                self.backward_device(batch, trainable)
+                self._t_dev.add_(1)
+                if optimizer == "adam":
+                    self.apply_optimizer(optimizer, lr, trainable, alpha_tab=alpha_tab, **kw)
+                else:
+                    self._apply_rmsprop_captured(lr, trainable, **kw)
+            self._tgraphs = {k: v for k, v in self._tgraphs.items() if k[7] == id(self._buf)}
+            self._tgraphs[key] = g
+            # capture does not execute: fall through to the first replay
+        g.replay()
+        self.step_count += 1
+        self.opt_steps[optimizer] = t_host + 1
+        self._dev_counters = (self.step_count, optimizer, t_host + 1)
+        self.release_slot()
+        if loss_out is not None:
+            loss_out.copy_(b["loss"])
+
+    def _apply_rmsprop_captured(self, lr, trainable, rho=0.9, eps=1e-7, **_):
+        """RMSprop has no step-dependent scalar: the eager kernels are captured as they are (host counter untouched)."""
+        if "rms" not in self.opt_state:
+            self.opt_state["rms"] = torch.zeros(self.n_flat, device=self.device)
+        for s, e in self._runs(trainable):
+            ops.rmsprop_flat(self.theta[s:e], self.grad[s:e], self.opt_state["rms"][s:e], lr, rho, eps)
+        self.refresh_operands(trainable)
 
     # ------------------------------------------------------------------ Grad-CAM
     def gradcam_batch(self, x, out_hw=None):

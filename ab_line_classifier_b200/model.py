@@ -331,9 +331,8 @@ class B200Model:
                 if nxt is not None:
                     eng.reserve(len(nxt[0]), True)
                     nslot = eng.stage(nxt[0], nxt[1], slot=slot ^ 1)
-                eng.train_step(None, None, trainable, apply_update=False, loss_out=ring[slot_i:slot_i + 1],
-                               global_batch=B * eng.world_size, slot=slot, batch=B, defer_reduce=True)
-                eng.apply_optimizer(opt.kind, opt.learning_rate, trainable, **kw)
+                eng.fit_step(trainable, opt.kind, opt.learning_rate, slot, B, B * eng.world_size,
+                             loss_out=ring[slot_i:slot_i + 1], **kw)
                 if self.metric_objs:
                     probs.append(eng._buf["probs"][:B].clone())
                     ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled

@@ -195,12 +195,18 @@ def gap_bwd_relu(dgap, a, dz, db=None):
 
 
 def head_fwd(gap, w, b, logits, probs, y=None, class_weight=None, inv_batch=1.0, loss_sum=None, dlogits=None,
-             keep_mask=None, keep_mask_in=False, training=False, dropout=0.0, seed=0, step=0, rank=0):
+             keep_mask=None, keep_mask_in=False, training=False, dropout=0.0, seed=0, step=0, rank=0, step_dev=None):
     for t in (gap, w, b, logits, probs, y, class_weight, loss_sum, dlogits):
         _chk(t, torch.float32, "tensor")
     _chk(keep_mask, torch.uint8, "keep_mask")
     B, Cc = gap.shape
     n = w.shape[1]
+    if step_dev is not None:       # dropout counter in device memory (CUDA-graph replays)
+        _chk(step_dev, torch.int32, "step_dev")
+        _native.call("abl_head_fwd_stepdev", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
+                     _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
+                     int(bool(training)), float(dropout), int(seed), _ptr(step_dev), int(rank), B, Cc, n, _stream())
+        return
     _native.call("abl_head_fwd", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
                  _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
                  int(bool(keep_mask_in)), int(bool(training)), float(dropout), int(seed), int(step), int(rank),
@@ -220,6 +226,15 @@ def adam_flat(theta, g, m, v, alpha_t, b1=0.9, b2=0.999, eps=1e-7):
         _chk(t, torch.float32, "tensor")
     _native.call("abl_adam_flat", _ptr(theta), _ptr(g), _ptr(m), _ptr(v), theta.numel(), float(alpha_t), float(b1),
                  float(b2), float(eps), _stream())
+
+
+def adam_flat_tab(theta, g, m, v, alpha_tab, t_dev, b1=0.9, b2=0.999, eps=1e-7):
+    """Adam with alpha_t looked up on the device: alpha_tab fp32 [T] (t = 1..T), t_dev int32 [1] (abl_adam_flat_tab)."""
+    for t in (theta, g, m, v, alpha_tab):
+        _chk(t, torch.float32, "tensor")
+    _chk(t_dev, torch.int32, "t_dev")
+    _native.call("abl_adam_flat_tab", _ptr(theta), _ptr(g), _ptr(m), _ptr(v), theta.numel(), _ptr(alpha_tab), _ptr(t_dev),
+                 alpha_tab.numel(), float(b1), float(b2), float(eps), _stream())
 
 
 def rmsprop_flat(theta, g, rms, lr, rho=0.9, eps=1e-7):

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 3
+#define ABL_ABI_VERSION 4
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -151,6 +151,12 @@ int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits
                  float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                  unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
                  void* stream);
+/* abl_head_fwd with the dropout step counter read from DEVICE memory (*step_dev) instead of passed by value, so the
+ * launch can be replayed from a CUDA graph while the counter advances on the device (mask always generated). */
+int abl_head_fwd_stepdev(const float* gap, const float* w, const float* b, float* logits, float* probs,
+                         const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
+                         float* dlogits, unsigned char* keep_mask, int training, float dropout, unsigned long long seed,
+                         const unsigned int* step_dev, unsigned int rank, int B, int C, int n, void* stream);
 /* dw[C][n] += h^T dlogits, db[n] += sum_i dlogits, dgap[i][c] = scale_ic * sum_j dlogits[i][j] w[c][j]
  * with h = gap * scale, scale_ic = keep_mask ? mask/(1-dropout) : 1. */
 int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,
@@ -160,6 +166,10 @@ int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const u
  * passes alpha_t = lr * sqrt(1-b2^t) / (1-b1^t).  Flat fp32 buffers of n elements. */
 int abl_adam_flat(float* theta, const float* g, float* m, float* v, long long n, float alpha_t, float b1,
                   float b2, float eps, void* stream);
+/* abl_adam_flat for CUDA-graph replays: alpha_t = alpha_tab[min(*t_dev, tab_len) - 1] with the 1-based step count t in
+ * DEVICE memory and a table the host filled with lr*sqrt(1-b2^t)/(1-b1^t) for t = 1..tab_len. */
+int abl_adam_flat_tab(float* theta, const float* g, float* m, float* v, long long n, const float* alpha_tab,
+                      const int* t_dev, int tab_len, float b1, float b2, float eps, void* stream);
 /* Keras 2.9 RMSprop (models.py:398), momentum 0, not centered. */
 int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, float lr, float rho, float eps,
                      void* stream);

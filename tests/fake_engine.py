@@ -85,6 +85,11 @@ class FakeEngine:
             return loss_out
         return t
 
+    def fit_step(self, trainable, optimizer, lr, slot, batch, global_batch, loss_out=None, **kw):
+        self.train_step(None, None, trainable, apply_update=False, loss_out=loss_out, global_batch=global_batch,
+                        slot=slot, batch=batch, defer_reduce=True)
+        self.apply_optimizer(optimizer, lr, trainable, **kw)
+
     def apply_optimizer(self, kind, lr, trainable, beta_1=0.9, beta_2=0.999, rho=0.9, eps=1e-7):
         FakeEngine.calls.append((kind, lr, frozenset(trainable)))
         t = self.steps.get(kind, 0) + 1

@@ -1,4 +1,5 @@
-"""Developer tool: full train step (all layers, Adam) at several batch sizes, CUDA events over 30 steps."""
+"""Developer tool: fit()'s per-batch step (all layers, Adam, device-resident frames) at several batch sizes, CUDA events
+over 30 steps.  ABL_TRAIN_GRAPHS=0 disables the whole-step CUDA graph used for batches <= 64."""
 import os
 import sys
 import time
@@ -15,14 +16,21 @@ for B in [int(a) for a in sys.argv[1:]] or [16, 32, 64, 128, 256]:
     fr, lab = synth.synth_frames(B, seed=1)
     x = torch.from_numpy(synth.vgg16_preprocess(fr)).cuda()
     y = torch.from_numpy(synth.one_hot(lab)).cuda()
-    for _ in range(5):
-        eng.train_step(x, y, tr)
+    eng.reserve(B, True)
+    kw = {"beta_1": 0.9, "beta_2": 0.999, "eps": 1e-7}
+
+    def step(i):      # what fit() does per batch (small batches replay the whole-step CUDA graph)
+        slot = eng.stage(x, y, slot=i & 1)
+        eng.fit_step(tr, "adam", 3e-4, slot, B, B, **kw)
+
+    for i in range(8):
+        step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     e0.record()
-    for _ in range(30):
-        eng.train_step(x, y, tr)
+    for i in range(30):
+        step(i)
     e1.record()
     cpu_ms = (time.perf_counter() - w0) / 30 * 1e3           # time to ENQUEUE a step (host side)
     torch.cuda.synchronize()
