@@ -467,3 +467,70 @@ def test_error_behaviour_bad_shapes_and_alignment():
     th = torch.zeros(9, device="cuda")
     with pytest.raises(RuntimeError, match="aligned"):
         ops.adam_flat(th[1:], th[1:], th[1:], th[1:], 1e-3)
+
+
+def _guarded(shape, dtype, fill=0):
+    """Output tensor carved out of the middle of a larger allocation whose margins hold a sentinel: an out-of-bounds
+    write by a kernel (compute-sanitizer is not available on this pool) shows up as a changed margin."""
+    n = int(np.prod(shape))
+    pad = 4096
+    raw = torch.full((n + 2 * pad,), 77 if dtype in (torch.uint8, torch.int16) else 7.0, device="cuda").to(dtype)
+    view = raw[pad:pad + n].view(shape)
+    view.fill_(fill)
+
+    def check(what):
+        sent = raw[0].item()
+        assert bool((raw[:pad] == sent).all()) and bool((raw[pad + n:] == sent).all()), f"{what}: wrote outside its buffer"
+    return view, check
+
+
+def test_kernels_do_not_write_outside_their_output_buffers():
+    ops = _ops()
+    g = torch.Generator().manual_seed(123)
+    bf = torch.bfloat16
+    for B in (1, 3):
+        # block1_conv2-shaped forward with pool + routing codes, then the un-pooling dgrad of the layer above it
+        x = (torch.randn(B, 128, 128, 64, generator=g) * 0.5).to(bf).cuda()
+        w = torch.randn(3, 3, 64, 64, generator=g) * 0.05
+        wf = torch.empty(9, 64, 64, device="cuda", dtype=bf); wd = torch.empty(9, 64, 64, device="cuda", dtype=bf)
+        ops.prep_conv_weights(w.cuda(), wf, wd)
+        full, c1 = _guarded((B, 128, 128, 64), bf); pool, c2 = _guarded((B, 64, 64, 64), bf)
+        code, c3 = _guarded((B, 64, 64, 8), torch.int16)
+        ops.conv3x3_igemm(x, wf, torch.zeros(64, device="cuda"), None, full, pool, ops.EPI_BIAS_RELU, pool_code=code)
+        c1("conv fwd full"); c2("conv fwd pooled"); c3("routing codes")
+        w2 = torch.randn(3, 3, 64, 128, generator=g) * 0.05
+        wd2 = torch.empty(9, 64, 128, device="cuda", dtype=bf)
+        ops.prep_conv_weights(w2.cuda(), None, wd2)
+        dz = (torch.randn(B, 64, 64, 128, generator=g) * 0.1).to(bf).cuda()
+        up, c4 = _guarded((B, 128, 128, 64), bf); db, c5 = _guarded((64,), torch.float32)
+        ops.conv3x3_dgrad_unpool(dz, wd2, pool, code, up, db)
+        c4("dgrad unpool"); c5("fused bias grad")
+        dzf, c6 = _guarded((B, 128, 128, 64), bf)
+        ops.maxpool_bwd_code(pool, code, dzf)
+        c6("maxpool_bwd_code")
+        # last conv with fused GAP partial sums; masked dgrad with column sums
+        x3 = (torch.randn(B, 32, 32, 256, generator=g) * 0.5).to(bf).cuda()
+        w3 = torch.randn(3, 3, 256, 256, generator=g) * 0.03
+        wf3 = torch.empty(9, 256, 256, device="cuda", dtype=bf); wd3 = torch.empty(9, 256, 256, device="cuda", dtype=bf)
+        ops.prep_conv_weights(w3.cuda(), wf3, wd3)
+        a3, c7 = _guarded((B, 32, 32, 256), bf); part, c8 = _guarded((B * 8, 256), torch.float32)
+        ops.conv3x3_igemm_gap(x3, wf3, torch.zeros(256, device="cuda"), a3, part)
+        c7("igemm_gap activation"); c8("gap partial sums")
+        dx3, c9 = _guarded((B, 32, 32, 256), bf); cs, c10 = _guarded((256,), torch.float32)
+        ops.conv3x3_igemm(x3, wd3, None, a3, dx3, None, ops.EPI_RELU_MASK, colsum=cs)
+        c9("masked dgrad"); c10("column sums")
+        # wgrad: gradient + workspace
+        ws_bytes = ops.wgrad_workspace_bytes(B, 128, 128, 64, 64)
+        ws, c11 = _guarded((ws_bytes,), torch.uint8); dw, c12 = _guarded((3, 3, 64, 64), torch.float32)
+        dbw, c13 = _guarded((64,), torch.float32)
+        ops.conv3x3_wgrad(x, full, dw, dbw, ws)
+        c11("wgrad workspace"); c12("wgrad dw"); c13("wgrad db")
+        # block1_conv1 forward (fp32 frames) and resize
+        frames = (torch.rand(B, 128, 128, 3, generator=g) * 255 - 110).cuda()
+        a1, c14 = _guarded((B, 128, 128, 64), bf)
+        ops.conv_first_fwd(frames, (torch.randn(3, 3, 3, 64, generator=g) * 0.1).cuda(), torch.zeros(64, device="cuda"), a1)
+        c14("conv_first fwd")
+        rs, c15 = _guarded((B, 128, 128, 3), torch.uint8)
+        ops.resize_nearest_u8(torch.randint(0, 256, (B, 77, 91, 3), generator=g, dtype=torch.uint8).cuda(), rs)
+        c15("resize")
+    torch.cuda.synchronize()
