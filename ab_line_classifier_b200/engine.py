@@ -151,7 +151,13 @@ class CutoffVGG16Engine:
         self._symm = None          # symmetric-memory handle (peer pointers + device barrier) when DP is fused
         self._grad_unreduced = False
         if self.world_size > 1 and self.fused_dp:
-            self._alloc_symmetric(off)
+            try:
+                self._alloc_symmetric(off)
+            except Exception as e:  # noqa: BLE001 -- e.g. a driver / container without peer-memory support
+                import sys
+                print(f"[ab_line_classifier_b200] symmetric memory unavailable ({type(e).__name__}: {e}); "
+                      "data parallel falls back to NCCL all-reduce + local optimizer", file=sys.stderr)
+                self._symm = None
         if self._symm is None:
             self.theta = torch.zeros(off, device=dev, dtype=torch.float32)
             self.grad = torch.zeros(off, device=dev, dtype=torch.float32)
