@@ -78,27 +78,37 @@ steps = 4
 for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
     eng.set_weights(w0)
     eng.opt_state.clear(); eng.opt_steps.clear()
+    th_steps = []
     for i in range(steps):
         eng.train_step(x[sl], y[sl], tr, opt, lr, keep_mask=keep[sl], global_batch=G)
-    torch.cuda.synchronize()
-    th_dp = eng.theta.clone()
+        torch.cuda.synchronize()
+        th_steps.append(eng.theta.clone())
+    th_dp = th_steps[-1]
     ths = [torch.empty_like(th_dp) for _ in range(world)]
     dist.all_gather(ths, th_dp)
     assert all(torch.equal(ths[0], t) for t in ths), f"{opt}: weights diverged across ranks"
-    # (a) same DP training through NCCL all-reduce + the local optimizer kernel: the per-rank gradients are the same
-    #     values up to float-atomic order, and the cross-rank summation order can differ for more than 2 ranks
+    # (a) same DP training through NCCL all-reduce + the local optimizer kernel.  After ONE step the two paths must agree
+    #     to fp32 rounding (same per-rank gradients up to float-atomic order; only the cross-rank summation differs).
+    #     Over several steps ANY two runs drift apart -- a 1e-8 weight difference flips a few ReLU masks, and the
+    #     normalised Adam / RMSprop steps amplify that (two NCCL-path runs differ by 6e-4 max / 1 % of the weights after
+    #     four RMSprop steps) -- so the multi-step comparison is statistical.
+    th_dp_1 = th_steps[0]
     symm_saved, eng._symm = eng._symm, None
     eng.set_weights(w0)
     eng.opt_state.clear(); eng.opt_steps.clear()
+    th_nccl_steps = []
     for i in range(steps):
         eng.train_step(x[sl], y[sl], tr, opt, lr, keep_mask=keep[sl], global_batch=G)
-    torch.cuda.synchronize()
-    th_nccl = eng.theta.clone()
+        torch.cuda.synchronize()
+        th_nccl_steps.append(eng.theta.clone())
+    th_nccl = th_nccl_steps[-1]
+    d1 = (th_dp_1 - th_nccl_steps[0]).abs()
     d = (th_dp - th_nccl).abs()
-    mark(f"{opt}: fused={symm_saved is not None}; vs NCCL all-reduce + local optimizer: max diff {float(d.max()):.3e}, "
+    mark(f"{opt}: fused={symm_saved is not None}; vs NCCL all-reduce + local optimizer: after 1 step max diff "
+         f"{float(d1.max()):.3e}; after {steps} steps max {float(d.max()):.3e}, "
          f"{float((d > 2e-5).float().mean()):.2e} of the weights differ by > 2e-5")
-    # (not bit-identical run to run: block1_conv1 / bias / head gradients are accumulated with float atomics)
-    assert float((d > 2e-5).float().mean()) < (1e-4 if world == 2 else 1e-2) and float(d.median()) < 1e-7
+    assert float(d1.max()) < 1e-7, "fused peer-memory optimizer != NCCL all-reduce + optimizer after one step"
+    assert float((d > 2e-5).float().mean()) < 5e-2 and float(d.median()) < 1e-6
     # (b) single-device training on the concatenated batch (world_size forced to 1).  Adam / RMSprop normalise the
     #     step, so an element whose gradient is at fp32-summation-noise level may step differently: bound the typical
     #     difference and the FRACTION of such elements, not the maximum.
