@@ -335,42 +335,63 @@ def test_ragged_single_and_empty_batches(setup):
 
 
 @pytest.mark.parametrize("optimizer,lr", [("adam", 3e-4), ("rmsprop", 1e-4)])
-def test_whole_step_cuda_graph_tracks_eager_training(setup, optimizer, lr, monkeypatch):
+def test_whole_step_cuda_graph_tracks_eager_training(setup, optimizer, lr):
     """fit()'s per-batch step for small batches replays a CUDA graph (forward, loss, backward, optimizer, operand
-    re-cast; dropout step and Adam step count advance on the device).  Six steps through the graph path (2 eager +
-    capture + 4 replays) must give the weights of six eager steps, up to the float-atomic order of bias / head grads,
-    and the same dropout masks (the device step counter tracks the host one)."""
+    re-cast; the dropout step and Adam's step count advance on the device).  From the SAME state (two eager steps, then a
+    snapshot) the third and fourth steps are run eagerly and through capture + replay: weights, loss and dropout masks
+    must agree to the float-atomic noise of a single step.  (Whole runs cannot be compared tightly: any two runs drift
+    apart chaotically after a few normalised optimizer steps.)"""
     eng, params = setup
     x, y, _ = _frames(16, seed=21)
     tr = frozenset(eng.layer_names())
     kw = {"beta_1": 0.9, "beta_2": 0.999, "eps": 1e-7} if optimizer == "adam" else {"rho": 0.9, "eps": 1e-7}
-    outs, masks = [], []
-    for use_graph in (False, True):
-        eng.train_graphs = use_graph
-        eng.set_weights(params)
-        eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
-        eng._tg_seen.clear(); eng._tgraphs.clear(); eng._dev_counters = None
-        eng.reserve(16, True)
-        losses = torch.zeros(6, device="cuda")
-        for i in range(6):
-            slot = eng.stage(x, y, slot=i & 1)
-            eng.fit_step(tr, optimizer, lr, slot, 16, 16, loss_out=losses[i:i + 1], **kw)
-        outs.append((eng.theta.clone(), losses.clone()))
-        masks.append(eng._buf["keep"][:16].clone())
-        assert eng.step_count == 6 and eng.opt_steps[optimizer] == 6
-        if use_graph:
-            assert len(eng._tgraphs) == 2           # one graph per input slot
     eng.train_graphs = True
-    (th_e, l_e), (th_g, l_g) = outs
-    assert torch.equal(masks[0], masks[1])
-    # Two EAGER runs of these six steps already differ (measured: median 1.8e-7, max 4.5e-4, losses in the 4th digit by
-    # step 6): Adam / RMSprop normalise the step, so the float-atomic noise of the bias and block1_conv1 gradients is
-    # amplified chaotically.  The graph path is held to that noise level; a wrong dropout step, alpha_t or stale operand
-    # would show up as a median difference >= 1e-5 and loss differences of order 0.1.
-    d = (th_e - th_g).abs()
-    assert float(d.median()) < 2e-6 and float((d > 2e-5).float().mean()) < 2e-2, (float(d.max()), float(d.median()))
-    assert float((l_e - l_g).abs().max()) < 5e-3 and float((l_e - l_g)[:3].abs().max()) < 1e-4
-    assert float((th_e - torch.from_numpy(np.concatenate([np.pad(params[k].ravel(), (0, (-params[k].size) % 4))
-                  for k in eng.segments])).cuda()).abs().max()) > 1e-5          # the weights really moved
+    eng.set_weights(params)
     eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+    eng._tg_seen.clear(); eng._tgraphs.clear(); eng._dev_counters = None
+    eng.reserve(16, True)
+
+    def step(i, loss):
+        slot = eng.stage(x, y, slot=i & 1)
+        eng.fit_step(tr, optimizer, lr, slot, 16, 16, loss_out=loss, **kw)
+
+    scratch = torch.zeros(1, device="cuda")
+    for i in range(4):                      # both input slots have now been seen twice -> later steps may use graphs
+        scratch.zero_()
+        step(i, scratch)
+    assert not eng._tgraphs
+    snap = (eng.theta.clone(), {k: v.clone() for k, v in eng.opt_state.items()}, eng.step_count, dict(eng.opt_steps))
+
+    def restore():
+        eng.theta.copy_(snap[0])
+        for k, v in snap[1].items():
+            eng.opt_state[k].copy_(v)
+        eng.step_count, eng.opt_steps = snap[2], dict(snap[3])
+        eng._dev_counters = None             # device-side counters are re-synchronised from the host values
+        eng.refresh_operands()
+
+    results = []
+    for use_graph in (False, True):
+        restore()
+        eng.train_graphs = use_graph
+        losses = torch.zeros(2, device="cuda")
+        out = []
+        for j in range(2):
+            step(4 + j, losses[j:j + 1])
+            out.append((eng.theta.clone(), eng._buf["keep"][:16].clone()))
+        results.append((out, losses.clone()))
+        assert eng.step_count == snap[2] + 2 and eng.opt_steps[optimizer] == snap[3][optimizer] + 2
+    eng.train_graphs = True
+    assert len(eng._tgraphs) == 2            # one captured graph per input slot
+    (eager, l_e), (graph, l_g) = results
+    moved = float((eager[1][0] - snap[0]).abs().max())
+    assert moved > 1e-5                      # the weights really moved
+    for j in range(2):
+        assert torch.equal(eager[j][1], graph[j][1])                          # same dropout masks: the device step counter tracks the host's
+    assert float((eager[0][0] - graph[0][0]).abs().max()) < 1e-6             # one step: float-atomic noise only
+    d = (eager[1][0] - graph[1][0]).abs()
+    assert float(d.median()) < 1e-7 and float((d > 2e-5).float().mean()) < 1e-3, (float(d.max()), float(d.median()))
+    assert float((l_e - l_g).abs().max()) < 1e-4
+    eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+    eng._tg_seen.clear(); eng._tgraphs.clear(); eng._dev_counters = None
     eng.set_weights(params)
