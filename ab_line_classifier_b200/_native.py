@@ -46,6 +46,10 @@ SIGNATURES = {
     "abl_resize_nearest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_clip_aggregate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "abl_opt_flat_dp": (_i, [_i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _f, _f, _f, _f, _vp]),
+    "abl_augment_workspace_bytes": (_ll, [_i, _i, _i]),
+    "abl_augment_frames": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "abl_metrics_counter_count": (_i, [_i, _i]),
+    "abl_metrics_accumulate": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "abl_gradcam": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
@@ -71,7 +75,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abl_abi_version() != 4:
+    if lib.abl_abi_version() != 5:
         raise RuntimeError("libabl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -8,15 +8,43 @@ resize then run on the device).  Two residencies:
     buffers (no per-epoch copy of the whole dataset), so the engine's H2D copies stay asynchronous;
   * device (``device="cuda"``): the whole dataset lives in HBM (180 GB per B200: 1 M uint8 frames = 49 GB) and a batch
     is one device-side gather -- the shuffle never touches the host.
+
+``augment=cfg['TRAIN']['DATA_AUG']`` reproduces ``prepare(..., augment=True)`` (preprocessor.py:56-63): x must then be
+RGB frames in [0,255] (uint8 or fp32, NOT yet preprocessed); every batch is augmented and preprocessed on the device
+(augment.py) and arrives as a device fp32 tensor.
 """
 import numpy as np
 import torch
+
+# Pinned batch buffers are refilled by the host while earlier asynchronous copies out of them may still be queued on a
+# CUDA stream (the host can run many steps ahead of the device).  Whoever enqueues such a copy reports it here; the
+# dataset waits for that event before it overwrites the buffer.
+_tracked, _copy_fences = set(), {}
+
+
+def note_async_copy(t, event=None):
+    """Called after an asynchronous H2D copy out of host tensor ``t`` was enqueued (``event``: recorded behind it)."""
+    if not torch.is_tensor(t) or t.is_cuda:
+        return
+    key = t.untyped_storage().data_ptr()
+    if key in _tracked:
+        if event is None:
+            event = torch.cuda.Event()
+            event.record()
+        _copy_fences[key] = event
+
+
+def _wait_async_copies(t):
+    ev = _copy_fences.pop(t.untyped_storage().data_ptr(), None)
+    if ev is not None:
+        ev.synchronize()
 
 
 class ArrayDataset:
     N_PINNED = 4      # rotating pinned batch buffers: a buffer is reused only after 3 later batches were staged
 
-    def __init__(self, x, y=None, batch_size=64, shuffle=False, seed=0, pin=True, device=None):
+    def __init__(self, x, y=None, batch_size=64, shuffle=False, seed=0, pin=True, device=None, augment=None,
+                 img_dim=None):
         x = np.asarray(x) if not torch.is_tensor(x) else x
         if not torch.is_tensor(x):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if x.dtype == np.uint8 else np.float32))
@@ -33,6 +61,11 @@ class ArrayDataset:
         self.rng = np.random.default_rng(seed)
         self._pinned = pin and torch.cuda.is_available() and self.device is None
         self._bufs, self._k = None, 0
+        self._aug, self.img_dim = None, (None if img_dim is None else tuple(img_dim))
+        if augment is not None and augment is not False:
+            from .augment import DeviceAugmenter
+            self._aug = DeviceAugmenter(None if augment is True else augment, seed=seed + 1,
+                                        device=self.device if self.device is not None else "cuda")
 
     def __len__(self):
         return (len(self.x) + self.batch_size - 1) // self.batch_size
@@ -53,15 +86,20 @@ class ArrayDataset:
             self._bufs = [(torch.empty((b,) + tuple(self.x.shape[1:]), dtype=self.x.dtype).pin_memory(),
                            None if self.y is None else torch.empty((b,) + tuple(self.y.shape[1:]), dtype=self.y.dtype).pin_memory())
                           for _ in range(self.N_PINNED)]
+            for bx, by in self._bufs:
+                _tracked.update(t.untyped_storage().data_ptr() for t in (bx, by) if t is not None)
         bx, by = self._bufs[self._k]
         self._k = (self._k + 1) % self.N_PINNED
+        _wait_async_copies(bx)
+        if by is not None:
+            _wait_async_copies(by)
         n = len(idx)
         torch.index_select(self.x, 0, idx, out=bx[:n])
         if self.y is not None:
             torch.index_select(self.y, 0, idx, out=by[:n])
         return bx[:n], (None if self.y is None else by[:n])
 
-    def __iter__(self):
+    def _batches(self):
         n = len(self.x)
         if not self.shuffle:
             for i in range(0, n, self.batch_size):
@@ -70,6 +108,37 @@ class ArrayDataset:
         perm = torch.from_numpy(self.rng.permutation(n))
         for i in range(0, n, self.batch_size):
             yield self._gather(perm[i:i + self.batch_size])
+
+    def _augmented(self, x):
+        """One batch of RGB frames -> device fp32, augmented and preprocessed (preprocessor.py:56-63)."""
+        if self.img_dim is not None and tuple(x.shape[1:3]) != self.img_dim:
+            if x.dtype != torch.uint8:
+                raise ValueError("only raw uint8 frames are resized on the device")
+            from . import ops
+            xd = x.to(self._aug.device, non_blocking=True)
+            note_async_copy(x)
+            x = torch.empty((x.shape[0],) + self.img_dim + (3,), device=xd.device, dtype=torch.uint8)
+            ops.resize_nearest_u8(xd, x)
+        out = self._aug(x)
+        note_async_copy(x)
+        return out
+
+    def __iter__(self):
+        if self._aug is None:
+            yield from self._batches()
+            return
+        for x, y in self._batches():
+            yield self._augmented(x), y
+
+    def __del__(self):
+        try:
+            for bx, by in (getattr(self, "_bufs", None) or []):
+                for t in (bx, by):
+                    if t is not None:
+                        _tracked.discard(t.untyped_storage().data_ptr())
+                        _copy_fences.pop(t.untyped_storage().data_ptr(), None)
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
 
     def unbatch(self):
         """(frame, label) pairs, like ``tf.data.Dataset.unbatch`` (train_utils.py:285)."""

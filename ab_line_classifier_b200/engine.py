@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .data import note_async_copy
 
 # Keras VGG16(include_top=False).layers[1:]: (name, kind, out_channels)  (third-party layer list,
 # sliced by the reference at models.py:410)
@@ -148,6 +149,7 @@ class CutoffVGG16Engine:
         self.n_flat = off
         self.n_params = sum(n for _, n, _ in self.segments.values())
         dev = self.device
+        self._metrics = None       # device-side Keras metric counters (metrics_begin)
         self._symm = None          # symmetric-memory handle (peer pointers + device barrier) when DP is fused
         self._grad_unreduced = False
         if self.world_size > 1 and self.fused_dp:
@@ -394,6 +396,11 @@ class CutoffVGG16Engine:
                 self._buf["y"][slot][:B].copy_(self._as_tensor(y, torch.float32), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
+        for t in (x, y):
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(self._copy_stream)   # a fresh gather / augmentation output is read on the copy stream
+            else:
+                note_async_copy(t, ev)               # a pinned batch buffer must not be refilled before this copy ran
         self._slot_u8[slot] = u8
         self._slot_ready[slot] = ev
         return slot
@@ -597,15 +604,47 @@ class CutoffVGG16Engine:
                 cw[int(k)] = float(v)
         self.class_weight.copy_(torch.from_numpy(cw))
 
-    def eval_batch(self, x, y, loss_out=None, inv_batch=1.0):
-        """Inference forward + unweighted categorical cross-entropy sum (Keras evaluate).  Device probs."""
+    def eval_batch(self, x, y, loss_out=None, inv_batch=1.0, metrics=False):
+        """Inference forward + unweighted categorical cross-entropy sum (Keras evaluate).  Device probs.
+        ``metrics``: also add the batch to the device-side metric counters (metrics_begin)."""
         B = x.shape[0]
         self._ensure(B, False)
         self.load_input(x, y)
         probs = self.forward_device(B, y=self._buf["y"][self._slot][:B], inv_batch=inv_batch, loss_out=loss_out,
                                     need_last_act=False)
-        self.release_slot()
+        if metrics:
+            self.metrics_update(B)
+        else:
+            self.release_slot()
         return probs
+
+    # ---- Keras metric state on the device (the reference's list: src/train.py:109-115)
+    def metrics_begin(self, auc_thresholds, class_thresholds):
+        """Zero the counters for a new epoch / evaluation.  Thresholds: fp32 arrays from metrics.device_plan()."""
+        m = self._metrics
+        key = (np.asarray(auc_thresholds, np.float32).tobytes(), np.asarray(class_thresholds, np.float32).tobytes())
+        if m is None or m["key"] != key:
+            thr = torch.from_numpy(np.ascontiguousarray(auc_thresholds, np.float32)).to(self.device)
+            cthr = torch.from_numpy(np.ascontiguousarray(class_thresholds, np.float32)).to(self.device)
+            if cthr.numel() != self.n_classes:
+                raise ValueError("one class threshold per class expected")
+            n = ops.metrics_counter_count(self.n_classes, thr.numel())
+            m = self._metrics = {"key": key, "thr": thr, "cthr": cthr,
+                                 "counters": torch.zeros(n, device=self.device, dtype=torch.int64)}
+        m["counters"].zero_()
+
+    def metrics_update(self, B):
+        """Add the batch just run (softmax output and the labels of the current input slot) to the counters, then
+        release the slot (its label buffer is read here, after the step's own release)."""
+        m = self._metrics
+        if m is None:
+            raise RuntimeError("metrics_begin() must be called first")
+        ops.metrics_accumulate(self._buf["probs"][:B], self._buf["y"][self._slot][:B], m["thr"], m["cthr"], m["counters"])
+        self.release_slot()
+
+    def metrics_read(self):
+        """The counters as a host int64 array (one small D2H copy; synchronises)."""
+        return self._metrics["counters"].cpu().numpy()
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
                    apply_update=True, bucket_bytes=2 << 20, loss_out=None, slot=None, batch=None, defer_reduce=False):

@@ -248,18 +248,27 @@ class B200Model:
         eng = self.engine
         eng._ensure(1, False)
         loss = torch.zeros(1, device=eng.device, dtype=torch.float32)
-        probs, ys = [], []
+        plan = M.device_plan(self.metric_objs, self.n_classes)
+        if plan is not None:
+            eng.metrics_begin(*plan)          # Keras metric state accumulates on the device (abl_metrics_accumulate)
+        probs, ys, n = [], [], 0
         for x, y in _iter_batches(data):
             if y is None:
                 raise ValueError("evaluate needs (x, y) batches")
-            probs.append(eng.eval_batch(x, y, loss_out=loss).clone())
-            ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled
-        if not probs:
+            n += len(x)
+            p = eng.eval_batch(x, y, loss_out=loss, metrics=plan is not None)
+            if plan is None:                  # a metric the counters cannot express: collect arrays for result()
+                probs.append(p.clone())
+                ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled
+        if n == 0:
             return [0.0] + [0.0] * len(self.metric_objs)
-        p = torch.cat(probs).cpu().numpy()
-        yt = _cat_labels(ys)
-        res = [float(loss.item()) / len(yt)]
-        res += [m.result(yt, p) for m in self.metric_objs]
+        res = [float(loss.item()) / n]
+        if plan is not None:
+            counts = M.MetricCounts(eng.metrics_read(), self.n_classes, *plan)
+            res += [m.from_counts(counts) for m in self.metric_objs]
+        else:
+            p, yt = torch.cat(probs).cpu().numpy(), _cat_labels(ys)
+            res += [m.result(yt, p) for m in self.metric_objs]
         return res
 
     def evaluate(self, test_data, verbose=1):
@@ -307,6 +316,9 @@ class B200Model:
             tot_loss, n_seen, slot_i = 0.0, 0, 0
             sizes, probs, ys = [], [], []
             ring.zero_()
+            plan = M.device_plan(self.metric_objs, self.n_classes) if self.metric_objs else None
+            if plan is not None:
+                eng.metrics_begin(*plan)
 
             def drain():
                 nonlocal tot_loss, slot_i
@@ -333,7 +345,9 @@ class B200Model:
                     nslot = eng.stage(nxt[0], nxt[1], slot=slot ^ 1)
                 eng.fit_step(trainable, opt.kind, opt.learning_rate, slot, B, B * eng.world_size,
                              loss_out=ring[slot_i:slot_i + 1], **kw)
-                if self.metric_objs:
+                if plan is not None:
+                    eng.metrics_update(B)      # training-batch outputs (dropout on), as Keras reports them
+                elif self.metric_objs:
                     probs.append(eng._buf["probs"][:B].clone())
                     ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled
                 sizes.append(B)
@@ -343,7 +357,11 @@ class B200Model:
                     drain()
             drain()
             logs = {"loss": tot_loss / max(n_seen, 1)}
-            if self.metric_objs and probs:
+            if plan is not None and n_seen:
+                counts = M.MetricCounts(eng.metrics_read(), self.n_classes, *plan)
+                for m in self.metric_objs:
+                    logs[m.name] = m.from_counts(counts)
+            elif self.metric_objs and probs:
                 p, yt = torch.cat(probs).cpu().numpy(), _cat_labels(ys)
                 for m in self.metric_objs:
                     logs[m.name] = m.result(yt, p)

@@ -252,6 +252,40 @@ def resize_nearest_u8(src, dst):
     _native.call("abl_resize_nearest_u8", _ptr(src), _ptr(dst), B, h, w, dst.shape[1], dst.shape[2], _stream())
 
 
+def augment_workspace_bytes(B, H, W):
+    return int(_native.load().abl_augment_workspace_bytes(int(B), int(H), int(W)))
+
+
+def augment_frames(src, params, dst, preprocess=True, workspace=None):
+    """src uint8|fp32 [B,H,W,3] RGB in [0,255], params fp32 [B,20] -> dst fp32 [B,H,W,3]: the reference's augmentation
+    Sequential + vgg16.preprocess_input in one launch (abl_augment_frames)."""
+    if src.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f"src: expected uint8 or float32, got {src.dtype}")
+    _chk(params, torch.float32, "params"); _chk(dst, torch.float32, "dst")
+    B, H, W, c = src.shape
+    assert c == 3 and tuple(dst.shape) == (B, H, W, 3) and tuple(params.shape) == (B, 20), (src.shape, dst.shape, params.shape)
+    if workspace is not None:
+        _chk(workspace, torch.uint8, "workspace")
+    _native.call("abl_augment_frames", _ptr(src), int(src.dtype == torch.uint8), _ptr(params), _ptr(dst),
+                 _ptr(workspace), 0 if workspace is None else workspace.numel(), B, H, W, int(bool(preprocess)), _stream())
+
+
+def metrics_counter_count(n_classes, num_thresholds):
+    return int(_native.load().abl_metrics_counter_count(int(n_classes), int(num_thresholds)))
+
+
+def metrics_accumulate(probs, y_true, auc_thresholds, class_thresholds, counters):
+    """Add one batch (probs, one-hot y: fp32 [B,n]) to the device-side Keras metric counters (abl_metrics_accumulate)."""
+    for t, n in ((probs, "probs"), (y_true, "y_true"), (auc_thresholds, "auc_thresholds"), (class_thresholds, "class_thresholds")):
+        _chk(t, torch.float32, n)
+    _chk(counters, torch.int64, "counters")
+    B, n = probs.shape
+    assert tuple(y_true.shape) == (B, n) and class_thresholds.numel() == n
+    assert counters.numel() >= metrics_counter_count(n, auc_thresholds.numel())
+    _native.call("abl_metrics_accumulate", _ptr(probs), _ptr(y_true), B, n, _ptr(auc_thresholds),
+                 auc_thresholds.numel(), _ptr(class_thresholds), _ptr(counters), _stream())
+
+
 def clip_aggregate(probs, clip_offsets, b_idx, threshold, window):
     """probs fp32 [N,n] (device), clip_offsets int64 [n_clips+1] (device) -> (mean [n_clips,n], run int32 [n_clips],
     win fp32 [n_clips]); see abl_clip_aggregate."""

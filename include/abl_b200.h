@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 4
+#define ABL_ABI_VERSION 5
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -178,6 +178,36 @@ int abl_rmsprop_flat(float* theta, const float* g, float* rms, long long n, floa
  * 76-80) on raw uint8 RGB frames: src [B,h,w,3] -> dst [B,H,W,3], TF2 half-pixel-centre rule
  * src_index = min(floor((dst_index + 0.5) * in / out), in - 1).  The output is what abl_conv_first_*_u8 consume. */
 int abl_resize_nearest_u8(const unsigned char* src, unsigned char* dst, int B, int h, int w, int H, int W, void* stream);
+
+/* Training-time augmentation + input scaling of one batch: the reference's tf.keras.Sequential([RandomZoom,
+ * RandomTranslation, RandomRotation, RandomFlip('horizontal'), RandomBrightness]) (src/data/preprocessor.py:25-32,
+ * applied per batch at preprocessor.py:56-57) followed by vgg16.preprocess_input (preprocessor.py:60-63), in one launch.
+ *   src     [B,H,W,3] RGB frames at IMG_DIM in [0,255]: uint8 (src_is_u8) or fp32
+ *   params  fp32 [B,20] per frame: the output->input affine maps [a0 a1 a2 b0 b1 b2] of the zoom, translation and
+ *           rotation layers in Keras' ImageProjectiveTransformV3 convention (x_in = a0*x + a1*y + a2, y_in = b0*x +
+ *           b1*y + b2), then flip (0/1) and the brightness delta already scaled to the [0,255] range.  The host draws
+ *           them (ab_line_classifier_b200/augment.py); the three resamplings are applied one after the other with
+ *           bilinear interpolation and constant fill 0, exactly as the three Keras layers do.
+ *   dst     fp32 [B,H,W,3]; preprocess != 0: BGR minus [103.939, 116.779, 123.68] (what block1_conv1 consumes),
+ *           preprocess == 0: the augmented RGB frame (what the Sequential returns).
+ *   workspace: abl_augment_workspace_bytes(B,H,W) bytes, 0 (NULL allowed) when two fp32 planes of a frame fit in one
+ *           SM's shared memory (H*W <= 29056, e.g. 128x128). */
+long long abl_augment_workspace_bytes(int B, int H, int W);
+int abl_augment_frames(const void* src, int src_is_u8, const float* params, float* dst, void* workspace,
+                       long long workspace_bytes, int B, int H, int W, int preprocess, void* stream);
+
+/* Device-side state of the Keras metrics the reference compiles the model with (src/train.py:109-115: 'accuracy',
+ * AUC(name='auc'), Precision/Recall(thresholds=1/n_classes, class_id=c)), accumulated batch by batch from the one-hot
+ * labels and the softmax output so fit()/evaluate() read back abl_metrics_counter_count() integers per epoch instead
+ * of every probability.  counters (uint64, zeroed by the caller at epoch start):
+ *   [0] frames, [1] frames with argmax(y) == argmax(p), [2+3c ..] tp, fp, fn of class c at class_thresholds[c],
+ *   then (num_thresholds+1) buckets for positive and (num_thresholds+1) for negative flattened (y, p) entries: bucket k
+ *   counts entries whose p is greater than exactly k of the ascending auc_thresholds (fp32, device), so
+ *   true_positives(t) = sum_{k>t} pos[k] as keras.metrics.AUC accumulates it. */
+int abl_metrics_counter_count(int n_classes, int num_thresholds);
+int abl_metrics_accumulate(const float* probs, const float* y_true, int B, int n_classes, const float* auc_thresholds,
+                           int num_thresholds, const float* class_thresholds, unsigned long long* counters,
+                           void* stream);
 
 /* Clip-level aggregation of frame probabilities (src/predict.py:159-166 with the helpers at 283-308 and 365-376),
  * all clips in one launch instead of the reference's per-clip Python loop.  probs fp32 [N_frames, n_classes] with the

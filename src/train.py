@@ -76,8 +76,14 @@ def synthetic_datasets(n_train, n_val, preprocessing_fn, seed=1234):
     nc = cfg['TRAIN']['N_CLASSES']
     bs = cfg['TRAIN']['BATCH_SIZE']
     oh = lambda l: np.eye(nc, dtype=np.float32)[l]
-    return (ArrayDataset(preprocessing_fn(xtr), oh(ltr), bs, shuffle=True, seed=cfg['TRAIN']['SEED']),
-            ArrayDataset(preprocessing_fn(xva), oh(lva), bs), ltr)
+    if cfg.get('B200', {}).get('AUGMENT', False):
+        # reference train_utils.py:85: prepare(train_set, shuffle=True, augment=True) -- RGB frames in, augmentation
+        # and the input scaler applied per batch (on the device here)
+        train = ArrayDataset(xtr, oh(ltr), bs, shuffle=True, seed=cfg['TRAIN']['SEED'],
+                             augment=cfg['TRAIN']['DATA_AUG'], img_dim=cfg['DATA']['IMG_DIM'])
+    else:
+        train = ArrayDataset(preprocessing_fn(xtr), oh(ltr), bs, shuffle=True, seed=cfg['TRAIN']['SEED'])
+    return train, ArrayDataset(preprocessing_fn(xva), oh(lva), bs), ltr
 
 
 def train_experiment(experiment='single_train', save_weights=False, epochs=None):

@@ -4,7 +4,7 @@ import numpy as np
 import torch
 
 from ab_line_classifier_b200.engine import build_plan
-from oracle import oracle, synth
+from oracle import metric_counts, oracle, synth
 
 
 class FakeEngine:
@@ -62,12 +62,25 @@ class FakeEngine:
         self._buf["probs"] = torch.from_numpy(p)
         return self._buf["probs"]
 
-    def eval_batch(self, x, y, loss_out=None, inv_batch=1.0):
+    def eval_batch(self, x, y, loss_out=None, inv_batch=1.0, metrics=False):
         out = oracle.forward(self.params, self._np(x), self.cutoff_layer, as_torch=True)
         li = oracle.loss_from_logits(out["logits"], self._np(y)) * len(x) * inv_batch
         if loss_out is not None:
             loss_out += float(li)
+        self._buf["probs"], self._last_y = out["probs"].detach(), self._np(y)
+        if metrics:
+            self.metrics_update(len(x))
         return out["probs"].detach()
+
+    def metrics_begin(self, auc_thresholds, class_thresholds):
+        self._met = [np.asarray(auc_thresholds, np.float32), np.asarray(class_thresholds, np.float32), None]
+
+    def metrics_update(self, B):
+        c = metric_counts.counts_from_arrays(self._last_y[:B], self._np(self._buf["probs"])[:B], self._met[0], self._met[1])
+        self._met[2] = c if self._met[2] is None else self._met[2] + c
+
+    def metrics_read(self):
+        return self._met[2]
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
                    apply_update=True, bucket_bytes=0, loss_out=None, slot=None, batch=None, defer_reduce=False):
@@ -78,7 +91,7 @@ class FakeEngine:
         self.step_count += 1
         loss, self.grads, fwd = oracle.loss_and_grads(self.params, x, y, self.class_weight, mask, self.dropout,
                                                       self.cutoff_layer, trainable)
-        self._buf["probs"] = torch.from_numpy(fwd["probs"])
+        self._buf["probs"], self._last_y = torch.from_numpy(fwd["probs"]), y
         t = torch.tensor([loss], dtype=torch.float32)
         if loss_out is not None:
             loss_out += t
