@@ -642,9 +642,24 @@ class CutoffVGG16Engine:
         ops.metrics_accumulate(self._buf["probs"][:B], self._buf["y"][self._slot][:B], m["thr"], m["cthr"], m["counters"])
         self.release_slot()
 
-    def metrics_read(self):
-        """The counters as a host int64 array (one small D2H copy; synchronises)."""
-        return self._metrics["counters"].cpu().numpy()
+    def metrics_read(self, reduce=True):
+        """The counters as a host int64 array (one small D2H copy; synchronises).  Data parallel: every metric is a
+        ratio of counts, so the SUM over ranks gives the metric of all frames seen by all ranks (``reduce``)."""
+        c = self._metrics["counters"]
+        if reduce and self.world_size > 1:
+            import torch.distributed as dist
+            c = c.clone()
+            dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.pg)
+        return c.cpu().numpy()
+
+    def sum_over_ranks(self, values):
+        """Host floats summed over the data-parallel ranks (epoch-end loss bookkeeping); identity on one GPU."""
+        if self.world_size == 1:
+            return [float(v) for v in values]
+        import torch.distributed as dist
+        t = torch.tensor([float(v) for v in values], device=self.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        return t.cpu().tolist()
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
                    apply_update=True, bucket_bytes=2 << 20, loss_out=None, slot=None, batch=None, defer_reduce=False):

@@ -260,9 +260,11 @@ class B200Model:
             if plan is None:                  # a metric the counters cannot express: collect arrays for result()
                 probs.append(p.clone())
                 ys.append(y.clone() if torch.is_tensor(y) else np.array(y, np.float32))   # batch buffers are recycled
+        # data parallel: every rank evaluated its own shard (or a replica) -- loss and metrics are those of all frames
+        loss_sum, n = eng.sum_over_ranks([float(loss.item()), n])
         if n == 0:
             return [0.0] + [0.0] * len(self.metric_objs)
-        res = [float(loss.item()) / n]
+        res = [loss_sum / n]
         if plan is not None:
             counts = M.MetricCounts(eng.metrics_read(), self.n_classes, *plan)
             res += [m.from_counts(counts) for m in self.metric_objs]
@@ -356,8 +358,11 @@ class B200Model:
                 if slot_i == ring.numel():
                     drain()
             drain()
-            logs = {"loss": tot_loss / max(n_seen, 1)}
-            if plan is not None and n_seen:
+            # each step's loss is sum_local(w_i l_i) / GLOBAL batch, so under data parallel the ranks' epoch sums add
+            # up to the sum of the global-batch means (what single-device Keras logs)
+            tot_loss, n_glob = eng.sum_over_ranks([tot_loss, n_seen])
+            logs = {"loss": tot_loss * eng.world_size / max(n_glob, 1)}
+            if plan is not None and n_glob:
                 counts = M.MetricCounts(eng.metrics_read(), self.n_classes, *plan)
                 for m in self.metric_objs:
                     logs[m.name] = m.from_counts(counts)

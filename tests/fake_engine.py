@@ -79,8 +79,11 @@ class FakeEngine:
         c = metric_counts.counts_from_arrays(self._last_y[:B], self._np(self._buf["probs"])[:B], self._met[0], self._met[1])
         self._met[2] = c if self._met[2] is None else self._met[2] + c
 
-    def metrics_read(self):
+    def metrics_read(self, reduce=True):
         return self._met[2]
+
+    def sum_over_ranks(self, values):
+        return [float(v) for v in values]
 
     def train_step(self, x, y, trainable, optimizer="adam", lr=3e-4, global_batch=None, keep_mask=None,
                    apply_update=True, bucket_bytes=0, loss_out=None, slot=None, batch=None, defer_reduce=False):

@@ -129,6 +129,26 @@ for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
     assert frac_off < 5e-2 and float(d.median()) < 1e-6 and moved > 1e-4, (opt, diff, frac_off, moved)
 eng.set_weights(w0)
 eng.opt_state.clear(); eng.opt_steps.clear()
+# ---- metric counters and epoch bookkeeping are summed over the ranks (every Keras metric is a ratio of counts)
+from ab_line_classifier_b200 import metrics as M  # noqa: E402
+plan = (M.auc_thresholds(200), np.full(2, 0.5, np.float32))
+eng.metrics_begin(*plan)
+eng.eval_batch(x[sl], y[sl], metrics=True)
+local = torch.from_numpy(eng.metrics_read(reduce=False)).cuda()
+glob = eng.metrics_read()
+parts = [torch.empty_like(local) for _ in range(world)]
+dist.all_gather(parts, local)
+assert np.array_equal(glob, sum(parts).cpu().numpy()) and int(glob[0]) == G, (glob[:8], G)
+eng.world_size = 1
+eng.metrics_begin(*plan)
+eng.eval_batch(x, y, metrics=True)
+full = eng.metrics_read()
+eng.world_size = world
+assert int(np.abs(glob - full).sum()) <= 2, (glob[:8], full[:8])      # same frames: shards vs one batch on one GPU
+tot = eng.sum_over_ranks([1.0, float(rank)])
+assert tot == [float(world), world * (world - 1) / 2.0], tot
+mark(f"metric counters: {int(glob[0])} frames, {int(glob[1])} correct over {world} ranks; equal to the single-GPU batch: "
+     f"{np.array_equal(glob, full)}")
 dist.barrier()
 faulthandler.cancel_dump_traceback_later()
 dist.destroy_process_group()
