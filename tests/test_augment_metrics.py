@@ -161,3 +161,21 @@ def test_evaluate_falls_back_to_arrays_for_custom_metrics():
     res2 = model.evaluate([(x[:4], y[:4]), (x[4:], y[4:])], verbose=0)
     assert res2[0] == pytest.approx(res[0]) and res2[1] == pytest.approx(res[1])
     assert res2[2] == pytest.approx(M.AUC().result(y, p), abs=1e-9)
+
+
+def test_oracles_reproduce_the_committed_fixture():
+    """tests/golden/augment_metrics_seed77.npz (made by tests/golden/make_golden_augment.py): drift guard."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_augment", os.path.join(here, "make_golden_augment.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(here, "augment_metrics_seed77.npz"))
+    frames, probs, y, thr = gen.inputs()
+    out = A.augment_batch(frames, gen.RAW, preprocess=True)
+    assert np.array_equal(out[:, ::4, ::4], gold["augmented_sub"])
+    assert np.allclose(out.astype(np.float64).sum(axis=(1, 2)), gold["augmented_sum"], rtol=0, atol=1e-6)
+    assert np.array_equal(probs, gold["probs"]) and np.array_equal(y, gold["y"])
+    assert np.array_equal(metric_counts.counts_from_arrays(y, probs, thr, [0.5, 0.5]), gold["counts"])
+    assert np.array_equal(out[0], frames[0].astype(np.float32)[..., ::-1] - A.BGR_MEAN)     # frame 0: identity draws

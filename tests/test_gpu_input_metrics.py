@@ -160,3 +160,24 @@ def test_fit_on_augmented_batches_from_the_dataset():
     model.fit(train, epochs=3, verbose=0)
     losses = model.history_extract.history["loss"] + model.history_finetune.history["loss"]
     assert np.isfinite(losses).all() and len(losses) == 4
+
+
+def test_kernels_reproduce_the_committed_fixture():
+    """The same inputs as tests/golden/make_golden_augment.py through the CUDA kernels == the committed vectors."""
+    import importlib.util
+    import os
+    from ab_line_classifier_b200 import augment as P
+    from ab_line_classifier_b200 import ops
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_augment", os.path.join(here, "make_golden_augment.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(here, "augment_metrics_seed77.npz"))
+    frames, probs, y, thr = gen.inputs()
+    out = P.DeviceAugmenter()(frames, params=P.params_from_raw(gen.RAW, 128, 128)).cpu().numpy()
+    assert np.array_equal(out[:, ::4, ::4], gold["augmented_sub"])
+    assert np.allclose(out.astype(np.float64).sum(axis=(1, 2)), gold["augmented_sum"], rtol=0, atol=1e-6)
+    counters = torch.zeros(ops.metrics_counter_count(2, 200), device="cuda", dtype=torch.int64)
+    ops.metrics_accumulate(torch.from_numpy(probs).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(thr).cuda(),
+                           torch.full((2,), 0.5, device="cuda"), counters)
+    assert np.array_equal(counters.cpu().numpy(), gold["counts"])
