@@ -15,10 +15,12 @@ N, B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192, int(sys.argv[2]) if len(
 hp = {"LR_EXTRACT": 0.0003, "LR_FINETUNE": 0.0000093, "DROPOUT": 0.45, "CUTOFF_LAYER": 10, "FINETUNE_LAYER": 7,
       "EXTRACT_EPOCHS": 2}
 fr, lab = synth.synth_frames(N, seed=3)
-mode = sys.argv[3] if len(sys.argv) > 3 else "host_fp32"       # host_fp32 | host_u8 | device_u8
-frames = fr if mode.endswith("u8") else synth.vgg16_preprocess(fr)
+mode = sys.argv[3] if len(sys.argv) > 3 else "host_fp32"       # host_fp32 | host_u8 | device_u8 | host_u8_aug | device_u8_aug
+aug = {"ZOOM_RANGE": 0.1, "WIDTH_SHIFT_RANGE": 0.2, "HEIGHT_SHIFT_RANGE": 0.2, "ROTATION_RANGE": 45,
+       "BRIGHTNESS_RANGE": 0.3} if mode.endswith("_aug") else None     # reference config.yml TRAIN.DATA_AUG
+frames = fr if "u8" in mode else synth.vgg16_preprocess(fr)
 dev = "cuda" if mode.startswith("device") else None
-train = ArrayDataset(frames, synth.one_hot(lab), B, shuffle=True, device=dev)
+train = ArrayDataset(frames, synth.one_hot(lab), B, shuffle=True, device=dev, augment=aug)
 val = ArrayDataset(frames[:1024], synth.one_hot(lab[:1024]), B, device=dev)
 mets = ["accuracy", M.AUC(name="auc"), M.Precision(name="precision_b_lines", class_id=1), M.Recall(name="recall_b_lines", class_id=1)]
 model = CutoffVGG16(hp, [128, 128, 3], mets, 2)
