@@ -76,8 +76,7 @@ class ArrayDataset:
 
     def _gather(self, idx):
         """Rows ``idx`` of (x, y): device gather, or host gather into the next rotating pinned buffer."""
-        if self.device is not None:
-            idx = idx.to(self.device)
+        if self.device is not None:        # idx already lives on the device (one permutation upload per epoch)
             return self.x.index_select(0, idx), (None if self.y is None else self.y.index_select(0, idx))
         if not self._pinned:
             return self.x[idx], (None if self.y is None else self.y[idx])
@@ -106,6 +105,9 @@ class ArrayDataset:
                 yield self.x[i:i + self.batch_size], (None if self.y is None else self.y[i:i + self.batch_size])
             return
         perm = torch.from_numpy(self.rng.permutation(n))
+        if self.device is not None:
+            # a per-batch upload of the indices from pageable memory would block the host behind all queued kernels
+            perm = perm.to(self.device)
         for i in range(0, n, self.batch_size):
             yield self._gather(perm[i:i + self.batch_size])
 

@@ -19,7 +19,15 @@ def _ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device.  The raw-handle query costs ~0.3 us; the public
+    torch.cuda.current_stream() ~14 us, a third of the host time of a launch."""
+    if _raw_stream is not None and _get_device is not None:
+        return _raw_stream(_get_device())
     return torch.cuda.current_stream().cuda_stream
 
 
