@@ -69,6 +69,49 @@ def test_conv3x3_forward_bias_relu_pool(cin, cout, H, W, pool, B, igemm_variant)
         assert torch.equal(pl.float().cpu(), ref)
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 128, 128), (2, 64, 64), (1, 8, 128)])
+def test_blocked_cin64_cout64_main_loop_matches_reference(B, H, W, monkeypatch):
+    """ABL_BLOCKED64=1: the main loop that treats four adjacent pixels as one GEMM row (conv3x3_blk64_kernel; off by
+    default until its epilogue is tuned) -- forward + fused pool + routing codes and dgrad + ReLU mask + fused bias
+    gradient against the CPU reference, like the default kernels."""
+    ops = _ops()
+    monkeypatch.setenv("ABL_BLOCKED64", "1")
+    g = torch.Generator().manual_seed(B + H)
+    x = _bf(torch.randn(B, H, W, 64, generator=g) * 0.5)
+    w = torch.randn(3, 3, 64, 64, generator=g) * (2.0 / 576) ** 0.5
+    b = torch.randn(64, generator=g) * 0.1
+    wf = torch.empty(9, 64, 64, device="cuda", dtype=torch.bfloat16)
+    wd = torch.empty(9, 64, 64, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weights(w.cuda(), wf, wd)
+    full = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pl = torch.full((B, H // 2, W // 2, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    code = torch.zeros(B, H // 2, W // 2, 8, device="cuda", dtype=torch.int16)
+    ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, full, pl, ops.EPI_BIAS_RELU, pool_code=code)
+    _close(full, _conv_cpu(x, w, b), 1.5 * BF16_ULP, "blocked conv fwd")
+    ref = F.max_pool2d(full.float().cpu().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(pl.float().cpu(), ref)
+    pl2 = torch.empty_like(pl)
+    ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, None, pl2, ops.EPI_BIAS_RELU)
+    assert torch.equal(pl, pl2)
+    # routing codes == MaxPoolGrad of the kernel's own output
+    dp = (torch.randn(B, H // 2, W // 2, 64, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dz_ref, dz_code = torch.empty_like(full), torch.empty_like(full)
+    ops.maxpool_bwd_relu(dp, full, pl, dz_ref, None)
+    ops.maxpool_bwd_code(torch.where(pl > 0, dp, torch.zeros_like(dp)), code, dz_code, None)
+    assert torch.equal(dz_ref, dz_code)
+    # dgrad + ReLU mask + fused BiasAddGrad
+    dz = _bf(torch.randn(B, H, W, 64, generator=g) * 0.1)
+    act = _bf(torch.relu(torch.randn(B, H, W, 64, generator=g)))
+    out = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    colsum = torch.full((64,), -1.0, device="cuda")
+    ops.conv3x3_igemm(dz.cuda().to(torch.bfloat16), wd, None, act.cuda().to(torch.bfloat16), out, None,
+                      ops.EPI_RELU_MASK, colsum=colsum)
+    dx = F.conv_transpose2d(dz.permute(0, 3, 1, 2), _bf(w).permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    _close(out, dx * (act > 0), 1.5 * BF16_ULP, "blocked dgrad")
+    _close(colsum + 1.0, out.float().sum(dim=(0, 1, 2)), 2e-5, "fused bias grad (blocked dgrad epilogue)")
+    assert (out.float().cpu()[act == 0] == 0).all()
+
+
 def test_prep_conv_weights_multi_equals_per_layer_launches():
     ops = _ops()
     g = torch.Generator().manual_seed(11)
