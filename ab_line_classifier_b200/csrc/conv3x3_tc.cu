@@ -898,7 +898,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // plus the two neighbours across the block boundary (left block's q=3 -> p=0, right block's q=0 -> p=3).  With the
 // filter rows of one kh stored as S = [W(kw=2); W(kw=1); W(kw=0)] every band is a CONTIGUOUS row range of S and a
 // contiguous column range of the accumulator, so one activation tile feeds N = 128 or 192 output columns per MMA
-// (N = 64 only for the two boundary terms): 84 MMA issues of 5376 tensor clocks per 512 output pixels instead of
+// (N = 64 only for the two boundary terms): 72 MMA issues worth 5376 tensor clocks per 512 output pixels instead of
 // 144 N = 64 issues (9216 clocks).  No FLOPs are wasted (the bands hold exactly the 9 taps) and no layout changes.
 //   A: per pixel slot q one TMA box {64 ch, q, W/4 blocks, rows+2, 1} of the 5-D view [C, 4, W/4, H, B] (a plane of
 //      every 4th pixel, haloed by one image row above/below: kh = descriptor row offset of W/4 rows), plus the same
