@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-o", LIB, *objs])
+    subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs])
     return LIB
 
 
