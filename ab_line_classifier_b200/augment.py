@@ -6,6 +6,12 @@ The host only DRAWS the random parameters (Keras 2.9 distributions, config keys 
 into the three output->input affine maps Keras hands to ImageProjectiveTransformV3; the resampling, flip, brightness
 and vgg16 preprocessing run in one CUDA kernel (``abl_augment_frames``).  TensorFlow's random stream cannot be
 reproduced, so the draws come from a seeded NumPy generator; given the same draws the result is what Keras computes.
+
+Brightness is the exception: the reference does NOT use Keras' RandomBrightness but its own layer
+(preprocessor.py:83-104), ``tf.image.stateless_random_brightness(inputs, factor, (123, 0))``: ONE delta in
+[-factor, factor) from a stateless generator with a constant seed -- the same value for every frame of every batch --
+added to the float image without scaling to the 0..255 range and without clipping.  ``reference_brightness_delta``
+restates TF's stateless Philox sampling of that constant.
 """
 import numpy as np
 import torch
@@ -13,6 +19,34 @@ import torch
 from . import ops
 
 N_PARAMS = 20      # [zoom a0..b2 | translation a0..b2 | rotation a0..b2 | flip | brightness delta]
+
+
+_M32 = 0xFFFFFFFF
+
+
+def _philox4x32_10(counter, key):
+    """One block of Philox4x32-10 as tensorflow/core/lib/random/philox_random.h computes it (uint32 lists in and out)."""
+    c, k = [int(v) & _M32 for v in counter], [int(v) & _M32 for v in key]
+    for rnd in range(10):
+        if rnd:
+            k = [(k[0] + 0x9E3779B9) & _M32, (k[1] + 0xBB67AE85) & _M32]
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & _M32, p1 & _M32, ((p0 >> 32) ^ c[3] ^ k[1]) & _M32, p0 & _M32]
+    return c
+
+
+def reference_brightness_delta(factor, seed=(123, 0)):
+    """``tf.image.stateless_random_brightness(x, factor, seed)``'s delta: stateless_random_uniform(shape=[],
+    minval=-factor, maxval=factor, seed) with TF 2.9's default Philox path -- the seed pair is scrambled into a key and
+    a counter by one Philox block under a fixed key (stateless_random_ops.cc GenerateKey), the first 32-bit output of
+    the next block becomes a float in [0, 1) by mantissa stuffing, and the result is u * (max - min) + min in fp32."""
+    f = np.float32
+    s0, s1 = int(seed[0]) & 0xFFFFFFFFFFFFFFFF, int(seed[1]) & 0xFFFFFFFFFFFFFFFF
+    mix = _philox4x32_10([s0 & _M32, s0 >> 32, s1 & _M32, s1 >> 32], [0x3EC8F720, 0x02461E29])
+    out = _philox4x32_10([0, 0, mix[2], mix[3]], [mix[0], mix[1]])
+    u = np.array([(127 << 23) | (out[0] & 0x7FFFFF)], np.uint32).view(f)[0] - f(1.0)
+    lo, hi = f(-factor), f(factor)
+    return f(u * (hi - lo) + lo)
 
 
 class AugmentConfig:
@@ -30,15 +64,16 @@ class AugmentConfig:
         for k in ("zoom", "height_shift", "width_shift", "rotation"):
             if getattr(self, k) < 0:
                 raise ValueError(f"DATA_AUG {k} range cannot be negative")      # as the Keras layers raise
-        if not 0.0 <= self.brightness <= 1.0:
-            raise ValueError("BRIGHTNESS_RANGE must be within [0, 1]")          # RandomBrightness' own check
+        if self.brightness < 0:
+            raise ValueError("max_delta must be non-negative.")                 # tf.image.stateless_random_brightness
+        self.brightness_delta = reference_brightness_delta(self.brightness)
 
 
 def draw_raw(rng, B, cfg):
     """The random draws of one batch, one per frame, in Keras' units: zoom factor, (dx, dy) as fractions of (W, H),
-    rotation angle in radians, flip (0/1), brightness factor.  Keras: RandomZoom draws U(1-z, 1+z) once and uses it
+    rotation angle in radians, flip (0/1), brightness delta.  Keras: RandomZoom draws U(1-z, 1+z) once and uses it
     for both axes (width_factor=None); RandomTranslation U(-f, f); RandomRotation U(-f*2pi, f*2pi); RandomFlip flips
-    each frame with probability 1/2; RandomBrightness U(-f, f) per frame."""
+    each frame with probability 1/2.  The brightness delta is the reference layer's constant (module docstring)."""
     f = np.float32
     return {
         "zoom": rng.uniform(1.0 - cfg.zoom, 1.0 + cfg.zoom, B).astype(f),
@@ -46,7 +81,7 @@ def draw_raw(rng, B, cfg):
         "dy": rng.uniform(-cfg.height_shift, cfg.height_shift, B).astype(f),
         "angle": rng.uniform(-cfg.rotation * 2.0 * np.pi, cfg.rotation * 2.0 * np.pi, B).astype(f),
         "flip": (rng.random(B) >= 0.5).astype(f),
-        "brightness": rng.uniform(-cfg.brightness, cfg.brightness, B).astype(f),
+        "brightness": np.full(B, cfg.brightness_delta, f),
     }
 
 
@@ -75,7 +110,7 @@ def params_from_raw(raw, H, W):
     p[:, 16] = cos
     p[:, 17] = (h1 - (sin * w1 + cos * h1)) / f(2.0)
     p[:, 18] = raw["flip"].astype(f)
-    p[:, 19] = raw["brightness"].astype(f) * f(255.0)       # value_range (0, 255)
+    p[:, 19] = raw["brightness"].astype(f)                  # added as is: tf.image.adjust_brightness on a float image
     return p
 
 

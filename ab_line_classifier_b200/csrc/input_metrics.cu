@@ -2,7 +2,8 @@
 // the Keras metric accumulators behind the softmax head.  Both are small HBM/latency-bound kernels.
 //
 // augment_kernel: the reference's `tf.keras.Sequential([RandomZoom, RandomTranslation, RandomRotation, RandomFlip,
-// RandomBrightness])` (src/data/preprocessor.py:25-32, applied to every training batch at preprocessor.py:56-57) followed
+// RandomBrightness])` (src/data/preprocessor.py:25-32 with its own RandomBrightness layer at 83-104; applied to every
+// training batch at preprocessor.py:56-57) followed
 // by `vgg16.preprocess_input` (preprocessor.py:60-63).  The three geometric layers are three successive
 // ImageProjectiveTransformV3 resamplings (bilinear, fill_mode='constant', fill value 0), each cropping to the frame;
 // the kernel reproduces them one after the other -- NOT as one composed warp, which would interpolate once and keep
@@ -75,7 +76,8 @@ augment_kernel(const TSrc* __restrict__ src, const float* __restrict__ params, f
     // RandomTranslation: plane 0 -> plane 1
     aug_stage<1>(buf0, H, W, p + 6, [&](int i, int, int, float v) { buf1[i] = v; });
     __syncthreads();
-    // RandomRotation, then RandomFlip('horizontal') as a mirrored store, RandomBrightness (+delta, clip to [0,255]) and
+    // RandomRotation, then RandomFlip('horizontal') as a mirrored store, the reference's own RandomBrightness layer
+    // (preprocessor.py:83-104: tf.image.adjust_brightness of a float image = "+ delta", no clipping) and
     // vgg16.preprocess_input (caffe mode: RGB -> BGR, minus the ImageNet channel mean, no scaling)
     const bool flip = p[18] != 0.f;
     const float delta = p[19];
@@ -83,7 +85,7 @@ augment_kernel(const TSrc* __restrict__ src, const float* __restrict__ params, f
     float* out = dst + static_cast<long long>(n) * plane * 3 + (preprocess ? 2 - c : c);
     asm volatile("" : "+l"(out));
     aug_stage<1>(buf1, H, W, p + 12, [&](int, int oy, int ox, float v) {
-        v = __fsub_rn(fminf(fmaxf(__fadd_rn(v, delta), 0.f), 255.f), mean);
+        v = __fsub_rn(__fadd_rn(v, delta), mean);
         out[(oy * W + (flip ? W - 1 - ox : ox)) * 3] = v;
     });
 }

@@ -185,7 +185,9 @@ int abl_resize_nearest_u8(const unsigned char* src, unsigned char* dst, int B, i
  *   src     [B,H,W,3] RGB frames at IMG_DIM in [0,255]: uint8 (src_is_u8) or fp32
  *   params  fp32 [B,20] per frame: the output->input affine maps [a0 a1 a2 b0 b1 b2] of the zoom, translation and
  *           rotation layers in Keras' ImageProjectiveTransformV3 convention (x_in = a0*x + a1*y + a2, y_in = b0*x +
- *           b1*y + b2), then flip (0/1) and the brightness delta already scaled to the [0,255] range.  The host draws
+ *           b1*y + b2), then flip (0/1) and the brightness delta that is ADDED to every value without clipping (the
+ *           reference's RandomBrightness layer, preprocessor.py:83-104, is tf.image.adjust_brightness on a float
+ *           image).  The host draws
  *           them (ab_line_classifier_b200/augment.py); the three resamplings are applied one after the other with
  *           bilinear interpolation and constant fill 0, exactly as the three Keras layers do.
  *   dst     fp32 [B,H,W,3]; preprocess != 0: BGR minus [103.939, 116.779, 123.68] (what block1_conv1 consumes),

@@ -1,16 +1,19 @@
 """TEST INFRASTRUCTURE ONLY (never imported by the product).  NumPy restatement of the augmentation pipeline the
 reference applies to training batches -- ``tf.keras.Sequential([RandomZoom(z, fill_mode='constant'),
 RandomTranslation(h, w, fill_mode='constant'), RandomRotation(r, fill_mode='constant'), RandomFlip("horizontal"),
-RandomBrightness(factor=b)])`` (src/data/preprocessor.py:25-32, 56-57) -- followed by ``vgg16.preprocess_input``
-(preprocessor.py:60-63).
+RandomBrightness(factor=b)])`` (src/data/preprocessor.py:25-32, 56-57; RandomBrightness is the reference's OWN layer,
+preprocessor.py:83-104) -- followed by ``vgg16.preprocess_input`` (preprocessor.py:60-63).
 
 The arithmetic lives in third-party code absent from /root/reference: tensorflow==2.9.0 (requirements.txt:13) with its
 bundled Keras 2.9 (keras/layers/preprocessing/image_preprocessing.py: get_zoom_matrix, get_translation_matrix,
-get_rotation_matrix, RandomFlip, RandomBrightness) and the ImageProjectiveTransformV3 CPU kernel
-(tensorflow/core/kernels/image/image_ops.h: ProjectiveGenerator, bilinear_interpolation, read_with_fill_value).  Their
+get_rotation_matrix, RandomFlip), the ImageProjectiveTransformV3 CPU kernel (tensorflow/core/kernels/image/
+image_ops.h: ProjectiveGenerator, bilinear_interpolation, read_with_fill_value), tf.image.stateless_random_brightness /
+adjust_brightness (python/ops/image_ops_impl.py) and the stateless Philox sampler behind it (core/kernels/
+stateless_random_ops.cc GenerateKey, core/lib/random/philox_random.h, random_distributions.h Uint32ToFloat).  Their
 published algorithm is restated below.  PARITY UNPINNED: TensorFlow cannot be installed here and the reference holds no
-fixtures for this path; the restatement is anchored on closed-form cases in tests/test_oracle.py.
-The random draws are inputs (TF's random stream is not reproducible outside TF)."""
+fixtures for this path; the restatement is anchored on closed-form cases in tests/test_augment_metrics.py.
+The random draws are inputs (TF's random stream is not reproducible outside TF), except the brightness delta, which
+the reference draws from a stateless generator with a constant seed."""
 import numpy as np
 
 F = np.float32
@@ -64,10 +67,39 @@ def projective_bilinear(img, t):
     return ((yc - y)[..., None] * v_lo + (y - yf)[..., None] * v_hi).astype(F)
 
 
+def philox_block(counter, key):
+    """Philox4x32-10 (philox_random.h): 10 rounds of (hi/lo products with 0xD2511F53 and 0xCD9E8D57, xor with the
+    neighbouring words and the key), the key raised by the Weyl constants between rounds."""
+    c = np.array(counter, np.uint64)
+    k = np.array(key, np.uint64)
+    mask = np.uint64(0xFFFFFFFF)
+    for r in range(10):
+        if r > 0:
+            k = (k + np.array([0x9E3779B9, 0xBB67AE85], np.uint64)) & mask
+        prod0 = np.uint64(0xD2511F53) * c[0]
+        prod1 = np.uint64(0xCD9E8D57) * c[2]
+        c = np.array([(prod1 >> np.uint64(32)) ^ c[1] ^ k[0], prod1 & mask, (prod0 >> np.uint64(32)) ^ c[3] ^ k[1],
+                      prod0 & mask], np.uint64) & mask
+    return [int(v) for v in c]
+
+
+def stateless_brightness_delta(max_delta, seed=(123, 0)):
+    """The delta of ``tf.image.stateless_random_brightness(image, max_delta, seed)`` (preprocessor.py:103): a scalar
+    stateless_random_uniform in [-max_delta, max_delta).  GenerateKey scrambles the seed: block(counter = seed words,
+    key = {0x3ec8f720, 0x02461e29}) -> key = words 0-1, counter = {0, 0, word 2, word 3}; the sample is word 0 of the
+    next block, turned into [0,1) by Uint32ToFloat and scaled in fp32."""
+    s0, s1 = int(seed[0]), int(seed[1])
+    mix = philox_block([s0 & 0xFFFFFFFF, (s0 >> 32) & 0xFFFFFFFF, s1 & 0xFFFFFFFF, (s1 >> 32) & 0xFFFFFFFF],
+                       [0x3EC8F720, 0x02461E29])
+    word = philox_block([0, 0, mix[2], mix[3]], [mix[0], mix[1]])[0]
+    u = np.array([(127 << 23) | (word & 0x7FFFFF)], np.uint32).view(F)[0] - F(1.0)
+    return F(u * (F(max_delta) - F(-max_delta)) + F(-max_delta))
+
+
 def augment_frame(rgb, zoom, dx_frac, dy_frac, angle, flip, brightness, preprocess=True):
     """One frame [H,W,3] (RGB, 0..255) through the five layers in the reference's order, then (optionally) the input
-    scaler.  Draw units as Keras draws them: zoom factor, shifts as fractions of (W, H), angle in radians, flip 0/1,
-    brightness factor (scaled by the 255-wide value range inside RandomBrightness)."""
+    scaler.  Draw units as Keras draws them: zoom factor, shifts as fractions of (W, H), angle in radians, flip 0/1;
+    ``brightness`` is the delta adjust_brightness adds to the float image (no 0..255 scaling, no clipping)."""
     x = np.asarray(rgb, F)
     H, W = x.shape[:2]
     x = projective_bilinear(x, zoom_transform(zoom, H, W))
@@ -75,7 +107,7 @@ def augment_frame(rgb, zoom, dx_frac, dy_frac, angle, flip, brightness, preproce
     x = projective_bilinear(x, rotation_transform(angle, H, W))
     if flip:
         x = x[:, ::-1]
-    x = np.clip(x + F(brightness) * F(255.0), F(0.0), F(255.0))
+    x = x + F(brightness)
     if preprocess:                                  # caffe mode: RGB -> BGR, subtract the ImageNet means, no scaling
         x = x[..., ::-1] - BGR_MEAN
     return np.ascontiguousarray(x, F)

@@ -48,17 +48,39 @@ def test_rotation_and_zoom_matrices():
 
 def test_augment_frame_order_flip_brightness_preprocess():
     img = _img()
-    # no geometry, flip on, +0.2 brightness: mirrored columns, +51 clipped at 255, then BGR minus means
+    # no geometry, flip on, brightness delta 0.2: mirrored columns, + 0.2 as adjust_brightness adds it (no 0..255
+    # scaling, no clipping: the reference's own RandomBrightness layer, preprocessor.py:83-104), then BGR minus means
     out = A.augment_frame(img, 1.0, 0.0, 0.0, 0.0, 1, 0.2, preprocess=False)
-    assert np.allclose(out, np.clip(img[:, ::-1] + np.float32(0.2) * 255, 0, 255), atol=1e-4)
+    assert np.array_equal(out, img[:, ::-1] + np.float32(0.2))
+    img[0, 0, 0] = 0                                                     # a black red value: goes below -mean, unclipped
     out = A.augment_frame(img, 1.0, 0.0, 0.0, 0.0, 0, -1.0, preprocess=True)
-    assert np.allclose(out, -A.BGR_MEAN, atol=1e-5)                      # clipped to 0 everywhere, then mean-subtracted
+    assert np.array_equal(out, (img - np.float32(1.0))[..., ::-1] - A.BGR_MEAN) and out.min() < -A.BGR_MEAN.max()
     out = A.augment_frame(img, 1.0, 0.0, 0.0, 0.0, 0, 0.0, preprocess=True)
     assert np.allclose(out, img[..., ::-1] - A.BGR_MEAN, atol=1e-5)
     # the stages crop: a frame pushed out by the translation does not come back with the rotation
     out = A.augment_frame(img, 1.0, 1.0, 0.0, 0.3, 0, 0.0, preprocess=False)
     assert (out == 0).all()
     assert A.augment_batch(np.zeros((0, 16, 20, 3), np.float32), {k: [] for k in ("zoom", "dx", "dy", "angle", "flip", "brightness")}).shape == (0, 16, 20, 3)
+
+
+def test_philox_known_answers_and_the_reference_brightness_constant():
+    """Philox4x32-10 against the published Random123 known-answer vectors (both restatements), and the constant delta
+    of ``tf.image.stateless_random_brightness(x, 0.3, (123, 0))`` (preprocessor.py:103) from product and oracle."""
+    kats = [([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+            ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+            ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+             [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1])]
+    for ctr, key, want in kats:
+        assert P._philox4x32_10(ctr, key) == want
+        assert A.philox_block(ctr, key) == want
+    for factor in (0.3, 0.05, 1.0):
+        d = P.reference_brightness_delta(factor)
+        assert d.dtype == np.float32 and d == A.stateless_brightness_delta(factor) and -factor <= d < factor
+    assert P.reference_brightness_delta(0.0) == 0.0
+    cfg = P.AugmentConfig({"BRIGHTNESS_RANGE": 0.3})
+    raw = P.draw_raw(np.random.default_rng(0), 7, cfg)
+    assert (raw["brightness"] == cfg.brightness_delta).all()          # one constant for every frame of every batch
+    assert np.array_equal(P.draw_raw(np.random.default_rng(1), 7, cfg)["brightness"], raw["brightness"])
 
 
 def test_host_parameter_builder_matches_keras_matrices_and_ranges():
@@ -77,10 +99,10 @@ def test_host_parameter_builder_matches_keras_matrices_and_ranges():
         want = np.concatenate([A.zoom_transform(raw["zoom"][i], H, W)[:6],
                                A.translation_transform(raw["dx"][i], raw["dy"][i], H, W)[:6],
                                A.rotation_transform(raw["angle"][i], H, W)[:6],
-                               [raw["flip"][i], np.float32(raw["brightness"][i]) * np.float32(255.0)]]).astype(np.float32)
+                               [raw["flip"][i], raw["brightness"][i]]]).astype(np.float32)
         assert np.array_equal(p[i], want)
     with pytest.raises(ValueError):
-        P.AugmentConfig({"BRIGHTNESS_RANGE": 1.5})
+        P.AugmentConfig({"BRIGHTNESS_RANGE": -0.5})
     with pytest.raises(ValueError):
         P.AugmentConfig({"ZOOM_RANGE": -0.1})
 

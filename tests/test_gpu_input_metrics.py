@@ -37,6 +37,7 @@ def test_augment_kernel_is_bit_exact_against_the_oracle(shape, u8, preprocess):
     if not u8:
         frames = (frames.astype(np.float32) + rng.random((B, H, W, 3)).astype(np.float32)).clip(0, 255)
     raw = _raw(B, seed=7)
+    raw["brightness"] = rng.uniform(-40, 40, B).astype(np.float32)    # any delta: added as is, nothing is clipped
     raw["zoom"][0], raw["dx"][0], raw["dy"][0], raw["angle"][0], raw["flip"][0], raw["brightness"][0] = 1, 0, 0, 0, 0, 0
     assert (ops.augment_workspace_bytes(B, H, W) > 0) == (H * W > 29056)
     aug = P.DeviceAugmenter(preprocess=preprocess)
@@ -146,8 +147,9 @@ def test_fit_on_augmented_batches_from_the_dataset():
         x0, y0 = batches[0]
         assert x0.is_cuda and x0.dtype == torch.float32 and tuple(x0.shape) == (32, 128, 128, 3)
         lo, hi = float(x0.min()), float(x0.max())
-        assert lo >= -123.68 - 1e-3 and hi <= 255 - 103.939 + 1e-3     # clipped to [0,255], then mean-subtracted
-        assert float((x0 == -103.939).float().mean()) > 0.001          # constant fill (0) where the warp left the frame
+        assert lo >= -123.68 - 0.5 and hi <= 255 - 103.939 + 0.5       # interpolated 0..255 + the small delta, mean-subtracted
+        fill_b = float(np.float32(ds._aug.cfg.brightness_delta) - np.float32(103.939))
+        assert float((x0 == fill_b).float().mean()) > 0.001            # constant fill (0 + delta) where the warp left the frame
     big = np.repeat(np.repeat(fr[:40], 2, axis=1), 2, axis=2)           # 256x256 raw frames
     ds = ArrayDataset(big, y[:40], 20, shuffle=True, seed=6, augment=cfg, img_dim=(128, 128))
     xb, _ = next(iter(ds))
