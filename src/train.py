@@ -70,20 +70,15 @@ def train_classifier(model_def, train_set, val_set, hparams, output_bias, class_
 
 
 def synthetic_datasets(n_train, n_val, preprocessing_fn, seed=1234):
+    """Seeded synthetic A-/B-line frames through the reference's data path (train_utils.py:84-88):
+    ``Preprocessor(preprocessing_fn).prepare(train, shuffle=True, augment=True)`` / ``prepare(val)``."""
     from ab_line_classifier_b200.synth import synth_frames
+    from src.data.preprocessor import Preprocessor
     xtr, ltr = synth_frames(n_train, seed=seed)
     xva, lva = synth_frames(n_val, seed=seed + 1)
-    nc = cfg['TRAIN']['N_CLASSES']
-    bs = cfg['TRAIN']['BATCH_SIZE']
-    oh = lambda l: np.eye(nc, dtype=np.float32)[l]
-    if cfg.get('B200', {}).get('AUGMENT', False):
-        # reference train_utils.py:85: prepare(train_set, shuffle=True, augment=True) -- RGB frames in, augmentation
-        # and the input scaler applied per batch (on the device here)
-        train = ArrayDataset(xtr, oh(ltr), bs, shuffle=True, seed=cfg['TRAIN']['SEED'],
-                             augment=cfg['TRAIN']['DATA_AUG'], img_dim=cfg['DATA']['IMG_DIM'])
-    else:
-        train = ArrayDataset(preprocessing_fn(xtr), oh(ltr), bs, shuffle=True, seed=cfg['TRAIN']['SEED'])
-    return train, ArrayDataset(preprocessing_fn(xva), oh(lva), bs), ltr
+    preprocessor = Preprocessor(preprocessing_fn)
+    train = preprocessor.prepare((xtr, ltr), shuffle=True, augment=bool(cfg.get('B200', {}).get('AUGMENT', False)))
+    return train, preprocessor.prepare((xva, lva), shuffle=False, augment=False), ltr
 
 
 def train_experiment(experiment='single_train', save_weights=False, epochs=None):

@@ -201,3 +201,38 @@ def test_oracles_reproduce_the_committed_fixture():
     assert np.array_equal(probs, gold["probs"]) and np.array_equal(y, gold["y"])
     assert np.array_equal(metric_counts.counts_from_arrays(y, probs, thr, [0.5, 0.5]), gold["counts"])
     assert np.array_equal(out[0], frames[0].astype(np.float32)[..., ::-1] - A.BGR_MEAN)     # frame 0: identity draws
+
+
+def test_preprocessor_prepare_mirrors_the_reference_pipeline():
+    """src/data/preprocessor.py: prepare(ds, shuffle, augment) -> batches of (frames, one-hot), short last batch;
+    resize = TF2 nearest neighbour; scaler paths (reference preprocessor.py:36-66, 69-80)."""
+    from oracle import preprocess as OP
+    from src.data import preprocessor as SP
+    from src.models.models import get_model
+    _, prep = get_model("cutoffvgg16")
+    rng = np.random.default_rng(2)
+    big = rng.integers(0, 256, (5, 150, 200, 3)).astype(np.uint8)
+    assert np.array_equal(SP.resize_nearest(big, (128, 128)), OP.nearest_resize_tf(big, (128, 128)))
+    assert SP.resize_nearest(big[:, :128, :128], (128, 128)) is not None
+    n = SP.cfg['TRAIN']['BATCH_SIZE'] + 3
+    frames = rng.integers(0, 256, (n, 128, 128, 3)).astype(np.uint8)
+    labels = rng.integers(0, 2, n)
+    p = SP.Preprocessor(prep)
+    ds = p.prepare((frames, labels), shuffle=False, augment=False)      # uint8 out: scaler + resize run on the device
+    batches = list(ds)
+    assert [len(b[0]) for b in batches] == [SP.cfg['TRAIN']['BATCH_SIZE'], 3]
+    assert batches[0][0].dtype.is_floating_point is False
+    assert np.array_equal(np.concatenate([b[1].numpy() for b in batches]), np.eye(2, dtype=np.float32)[labels])
+    aug = p.prepare((frames, labels), shuffle=True, augment=True)
+    assert aug._aug is not None and aug.shuffle and aug.img_dim == (128, 128)
+    assert aug._aug.cfg.rotation == SP.cfg['TRAIN']['DATA_AUG']['ROTATION_RANGE']
+    # no scaler: x / 255 on the host (preprocessor.py:61); a foreign scaler is applied on the host as well
+    x0 = next(iter(SP.Preprocessor(None).prepare((big, None))))[0].numpy()
+    assert x0.shape == (5, 128, 128, 3) and np.allclose(x0, SP.resize_nearest(big, (128, 128)) / 255.)
+    x1 = next(iter(SP.Preprocessor(lambda x: x * 2).prepare((big, None))))[0].numpy()
+    assert np.allclose(x1, SP.resize_nearest(big, (128, 128)).astype(np.float32) * 2)
+    with pytest.raises(NotImplementedError):
+        SP.Preprocessor(None).prepare((frames, labels), augment=True)
+    with pytest.raises(NotImplementedError):
+        SP.Preprocessor(prep, resize_interpolation='bilinear')
+    assert SP.RandomBrightness(0.3)(np.zeros((1, 2, 2, 3)))[0, 0, 0, 0] == P.reference_brightness_delta(0.3)

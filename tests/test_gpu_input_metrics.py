@@ -154,6 +154,11 @@ def test_fit_on_augmented_batches_from_the_dataset():
     ds = ArrayDataset(big, y[:40], 20, shuffle=True, seed=6, augment=cfg, img_dim=(128, 128))
     xb, _ = next(iter(ds))
     assert tuple(xb.shape) == (20, 128, 128, 3)
+    # the reference-facing wrapper: Preprocessor(scale_fn).prepare(ds, shuffle=True, augment=True) (train_utils.py:84-85)
+    from src.data.preprocessor import Preprocessor
+    prepared = Preprocessor(get_model("cutoffvgg16")[1]).prepare((big[:8], lab[:8]), shuffle=True, augment=True)
+    xb, yb = next(iter(prepared))
+    assert xb.is_cuda and xb.dtype == torch.float32 and tuple(xb.shape) == (8, 128, 128, 3) and tuple(yb.shape) == (8, 2)
     model_def, _ = get_model("cutoffvgg16")
     hp = {"LR_EXTRACT": 3e-4, "LR_FINETUNE": 1e-5, "DROPOUT": 0.45, "CUTOFF_LAYER": 10, "FINETUNE_LAYER": 7,
           "EXTRACT_EPOCHS": 2}
