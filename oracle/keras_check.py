@@ -4,7 +4,8 @@ TensorFlow 2.9 (reference requirements.txt:13) cannot be installed in this image
 reports "parity unpinned" and exits 0.  On a machine with TensorFlow it builds the reference graph exactly as
 src/models/models.py:407-417 does (VGG16(include_top=False) layers[1:10] -> GlobalAveragePooling2D -> Dropout
 -> Dense softmax), loads OUR seeded Glorot weights (oracle/synth.py, Keras names and layouts), and compares
-logits / probabilities / one training-step loss with oracle/oracle.py on the committed golden frames.
+logits / probabilities / one training-step loss with oracle/oracle.py on the committed golden frames; it also pins
+the brightness constant, the projective-transform resampling and the metric definitions (section 8 f4).
 
     python oracle/keras_check.py            # prints PINNED ok / UNPINNED (TensorFlow missing) / mismatch
 """
@@ -58,8 +59,43 @@ def main():
     loss_ref, _, _ = oracle.loss_and_grads(params, x, y, None, np.ones((len(x), 256), np.float32), dropout=0.0)
     print(f"categorical_crossentropy: Keras {loss_keras:.6f}  oracle {float(loss_ref):.6f}")
     ok = ok and dp < 1e-4 and abs(loss_keras - float(loss_ref)) < 1e-4
+    ok = pin_input_pipeline_and_metrics(tf) and ok
     print("PINNED ok" if ok else "MISMATCH between Keras and the oracle")
     return 0 if ok else 1
+
+
+def pin_input_pipeline_and_metrics(tf):
+    """The pieces either side of the network: the reference's brightness constant
+    (preprocessor.py:103), the projective-transform resampling behind RandomZoom/Translation/Rotation
+    (preprocessor.py:26-29) and the Keras metric definitions (train.py:109-115) against oracle/augment.py and
+    ab_line_classifier_b200/metrics.py."""
+    from ab_line_classifier_b200 import metrics as M
+    from oracle import augment as A
+    ok = True
+    d_tf = float(tf.image.stateless_random_brightness(tf.zeros((1, 2, 2, 3)), 0.3, (123, 0)).numpy().ravel()[0])
+    d_or = float(A.stateless_brightness_delta(0.3))
+    print(f"stateless_random_brightness delta: TF {d_tf:.9f}  oracle {d_or:.9f}")
+    ok = ok and abs(d_tf - d_or) < 1e-7
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (1, 64, 96, 3)).astype(np.float32)
+    for t in (A.zoom_transform(0.93, 64, 96), A.translation_transform(0.15, -0.1, 64, 96), A.rotation_transform(0.7, 64, 96)):
+        got = tf.raw_ops.ImageProjectiveTransformV3(images=img, transforms=t[None], output_shape=[64, 96],
+                                                    fill_value=0.0, interpolation="BILINEAR", fill_mode="CONSTANT").numpy()[0]
+        err = float(np.abs(got - A.projective_bilinear(img[0], t)).max())
+        print(f"ImageProjectiveTransformV3 vs oracle: max |diff| = {err:.3e}")
+        ok = ok and err < 1e-3
+    z = rng.normal(size=(500, 2)).astype(np.float32) * 2
+    p = (np.exp(z) / np.exp(z).sum(-1, keepdims=True)).astype(np.float32)
+    y = np.eye(2, dtype=np.float32)[rng.integers(0, 2, 500)]
+    pairs = [(tf.keras.metrics.AUC(name="auc"), M.AUC()), (tf.keras.metrics.CategoricalAccuracy(), M.CategoricalAccuracy()),
+             (tf.keras.metrics.Precision(thresholds=0.5, class_id=1), M.Precision(thresholds=0.5, class_id=1)),
+             (tf.keras.metrics.Recall(thresholds=0.5, class_id=0), M.Recall(thresholds=0.5, class_id=0))]
+    for km, mm in pairs:
+        km.update_state(y, p)
+        a, b = float(km.result().numpy()), mm.result(y, p)
+        print(f"{type(mm).__name__}: Keras {a:.6f}  here {b:.6f}")
+        ok = ok and abs(a - b) < 1e-5
+    return ok
 
 
 if __name__ == "__main__":
