@@ -44,7 +44,7 @@ class ArrayDataset:
     N_PINNED = 4      # rotating pinned batch buffers: a buffer is reused only after 3 later batches were staged
 
     def __init__(self, x, y=None, batch_size=64, shuffle=False, seed=0, pin=True, device=None, augment=None,
-                 img_dim=None):
+                 img_dim=None, rank=0, world_size=1):
         x = np.asarray(x) if not torch.is_tensor(x) else x
         if not torch.is_tensor(x):
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if x.dtype == np.uint8 else np.float32))
@@ -59,6 +59,15 @@ class ArrayDataset:
         self.x, self.y = x, y
         self.batch_size, self.shuffle = int(batch_size), shuffle
         self.rng = np.random.default_rng(seed)
+        # data parallel: batch_size is the GLOBAL batch; every rank walks the same (seeded) order
+        # and takes its contiguous 1/world_size of each global batch, so the ranks' gradient SUM is the single-device
+        # gradient on the whole batch.  A short last batch is cut to a multiple of world_size (at most world_size - 1
+        # frames of an epoch are skipped) so that all ranks see equal local batches.
+        self.rank, self.world_size = int(rank), int(world_size)
+        if not 0 <= self.rank < self.world_size:
+            raise ValueError("need 0 <= rank < world_size")
+        if self.batch_size % self.world_size:
+            raise ValueError("the global batch size must be a multiple of world_size")
         self._pinned = pin and torch.cuda.is_available() and self.device is None
         self._bufs, self._k = None, 0
         self._aug, self.img_dim = None, (None if img_dim is None else tuple(img_dim))
@@ -68,7 +77,14 @@ class ArrayDataset:
                                         device=self.device if self.device is not None else "cuda")
 
     def __len__(self):
-        return (len(self.x) + self.batch_size - 1) // self.batch_size
+        n = len(self.x)
+        full, rest = divmod(n, self.batch_size)
+        return full + (1 if rest >= self.world_size else 0)
+
+    def _local(self, lo, hi):
+        """This rank's contiguous share [lo', hi') of the global batch [lo, hi)."""
+        per = (hi - lo) // self.world_size
+        return lo + self.rank * per, lo + (self.rank + 1) * per
 
     @property
     def n_frames(self):
@@ -81,7 +97,7 @@ class ArrayDataset:
         if not self._pinned:
             return self.x[idx], (None if self.y is None else self.y[idx])
         if self._bufs is None:
-            b = self.batch_size
+            b = self.batch_size // self.world_size
             self._bufs = [(torch.empty((b,) + tuple(self.x.shape[1:]), dtype=self.x.dtype).pin_memory(),
                            None if self.y is None else torch.empty((b,) + tuple(self.y.shape[1:]), dtype=self.y.dtype).pin_memory())
                           for _ in range(self.N_PINNED)]
@@ -102,14 +118,18 @@ class ArrayDataset:
         n = len(self.x)
         if not self.shuffle:
             for i in range(0, n, self.batch_size):
-                yield self.x[i:i + self.batch_size], (None if self.y is None else self.y[i:i + self.batch_size])
+                lo, hi = self._local(i, min(i + self.batch_size, n))
+                if hi > lo:
+                    yield self.x[lo:hi], (None if self.y is None else self.y[lo:hi])
             return
         perm = torch.from_numpy(self.rng.permutation(n))
         if self.device is not None:
             # a per-batch upload of the indices from pageable memory would block the host behind all queued kernels
             perm = perm.to(self.device)
         for i in range(0, n, self.batch_size):
-            yield self._gather(perm[i:i + self.batch_size])
+            lo, hi = self._local(i, min(i + self.batch_size, n))
+            if hi > lo:
+                yield self._gather(perm[lo:hi])
 
     def _augmented(self, x):
         """One batch of RGB frames -> device fp32, augmented and preprocessed (preprocessor.py:56-63)."""

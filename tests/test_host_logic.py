@@ -217,3 +217,31 @@ def test_array_dataset_batches_shuffle_and_short_last_batch():
         assert sizes == [4, 4, 2] and sorted(seen) == list(range(10))          # every frame once, last batch short
     assert len(ds) == 3 and ds.n_frames == 10
     assert [len(b[0]) for b in ArrayDataset(x, None, 4)] == [4, 4, 2]
+
+
+def test_array_dataset_data_parallel_shards_partition_every_global_batch():
+    """the global batch is split contiguously, 1/world_size per rank; all ranks walk the same
+    seeded order; a short last batch is cut to a multiple of world_size so local batches stay equal."""
+    from ab_line_classifier_b200.data import ArrayDataset
+    n, world, gb = 23, 4, 8
+    x = np.arange(n * 3, dtype=np.float32).reshape(n, 1, 1, 3)
+    y = np.eye(2, dtype=np.float32)[np.arange(n) % 2]
+    for shuffle in (False, True):
+        whole = [xb[:, 0, 0, 0].tolist() for xb, _ in ArrayDataset(x, y, gb, shuffle=shuffle, seed=9, pin=False)]
+        parts = [[xb[:, 0, 0, 0].tolist() for xb, _ in ArrayDataset(x, y, gb, shuffle=shuffle, seed=9, pin=False,
+                                                                  rank=r, world_size=world)] for r in range(world)]
+        assert [len(p) for p in parts] == [3] * world                       # 8, 8 and 7 -> 4 frames: one dropped
+        for b in range(3):
+            local = [parts[r][b] for r in range(world)]
+            assert len({len(l) for l in local}) == 1                        # equal local batches
+            joined = sum(local, [])
+            assert joined == whole[b][:len(joined)]                         # contiguous shares, in rank order
+        assert len(sum(parts[0], [])) * world == 20
+        assert len(ArrayDataset(x, y, gb, rank=1, world_size=world)) == 3
+    # fewer leftover frames than ranks: the short batch is skipped on every rank
+    assert [len(b[0]) for b in ArrayDataset(x[:18], None, gb, pin=False, rank=3, world_size=world)] == [2, 2]
+    assert len(ArrayDataset(x[:18], None, gb, rank=3, world_size=world)) == 2
+    with pytest.raises(ValueError):
+        ArrayDataset(x, y, 6, world_size=4)
+    with pytest.raises(ValueError):
+        ArrayDataset(x, y, 8, rank=4, world_size=4)
