@@ -1083,6 +1083,186 @@ conv3x3_blk64_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
 }
 
+// Second cut of the blocked main loop (ABL_BLOCKED64=2; written after the first hardware profile of the kernel above,
+// NOT yet run on hardware): ncu showed the MMA thread waiting for activation planes 22 % of the time with a 4-slot
+// ring, so the 8 KiB of zero filter rows go (the accumulator columns are opened by two ordinary MMAs instead of one
+// N = 256 MMA over [S0; zeros]) and the ring gets a fifth slot.  Everything else is identical.
+struct Blk64bCfg {
+    static constexpr int kSlots = 5;
+    static constexpr int kMaxARows = 192;                       // (rows + 2) * (W/4): 6 x 32 (W = 128), 10 x 16 (W = 64)
+    static constexpr int kASlot = kMaxARows * 128;              // 24 KiB
+    static constexpr int kBKh = 3 * 64 * 128;                   // S of one kh: 192 rows x 128 B
+    static constexpr int kBBytes = 3 * kBKh;                    // S0 | S1 | S2 (no zero rows: see the MMA issuer)
+    static constexpr int kStagingBytes = 2 * kABytes;           // kEpiN = 128
+    static constexpr int kBarBytes = 2048;
+    static constexpr int kSmemBytes = kSlots * kASlot + kBBytes + kStagingBytes + kBarBytes;
+    static_assert(kSmemBytes <= 227 * 1024, "blocked conv: shared memory");
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
+    using Cfg = Blk64bCfg;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kSlots * Cfg::kASlot;
+    uint8_t* staging = smem_b + Cfg::kBBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+    uint64_t* afull_bar = bars;
+    uint64_t* aempty_bar = afull_bar + Cfg::kSlots;
+    uint64_t* bfull_bar = aempty_bar + Cfg::kSlots;
+    uint64_t* tfull_bar = bfull_bar + 1;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* csum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+
+    const int warp = threadIdx.x >> 5;
+    const int wb = p.W;                             // blocks per image row (blocked view: W/4)
+    const int rows = p.box_h;                       // image rows per tile: 128 / wb
+    const int num_tiles = p.num_m_tiles;
+    const uint32_t a_bytes = static_cast<uint32_t>((rows + 2) * wb * 128);
+    if (p.colsum != nullptr)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) csum[i] = 0.f;
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < Cfg::kSlots; ++s) {
+            mbar_init(&afull_bar[s], 1);
+            mbar_init(&aempty_bar[s], 1);
+        }
+        mbar_init(bfull_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], kEpiThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<512>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    auto s_off = [](int kh) { return kh * Blk64bCfg::kBKh; };      // byte offset of S(kh) in the filter area
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ A producer: 6 haloed pixel-slot planes per tile
+        if (elect_one()) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int img = tile / p.tiles_h;
+                const int h0 = (tile - img * p.tiles_h) * rows;
+#pragma unroll 1
+                for (int j = 0; j < 6; ++j) {
+                    // consumption order: q = 1 first (initialises columns 0-191), then 0, 2 (initialises 192-255), 3, left, right
+                    const int q = j == 0 ? 1 : (j == 1 ? 0 : (j == 2 ? 2 : (j == 5 ? 0 : 3)));
+                    const int xb = j == 4 ? -1 : (j == 5 ? 1 : 0);
+                    mbar_wait(&aempty_bar[slot], phase ^ 1);
+                    mbar_expect_tx(&afull_bar[slot], a_bytes);
+                    tma_load_5d(&map_a, &afull_bar[slot], smem_a + slot * Cfg::kASlot, 0, q, xb, h0 - 1, img);
+                    if (++slot == Cfg::kSlots) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ filter: loaded once, S(kh) = [W(kw=2); W(kw=1); W(kw=0)]
+        if (elect_one() && blockIdx.x < num_tiles) {
+            mbar_expect_tx(bfull_bar, 9 * 64 * 128);
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw)        // w_kmajor taps are kw-major: tap' = kw*3 + kh
+                    tma_load_3d(&map_b, bfull_bar, smem_b + s_off(kh) + (2 - kw) * (64 * 128), 0, 0, kw * 3 + kh);
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (elect_one()) {
+            constexpr uint32_t id64 = make_idesc_bf16(kTileM, 64, 0, 0), id128 = make_idesc_bf16(kTileM, 128, 0, 0);
+            constexpr uint32_t id192 = make_idesc_bf16(kTileM, 192, 0, 0);
+            constexpr uint32_t dhi = desc_hi_sw128(1024);
+            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a), 16);
+            const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_b), 16);
+            const uint32_t kh_rows = static_cast<uint32_t>(wb * 128) >> 4;      // descriptor units per image row
+            int slot = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            mbar_wait(bfull_bar, 0);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * 256;
+#pragma unroll 1
+                for (int j = 0; j < 6; ++j) {
+                    mbar_wait(&afull_bar[slot], phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + slot * (Cfg::kASlot >> 4);
+                    // band of this plane: filter rows [brow, brow + n) of S, accumulator columns [dcol, dcol + n)
+                    //   j: 0 (q=1)  1 (q=0)  2 (q=2)  3 (q=3)  4 (left, q=3 -> p=0, kw=0)  5 (right, q=0 -> p=3, kw=2)
+                    const int brow = j == 1 ? 64 : (j == 4 ? 128 : 0);
+                    const int dcol = j == 2 ? 64 : (j == 3 ? 128 : (j == 5 ? 192 : 0));
+                    const uint32_t idesc = (j == 0 || j == 2) ? id192 : (j >= 4 ? id64 : id128);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint32_t b_lo = b_lo0 + ((s_off(kh) + brow * 128) >> 4);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // First touches: plane q = 1 opens columns 0-191 (accumulate off on its very first MMA);
+                            // columns 192-255 are opened by the first k-step of plane q = 2, issued as N = 128
+                            // (columns 64-191, accumulating) + N = 64 (columns 192-255, accumulate off).
+                            if (j == 2 && (kh | k) == 0) {
+                                umma_bf16_lohi(tmem_d + 64, a_lo, dhi, b_lo, dhi, id128, 1u);
+                                umma_bf16_lohi(tmem_d + 192, a_lo, dhi, b_lo + ((128 * 128) >> 4), dhi, id64, 0u);
+                            } else {
+                                umma_bf16_lohi(tmem_d + dcol, a_lo + kh * kh_rows + k * 2, dhi, b_lo + k * 2, dhi, idesc,
+                                               (j | kh | k) == 0 ? 0u : 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&aempty_bar[slot]);
+                    if (++slot == Cfg::kSlots) { slot = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (8 warps): a 256-channel conv on [B, H, W/4]
+        const int et = threadIdx.x - 128;
+        int it = 0;
+        uint32_t pass_ctr = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int img = tile / p.tiles_h;
+            const int h0 = (tile - img * p.tiles_h) * rows;
+            const int as = it & 1;
+            long long next_origin = -1;
+            if ((p.flags & ABL_EPI_RELU_MASK) && tile + static_cast<int>(gridDim.x) < num_tiles) {
+                const int t2 = tile + gridDim.x;
+                const int img2 = t2 / p.tiles_h;
+                next_origin = ((static_cast<long long>(img2) * p.H + (t2 - img2 * p.tiles_h) * rows) * p.W) * p.Cout;
+            }
+            epilogue_tile<256, 128, 1>(p, &map_out, staging, tmem_base + as * 256, img, h0, 0, 0, wb, et, pass_ctr,
+                                       &tfull_bar[as], (it >> 1) & 1, &tempty_bar[as],
+                                       p.colsum != nullptr ? csum : nullptr, next_origin);
+        }
+        if (et == 0) tma_store_wait_all();
+        if (p.colsum != nullptr) {           // the four pixel slots of a channel fold into one bias-gradient entry
+            named_bar_sync(1, kEpiThreads);
+            for (int i = et; i < 256; i += kEpiThreads) atomicAdd(p.colsum + (i & 63), csum[i]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+
 // Pick the tile rectangle: box_w = largest of {64,32,16,8} with W % box_w == 0 and
 // H % (128 / box_w) == 0 (box_w >= 8 keeps a tile row a whole number of 1024-byte swizzle atoms).
 static int pick_box(int H, int W, int* box_h, int* box_w) {
@@ -1183,7 +1363,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         const char* blk = getenv("ABL_BLOCKED64");
         const bool shape_ok = Cin == 64 && Cout == 64 && (W == 128 || W == 64) && H % (512 / W) == 0 && !out_unpool &&
                               !gap_part && (!out_pool || ((512 / W) % 2 == 0));
-        if (blk && blk[0] == '1' && shape_ok) {
+        if (blk && (blk[0] == '1' || blk[0] == '2') && shape_ok) {
+            const bool v2 = blk[0] == '2';
             const int wb = W / 4, rows = 512 / W;
             a.W = wb; a.Cout = 256; a.blocked = 1; a.cmask = 63;
             a.box_w = wb; a.box_h = rows; a.tiles_h = H / rows; a.tiles_w = 1;
@@ -1224,12 +1405,16 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
             cudaGetDevice(&dev);
             if (!attr_done[dev & 63]) {
                 if (cudaFuncSetAttribute(conv3x3_blk64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Blk64Cfg::kSmemBytes) != cudaSuccess)
+                                         Blk64Cfg::kSmemBytes) != cudaSuccess ||
+                    cudaFuncSetAttribute(conv3x3_blk64b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Blk64bCfg::kSmemBytes) != cudaSuccess)
                     return check_launch();
                 attr_done[dev & 63] = true;
             }
             const int grid = a.num_m_tiles < sm_count() ? a.num_m_tiles : sm_count();
-            conv3x3_blk64_kernel<<<grid, kThreads, Blk64Cfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, mo, a);
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            if (v2) conv3x3_blk64b_kernel<<<grid, kThreads, Blk64bCfg::kSmemBytes, st>>>(ma, mb, mo, a);
+            else conv3x3_blk64_kernel<<<grid, kThreads, Blk64Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
             return check_launch();
         }
     }

@@ -1,6 +1,7 @@
 """Developer tool: the blocked main loop for Cin = Cout = 64 (ABL_BLOCKED64=1, conv3x3_blk64_kernel) against the default
 haloed-tile kernel on the same inputs -- forward (+pool, +routing codes), dgrad (+ReLU mask, +fused bias gradient) --
-and their device times at batch 256.  python tools/blk64_check.py [B_time]"""
+and their device times at batch 256.  python tools/blk64_check.py [B_time] [variant: 1 (default) | 2]
+Variant 2 (ABL_BLOCKED64=2: five ring slots, no zero filter rows) has not been run on hardware yet."""
 import os
 import sys
 
@@ -10,8 +11,11 @@ import torch  # noqa: E402
 from ab_line_classifier_b200 import ops  # noqa: E402
 
 
+VARIANT = sys.argv[2] if len(sys.argv) > 2 else "1"
+
+
 def run(blocked, fn):
-    os.environ["ABL_BLOCKED64"] = "1" if blocked else "0"
+    os.environ["ABL_BLOCKED64"] = VARIANT if blocked else "0"
     try:
         return fn()
     finally:
