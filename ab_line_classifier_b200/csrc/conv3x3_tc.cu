@@ -1094,11 +1094,12 @@ struct Blk64bCfg {
     static constexpr int kBKh = 3 * 64 * 128;                   // S of one kh: 192 rows x 128 B
     static constexpr int kBBytes = 3 * kBKh;                    // S0 | S1 | S2 (no zero rows: see the MMA issuer)
     static constexpr int kStagingBytes = 2 * kABytes;           // kEpiN = 128
-    static constexpr int kBarBytes = 2048;
+    static constexpr int kBarBytes = 3072;                      // barriers, then csum [256] fp32 OR the pooled epilogue's h-bits (2 KiB)
     static constexpr int kSmemBytes = kSlots * kASlot + kBBytes + kStagingBytes + kBarBytes;
     static_assert(kSmemBytes <= 227 * 1024, "blocked conv: shared memory");
 };
 
+template <bool kPoolEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
@@ -1231,6 +1232,98 @@ conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (8 warps): a 256-channel conv on [B, H, W/4]
         const int et = threadIdx.x - 128;
+        if constexpr (kPoolEpi) {
+            // Pooled-only forward epilogue (training/inference forward of block1_conv2: bias + ReLU + 2x2 max-pool
+            // [+ routing codes], no full-resolution output).  One GEMM row holds four adjacent pixels, so the
+            // horizontal half of the pool is a max between column groups inside the thread's registers; only the
+            // h-pooled values (half of the generic staging) cross shared memory for the vertical half.
+            //   thread = (TMEM lane = GEMM row, hsel): hsel 0 -> pixels p0,p1 (pooled column 2*xb), hsel 1 -> p2,p3
+            //   write phase: staging[hsel][row][128 B swizzled] = h-max of 64 channels, hbits[(hsel*128+row)*2 + c] =
+            //                bit ch set where the RIGHT pixel is strictly greater (first maximum wins, as TF)
+            //   read phase : (row pair, block, hsel, 8-channel chunk): v-max of the two rows, routing code =
+            //                top >= bottom ? hbit_top : 2 + hbit_bottom  (index of the first maximum in scan order)
+            const int lane_row = ((et >> 5) & 3) * 32 + (et & 31);
+            const int hsel = et >> 7;
+            uint32_t* hbits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 512);
+            auto bf2_max = [](uint32_t a, uint32_t b) {
+                const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&b));
+                return *reinterpret_cast<const uint32_t*>(&m);
+            };
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int img = tile / p.tiles_h;
+                const int h0 = (tile - img * p.tiles_h) * rows;
+                const int as = it & 1;
+                mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + as * 256 + hsel * 128 + (static_cast<uint32_t>(lane_row & ~31) << 16);
+                uint8_t* hrow = staging + hsel * kABytes + lane_row * 128;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(tacc + c * 32, ra);            // left pixel of the pair, channels 32c .. 32c+31
+                    tmem_ld_32x32b_x32(tacc + 64 + c * 32, rb);       // right pixel
+                    tmem_ld_wait();
+                    const float4* bs = reinterpret_cast<const float4*>(p.bias + c * 32);
+                    uint32_t hm[16], bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(bs + j);
+                        const uint32_t a0 = pack_bf16x2(fmaxf(__uint_as_float(ra[4 * j]) + b4.x, 0.f),
+                                                        fmaxf(__uint_as_float(ra[4 * j + 1]) + b4.y, 0.f));
+                        const uint32_t a1 = pack_bf16x2(fmaxf(__uint_as_float(ra[4 * j + 2]) + b4.z, 0.f),
+                                                        fmaxf(__uint_as_float(ra[4 * j + 3]) + b4.w, 0.f));
+                        const uint32_t c0 = pack_bf16x2(fmaxf(__uint_as_float(rb[4 * j]) + b4.x, 0.f),
+                                                        fmaxf(__uint_as_float(rb[4 * j + 1]) + b4.y, 0.f));
+                        const uint32_t c1 = pack_bf16x2(fmaxf(__uint_as_float(rb[4 * j + 2]) + b4.z, 0.f),
+                                                        fmaxf(__uint_as_float(rb[4 * j + 3]) + b4.w, 0.f));
+                        hm[2 * j] = bf2_max(a0, c0);
+                        hm[2 * j + 1] = bf2_max(a1, c1);
+                        // post-ReLU values are >= +0: bit equality is value equality; the right pixel wins only if the
+                        // left one is not the maximum
+                        const uint32_t n0 = ~__vcmpeq2(a0, hm[2 * j]), n1 = ~__vcmpeq2(a1, hm[2 * j + 1]);
+                        bits |= ((n0 & 1u) | ((n0 >> 15) & 2u) | ((n1 & 1u) << 2) | ((n1 >> 13) & 8u)) << (4 * j);
+                    }
+                    if (c == 1) {               // all TMEM reads of this thread are done
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[as]);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        *reinterpret_cast<uint4*>(hrow + (((c * 4 + cc) ^ (lane_row & 7)) << 4)) =
+                            make_uint4(hm[4 * cc], hm[4 * cc + 1], hm[4 * cc + 2], hm[4 * cc + 3]);
+                    hbits[(hsel * 128 + lane_row) * 2 + c] = bits;
+                }
+                named_bar_sync(1, kEpiThreads);                     // h-pooled rows and bits of the tile are in shared memory
+                const int npos = (kTileM / 2) * 2 * 8;              // (row pairs x blocks) x pixel pair x 8-channel chunks
+                for (int q = et; q < npos; q += kEpiThreads) {
+                    const int c8 = q & 7, pp = (q >> 3) & 1, pos = q >> 4;
+                    const int xb = pos % wb, rp = pos / wb;
+                    const int m0 = (2 * rp) * wb + xb, m1 = m0 + wb;
+                    const uint8_t* hb = staging + pp * kABytes;
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(hb + m0 * 128 + ((c8 ^ (m0 & 7)) << 4));
+                    const uint4 b4 = *reinterpret_cast<const uint4*>(hb + m1 * 128 + ((c8 ^ (m1 & 7)) << 4));
+                    const uint32_t tb = (hbits[(pp * 128 + m0) * 2 + (c8 >> 2)] >> ((c8 & 3) * 8)) & 0xFFu;
+                    const uint32_t bb = (hbits[(pp * 128 + m1) * 2 + (c8 >> 2)] >> ((c8 & 3) * 8)) & 0xFFu;
+                    const uint32_t tv[4] = {t4.x, t4.y, t4.z, t4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                    uint32_t o[4], code = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        o[j] = bf2_max(tv[j], bv[j]);
+                        const uint32_t et2 = __vcmpeq2(tv[j], o[j]);          // 0xFFFF where the top row holds the maximum
+                        const uint32_t k0 = 2 * j, k1 = 2 * j + 1;
+                        const uint32_t c_lo = (et2 & 1u) ? ((tb >> k0) & 1u) : (2u + ((bb >> k0) & 1u));
+                        const uint32_t c_hi = (et2 & 0x10000u) ? ((tb >> k1) & 1u) : (2u + ((bb >> k1) & 1u));
+                        code |= (c_lo << (2 * k0)) | (c_hi << (2 * k1));
+                    }
+                    const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1) + rp) * (2 * wb) + 2 * xb + pp) * 64 + c8 * 8;
+                    *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
+                }
+                named_bar_sync(1, kEpiThreads);                     // the exchange buffers may be overwritten by the next tile
+            }
+        } else {
         int it = 0;
         uint32_t pass_ctr = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -1251,6 +1344,7 @@ conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (p.colsum != nullptr) {           // the four pixel slots of a channel fold into one bias-gradient entry
             named_bar_sync(1, kEpiThreads);
             for (int i = et; i < 256; i += kEpiThreads) atomicAdd(p.colsum + (i & 63), csum[i]);
+        }
         }
     }
 
@@ -1364,7 +1458,9 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         const bool shape_ok = Cin == 64 && Cout == 64 && (W == 128 || W == 64) && H % (512 / W) == 0 && !out_unpool &&
                               !gap_part && (!out_pool || ((512 / W) % 2 == 0));
         if (blk && (blk[0] == '1' || blk[0] == '2') && shape_ok) {
-            const bool v2 = blk[0] == '2';
+            const bool v2 = blk[0] == '2' || blk[0] == '3';
+            // '3': v2 main loop + the pooled-only forward epilogue where it applies (else the generic epilogue)
+            const bool pool_epi = blk[0] == '3' && out_pool && !out_full && !colsum && (flags & ABL_EPI_BIAS_RELU);
             const int wb = W / 4, rows = 512 / W;
             a.W = wb; a.Cout = 256; a.blocked = 1; a.cmask = 63;
             a.box_w = wb; a.box_h = rows; a.tiles_h = H / rows; a.tiles_w = 1;
@@ -1406,14 +1502,17 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
             if (!attr_done[dev & 63]) {
                 if (cudaFuncSetAttribute(conv3x3_blk64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Blk64Cfg::kSmemBytes) != cudaSuccess ||
-                    cudaFuncSetAttribute(conv3x3_blk64b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    cudaFuncSetAttribute(conv3x3_blk64b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Blk64bCfg::kSmemBytes) != cudaSuccess ||
+                    cudaFuncSetAttribute(conv3x3_blk64b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Blk64bCfg::kSmemBytes) != cudaSuccess)
                     return check_launch();
                 attr_done[dev & 63] = true;
             }
             const int grid = a.num_m_tiles < sm_count() ? a.num_m_tiles : sm_count();
             cudaStream_t st = static_cast<cudaStream_t>(stream);
-            if (v2) conv3x3_blk64b_kernel<<<grid, kThreads, Blk64bCfg::kSmemBytes, st>>>(ma, mb, mo, a);
+            if (pool_epi) conv3x3_blk64b_kernel<true><<<grid, kThreads, Blk64bCfg::kSmemBytes, st>>>(ma, mb, mo, a);
+            else if (v2) conv3x3_blk64b_kernel<false><<<grid, kThreads, Blk64bCfg::kSmemBytes, st>>>(ma, mb, mo, a);
             else conv3x3_blk64_kernel<<<grid, kThreads, Blk64Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
             return check_launch();
         }

@@ -1,7 +1,8 @@
 """Developer tool: the blocked main loop for Cin = Cout = 64 (ABL_BLOCKED64=1, conv3x3_blk64_kernel) against the default
 haloed-tile kernel on the same inputs -- forward (+pool, +routing codes), dgrad (+ReLU mask, +fused bias gradient) --
-and their device times at batch 256.  python tools/blk64_check.py [B_time] [variant: 1 (default) | 2]
-Variant 2 (ABL_BLOCKED64=2: five ring slots, no zero filter rows) has not been run on hardware yet."""
+and their device times at batch 256.  python tools/blk64_check.py [B_time] [variant: 1 (default) | 2 | 3]
+Variants 2 (ABL_BLOCKED64=2: five ring slots, no zero filter rows) and 3 (= 2 + the pooled-only forward epilogue that
+pools horizontally in registers) have not been run on hardware yet."""
 import os
 import sys
 
