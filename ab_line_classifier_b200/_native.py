@@ -50,6 +50,7 @@ SIGNATURES = {
     "abl_augment_frames": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "abl_metrics_counter_count": (_i, [_i, _i]),
     "abl_metrics_accumulate": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "abl_dev_mma_rate_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "abl_gradcam": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
@@ -75,7 +76,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abl_abi_version() != 5:
+    if lib.abl_abi_version() != 6:
         raise RuntimeError("libabl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabl_b200.so")
-SOURCES = ["host_util.cu", "conv3x3_tc.cu", "wgrad_tc.cu", "conv_first_tc.cu", "pointwise.cu", "input_metrics.cu"]
+SOURCES = ["host_util.cu", "conv3x3_tc.cu", "wgrad_tc.cu", "conv_first_tc.cu", "pointwise.cu", "input_metrics.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

@@ -1,0 +1,89 @@
+// Developer probe, not part of the reference-facing path: how many SM clocks does one tcgen05.mma (M = 128, K = 16,
+// bf16, operands in shared memory) take as a function of N and of the issue pattern?  The conv kernels' ceilings are
+// set by this number (ncu: N = 64 issues once per ~64 clocks although the math needs 32), so the blocked main loop
+// (conv3x3_blk64_kernel) was designed around it; this kernel measures it directly instead of inferring it from
+// whole-kernel timings.  One thread issues `iters` groups of four K-steps back to back from fixed operand tiles,
+// commits to an mbarrier, and the CTA reports clock64() deltas.
+//   mode 0: plain SS MMAs into one accumulator
+//   mode 1: weight-stationary pairs (collector b0 fill -> lastuse): two A tiles / two accumulators share each B read
+//   mode 2: like 0, but every MMA of a group uses a different 8 KiB-aligned window of B (no operand reuse at all)
+#include <stdint.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace abl {
+
+constexpr int kProbeA = 2 * 128 * 128;        // two A tiles [128 rows][128 B]
+constexpr int kProbeB = 4 * 256 * 128;        // four B tiles [256 rows][128 B]
+constexpr int kProbeSmem = kProbeA + kProbeB + 1024;
+
+__global__ void __launch_bounds__(128, 1)
+mma_rate_probe_kernel(int n, int mode, int iters, unsigned long long* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kProbeA;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_b + kProbeB);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    for (int i = threadIdx.x; i < (kProbeA + kProbeB) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 1 && elect_one()) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1 && elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(n), 0, 0);
+        constexpr uint32_t dhi = desc_hi_sw128(1024);
+        const uint32_t a_lo = desc_lo_sw128(smem_u32(smem_a), 16);
+        const uint32_t b_lo = desc_lo_sw128(smem_u32(smem_b), 16);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (mode == 1) {
+                    umma_bf16_lohi_ws<0>(tmem_base, a_lo + k * 2, dhi, b_lo + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
+                    umma_bf16_lohi_ws<1>(tmem_base + 256, a_lo + ((128 * 128) >> 4) + k * 2, dhi, b_lo + k * 2, dhi, idesc,
+                                         (it | k) != 0 ? 1u : 0u);
+                } else {
+                    const uint32_t boff = mode == 2 ? static_cast<uint32_t>(((it * 4 + k) & 3) * ((256 * 128) >> 4)) : 0u;
+                    umma_bf16_lohi(tmem_base, a_lo + k * 2, dhi, b_lo + boff + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        umma_commit(bar);
+        mbar_wait(bar, 0);
+        const long long t2 = clock64();
+        out[blockIdx.x * 2] = static_cast<unsigned long long>(t1 - t0);        // issue loop (back-pressure included)
+        out[blockIdx.x * 2 + 1] = static_cast<unsigned long long>(t2 - t0);    // until the last MMA retired
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace abl
+
+using namespace abl;
+
+extern "C" int abl_dev_mma_rate_probe(int n, int mode, int iters, int ctas, unsigned long long* out_cycles, void* stream) {
+    if (!out_cycles) { set_error("abl_dev_mma_rate_probe: null pointer"); return ABL_ERR_NULL; }
+    if (n < 16 || n > 256 || (n & 15) || mode < 0 || mode > 2 || iters <= 0 || ctas <= 0) {
+        set_error("abl_dev_mma_rate_probe: need N in 16..256 (multiple of 16), mode 0..2, iters > 0, ctas > 0");
+        return ABL_ERR_SHAPE;
+    }
+    if (cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmem) != cudaSuccess)
+        return check_launch();
+    mma_rate_probe_kernel<<<ctas, 128, kProbeSmem, static_cast<cudaStream_t>(stream)>>>(n, mode, iters, out_cycles);
+    return check_launch();
+}

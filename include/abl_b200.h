@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 5
+#define ABL_ABI_VERSION 6
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -210,6 +210,12 @@ int abl_metrics_counter_count(int n_classes, int num_thresholds);
 int abl_metrics_accumulate(const float* probs, const float* y_true, int B, int n_classes, const float* auc_thresholds,
                            int num_thresholds, const float* class_thresholds, unsigned long long* counters,
                            void* stream);
+
+/* Developer probe (not used by the product path): SM clocks per tcgen05.mma (M = 128, K = 16, bf16, operands in shared
+ * memory) for a given N and issue pattern -- mode 0 plain, 1 weight-stationary pairs, 2 a different filter window per
+ * MMA.  `ctas` CTAs (one per SM) each issue 4*iters MMAs (8*iters in mode 1) and write two uint64 to out_cycles
+ * [ctas][2]: clocks of the issue loop and clocks until the last MMA retired.  tools/mma_rate.py prints the table. */
+int abl_dev_mma_rate_probe(int n, int mode, int iters, int ctas, unsigned long long* out_cycles, void* stream);
 
 /* Clip-level aggregation of frame probabilities (src/predict.py:159-166 with the helpers at 283-308 and 365-376),
  * all clips in one launch instead of the reference's per-clip Python loop.  probs fp32 [N_frames, n_classes] with the
