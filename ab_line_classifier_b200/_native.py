@@ -19,26 +19,31 @@ _u, _ull = C.c_uint, C.c_ulonglong
 SIGNATURES = {
     "abl_abi_version": (_i, []),
     "abl_last_error": (C.c_char_p, []),
-    "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "abl_parts_bytes": (_ll, [_i]),
+    "abl_parts_reduce": (_i, [_vp, _vp, _i, _i, _vp]),
+    "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_igemm_gap": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_gap_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "abl_conv3x3_dgrad_unpool": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "abl_conv3x3_dgrad_unpool": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
-    "abl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
-    "abl_bias_grad": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "abl_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "abl_bias_grad": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),
     "abl_conv_first_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "abl_conv_first_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_conv_first_wgrad_workspace_bytes": (_ll, []),
+    "abl_conv_first_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "abl_conv_first_fwd_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "abl_conv_first_wgrad_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_conv_first_wgrad_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "abl_prep_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "abl_prep_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "abl_maxpool_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "abl_maxpool_bwd_code": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "abl_maxpool_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "abl_maxpool_bwd_code": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "abl_gap_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "abl_head_loss_ws_bytes": (_ll, [_i]),
     "abl_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _ull, _u, _u,
-                          _i, _i, _i, _vp]),
-    "abl_head_fwd_stepdev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _f, _ull, _vp, _u, _i, _i, _i, _vp]),
+                          _i, _i, _i, _i, _vp, _vp]),
+    "abl_head_fwd_stepdev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _f, _ull, _vp, _u, _i, _i, _i,
+                                  _i, _vp, _vp]),
     "abl_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "abl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "abl_adam_flat_tab": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _f, _f, _f, _vp]),
@@ -56,8 +61,8 @@ SIGNATURES = {
 
 _lib = None
 
-# kernels launched per entry point (abl_conv3x3_wgrad: GEMM + slice reduction [+ bias grad])
-LAUNCHES_PER_CALL = {"abl_conv3x3_wgrad": 3}
+# kernels launched per entry point (GEMM + fixed-order reduction of the per-CTA sums)
+LAUNCHES_PER_CALL = {"abl_conv3x3_wgrad": 2, "abl_conv_first_wgrad": 2, "abl_conv_first_wgrad_u8": 2}
 launch_count = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
 timing = None             # set to a list to record (name, args, start_event, end_event) per call
 
@@ -76,7 +81,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abl_abi_version() != 6:
+    if lib.abl_abi_version() != 7:
         raise RuntimeError("libabl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -23,6 +23,7 @@
 
 #include "host_util.h"
 #include "ptx.cuh"
+#include "parts.cuh"
 #include "../../include/abl_b200.h"
 
 namespace abl {
@@ -43,7 +44,8 @@ struct ConvArgs {
     const __nv_bfloat16* mask_src;  // [B,H,W,Cout] (ABL_EPI_RELU_MASK)
     __nv_bfloat16* out_full;        // [B,H,W,Cout] or null
     __nv_bfloat16* out_pool;        // [B,H/2,W/2,Cout] or null
-    float* colsum;                  // [Cout] fp32 += column sums of out_full (fused BiasAddGrad) or null
+    float* colsum;                  // parts buffer (include/abl_b200.h): row blockIdx.x = this CTA's fp32 column sums of
+                                    // the values it wrote (fused BiasAddGrad of the layer below) or null
     uint16_t* pool_code;            // [B,H/2,W/2,Cout/8]: 2-bit index of the window's first maximum per channel, or null
     // dgrad through a max-pool: route each output value straight to the 2x2 window element named by the forward's
     // routing code (MaxPoolGrad fused into the epilogue; the pooled-resolution gradient never reaches HBM)
@@ -52,11 +54,6 @@ struct ConvArgs {
     // fused GlobalAveragePooling partial sums: row (8x16-pixel rectangle index) x Cout fp32, plain stores (each value
     // has exactly one writer -> deterministic); abl_gap_reduce adds the rectangles of a frame in fixed order
     float* gap_part;                // [B * (H/8) * (W/16)][Cout] or null
-    // "blocked" view (conv3x3_blk64_kernel): the tensor is seen as [B, H, W/4, 4*64] -- four horizontally adjacent pixels
-    // form one GEMM row with 256 channels (the SAME bytes as NHWC with 64 channels).  W and Cout above then hold W/4
-    // and 256; per-channel vectors (bias, colsum) are indexed modulo 64 and the 2x2 max-pool pairs channel groups.
-    int blocked;
-    int cmask;                      // 63 in the blocked view, else all ones: bias index = column & cmask
 };
 
 // 2x2 max-pool of 8 channels (four packed bf16x2 words per window element) + optional routing code: for every
@@ -175,7 +172,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
             uint32_t packed[16];
             if (p.flags & ABL_EPI_BIAS_RELU) {
                 // warp-uniform address: one broadcast transaction per load, L1-resident
-                const float4* bs = reinterpret_cast<const float4*>(p.bias + ((n0 + col) & p.cmask));
+                const float4* bs = reinterpret_cast<const float4*>(p.bias + n0 + col);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b4 = __ldg(bs + j);
@@ -281,26 +278,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
                 }
             }
         }
-        if (p.out_pool != nullptr && p.blocked) {
-            // blocked view (kEpiN == 128): this pass staged the pixel pair (2*pass, 2*pass+1) of every 4-pixel block as
-            // boxes 0 and 1; a pooling window = those two boxes x two vertically adjacent tile rows (box_w GEMM rows apart)
-            const int npos = (kTileM / 2) * 8;                        // (row pairs x blocks) x 8-channel chunks
-            for (int q = et; q < npos; q += kEpiThreads) {
-                const int c8 = q & 7, pos = q >> 3;
-                const int xb = pos % box_w, rp = pos / box_w;
-                const int m0 = (2 * rp) * box_w + xb, m1 = m0 + box_w;
-                const uint4 a = *reinterpret_cast<const uint4*>(stg + m0 * 128 + ((c8 ^ (m0 & 7)) << 4));
-                const uint4 b = *reinterpret_cast<const uint4*>(stg + kABytes + m0 * 128 + ((c8 ^ (m0 & 7)) << 4));
-                const uint4 c2 = *reinterpret_cast<const uint4*>(stg + m1 * 128 + ((c8 ^ (m1 & 7)) << 4));
-                const uint4 d = *reinterpret_cast<const uint4*>(stg + kABytes + m1 * 128 + ((c8 ^ (m1 & 7)) << 4));
-                uint32_t o[4], code;
-                pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
-                // pooled tensor [B, H/2, 2*box_w, 64]: pixel (h0/2 + rp, 2*xb + pass)
-                const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1) + rp) * (2 * box_w) + 2 * xb + pass) * 64 + c8 * 8;
-                *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
-            }
-        } else if (p.out_pool != nullptr) {
+        if (p.out_pool != nullptr) {
             constexpr int kChunks16 = kEpiN / 8;
             const int pw_n = box_w >> 1;
 #pragma unroll
@@ -830,11 +808,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
             }
             if (gt == 0) tma_store_wait_all();
-            if (p.colsum != nullptr) {        // chunk sums of all 256 threads -> csum -> one global atomic per channel
+            if (p.colsum != nullptr) {
+                // chunk sums of all 256 threads -> this CTA's row of the parts buffer, in a FIXED order: thread t parks
+                // its 8 sums in the (now idle) staging area, then channel c adds the 32 threads t with (t & 7) == c / 8
+                // in increasing t.  No atomics: the bias gradient is bit-reproducible.
+                named_bar_sync(3, kEpiThreads);      // ids 1 and 2 belong to the two groups; all stores have been read
+                float* park = reinterpret_cast<float*>(staging);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) atomicAdd(&csum[(gt & 7) * 8 + j], bacc[j]);
-                named_bar_sync(3, kEpiThreads);      // ids 1 and 2 belong to the two groups
-                for (int i = et; i < NTILE; i += kEpiThreads) atomicAdd(p.colsum + i, csum[i]);
+                for (int j = 0; j < 8; ++j) park[et * 8 + j] = bacc[j];
+                named_bar_sync(3, kEpiThreads);
+                if (et < NTILE) {
+                    float sacc = 0.f;
+                    for (int t = et >> 3; t < kEpiThreads; t += 8) sacc += park[t * 8 + (et & 7)];
+                    p.colsum[ABL_PARTS_HEADER + static_cast<size_t>(blockIdx.x) * NTILE + et] = sacc;
+                }
+                if (blockIdx.x == 0 && et == 0) *reinterpret_cast<int*>(p.colsum) = static_cast<int>(gridDim.x);
             }
         } else {
         int it = 0;
@@ -873,9 +861,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
-        if (p.colsum != nullptr) {           // one flush per CTA (host guarantees a single N tile)
+        if (p.colsum != nullptr) {           // one row per CTA (host guarantees a single N tile); no atomics
             named_bar_sync(1, kEpiThreads);
-            for (int i = et; i < NTILE; i += kEpiThreads) atomicAdd(p.colsum + i, csum[i]);
+            for (int i = et; i < NTILE; i += kEpiThreads)
+                p.colsum[ABL_PARTS_HEADER + static_cast<size_t>(blockIdx.x) * NTILE + i] = csum[i];
+            if (blockIdx.x == 0 && et == 0) *reinterpret_cast<int*>(p.colsum) = static_cast<int>(gridDim.x);
         }
         }
     }
@@ -889,204 +879,31 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// "Blocked" main loop for Cin = Cout = 64 (block1_conv2 forward and dgrad).  An SS-mode MMA reads its A tile from
-// shared memory at ~128 B/clock whatever N is, so N = 64 convolutions are pinned at half the tensor rate (ncu: one
-// M128.N64.K16 MMA per 64 clocks).  Here four horizontally adjacent pixels form ONE GEMM row: the NHWC tensor
-// [B,H,W,64] is read as [B,H,W/4,4*64] (the same bytes), and the 3x3 convolution becomes, per kh, a banded
-// [4*64] x [4*64] product over pixel slots q (input) and p (output) with kw = q - p + 1:
+// "Blocked" main loop for the pooled forward of a Cin = Cout = 64 layer (block1_conv2: bias + ReLU + 2x2 max-pool
+// [+ routing codes], no full-resolution output).  An SS-mode MMA reads its A tile (4 KiB) and its B tile from shared
+// memory at 128 B/clock, so an M128.N64.K16 MMA cannot retire faster than every 48 clocks although the math needs 32
+// (tools/mma_rate.py on B200: 49.7 with independent accumulators, 94 back to back into one accumulator).  Here four
+// horizontally adjacent pixels form ONE GEMM row: the NHWC tensor [B,H,W,64] is read as [B,H,W/4,4*64] (the same
+// bytes), and the 3x3 convolution becomes, per kh, a banded [4*64] x [4*64] product over pixel slots q (input) and p
+// (output) with kw = q - p + 1:
 //     q=0 -> p in {0,1}   q=1 -> p in {0,1,2}   q=2 -> p in {1,2,3}   q=3 -> p in {2,3}
 // plus the two neighbours across the block boundary (left block's q=3 -> p=0, right block's q=0 -> p=3).  With the
 // filter rows of one kh stored as S = [W(kw=2); W(kw=1); W(kw=0)] every band is a CONTIGUOUS row range of S and a
 // contiguous column range of the accumulator, so one activation tile feeds N = 128 or 192 output columns per MMA
 // (N = 64 only for the two boundary terms): 72 MMA issues worth 5376 tensor clocks per 512 output pixels instead of
-// 144 N = 64 issues (9216 clocks).  No FLOPs are wasted (the bands hold exactly the 9 taps) and no layout changes.
+// 144 N = 64 issues.  No FLOPs are wasted (the bands hold exactly the 9 taps) and no layout changes.
 //   A: per pixel slot q one TMA box {64 ch, q, W/4 blocks, rows+2, 1} of the 5-D view [C, 4, W/4, H, B] (a plane of
 //      every 4th pixel, haloed by one image row above/below: kh = descriptor row offset of W/4 rows), plus the same
 //      box shifted by -1 / +1 block for the boundary terms (out-of-range blocks and rows are TMA zero fill = SAME
-//      padding).  Six 24 KiB boxes per tile travel through a 4-slot ring.
-//   B: the whole filter stays resident (3 kh x 24 KiB) followed by 8 KiB of zeros, which widen the very first MMA of a
-//      tile to N = 256 so that it initialises every accumulator column.
-//   D: 128 GEMM rows x 256 columns fp32 in TMEM, double buffered (all 512 columns); the shared epilogue sees a conv
-//      with 256 output channels on a [B, H, W/4] image (bias index modulo 64, max-pool across channel groups).
-struct Blk64Cfg {
-    static constexpr int kSlots = 4;
-    static constexpr int kMaxARows = 192;                       // (rows + 2) * (W/4): 6 x 32 (W = 128), 10 x 16 (W = 64)
-    static constexpr int kASlot = kMaxARows * 128;              // 24 KiB
-    static constexpr int kBKh = 3 * 64 * 128;                   // S of one kh: 192 rows x 128 B
-    static constexpr int kBBytes = 3 * kBKh + 64 * 128;         // + 64 zero rows behind S of kh = 0 ... see kZeroOff
-    static constexpr int kZeroOff = kBKh;                       // layout: S0 | zeros | S1 | S2
-    static constexpr int kStagingBytes = 2 * kABytes;           // kEpiN = 128
-    static constexpr int kBarBytes = 2048;
-    static constexpr int kSmemBytes = kSlots * kASlot + kBBytes + kStagingBytes + kBarBytes;
-    static_assert(kSmemBytes <= 227 * 1024, "blocked conv: shared memory");
-};
-
-__global__ void __launch_bounds__(kThreads, 1)
-conv3x3_blk64_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
-    using Cfg = Blk64Cfg;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + Cfg::kSlots * Cfg::kASlot;
-    uint8_t* staging = smem_b + Cfg::kBBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
-    uint64_t* afull_bar = bars;
-    uint64_t* aempty_bar = afull_bar + Cfg::kSlots;
-    uint64_t* bfull_bar = aempty_bar + Cfg::kSlots;
-    uint64_t* tfull_bar = bfull_bar + 1;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* csum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
-
-    const int warp = threadIdx.x >> 5;
-    const int wb = p.W;                             // blocks per image row (blocked view: W/4)
-    const int rows = p.box_h;                       // image rows per tile: 128 / wb
-    const int num_tiles = p.num_m_tiles;
-    const uint32_t a_bytes = static_cast<uint32_t>((rows + 2) * wb * 128);
-    if (p.colsum != nullptr)
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) csum[i] = 0.f;
-    {   // zero rows behind S(kh = 0)
-        uint4* z = reinterpret_cast<uint4*>(smem_b + Cfg::kZeroOff);
-        for (int i = threadIdx.x; i < 64 * 128 / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        fence_proxy_async_smem();
-    }
-    if (warp == 0 && elect_one()) {
-        tma_prefetch_desc(&map_a);
-        tma_prefetch_desc(&map_b);
-        tma_prefetch_desc(&map_out);
-    }
-    if (warp == 1 && elect_one()) {
-        for (int s = 0; s < Cfg::kSlots; ++s) {
-            mbar_init(&afull_bar[s], 1);
-            mbar_init(&aempty_bar[s], 1);
-        }
-        mbar_init(bfull_bar, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], kEpiThreads);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 2) {
-        tmem_alloc<512>(tmem_slot);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    // byte offset of S(kh) in the filter area: S0 | zeros | S1 | S2
-    auto s_off = [](int kh) { return kh == 0 ? 0 : Blk64Cfg::kBKh + 64 * 128 + (kh - 1) * Blk64Cfg::kBKh; };
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ A producer: 6 haloed pixel-slot planes per tile
-        if (elect_one()) {
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int img = tile / p.tiles_h;
-                const int h0 = (tile - img * p.tiles_h) * rows;
-#pragma unroll 1
-                for (int j = 0; j < 6; ++j) {
-                    // consumption order: q = 1 first (its first MMA initialises all columns), then 0, 2, 3, left, right
-                    const int q = j == 0 ? 1 : (j == 1 ? 0 : (j == 2 ? 2 : (j == 5 ? 0 : 3)));
-                    const int xb = j == 4 ? -1 : (j == 5 ? 1 : 0);
-                    mbar_wait(&aempty_bar[slot], phase ^ 1);
-                    mbar_expect_tx(&afull_bar[slot], a_bytes);
-                    tma_load_5d(&map_a, &afull_bar[slot], smem_a + slot * Cfg::kASlot, 0, q, xb, h0 - 1, img);
-                    if (++slot == Cfg::kSlots) { slot = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 3) {
-        // ------------------------------------------------------------ filter: loaded once, S(kh) = [W(kw=2); W(kw=1); W(kw=0)]
-        if (elect_one() && blockIdx.x < num_tiles) {
-            mbar_expect_tx(bfull_bar, 9 * 64 * 128);
-            for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw)        // w_kmajor taps are kw-major: tap' = kw*3 + kh
-                    tma_load_3d(&map_b, bfull_bar, smem_b + s_off(kh) + (2 - kw) * (64 * 128), 0, 0, kw * 3 + kh);
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (elect_one()) {
-            constexpr uint32_t id64 = make_idesc_bf16(kTileM, 64, 0, 0), id128 = make_idesc_bf16(kTileM, 128, 0, 0);
-            constexpr uint32_t id192 = make_idesc_bf16(kTileM, 192, 0, 0), id256 = make_idesc_bf16(kTileM, 256, 0, 0);
-            constexpr uint32_t dhi = desc_hi_sw128(1024);
-            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a), 16);
-            const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_b), 16);
-            const uint32_t kh_rows = static_cast<uint32_t>(wb * 128) >> 4;      // descriptor units per image row
-            int slot = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            mbar_wait(bfull_bar, 0);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * 256;
-#pragma unroll 1
-                for (int j = 0; j < 6; ++j) {
-                    mbar_wait(&afull_bar[slot], phase);
-                    tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + slot * (Cfg::kASlot >> 4);
-                    // band of this plane: filter rows [brow, brow + n) of S, accumulator columns [dcol, dcol + n)
-                    //   j: 0 (q=1)  1 (q=0)  2 (q=2)  3 (q=3)  4 (left, q=3 -> p=0, kw=0)  5 (right, q=0 -> p=3, kw=2)
-                    const int brow = j == 1 ? 64 : (j == 4 ? 128 : 0);
-                    const int dcol = j == 2 ? 64 : (j == 3 ? 128 : (j == 5 ? 192 : 0));
-                    const uint32_t idesc = (j == 0 || j == 2) ? id192 : (j >= 4 ? id64 : id128);
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const uint32_t b_lo = b_lo0 + ((s_off(kh) + brow * 128) >> 4);
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            const bool first = (j | kh | k) == 0;      // N = 256 over [S0; zeros]: initialises all columns
-                            umma_bf16_lohi(tmem_d + dcol, a_lo + kh * kh_rows + k * 2, dhi, b_lo + k * 2, dhi,
-                                           first ? id256 : idesc, first ? 0u : 1u);
-                        }
-                    }
-                    umma_commit(&aempty_bar[slot]);
-                    if (++slot == Cfg::kSlots) { slot = 0; phase ^= 1; }
-                }
-                umma_commit(&tfull_bar[as]);
-            }
-        }
-    } else if (warp >= 4) {
-        // ------------------------------------------------------------ epilogue (8 warps): a 256-channel conv on [B, H, W/4]
-        const int et = threadIdx.x - 128;
-        int it = 0;
-        uint32_t pass_ctr = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int img = tile / p.tiles_h;
-            const int h0 = (tile - img * p.tiles_h) * rows;
-            const int as = it & 1;
-            long long next_origin = -1;
-            if ((p.flags & ABL_EPI_RELU_MASK) && tile + static_cast<int>(gridDim.x) < num_tiles) {
-                const int t2 = tile + gridDim.x;
-                const int img2 = t2 / p.tiles_h;
-                next_origin = ((static_cast<long long>(img2) * p.H + (t2 - img2 * p.tiles_h) * rows) * p.W) * p.Cout;
-            }
-            epilogue_tile<256, 128, 1>(p, &map_out, staging, tmem_base + as * 256, img, h0, 0, 0, wb, et, pass_ctr,
-                                       &tfull_bar[as], (it >> 1) & 1, &tempty_bar[as],
-                                       p.colsum != nullptr ? csum : nullptr, next_origin);
-        }
-        if (et == 0) tma_store_wait_all();
-        if (p.colsum != nullptr) {           // the four pixel slots of a channel fold into one bias-gradient entry
-            named_bar_sync(1, kEpiThreads);
-            for (int i = et; i < 256; i += kEpiThreads) atomicAdd(p.colsum + (i & 63), csum[i]);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
-// Second cut of the blocked main loop (ABL_BLOCKED64=2; written after the first hardware profile of the kernel above,
-// NOT yet run on hardware): ncu showed the MMA thread waiting for activation planes 22 % of the time with a 4-slot
-// ring, so the 8 KiB of zero filter rows go (the accumulator columns are opened by two ordinary MMAs instead of one
-// N = 256 MMA over [S0; zeros]) and the ring gets a fifth slot.  Everything else is identical.
+//      padding).  Six 24 KiB boxes per tile travel through a 5-slot ring.
+//   B: the whole filter stays resident (3 kh x 24 KiB).
+//   D: 128 GEMM rows x 256 columns fp32 in TMEM, double buffered (all 512 columns).
+//   Epilogue: one GEMM row holds four adjacent pixels, so the horizontal half of the max-pool is a max between column
+//      groups inside a thread's registers; only the h-pooled values cross shared memory for the vertical half.
+// Measured on B200, batch 256 (tools/blk64_check.py): 237 us against 288 us for the haloed N = 64 kernel.  The same
+// main loop with the generic full-resolution epilogue (forward with out_full, dgrad + ReLU mask) was built and
+// measured in round 1/2 and was NOT faster than the haloed kernel there (267 vs 288 us forward, 463 vs 444 us dgrad:
+// its epilogue moves twice the bytes through shared memory), so those variants were removed.
 struct Blk64bCfg {
     static constexpr int kSlots = 5;
     static constexpr int kMaxARows = 192;                       // (rows + 2) * (W/4): 6 x 32 (W = 128), 10 x 16 (W = 64)
@@ -1099,9 +916,8 @@ struct Blk64bCfg {
     static_assert(kSmemBytes <= 227 * 1024, "blocked conv: shared memory");
 };
 
-template <bool kPoolEpi>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+conv3x3_blk64_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_out, const ConvArgs p) {
     using Cfg = Blk64bCfg;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -1115,15 +931,12 @@ conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint64_t* tfull_bar = bfull_bar + 1;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* csum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
     const int warp = threadIdx.x >> 5;
     const int wb = p.W;                             // blocks per image row (blocked view: W/4)
     const int rows = p.box_h;                       // image rows per tile: 128 / wb
     const int num_tiles = p.num_m_tiles;
     const uint32_t a_bytes = static_cast<uint32_t>((rows + 2) * wb * 128);
-    if (p.colsum != nullptr)
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) csum[i] = 0.f;
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
@@ -1232,7 +1045,7 @@ conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (8 warps): a 256-channel conv on [B, H, W/4]
         const int et = threadIdx.x - 128;
-        if constexpr (kPoolEpi) {
+        {
             // Pooled-only forward epilogue (training/inference forward of block1_conv2: bias + ReLU + 2x2 max-pool
             // [+ routing codes], no full-resolution output).  One GEMM row holds four adjacent pixels, so the
             // horizontal half of the pool is a max between column groups inside the thread's registers; only the
@@ -1323,28 +1136,6 @@ conv3x3_blk64b_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 }
                 named_bar_sync(1, kEpiThreads);                     // the exchange buffers may be overwritten by the next tile
             }
-        } else {
-        int it = 0;
-        uint32_t pass_ctr = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int img = tile / p.tiles_h;
-            const int h0 = (tile - img * p.tiles_h) * rows;
-            const int as = it & 1;
-            long long next_origin = -1;
-            if ((p.flags & ABL_EPI_RELU_MASK) && tile + static_cast<int>(gridDim.x) < num_tiles) {
-                const int t2 = tile + gridDim.x;
-                const int img2 = t2 / p.tiles_h;
-                next_origin = ((static_cast<long long>(img2) * p.H + (t2 - img2 * p.tiles_h) * rows) * p.W) * p.Cout;
-            }
-            epilogue_tile<256, 128, 1>(p, &map_out, staging, tmem_base + as * 256, img, h0, 0, 0, wb, et, pass_ctr,
-                                       &tfull_bar[as], (it >> 1) & 1, &tempty_bar[as],
-                                       p.colsum != nullptr ? csum : nullptr, next_origin);
-        }
-        if (et == 0) tma_store_wait_all();
-        if (p.colsum != nullptr) {           // the four pixel slots of a channel fold into one bias-gradient entry
-            named_bar_sync(1, kEpiThreads);
-            for (int i = et; i < 256; i += kEpiThreads) atomicAdd(p.colsum + (i & 63), csum[i]);
-        }
         }
     }
 
@@ -1414,10 +1205,10 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
 using namespace abl;
 
 // See include/abl_b200.h for the contract.
-extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
+extern "C" int abl_bias_grad(const void* dz, float* db_parts, long long db_parts_bytes, long long rows, int C, void* stream);
 
 static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                           void* out_full, void* out_pool, unsigned short* pool_code, float* colsum,
+                           void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, long long colsum_bytes,
                            void* out_unpool, const unsigned short* unpool_code, float* gap_part, int B, int H, int W,
                            int Cin, int Cout, int flags, void* stream) {
     if (colsum && !out_full && !out_unpool) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
@@ -1445,35 +1236,31 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
     }
     ConvArgs a;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
-    a.blocked = 0; a.cmask = 0x7fffffff;
     if (pick_box(H, W, &a.box_h, &a.box_w) != ABL_OK) {
         set_error("abl_conv3x3_igemm: H x W cannot be tiled into 128-pixel rectangles (need W % 8 == 0 etc.)");
         return ABL_ERR_SHAPE;
     }
     if (out_pool && (a.box_h & 1)) { set_error("abl_conv3x3_igemm: pooled output needs an even tile height"); return ABL_ERR_SHAPE; }
     {
-        // Blocked main loop (four pixels per GEMM row) for the Cin = Cout = 64 layers.  ABL_BLOCKED64=1 enables it:
-        // written and compiled in round 1, to be validated on hardware before it becomes the default.
+        // Blocked main loop (four pixels per GEMM row) for the pooled-only forward of a Cin = Cout = 64 layer
+        // (block1_conv2 in training and inference).  ABL_BLOCKED64=0 falls back to the haloed kernel (A/B runs, tests).
         const char* blk = getenv("ABL_BLOCKED64");
-        const bool shape_ok = Cin == 64 && Cout == 64 && (W == 128 || W == 64) && H % (512 / W) == 0 && !out_unpool &&
-                              !gap_part && (!out_pool || ((512 / W) % 2 == 0));
-        if (blk && (blk[0] == '1' || blk[0] == '2') && shape_ok) {
-            const bool v2 = blk[0] == '2' || blk[0] == '3';
-            // '3': v2 main loop + the pooled-only forward epilogue where it applies (else the generic epilogue)
-            const bool pool_epi = blk[0] == '3' && out_pool && !out_full && !colsum && (flags & ABL_EPI_BIAS_RELU);
+        const bool shape_ok = Cin == 64 && Cout == 64 && (W == 128 || W == 64) && H % (512 / W) == 0 && (512 / W) % 2 == 0;
+        if (shape_ok && out_pool && !out_full && !colsum && !out_unpool && !gap_part && flags == ABL_EPI_BIAS_RELU &&
+            !(blk && blk[0] == '0')) {
             const int wb = W / 4, rows = 512 / W;
-            a.W = wb; a.Cout = 256; a.blocked = 1; a.cmask = 63;
+            a.W = wb; a.Cout = 256;
             a.box_w = wb; a.box_h = rows; a.tiles_h = H / rows; a.tiles_w = 1;
             a.num_m_tiles = B * a.tiles_h; a.num_n_tiles = 1; a.kchunks = 1;
             a.flags = flags;
             a.bias = bias;
-            a.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
-            a.out_full = static_cast<__nv_bfloat16*>(out_full);
+            a.mask_src = nullptr;
+            a.out_full = nullptr;
             a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
             a.pool_code = pool_code;
-            a.colsum = colsum;
+            a.colsum = nullptr;
             a.out_unpool = nullptr; a.unpool_code = nullptr; a.gap_part = nullptr;
-            CUtensorMap ma, mb, mo;
+            CUtensorMap ma, mb;
             {
                 const uint64_t dims[5] = {64, 4, (uint64_t)wb, (uint64_t)H, (uint64_t)B};
                 const uint64_t strides[4] = {64 * 2, 4 * 64 * 2, (uint64_t)W * 64 * 2, (uint64_t)H * W * 64 * 2};
@@ -1488,32 +1275,17 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
                 int r = encode_tiled(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w_kmajor, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
                 if (r != ABL_OK) return r;
             }
-            mo = ma;
-            if (out_full) {
-                const uint64_t dims[4] = {256, (uint64_t)wb, (uint64_t)H, (uint64_t)B};
-                const uint64_t strides[3] = {256 * 2, (uint64_t)wb * 256 * 2, (uint64_t)H * wb * 256 * 2};
-                const uint32_t box[4] = {64, (uint32_t)wb, (uint32_t)rows, 1};
-                int r = encode_tiled(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out_full, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-                if (r != ABL_OK) return r;
-            }
             static bool attr_done[64] = {false};
             int dev = 0;
             cudaGetDevice(&dev);
             if (!attr_done[dev & 63]) {
-                if (cudaFuncSetAttribute(conv3x3_blk64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Blk64Cfg::kSmemBytes) != cudaSuccess ||
-                    cudaFuncSetAttribute(conv3x3_blk64b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Blk64bCfg::kSmemBytes) != cudaSuccess ||
-                    cudaFuncSetAttribute(conv3x3_blk64b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                if (cudaFuncSetAttribute(conv3x3_blk64_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Blk64bCfg::kSmemBytes) != cudaSuccess)
                     return check_launch();
                 attr_done[dev & 63] = true;
             }
             const int grid = a.num_m_tiles < sm_count() ? a.num_m_tiles : sm_count();
-            cudaStream_t st = static_cast<cudaStream_t>(stream);
-            if (pool_epi) conv3x3_blk64b_kernel<true><<<grid, kThreads, Blk64bCfg::kSmemBytes, st>>>(ma, mb, mo, a);
-            else if (v2) conv3x3_blk64b_kernel<false><<<grid, kThreads, Blk64bCfg::kSmemBytes, st>>>(ma, mb, mo, a);
-            else conv3x3_blk64_kernel<<<grid, kThreads, Blk64Cfg::kSmemBytes, st>>>(ma, mb, mo, a);
+            conv3x3_blk64_pool_kernel<<<grid, kThreads, Blk64bCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, ma, a);
             return check_launch();
         }
     }
@@ -1583,6 +1355,11 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         }
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         int r;
+        if (fuse_colsum) {
+            const int tiles = a.num_m_tiles * a.num_n_tiles;
+            r = parts_check(colsum, colsum_bytes, tiles < sm_count() ? tiles : sm_count(), Cout, "abl_conv3x3_igemm");
+            if (r != ABL_OK) return r;
+        }
         switch (ntile) {
             case 256: r = launch_halo<256, 1>(ma, mb, mo, a, st); break;
             case 128: r = launch_halo<128, 2>(ma, mb, mo, a, st); break;
@@ -1590,7 +1367,7 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
                                                     : launch_halo<64, 2, false>(ma, mb, mo, a, st);
         }
         if (r == ABL_OK && colsum != nullptr && !fuse_colsum)
-            r = abl_bias_grad(out_full, colsum, static_cast<long long>(B) * H * W, Cout, stream);
+            r = abl_bias_grad(out_full, colsum, colsum_bytes, static_cast<long long>(B) * H * W, Cout, stream);
         return r;
     }
     if (out_unpool) { set_error("abl_conv3x3_dgrad_unpool: needs W % 16 == 0 and H % 16 == 0"); return ABL_ERR_SHAPE; }
@@ -1643,30 +1420,32 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         case 128: r = launch_conv<128, 1>(ma, mb, mo, a, st); break;
         default: r = taps3 ? launch_conv<64, 3>(ma, mb, mo, a, st) : launch_conv<64, 1>(ma, mb, mo, a, st);
     }
-    if (r == ABL_OK && colsum != nullptr) r = abl_bias_grad(out_full, colsum, static_cast<long long>(B) * H * W, Cout, stream);
+    if (r == ABL_OK && colsum != nullptr)
+        r = abl_bias_grad(out_full, colsum, colsum_bytes, static_cast<long long>(B) * H * W, Cout, stream);
     return r;
 }
 
 extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                                 void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B,
-                                 int H, int W, int Cin, int Cout, int flags, void* stream) {
-    return conv_igemm_impl(x, w_kmajor, bias, mask_src, out_full, out_pool, pool_code, colsum, nullptr, nullptr, nullptr, B,
-                           H, W, Cin, Cout, flags, stream);
+                                 void* out_full, void* out_pool, unsigned short* pool_code, float* colsum_parts,
+                                 long long colsum_parts_bytes, int B, int H, int W, int Cin, int Cout, int flags,
+                                 void* stream) {
+    return conv_igemm_impl(x, w_kmajor, bias, mask_src, out_full, out_pool, pool_code, colsum_parts, colsum_parts_bytes,
+                           nullptr, nullptr, nullptr, B, H, W, Cin, Cout, flags, stream);
 }
 
 // See include/abl_b200.h: forward conv + bias + ReLU with the GlobalAveragePooling partial sums fused in.
 extern "C" int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full,
                                      float* gap_part, int B, int H, int W, int Cin, int Cout, void* stream) {
     if (!gap_part) { set_error("abl_conv3x3_igemm_gap: gap_part is null"); return ABL_ERR_NULL; }
-    return conv_igemm_impl(x, w_kmajor, bias, nullptr, out_full, nullptr, nullptr, nullptr, nullptr, nullptr, gap_part, B, H,
-                           W, Cin, Cout, ABL_EPI_BIAS_RELU, stream);
+    return conv_igemm_impl(x, w_kmajor, bias, nullptr, out_full, nullptr, nullptr, nullptr, 0, nullptr, nullptr, gap_part,
+                           B, H, W, Cin, Cout, ABL_EPI_BIAS_RELU, stream);
 }
 
 // See include/abl_b200.h: dgrad through a max-pool in one kernel.
 extern "C" int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, const void* pooled,
-                                        const unsigned short* pool_code, void* dz_out, float* db, int B, int H, int W,
-                                        int Cin, int Cout, void* stream) {
+                                        const unsigned short* pool_code, void* dz_out, float* db_parts,
+                                        long long db_parts_bytes, int B, int H, int W, int Cin, int Cout, void* stream) {
     if (!pooled || !pool_code || !dz_out) { set_error("abl_conv3x3_dgrad_unpool: null pointer"); return ABL_ERR_NULL; }
-    return conv_igemm_impl(dz, w_dgrad, nullptr, pooled, nullptr, nullptr, nullptr, db, dz_out, pool_code, nullptr, B, H, W,
-                           Cin, Cout, ABL_EPI_RELU_MASK, stream);
+    return conv_igemm_impl(dz, w_dgrad, nullptr, pooled, nullptr, nullptr, nullptr, db_parts, db_parts_bytes, dz_out,
+                           pool_code, nullptr, B, H, W, Cin, Cout, ABL_EPI_RELU_MASK, stream);
 }

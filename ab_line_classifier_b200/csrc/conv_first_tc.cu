@@ -35,8 +35,7 @@ struct FirstArgs {
     const uint8_t* x8;     // [B,H,W,3] uint8 RGB: preprocessing fused into the gather (kU8 kernels)
     const float* w;        // [27][64] fp32 (HWIO flattened)
     const float* bias;     // [64]
-    float* dw;             // [27][64]  (wgrad)
-    float* db;             // [64] or null
+    float* part;           // wgrad: per-CTA partial sums [gridDim.x][55][64] (rows 0..26 hi, 27..53 lo, 54 = bias)
     int H, W;
     long long total_pix;   // B*H*W
     int num_tiles;         // total_pix / 128
@@ -45,6 +44,7 @@ struct FirstArgs {
     int patch_ok;
 };
 
+constexpr int kF_PartRows = 55;                                // hi rows 0..26, lo rows 27..53, ones row 54
 constexpr int kF_PatchRegs = 10;                               // ceil(3 * 130 * 3 / 128) elements per producer thread
 constexpr int kF_PatchFloats = kF_PatchRegs * 128;             // one group's haloed fp32 patch (5 KiB)
 
@@ -362,7 +362,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
-// Persistent CTAs; each accumulates D[slot][co] over its tiles in TMEM, then adds rows 0..54 to dw / db.
+// Persistent CTAs; each accumulates D[slot][co] over its tiles in TMEM, then stores rows 0..54 as its partial sums.
 template <bool kU8>
 __global__ void __launch_bounds__(kF_Threads, 1)
 conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const FirstArgs p) {
@@ -445,13 +445,13 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + c * 32, r);
                 tmem_ld_wait();
-                if (row < 54) {
-                    float* dst = p.dw + (row % 27) * kF_Cout + c * 32;
+                if (row < kF_PartRows) {
+                    // plain stores of this CTA's sums; conv_first_wgrad_reduce_kernel adds the CTAs in a fixed order
+                    float4* dst = reinterpret_cast<float4*>(p.part + (static_cast<size_t>(blockIdx.x) * kF_PartRows + row) * kF_Cout + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
-                } else if (row == 54 && p.db != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(p.db + c * 32 + j, __uint_as_float(r[j]));
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                 }
             }
         }
@@ -461,6 +461,40 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<64>(tmem_base);
+    }
+}
+
+// dw[k][co] = sum_cta (part[cta][k][co] + part[cta][27 + k][co]), db[co] = sum_cta part[cta][54][co], CTAs in a fixed
+// order: block = 4 float4 columns x 64 CTA groups (thread (col, g) adds CTAs g, g+64, ...; groups combined in order).
+__global__ void __launch_bounds__(256)
+conv_first_wgrad_reduce_kernel(const float4* __restrict__ part, int n_cta, float4* __restrict__ dw, float4* __restrict__ db) {
+    __shared__ float4 red[64][4];
+    constexpr int kRow4 = kF_Cout / 4, kDw4 = 27 * kRow4, kOut4 = kDw4 + kRow4, kCta4 = kF_PartRows * kRow4;
+    const int cl = threadIdx.x & 3, g = threadIdx.x >> 2;
+    const int o4 = blockIdx.x * 4 + cl;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o4 < kOut4) {
+        const int src = o4 < kDw4 ? o4 : 54 * kRow4 + (o4 - kDw4);
+        for (int c = g; c < n_cta; c += 64) {
+            const float4 v = __ldcg(part + static_cast<size_t>(c) * kCta4 + src);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            if (o4 < kDw4) {
+                const float4 l = __ldcg(part + static_cast<size_t>(c) * kCta4 + src + kDw4);
+                s.x += l.x; s.y += l.y; s.z += l.z; s.w += l.w;
+            }
+        }
+    }
+    red[g][cl] = s;
+    __syncthreads();
+    if (g == 0 && o4 < kOut4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int q = 0; q < 64; ++q) {
+            const float4 v = red[q][cl];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        if (o4 < kDw4) dw[o4] = t;
+        else if (db != nullptr) db[o4 - kDw4] = t;
     }
 }
 
@@ -476,7 +510,7 @@ static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W,
     a->H = H; a->W = W;
     a->total_pix = static_cast<long long>(B) * H * W;
     a->num_tiles = static_cast<int>(a->total_pix / kF_TileM);
-    a->w = nullptr; a->bias = nullptr; a->dw = nullptr; a->db = nullptr;
+    a->w = nullptr; a->bias = nullptr; a->part = nullptr;
     // staged patch: a tile (128 raster pixels) must be a rectangle inside one frame
     const int wt = W < kF_TileM ? W : kF_TileM;
     const bool pow2 = (wt & (wt - 1)) == 0;
@@ -523,14 +557,21 @@ static int first_fwd(const void* x, const float* w_hwio, const float* bias, void
 }
 
 template <bool kU8>
-static int first_wgrad(const void* x, const void* dz, float* dw, float* db, int B, int H, int W, int Cout, void* stream,
-                       const char* who) {
-    if (!x || !dz || !dw) { set_error("abl_conv_first_wgrad: null pointer"); return ABL_ERR_NULL; }
-    if (reinterpret_cast<uintptr_t>(dz) & 15) { set_error("abl_conv_first_wgrad: dz must be 16-byte aligned"); return ABL_ERR_ALIGN; }
+static int first_wgrad(const void* x, const void* dz, float* dw, float* db, void* workspace, long long workspace_bytes,
+                       int B, int H, int W, int Cout, void* stream, const char* who) {
+    if (!x || !dz || !dw || !workspace) { set_error("abl_conv_first_wgrad: null pointer"); return ABL_ERR_NULL; }
+    if ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(db) |
+         reinterpret_cast<uintptr_t>(workspace)) & 15) {
+        set_error("abl_conv_first_wgrad: dz, dw, db and workspace must be 16-byte aligned"); return ABL_ERR_ALIGN;
+    }
     FirstArgs a;
     int r = first_args(&a, x, kU8, B, H, W, Cout, who);
     if (r != ABL_OK) return r;
-    a.dw = dw; a.db = db;
+    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+    if (workspace_bytes < static_cast<long long>(grid) * kF_PartRows * kF_Cout * 4) {
+        set_error("abl_conv_first_wgrad: workspace too small (abl_conv_first_wgrad_workspace_bytes)"); return ABL_ERR_SHAPE;
+    }
+    a.part = static_cast<float*>(workspace);
     CUtensorMap mz;
     r = pixel_map(&mz, dz, a.total_pix);
     if (r != ABL_OK) return r;
@@ -543,8 +584,13 @@ static int first_wgrad(const void* x, const void* dz, float* dw, float* db, int 
             return check_launch();
         attr_done[dev & 63] = true;
     }
-    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
-    conv_first_wgrad_tc_kernel<kU8><<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mz, a);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    conv_first_wgrad_tc_kernel<kU8><<<grid, kF_Threads, smem_bytes, st>>>(mz, a);
+    r = check_launch();
+    if (r != ABL_OK) return r;
+    constexpr int kOut4 = 28 * (kF_Cout / 4);
+    conv_first_wgrad_reduce_kernel<<<(kOut4 + 3) / 4, 256, 0, st>>>(static_cast<const float4*>(workspace), grid,
+                                                                   reinterpret_cast<float4*>(dw), reinterpret_cast<float4*>(db));
     return check_launch();
 }
 
@@ -560,11 +606,16 @@ extern "C" int abl_conv_first_fwd_u8(const unsigned char* frames_rgb, const floa
                                      int B, int H, int W, int Cout, void* stream) {
     return first_fwd<true>(frames_rgb, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd_u8");
 }
-extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W,
-                                    int Cout, void* stream) {
-    return first_wgrad<false>(x, dz, dw, db, B, H, W, Cout, stream, "abl_conv_first_wgrad");
+extern "C" long long abl_conv_first_wgrad_workspace_bytes(void) {
+    return static_cast<long long>(sm_count()) * kF_PartRows * kF_Cout * 4;
 }
-extern "C" int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db, int B,
-                                       int H, int W, int Cout, void* stream) {
-    return first_wgrad<true>(frames_rgb, dz, dw, db, B, H, W, Cout, stream, "abl_conv_first_wgrad_u8");
+extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, void* workspace,
+                                    long long workspace_bytes, int B, int H, int W, int Cout, void* stream) {
+    return first_wgrad<false>(x, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream, "abl_conv_first_wgrad");
+}
+extern "C" int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db,
+                                       void* workspace, long long workspace_bytes, int B, int H, int W, int Cout,
+                                       void* stream) {
+    return first_wgrad<true>(frames_rgb, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream,
+                             "abl_conv_first_wgrad_u8");
 }

@@ -1,8 +1,11 @@
 // HBM-bound kernels of the cutoffvgg16 path: weight re-layout, max-pool/ReLU backward, global
 // average pool (+backward), Dense/softmax/cross-entropy head, Adam / RMSprop, Grad-CAM.
 // All are grid-stride / vectorised (16-byte) kernels sized in multiples of the SM count.
+#include <stdio.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
+#include "parts.cuh"
 
 namespace abl {
 
@@ -61,18 +64,21 @@ __global__ void prep_conv_weights_multi_kernel(const __grid_constant__ PrepMulti
 // pooled value and dP; writes the 4 dZ chunks.  First maximum in window scan order wins.
 // Block-level finish of a fused BiasAddGrad: every thread owns ONE 8-channel chunk for its whole grid-stride
 // walk (blockDim % C8 == 0 and the stride is a multiple of blockDim), so it arrives here with 8 partial sums;
-// they are reduced over the blockDim/C8 threads sharing the chunk in shared memory, then one atomicAdd per
-// channel and block goes to db.
-__device__ __forceinline__ void bias_partial_flush(const float (&acc)[8], float* __restrict__ db, int C8, float* red) {
+// they are reduced over the blockDim/C8 threads sharing the chunk in shared memory (fixed order) and the block
+// stores ONE row of a parts buffer (include/abl_b200.h "Partial-sum buffers"): no floating-point atomics, the
+// consumer (abl_conv3x3_wgrad / abl_parts_reduce) adds the rows in a fixed order -> bit-reproducible gradients.
+__device__ __forceinline__ void bias_partial_flush(const float (&acc)[8], float* __restrict__ parts, int C8, float* red) {
     const int chunk = threadIdx.x % C8, rg = threadIdx.x / C8, rgs = blockDim.x / C8, C = C8 * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[rg * C + chunk * 8 + j] = acc[j];
     __syncthreads();
+    float* row = parts + ABL_PARTS_HEADER + static_cast<size_t>(blockIdx.x) * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
         for (int g = 0; g < rgs; ++g) s += red[g * C + c];
-        atomicAdd(db + c, s);
+        row[c] = s;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(parts) = static_cast<int>(gridDim.x);
 }
 
 __global__ void __launch_bounds__(256)
@@ -264,17 +270,24 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
 constexpr int kMaxClasses = 8;
 
 // One warp per frame: lanes stride over channels, shuffle-reduce the n logits.
+// Loss: every block adds its (<= 4) frames in warp order and stores ONE partial into loss_ws; the block that arrives
+// last (integer ticket in loss_ws word 0, reset for the next launch) adds all partials in block order and does the
+// single read-modify-write of *loss_sum -> the loss is bit-reproducible (no floating-point atomics).
 __global__ void __launch_bounds__(128)
 head_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ logits, float* __restrict__ probs, const float* __restrict__ y,
                 const float* __restrict__ cw, float inv_batch, float* __restrict__ loss_sum,
                 float* __restrict__ dlogits, unsigned char* __restrict__ keep_mask, int keep_mask_in, int training,
                 float dropout, unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                const unsigned int* __restrict__ step_dev) {
+                unsigned int* __restrict__ step_dev, float* __restrict__ loss_ws, int loss_accumulate) {
+    __shared__ float wloss[4];
+    __shared__ float red[128];
+    __shared__ int is_last;
     if (step_dev != nullptr) step = *step_dev;      // CUDA-graph replays: the counter lives on the device
     const int lane = threadIdx.x & 31;
     const int frame = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (frame >= B) return;
+    float my_loss = 0.f;
+    if (frame < B) {
     const float keep_scale = 1.f / (1.f - dropout);
     const uint32_t thresh = static_cast<uint32_t>(fminf(dropout, 0.99999994f) * 4294967296.0);
     float z[kMaxClasses];
@@ -323,26 +336,59 @@ head_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, cons
         }
         if (y) {
             const float lse = mx + logf(s);
-            if (loss_sum) atomicAdd(loss_sum, wi * (lse - zy) * inv_batch);
+            my_loss = wi * (lse - zy) * inv_batch;
             if (dlogits)
                 for (int j = 0; j < n; ++j) dlogits[frame * n + j] = wi * inv_batch * (e[j] * inv - y[frame * n + j]);
         }
     }
+    }
+    if (loss_sum == nullptr || y == nullptr) return;          // uniform for the whole grid
+    if (lane == 0) wloss[threadIdx.x >> 5] = my_loss;
+    __syncthreads();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(loss_ws);
+    float* part = loss_ws + ABL_PARTS_HEADER;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = (wloss[0] + wloss[1]) + (wloss[2] + wloss[3]);
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;     // integer ticket: order-independent
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float s = 0.f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(part + i);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *loss_sum = loss_accumulate ? *loss_sum + red[0] : red[0];
+        *ticket = 0u;
+        // CUDA-graph replays: every block has read the dropout step by now (its ticket came after its frames), so the
+        // last block advances the device-side counters: [0] dropout step, [1] optimizer step (read by abl_adam_flat_tab
+        // later in the same step)
+        if (step_dev != nullptr) { step_dev[0] = step + 1u; step_dev[1] += 1u; }
+    }
 }
 
-// grid = (C / 32 channel groups... ) simple: one block per slice of frames; thread = channel.
-__global__ void head_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ w,
-                                const float* __restrict__ dlogits, const unsigned char* __restrict__ keep_mask,
-                                float dropout, float* __restrict__ dw, float* __restrict__ db,
-                                float* __restrict__ dgap, int B, int C, int n, int frames_per_block) {
+// Deterministic Dense backward without partial buffers: block = 8 channels x 32 frame lanes (one warp per channel,
+// lane l walks frames l, l+32, ...), so every (frame, channel) element is visited by exactly one thread (dgap) and a
+// channel's dw[c][:] is one fixed-shape shuffle tree over its warp.  db[j] = sum_f dlogits[f][j] is block 0's job.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, const float* __restrict__ dlogits,
+                const unsigned char* __restrict__ keep_mask, float dropout, float* __restrict__ dw,
+                float* __restrict__ db, float* __restrict__ dgap, int B, int C, int n) {
+    __shared__ float red[256];
     const float keep_scale = 1.f / (1.f - dropout);
-    const int f0 = blockIdx.x * frames_per_block;
-    const int f1 = min(B, f0 + frames_per_block);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c < C) {
         float wrow[kMaxClasses], acc[kMaxClasses];
 #pragma unroll
         for (int j = 0; j < kMaxClasses; ++j) { wrow[j] = j < n ? w[c * n + j] : 0.f; acc[j] = 0.f; }
-        for (int f = f0; f < f1; ++f) {
+        for (int f = lane; f < B; f += 32) {
             const size_t idx = static_cast<size_t>(f) * C + c;
             const float scale = keep_mask ? (keep_mask[idx] ? keep_scale : 0.f) : 1.f;
             const float h = gap[idx] * scale;
@@ -350,7 +396,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ gap, const float* __re
 #pragma unroll
             for (int j = 0; j < kMaxClasses; ++j)
                 if (j < n) {
-                    const float d = dlogits[f * n + j];
+                    const float d = __ldg(dlogits + f * n + j);
                     acc[j] += h * d;
                     dg += d * wrow[j];
                 }
@@ -358,16 +404,43 @@ __global__ void head_bwd_kernel(const float* __restrict__ gap, const float* __re
         }
 #pragma unroll
         for (int j = 0; j < kMaxClasses; ++j)
-            if (j < n) atomicAdd(dw + c * n + j, acc[j]);
+            if (j < n) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+                if (lane == 0) dw[c * n + j] = acc[j];
+            }
     }
-    if (threadIdx.x < n) {
-        float s = 0.f;
-        for (int f = f0; f < f1; ++f) s += dlogits[f * n + threadIdx.x];
-        atomicAdd(db + threadIdx.x, s);
+    if (blockIdx.x == 0) {
+        for (int j = 0; j < n; ++j) {
+            float s = 0.f;
+            for (int f = threadIdx.x; f < B; f += blockDim.x) s += __ldg(dlogits + f * n + j);
+            red[threadIdx.x] = s;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) db[j] = red[0];
+            __syncthreads();
+        }
     }
 }
 
 // ------------------------------------------------------------------ optimizers (28 / 20 B per param)
+// One element of Keras 2.9 Adam / RMSprop.  Shared by the local kernels and the peer-memory data-parallel kernel and
+// written with explicit roundings (no FMA contraction left to the compiler), so both paths produce the SAME bits from
+// the same gradient.
+__device__ __forceinline__ void adam_update(float& t, float& m, float& v, float g, float alpha, float b1, float b2,
+                                            float ob1, float ob2, float eps) {
+    m = __fadd_rn(__fmul_rn(b1, m), __fmul_rn(ob1, g));
+    v = __fadd_rn(__fmul_rn(b2, v), __fmul_rn(ob2, __fmul_rn(g, g)));
+    t = __fsub_rn(t, __fdiv_rn(__fmul_rn(alpha, m), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+__device__ __forceinline__ void rmsprop_update(float& t, float& r, float g, float lr, float rho, float orho, float eps) {
+    r = __fadd_rn(__fmul_rn(rho, r), __fmul_rn(orho, __fmul_rn(g, g)));
+    t = __fsub_rn(t, __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(__fsqrt_rn(r), eps)));
+}
+
 __global__ void adam_flat_kernel(float4* __restrict__ theta, const float4* __restrict__ g, float4* __restrict__ m,
                                  float4* __restrict__ v, long long n4, float* theta_tail, const float* g_tail,
                                  float* m_tail, float* v_tail, int tail, float alpha, float b1, float b2, float eps,
@@ -380,21 +453,17 @@ __global__ void adam_flat_kernel(float4* __restrict__ theta, const float4* __res
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float4 gg = g[i];
         float4 mm = m[i], vv = v[i], tt = theta[i];
-        mm.x = b1 * mm.x + ob1 * gg.x; mm.y = b1 * mm.y + ob1 * gg.y;
-        mm.z = b1 * mm.z + ob1 * gg.z; mm.w = b1 * mm.w + ob1 * gg.w;
-        vv.x = b2 * vv.x + ob2 * gg.x * gg.x; vv.y = b2 * vv.y + ob2 * gg.y * gg.y;
-        vv.z = b2 * vv.z + ob2 * gg.z * gg.z; vv.w = b2 * vv.w + ob2 * gg.w * gg.w;
-        tt.x -= alpha * mm.x / (sqrtf(vv.x) + eps); tt.y -= alpha * mm.y / (sqrtf(vv.y) + eps);
-        tt.z -= alpha * mm.z / (sqrtf(vv.z) + eps); tt.w -= alpha * mm.w / (sqrtf(vv.w) + eps);
+        adam_update(tt.x, mm.x, vv.x, gg.x, alpha, b1, b2, ob1, ob2, eps);
+        adam_update(tt.y, mm.y, vv.y, gg.y, alpha, b1, b2, ob1, ob2, eps);
+        adam_update(tt.z, mm.z, vv.z, gg.z, alpha, b1, b2, ob1, ob2, eps);
+        adam_update(tt.w, mm.w, vv.w, gg.w, alpha, b1, b2, ob1, ob2, eps);
         m[i] = mm; v[i] = vv; theta[i] = tt;
     }
     if (blockIdx.x == 0 && threadIdx.x < tail) {
         const int i = threadIdx.x;
-        const float gg = g_tail[i];
-        const float mm = b1 * m_tail[i] + ob1 * gg;
-        const float vv = b2 * v_tail[i] + ob2 * gg * gg;
-        theta_tail[i] -= alpha * mm / (sqrtf(vv) + eps);
-        m_tail[i] = mm; v_tail[i] = vv;
+        float tt = theta_tail[i], mm = m_tail[i], vv = v_tail[i];
+        adam_update(tt, mm, vv, g_tail[i], alpha, b1, b2, ob1, ob2, eps);
+        theta_tail[i] = tt; m_tail[i] = mm; v_tail[i] = vv;
     }
 }
 
@@ -406,18 +475,17 @@ __global__ void rmsprop_flat_kernel(float4* __restrict__ theta, const float4* __
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float4 gg = g[i];
         float4 rr = rms[i], tt = theta[i];
-        rr.x = rho * rr.x + orho * gg.x * gg.x; rr.y = rho * rr.y + orho * gg.y * gg.y;
-        rr.z = rho * rr.z + orho * gg.z * gg.z; rr.w = rho * rr.w + orho * gg.w * gg.w;
-        tt.x -= lr * gg.x / (sqrtf(rr.x) + eps); tt.y -= lr * gg.y / (sqrtf(rr.y) + eps);
-        tt.z -= lr * gg.z / (sqrtf(rr.z) + eps); tt.w -= lr * gg.w / (sqrtf(rr.w) + eps);
+        rmsprop_update(tt.x, rr.x, gg.x, lr, rho, orho, eps);
+        rmsprop_update(tt.y, rr.y, gg.y, lr, rho, orho, eps);
+        rmsprop_update(tt.z, rr.z, gg.z, lr, rho, orho, eps);
+        rmsprop_update(tt.w, rr.w, gg.w, lr, rho, orho, eps);
         rms[i] = rr; theta[i] = tt;
     }
     if (blockIdx.x == 0 && threadIdx.x < tail) {
         const int i = threadIdx.x;
-        const float gg = g_tail[i];
-        const float rr = rho * rms_tail[i] + orho * gg * gg;
-        theta_tail[i] -= lr * gg / (sqrtf(rr) + eps);
-        rms_tail[i] = rr;
+        float tt = theta_tail[i], rr = rms_tail[i];
+        rmsprop_update(tt, rr, g_tail[i], lr, rho, orho, eps);
+        theta_tail[i] = tt; rms_tail[i] = rr;
     }
 }
 
@@ -548,20 +616,18 @@ __global__ void opt_flat_dp_kernel(const __grid_constant__ PeerBufs pb, float4* 
         if (kKind == 0) {
             const float ob1 = 1.f - p1, ob2 = 1.f - p2;
             float4 mm = m[i], vv = v[i];
-            mm.x = p1 * mm.x + ob1 * g.x; mm.y = p1 * mm.y + ob1 * g.y;
-            mm.z = p1 * mm.z + ob1 * g.z; mm.w = p1 * mm.w + ob1 * g.w;
-            vv.x = p2 * vv.x + ob2 * g.x * g.x; vv.y = p2 * vv.y + ob2 * g.y * g.y;
-            vv.z = p2 * vv.z + ob2 * g.z * g.z; vv.w = p2 * vv.w + ob2 * g.w * g.w;
-            tt.x -= p0 * mm.x / (sqrtf(vv.x) + eps); tt.y -= p0 * mm.y / (sqrtf(vv.y) + eps);
-            tt.z -= p0 * mm.z / (sqrtf(vv.z) + eps); tt.w -= p0 * mm.w / (sqrtf(vv.w) + eps);
+            adam_update(tt.x, mm.x, vv.x, g.x, p0, p1, p2, ob1, ob2, eps);
+            adam_update(tt.y, mm.y, vv.y, g.y, p0, p1, p2, ob1, ob2, eps);
+            adam_update(tt.z, mm.z, vv.z, g.z, p0, p1, p2, ob1, ob2, eps);
+            adam_update(tt.w, mm.w, vv.w, g.w, p0, p1, p2, ob1, ob2, eps);
             m[i] = mm; v[i] = vv;
         } else {
             const float orho = 1.f - p1;
             float4 rr = m[i];
-            rr.x = p1 * rr.x + orho * g.x * g.x; rr.y = p1 * rr.y + orho * g.y * g.y;
-            rr.z = p1 * rr.z + orho * g.z * g.z; rr.w = p1 * rr.w + orho * g.w * g.w;
-            tt.x -= p0 * g.x / (sqrtf(rr.x) + eps); tt.y -= p0 * g.y / (sqrtf(rr.y) + eps);
-            tt.z -= p0 * g.z / (sqrtf(rr.z) + eps); tt.w -= p0 * g.w / (sqrtf(rr.w) + eps);
+            rmsprop_update(tt.x, rr.x, g.x, p0, p1, orho, eps);
+            rmsprop_update(tt.y, rr.y, g.y, p0, p1, orho, eps);
+            rmsprop_update(tt.z, rr.z, g.z, p0, p1, orho, eps);
+            rmsprop_update(tt.w, rr.w, g.w, p0, p1, orho, eps);
             m[i] = rr;
         }
 #pragma unroll 1
@@ -643,6 +709,12 @@ gradcam_kernel(const uint4* __restrict__ a, const float* __restrict__ probs, con
     }
 }
 
+__global__ void __launch_bounds__(256)
+parts_reduce_kernel(const float* __restrict__ parts, float* __restrict__ out, int C, int accumulate) {
+    __shared__ float4 red[64][4];
+    parts_reduce_block(parts + ABL_PARTS_HEADER, parts_rows(parts), C, out, accumulate, blockIdx.x, red);
+}
+
 static inline int grid_for(long long work_items, int threads, int waves) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = static_cast<long long>(sm_count()) * waves;
@@ -685,35 +757,52 @@ extern "C" int abl_prep_conv_weights_multi(const float* const* w_hwio, void* con
     return check_launch();
 }
 
-extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
+extern "C" int abl_bias_grad(const void* dz, float* db_parts, long long db_parts_bytes, long long rows, int C, void* stream);
 
-extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db, int B,
-                                    int H, int W, int C, void* stream) {
+extern "C" long long abl_parts_bytes(int C) {
+    if (C <= 0) return -1;
+    return (static_cast<long long>(ABL_PARTS_HEADER) + static_cast<long long>(sm_count()) * kPartWaves * C) * 4;
+}
+
+extern "C" int abl_parts_reduce(const float* parts, float* out, int C, int accumulate, void* stream) {
+    if (!parts || !out) { set_error("abl_parts_reduce: null pointer"); return ABL_ERR_NULL; }
+    if (C <= 0 || (C & 3) || ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+        set_error("abl_parts_reduce: C must be a multiple of 4 and the buffers 16-byte aligned"); return ABL_ERR_ALIGN;
+    }
+    parts_reduce_kernel<<<(C / 4 + 3) / 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, out, C, accumulate);
+    return check_launch();
+}
+
+extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db_parts,
+                                    long long db_parts_bytes, int B, int H, int W, int C, void* stream) {
     if (!dp || !a || !pooled || !dz) { set_error("abl_maxpool_bwd_relu: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_relu: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    const bool fuse = db != nullptr && (256 % (C / 8)) == 0;      // a thread keeps one channel chunk
-    maxpool_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, fuse ? 256 * 8 * sizeof(float) : 0,
-                              static_cast<cudaStream_t>(stream)>>>(
+    const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;      // a thread keeps one channel chunk
+    const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);
+    if (fuse) { int r = parts_check(db_parts, db_parts_bytes, grid, C, "abl_maxpool_bwd_relu"); if (r != ABL_OK) return r; }
+    maxpool_bwd_relu_kernel<<<grid, 256, fuse ? 256 * 8 * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(dp), static_cast<const uint4*>(a), static_cast<const uint4*>(pooled),
-        static_cast<uint4*>(dz), B, H, W, C / 8, fuse ? db : nullptr);
+        static_cast<uint4*>(dz), B, H, W, C / 8, fuse ? db_parts : nullptr);
     int r = check_launch();
-    if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, C, stream);
+    if (r == ABL_OK && db_parts != nullptr && !fuse)
+        r = abl_bias_grad(dz, db_parts, db_parts_bytes, static_cast<long long>(B) * H * W, C, stream);
     return r;
 }
 
-extern "C" int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db, int B, int H,
-                                    int W, int C, void* stream) {
+extern "C" int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db_parts,
+                                    long long db_parts_bytes, int B, int H, int W, int C, void* stream) {
     if (!dp || !pool_code || !dz) { set_error("abl_maxpool_bwd_code: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_code: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    const bool fuse = db != nullptr && (256 % (C / 8)) == 0;
-    maxpool_bwd_code_kernel<<<grid_for(total, 256, 16), 256, fuse ? 256 * 8 * sizeof(float) : 0,
-                              static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(dp), pool_code,
-                                                                   static_cast<uint4*>(dz), B, H, W, C / 8,
-                                                                   fuse ? db : nullptr);
+    const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;
+    const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);
+    if (fuse) { int r = parts_check(db_parts, db_parts_bytes, grid, C, "abl_maxpool_bwd_code"); if (r != ABL_OK) return r; }
+    maxpool_bwd_code_kernel<<<grid, 256, fuse ? 256 * 8 * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(dp), pool_code, static_cast<uint4*>(dz), B, H, W, C / 8, fuse ? db_parts : nullptr);
     int r = check_launch();
-    if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, C, stream);
+    if (r == ABL_OK && db_parts != nullptr && !fuse)
+        r = abl_bias_grad(dz, db_parts, db_parts_bytes, static_cast<long long>(B) * H * W, C, stream);
     return r;
 }
 
@@ -734,18 +823,20 @@ extern "C" int abl_gap_reduce(const float* gap_part, float* gap, int B, int part
     return check_launch();
 }
 
-extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db, int B, int HW, int C,
-                                void* stream) {
+extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db_parts, long long db_parts_bytes,
+                                int B, int HW, int C, void* stream) {
     if (!dgap || !a || !dz) { set_error("abl_gap_bwd_relu: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || HW <= 0 || (C & 7)) { set_error("abl_gap_bwd_relu: need C % 8 == 0"); return ABL_ERR_SHAPE; }
     const long long total = static_cast<long long>(B) * HW * (C / 8);
-    const bool fuse = db != nullptr && (256 % (C / 8)) == 0;
-    gap_bwd_relu_kernel<<<grid_for(total, 256, 16), 256, fuse ? 256 * 8 * sizeof(float) : 0,
-                          static_cast<cudaStream_t>(stream)>>>(
+    const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;
+    const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);
+    if (fuse) { int r = parts_check(db_parts, db_parts_bytes, grid, C, "abl_gap_bwd_relu"); if (r != ABL_OK) return r; }
+    gap_bwd_relu_kernel<<<grid, 256, fuse ? 256 * 8 * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
         dgap, static_cast<const uint4*>(a), static_cast<uint4*>(dz), B, HW, C / 8, 1.f / static_cast<float>(HW),
-        fuse ? db : nullptr);
+        fuse ? db_parts : nullptr);
     int r = check_launch();
-    if (r == ABL_OK && db != nullptr && !fuse) r = abl_bias_grad(dz, db, static_cast<long long>(B) * HW, C, stream);
+    if (r == ABL_OK && db_parts != nullptr && !fuse)
+        r = abl_bias_grad(dz, db_parts, db_parts_bytes, static_cast<long long>(B) * HW, C, stream);
     return r;
 }
 
@@ -753,43 +844,49 @@ static int head_fwd_impl(const float* gap, const float* w, const float* b, float
                          const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                          float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                          unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                         const unsigned int* step_dev, void* stream) {
+                         unsigned int* step_dev, int loss_accumulate, float* loss_ws, void* stream) {
     if (!gap || !w || !b || !logits || !probs) { set_error("abl_head_fwd: null pointer"); return ABL_ERR_NULL; }
+    if (loss_sum && y_onehot && !loss_ws) { set_error("abl_head_fwd: the loss needs loss_ws (abl_head_loss_ws_bytes)"); return ABL_ERR_NULL; }
     if (training && !keep_mask) { set_error("abl_head_fwd: training needs a keep_mask buffer"); return ABL_ERR_NULL; }
     if (B <= 0 || C <= 0 || n <= 0 || n > kMaxClasses) { set_error("abl_head_fwd: need 1 <= n <= 8"); return ABL_ERR_SHAPE; }
     if (training && !(dropout >= 0.f && dropout < 1.f)) { set_error("abl_head_fwd: dropout must be in [0,1)"); return ABL_ERR_SHAPE; }
     head_fwd_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, keep_mask_in,
-        training, training ? dropout : 0.f, seed, step, rank, B, C, n, step_dev);
+        training, training ? dropout : 0.f, seed, step, rank, B, C, n, step_dev, loss_ws, loss_accumulate);
     return check_launch();
+}
+
+extern "C" long long abl_head_loss_ws_bytes(int B) {
+    if (B <= 0) return -1;
+    return (static_cast<long long>(ABL_PARTS_HEADER) + (B + 3) / 4) * 4;
 }
 
 extern "C" int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
                             const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                             float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                             unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                            void* stream) {
+                            int loss_accumulate, float* loss_ws, void* stream) {
     return head_fwd_impl(gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask,
-                         keep_mask_in, training, dropout, seed, step, rank, B, C, n, nullptr, stream);
+                         keep_mask_in, training, dropout, seed, step, rank, B, C, n, nullptr, loss_accumulate, loss_ws, stream);
 }
 
 extern "C" int abl_head_fwd_stepdev(const float* gap, const float* w, const float* b, float* logits, float* probs,
                                     const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                                     float* dlogits, unsigned char* keep_mask, int training, float dropout,
-                                    unsigned long long seed, const unsigned int* step_dev, unsigned int rank, int B,
-                                    int C, int n, void* stream) {
+                                    unsigned long long seed, unsigned int* step_dev, unsigned int rank, int B,
+                                    int C, int n, int loss_accumulate, float* loss_ws, void* stream) {
     if (!step_dev) { set_error("abl_head_fwd_stepdev: step_dev is null"); return ABL_ERR_NULL; }
+    if (!loss_sum || !y_onehot) { set_error("abl_head_fwd_stepdev: needs y_onehot and loss_sum (the counters advance with the loss)"); return ABL_ERR_NULL; }
     return head_fwd_impl(gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, 0,
-                         training, dropout, seed, 0u, rank, B, C, n, step_dev, stream);
+                         training, dropout, seed, 0u, rank, B, C, n, step_dev, loss_accumulate, loss_ws, stream);
 }
 
 extern "C" int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,
                             float dropout, float* dw, float* db, float* dgap, int B, int C, int n, void* stream) {
     if (!gap || !w || !dlogits || !dw || !db || !dgap) { set_error("abl_head_bwd: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || C <= 0 || n <= 0 || n > kMaxClasses) { set_error("abl_head_bwd: need 1 <= n <= 8"); return ABL_ERR_SHAPE; }
-    const int fpb = 16;
-    head_bwd_kernel<<<(B + fpb - 1) / fpb, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        gap, w, dlogits, keep_mask, keep_mask ? dropout : 0.f, dw, db, dgap, B, C, n, fpb);
+    head_bwd_kernel<<<(C + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gap, w, dlogits, keep_mask, keep_mask ? dropout : 0.f, dw, db, dgap, B, C, n);
     return check_launch();
 }
 

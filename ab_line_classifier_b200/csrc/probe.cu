@@ -7,6 +7,9 @@
 //   mode 0: plain SS MMAs into one accumulator
 //   mode 1: weight-stationary pairs (collector b0 fill -> lastuse): two A tiles / two accumulators share each B read
 //   mode 2: like 0, but every MMA of a group uses a different 8 KiB-aligned window of B (no operand reuse at all)
+//   mode 3: plain SS MMAs issued round-robin over FOUR accumulators (N <= 128), two alternating A tiles, one B
+//   mode 4: plain SS MMAs issued round-robin over TWO accumulators (same pattern as mode 1 without .ws)
+//   mode 5: weight-stationary quads (collector b0 fill -> use -> use -> lastuse) over four accumulators (N <= 128)
 #include <stdint.h>
 
 #include "host_util.h"
@@ -47,7 +50,19 @@ mma_rate_probe_kernel(int n, int mode, int iters, unsigned long long* __restrict
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (mode == 1) {
+                if (mode == 3 || mode == 4) {
+                    const int nacc = mode == 3 ? 4 : 2;
+                    for (int q = 0; q < nacc; ++q)
+                        umma_bf16_lohi(tmem_base + q * (512 / nacc), a_lo + (q & 1) * ((128 * 128) >> 4) + k * 2, dhi, b_lo + k * 2,
+                                       dhi, idesc, (it | k) != 0 ? 1u : 0u);
+                } else if (mode == 5) {
+                    umma_bf16_lohi_ws<0>(tmem_base, a_lo + k * 2, dhi, b_lo + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
+                    umma_bf16_lohi_ws<2>(tmem_base + 128, a_lo + ((128 * 128) >> 4) + k * 2, dhi, b_lo + k * 2, dhi, idesc,
+                                         (it | k) != 0 ? 1u : 0u);
+                    umma_bf16_lohi_ws<2>(tmem_base + 256, a_lo + k * 2, dhi, b_lo + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
+                    umma_bf16_lohi_ws<1>(tmem_base + 384, a_lo + ((128 * 128) >> 4) + k * 2, dhi, b_lo + k * 2, dhi, idesc,
+                                         (it | k) != 0 ? 1u : 0u);
+                } else if (mode == 1) {
                     umma_bf16_lohi_ws<0>(tmem_base, a_lo + k * 2, dhi, b_lo + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
                     umma_bf16_lohi_ws<1>(tmem_base + 256, a_lo + ((128 * 128) >> 4) + k * 2, dhi, b_lo + k * 2, dhi, idesc,
                                          (it | k) != 0 ? 1u : 0u);
@@ -78,10 +93,12 @@ using namespace abl;
 
 extern "C" int abl_dev_mma_rate_probe(int n, int mode, int iters, int ctas, unsigned long long* out_cycles, void* stream) {
     if (!out_cycles) { set_error("abl_dev_mma_rate_probe: null pointer"); return ABL_ERR_NULL; }
-    if (n < 16 || n > 256 || (n & 15) || mode < 0 || mode > 2 || iters <= 0 || ctas <= 0) {
-        set_error("abl_dev_mma_rate_probe: need N in 16..256 (multiple of 16), mode 0..2, iters > 0, ctas > 0");
+    if (n < 16 || n > 256 || (n & 15) || mode < 0 || mode > 5 || iters <= 0 || ctas <= 0) {
+        set_error("abl_dev_mma_rate_probe: need N in 16..256 (multiple of 16), mode 0..5, iters > 0, ctas > 0");
         return ABL_ERR_SHAPE;
     }
+    if ((mode == 1 || mode == 5) && n != 64 && n != 128 && n != 256) { set_error("abl_dev_mma_rate_probe: .ws needs N in {64,128,256}"); return ABL_ERR_SHAPE; }
+    if ((mode == 3 || mode == 5) && n > 128) { set_error("abl_dev_mma_rate_probe: four accumulators need N <= 128"); return ABL_ERR_SHAPE; }
     if (cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmem) != cudaSuccess)
         return check_launch();
     mma_rate_probe_kernel<<<ctas, 128, kProbeSmem, static_cast<cudaStream_t>(stream)>>>(n, mode, iters, out_cycles);

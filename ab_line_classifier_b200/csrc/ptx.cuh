@@ -176,7 +176,7 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
 }
 // Weight-stationary form: the B operand of a `fill` MMA is latched in collector buffer b0 and re-used by the
 // following `lastuse` MMA (same B, different A / D), so B is read from shared memory once per pair.
-// kUse: 0 = collector::b0::fill, 1 = collector::b0::lastuse.
+// kUse: 0 = collector::b0::fill, 1 = collector::b0::lastuse, 2 = collector::b0::use.
 template <int kUse>
 __device__ __forceinline__ void umma_bf16_lohi_ws(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
@@ -189,6 +189,18 @@ __device__ __forceinline__ void umma_bf16_lohi_ws(uint32_t tmem_d, uint32_t a_lo
             "mov.b64 da, {%1, %2};\n\t"
             "mov.b64 db, {%3, %4};\n\t"
             "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], da, db, %5, p;\n\t"
+            "}\n"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if (kUse == 2) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use [%0], da, db, %5, p;\n\t"
             "}\n"
             ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
             : "memory");

@@ -19,6 +19,7 @@
 
 #include "host_util.h"
 #include "ptx.cuh"
+#include "parts.cuh"
 
 namespace abl {
 
@@ -37,7 +38,7 @@ struct WgradArgs {
     int co_blocks;       // Cout/NT
     int units, splits, stages, stage_bytes;
     float* partial;      // [splits][9][Cin][Cout] fp32
-    float* db;           // wgrad64 only: bias gradient [Cout] (atomic accumulation) or null
+    float* db_rows;      // wgrad64 only: bias-gradient partial rows [splits][Cout] (ones row of the GEMM) or null
 };
 
 template <int NT>
@@ -331,10 +332,14 @@ wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         for (int j = 0; j < 8; ++j)
                             d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                    } else if (row == 64 && n == 1 && p.db != nullptr && have_work) {
-                        // ones row x un-shifted dZ window: every pixel of this CTA's slice exactly once
+                    } else if (row == 64 && n == 1 && p.db_rows != nullptr) {
+                        // ones row x un-shifted dZ window: every pixel of this CTA's slice exactly once.  One row per
+                        // pixel slice (zeros from a CTA without work); wgrad_reduce_kernel adds the slices in order.
+                        float4* d4 = reinterpret_cast<float4*>(p.db_rows + static_cast<size_t>(split) * p.Cout + co0 + c * 32);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(p.db + co0 + c * 32 + j, __uint_as_float(r[j]));
+                        for (int j = 0; j < 8; ++j)
+                            d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                     }
                 }
             }
@@ -352,12 +357,22 @@ wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 // thread (c, g) adds splits g, g+8, g+16, ... (several loads in flight), then the 8 group sums are combined in group
 // order through shared memory.  (v1 gave one thread a whole column: up to 148 dependent loads in only 36 blocks,
 // 38 us for 22 MB; this form is bandwidth-bound.)
+// The last `bias_blocks` blocks finish the layer's BiasAddGrad the same way: db = sum of the partial rows that the
+// kernel producing dZ (or this wgrad's own ones row) left behind -- db_rows/db_nrows, or a parts buffer whose header
+// holds the row count (db_nrows < 0).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, long long n4, int splits,
-                    int accumulate) {
+                    int accumulate, int w_blocks, const float* __restrict__ db_rows, int db_nrows, float* __restrict__ db,
+                    int Cout) {
     __shared__ float4 red[8][32];
+    if (static_cast<int>(blockIdx.x) >= w_blocks) {
+        const float* rows = db_nrows < 0 ? db_rows + ABL_PARTS_HEADER : db_rows;
+        const int nrows = db_nrows < 0 ? parts_rows(db_rows) : db_nrows;
+        parts_reduce_block(rows, nrows, Cout, db, 0, blockIdx.x - w_blocks, reinterpret_cast<float4(*)[4]>(red));
+        return;
+    }
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-    for (long long base = static_cast<long long>(blockIdx.x) * 32; base < n4; base += static_cast<long long>(gridDim.x) * 32) {
+    for (long long base = static_cast<long long>(blockIdx.x) * 32; base < n4; base += static_cast<long long>(w_blocks) * 32) {
         const long long i = base + c;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n4) {
@@ -382,9 +397,11 @@ wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw,
     }
 }
 
-// db[c] += sum_rows dz[row][c]  (BiasAddGrad); thread = 8-channel chunk, block-level smem reduce, atomics.
+// Partial rows of db[c] = sum_rows dz[row][c] (BiasAddGrad): thread = 8-channel chunk, block-level reduce in shared
+// memory (fixed order), ONE parts row per block -- the stand-alone producer for the paths that cannot fuse the column
+// sums into the kernel that writes dz.
 __global__ void __launch_bounds__(256)
-bias_grad_kernel(const uint4* __restrict__ dz, float* __restrict__ db, long long rows, int C8) {
+bias_grad_kernel(const uint4* __restrict__ dz, float* __restrict__ parts, long long rows, int C8) {
     extern __shared__ float red[];   // [256/C8 row groups][C8*8]
     const int chunk = threadIdx.x % C8;
     const int rg = threadIdx.x / C8;
@@ -402,11 +419,13 @@ bias_grad_kernel(const uint4* __restrict__ dz, float* __restrict__ db, long long
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[rg * C + chunk * 8 + j] = acc[j];
     __syncthreads();
+    float* row = parts + ABL_PARTS_HEADER + static_cast<size_t>(blockIdx.x) * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
         for (int g = 0; g < rgs; ++g) s += red[g * C + c];
-        atomicAdd(db + c, s);
+        row[c] = s;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(parts) = static_cast<int>(gridDim.x);
 }
 
 static int wgrad_plan(int B, int H, int W, int Cin, int Cout, WgradArgs* a, int* nt_out) {
@@ -467,31 +486,41 @@ static int nhwc_block_map(CUtensorMap* m, const void* base, int B, int H, int W,
 
 using namespace abl;
 
+// workspace layout: [splits][9][Cin][Cout] fp32 slice sums | [splits][Cout] fp32 bias rows of the Cin == 64 kernel's ones
+// row | a parts buffer for the stand-alone bias pass (db requested, no db_parts given, Cin != 64)
+static long long wgrad_ws_dw_bytes(const WgradArgs& a) { return static_cast<long long>(a.splits) * 9 * a.Cin * a.Cout * 4; }
+static long long wgrad_ws_rows_bytes(const WgradArgs& a) { return static_cast<long long>(a.splits) * a.Cout * 4; }
+
+extern "C" long long abl_parts_bytes(int C);
+
 extern "C" long long abl_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
     WgradArgs a;
     int nt;
     if (wgrad_plan(B, H, W, Cin, Cout, &a, &nt) != ABL_OK) return -1;
-    return static_cast<long long>(a.splits) * 9 * Cin * Cout * 4;
+    return wgrad_ws_dw_bytes(a) + wgrad_ws_rows_bytes(a) + abl_parts_bytes(Cout);
 }
 
-extern "C" int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream) {
-    if (!dz || !db) { set_error("abl_bias_grad: null pointer"); return ABL_ERR_NULL; }
+extern "C" int abl_bias_grad(const void* dz, float* db_parts, long long db_parts_bytes, long long rows, int C, void* stream) {
+    if (!dz || !db_parts) { set_error("abl_bias_grad: null pointer"); return ABL_ERR_NULL; }
     if (rows <= 0 || (C % 8) != 0 || C > 2048 || (256 % (C / 8)) != 0) {
         set_error("abl_bias_grad: need C % 8 == 0 and C/8 dividing 256"); return ABL_ERR_SHAPE;
     }
     const int C8 = C / 8, rgs = 256 / C8;
     long long blocks = (rows + rgs - 1) / rgs;
-    const long long cap = static_cast<long long>(sm_count()) * 8;
+    const long long cap = static_cast<long long>(sm_count()) * kPartWaves;
     if (blocks > cap) blocks = cap;
+    int r = parts_check(db_parts, db_parts_bytes, static_cast<int>(blocks), C, "abl_bias_grad");
+    if (r != ABL_OK) return r;
     bias_grad_kernel<<<static_cast<int>(blocks), 256, rgs * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(dz), db, rows, C8);
+        static_cast<const uint4*>(dz), db_parts, rows, C8);
     return check_launch();
 }
 
-extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float* db, void* workspace,
-                                 long long workspace_bytes, int accumulate, int B, int H, int W, int Cin, int Cout,
-                                 void* stream) {
+extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float* db, const float* db_parts,
+                                 void* workspace, long long workspace_bytes, int accumulate, int B, int H, int W, int Cin,
+                                 int Cout, void* stream) {
     if (!x || !dz || !dw || !workspace) { set_error("abl_conv3x3_wgrad: null pointer"); return ABL_ERR_NULL; }
+    if (db_parts && !db) { set_error("abl_conv3x3_wgrad: db_parts given without db"); return ABL_ERR_NULL; }
     WgradArgs a;
     int nt = 0;
     if (wgrad_plan(B, H, W, Cin, Cout, &a, &nt) != ABL_OK) {
@@ -499,14 +528,19 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
                   "W % 16 == 0, H % 4 == 0)");
         return ABL_ERR_SHAPE;
     }
-    const long long need = static_cast<long long>(a.splits) * 9 * Cin * Cout * 4;
+    const long long need = wgrad_ws_dw_bytes(a) + wgrad_ws_rows_bytes(a) + abl_parts_bytes(Cout);
     if (workspace_bytes < need) { set_error("abl_conv3x3_wgrad: workspace too small"); return ABL_ERR_SHAPE; }
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dw) |
-         reinterpret_cast<uintptr_t>(workspace)) & 15) {
+         reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(db) | reinterpret_cast<uintptr_t>(db_parts)) & 15) {
         set_error("abl_conv3x3_wgrad: pointers must be 16-byte aligned"); return ABL_ERR_ALIGN;
     }
     a.partial = static_cast<float*>(workspace);
-    a.db = a.mode == 2 ? db : nullptr;
+    float* ws_rows = reinterpret_cast<float*>(static_cast<char*>(workspace) + wgrad_ws_dw_bytes(a));
+    float* ws_parts = reinterpret_cast<float*>(static_cast<char*>(workspace) + wgrad_ws_dw_bytes(a) + wgrad_ws_rows_bytes(a));
+    // where db comes from: partial rows the producer of dz left (db_parts), the ones row of the Cin == 64 GEMM, or a
+    // stand-alone pass over dz into this call's workspace
+    const bool own_rows = db != nullptr && db_parts == nullptr && a.mode == 2;
+    a.db_rows = own_rows ? ws_rows : nullptr;
     CUtensorMap mx, mdz;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int r;
@@ -534,14 +568,24 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
         r = (nt == 128) ? launch_wgrad<128>(mx, mdz, a, st) : launch_wgrad<64>(mx, mdz, a, st);
     }
     if (r != ABL_OK) return r;
+    const float* rows_src = nullptr;
+    int nrows = 0;
+    if (db != nullptr) {
+        if (db_parts != nullptr) { rows_src = db_parts; nrows = -1; }
+        else if (own_rows) { rows_src = ws_rows; nrows = a.splits; }
+        else {
+            r = abl_bias_grad(dz, ws_parts, abl_parts_bytes(Cout), static_cast<long long>(B) * H * W, Cout, stream);
+            if (r != ABL_OK) return r;
+            rows_src = ws_parts; nrows = -1;
+        }
+    }
     const long long n4 = 9LL * Cin * Cout / 4;
     long long blocks = (n4 + 31) / 32;
     const long long cap = static_cast<long long>(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
-    wgrad_reduce_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const float4*>(workspace),
-                                                                reinterpret_cast<float4*>(dw), n4, a.splits, accumulate);
-    r = check_launch();
-    if (r != ABL_OK) return r;
-    if (db && a.mode != 2) return abl_bias_grad(dz, db, static_cast<long long>(B) * H * W, Cout, stream);
-    return ABL_OK;
+    const int bias_blocks = db != nullptr ? (Cout / 4 + 3) / 4 : 0;
+    wgrad_reduce_kernel<<<static_cast<int>(blocks) + bias_blocks, 256, 0, st>>>(
+        static_cast<const float4*>(workspace), reinterpret_cast<float4*>(dw), n4, a.splits, accumulate,
+        static_cast<int>(blocks), rows_src, nrows, db, Cout);
+    return check_launch();
 }

@@ -277,7 +277,13 @@ class CutoffVGG16Engine:
         b["probs"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["y"] = [torch.empty(cap, n, device=dev, dtype=torch.float32) for _ in range(2)]
         b["loss"] = torch.zeros(1, device=dev, dtype=torch.float32)
+        b["loss_ws"] = ops.head_loss_ws(cap, dev)       # per-block loss sums + ticket (deterministic batch loss)
         if training:
+            # per-CTA partial sums of the fused bias gradients: written by the kernel that produces a layer's dZ, added
+            # in a fixed order by that layer's wgrad reduction (no float atomics anywhere: bit-reproducible training)
+            b["bpart"] = ops.parts_buffer(max(s.cout for s in self.specs), dev)
+            b["first_ws"] = torch.empty(ops.conv_first_wgrad_workspace_bytes(), device=dev, dtype=torch.uint8)
+            b["head_scratch"] = torch.zeros(C * n + 4 + n, device=dev, dtype=torch.float32)
             b["dlogits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
             b["keep"] = torch.empty(cap, C, device=dev, dtype=torch.uint8)
             b["dgap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
@@ -331,17 +337,19 @@ class CutoffVGG16Engine:
         else:
             feat = b["pool_" + last.name][:B] if last.pool else b["act_" + last.name][:B]
             ops.gap_fwd(feat, b["gap"][:B])
+        # the step's loss OVERWRITES its destination in training (one deterministic sum per batch); evaluation
+        # accumulates batch after batch into the caller's scalar (loss_out given) or overwrites the engine's own
+        accumulate = loss_out is not None and not training
         if loss_out is None:
             loss_out = b["loss"]
-            loss_out.zero_()
         if training:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
                          b["probs"][:B], y, self.class_weight, inv_batch, loss_out, b["dlogits"][:B],
                          b["keep"][:B], keep_mask_in, True, self.dropout, self.seed, self.step_count, self.rank,
-                         step_dev=step_dev)
+                         step_dev=step_dev, loss_ws=b["loss_ws"], loss_accumulate=False)
         elif y is not None:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
-                         b["probs"][:B], y, None, inv_batch, loss_out)
+                         b["probs"][:B], y, None, inv_batch, loss_out, loss_ws=b["loss_ws"], loss_accumulate=accumulate)
         else:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
                          b["probs"][:B])
@@ -475,13 +483,13 @@ class CutoffVGG16Engine:
         reduce_hook(start, end) is called as soon as grad[start:end] is final (DP buckets)."""
         b = self._buf
         names, tr, lowest = self.trainable_suffix(trainable)
-        self.grad.zero_()
+        # no zero-fill: every kernel below OVERWRITES its slice of self.grad (fixed-order sums, no atomics)
         keep = b["keep"][:B]
         if tr[-1]:
             dwk, dbk = self.view("output/kernel", self.grad), self.view("output/bias", self.grad)
         else:   # still need dgap; dump head grads in scratch
-            dwk = torch.zeros_like(self.view("output/kernel"))
-            dbk = torch.zeros_like(self.view("output/bias"))
+            nk = self.feat_shape[2] * self.n_classes
+            dwk, dbk = b["head_scratch"][:nk], b["head_scratch"][(nk + 3) // 4 * 4:][: self.n_classes]
         ops.head_bwd(b["gap"][:B], self.view("output/kernel"), b["dlogits"][:B], keep, self.dropout, dwk, dbk,
                      b["dgap"][:B])
         if reduce_hook and tr[-1]:
@@ -495,27 +503,26 @@ class CutoffVGG16Engine:
         cur, other = b["dz_a"], b["dz_b"]
         dz = cur[: B * last.h * last.w * last.cout].view(B, last.h, last.w, last.cout)
         # BiasAddGrad of a layer is fused into whichever kernel PRODUCES that layer's dZ (GAP backward, max-pool
-        # backward, or the dgrad epilogue of the layer above), so dZ is never re-read for it; block1_conv1's
-        # bias gradient comes out of its own wgrad GEMM (ones column).
-        # ... except for Cin == 64 layers, whose wgrad GEMM has idle accumulator rows that a ones block turns
-        # into the bias gradient for free (wgrad64_tc_kernel).
+        # backward, or the dgrad epilogue of the layer above): it leaves per-CTA partial sums in b["bpart"], and the
+        # layer's own wgrad reduction adds them in a fixed order -- dZ is never re-read for it.  Exceptions:
+        # block1_conv1's bias gradient comes out of its own wgrad GEMM (ones column), and so does that of the
+        # Cin == 64 layers, whose wgrad GEMM has idle accumulator rows (wgrad64_tc_kernel).
         def wgrad_has_bias(i):
             return i > 0 and self.specs[i].cin == 64 and ops.wgrad_fuses_bias(self.specs[i].cin)
 
-        def bias_grad_of(i):
-            return self.view(self.specs[i].name + "/bias", self.grad) if (tr[i] and i > 0 and not wgrad_has_bias(i)) else None
+        def bias_parts_of(i):
+            return b["bpart"] if (tr[i] and i > 0 and not wgrad_has_bias(i)) else None
 
-        ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, bias_grad_of(nconv - 1))
+        ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, db_parts=bias_parts_of(nconv - 1))
         for li in range(nconv - 1, lowest - 1, -1):
             s = self.specs[li]
             if tr[li]:
                 dw = self.view(s.name + "/kernel", self.grad)
                 if li == 0:
-                    ops.conv_first_wgrad(self._x(B), dz, dw, self.view(s.name + "/bias", self.grad))
+                    ops.conv_first_wgrad(self._x(B), dz, dw, self.view(s.name + "/bias", self.grad), b["first_ws"])
                 else:
-                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw,
-                                      self.view(s.name + "/bias", self.grad) if wgrad_has_bias(li) else None, b["ws"],
-                                      accumulate=False)
+                    ops.conv3x3_wgrad(self._in_act(li, B), dz, dw, self.view(s.name + "/bias", self.grad), b["ws"],
+                                      accumulate=False, db_parts=bias_parts_of(li))
                 if reduce_hook:
                     reduce_hook(*self.layer_ranges[s.name])
             if li > lowest:
@@ -527,20 +534,20 @@ class CutoffVGG16Engine:
                     if code is not None and self.fuse_unpool and ops.dgrad_unpool_supported(s.h, s.w, s.cin):
                         # dgrad + relu'(pooled) + MaxPoolGrad (+ BiasAddGrad) in one kernel
                         ops.conv3x3_dgrad_unpool(dz, self.w_dgrad[s.name], b["pool_" + prev.name][:B], code[:B], ndz,
-                                                 bias_grad_of(li - 1))
+                                                 db_parts=bias_parts_of(li - 1))
                     elif code is not None:
                         # relu'(pooled) in the dgrad epilogue, then routing by the forward's 2-bit codes
                         ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["pool_" + prev.name][:B], dp, None,
                                           ops.EPI_RELU_MASK)
-                        ops.maxpool_bwd_code(dp, code[:B], ndz, bias_grad_of(li - 1))
+                        ops.maxpool_bwd_code(dp, code[:B], ndz, db_parts=bias_parts_of(li - 1))
                     else:
                         ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, None, dp, None, 0)
                         ops.maxpool_bwd_relu(dp, b["act_" + prev.name][:B], b["pool_" + prev.name][:B], ndz,
-                                             bias_grad_of(li - 1))
+                                             db_parts=bias_parts_of(li - 1))
                 else:
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
                     ops.conv3x3_igemm(dz, self.w_dgrad[s.name], None, b["act_" + prev.name][:B], ndz, None,
-                                      ops.EPI_RELU_MASK, colsum=bias_grad_of(li - 1))
+                                      ops.EPI_RELU_MASK, colsum_parts=bias_parts_of(li - 1))
                 dz = ndz
                 cur, other = other, cur
 
@@ -724,11 +731,12 @@ class CutoffVGG16Engine:
             return
         b = self._buf
         if self._step_dev is None:
-            self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
-            self._t_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+            # {dropout step, optimizer step}: both advanced on the device by the head kernel's last block
+            self._step_dev = torch.zeros(2, device=self.device, dtype=torch.int32)
+            self._t_dev = self._step_dev[1:2]
         t_host = self.opt_steps.get(optimizer, 0)
         if self._dev_counters != (self.step_count, optimizer, t_host):      # re-sync after eager steps
-            self._step_dev.fill_(self.step_count)
+            self._step_dev[0:1].fill_(self.step_count)
             self._t_dev.fill_(t_host)
         g = self._tgraphs.get(key)
         self.use_slot(slot)
@@ -747,12 +755,10 @@ class CutoffVGG16Engine:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                b["loss"].zero_()
+                # the head kernel overwrites the loss and advances both device counters: no fill / add kernels
                 self.forward_device(batch, training=True, y=b["y"][slot][:batch], inv_batch=1.0 / float(global_batch),
                                     loss_out=b["loss"], step_dev=self._step_dev)
-                self._step_dev.add_(1)
                 self.backward_device(batch, trainable)
-                self._t_dev.add_(1)
                 if optimizer == "adam":
                     self.apply_optimizer(optimizer, lr, trainable, alpha_tab=alpha_tab, **kw)
                 else:

@@ -36,10 +36,55 @@ def _chk(t, dtype, name):
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
+PARTS_HEADER = 64          # ABL_PARTS_HEADER: floats before the first row of a parts buffer
+_scratch_cache = {}
+
+
+def _scratch(device, key, nbytes):
+    """Cached zero-initialised fp32 device scratch (grows on demand): parts buffers / workspaces for the convenience
+    forms below.  The engine passes its own buffers instead."""
+    k = (str(device), key)
+    t = _scratch_cache.get(k)
+    n = (int(nbytes) + 3) // 4
+    if t is None or t.numel() < n:
+        t = _scratch_cache[k] = torch.zeros(n, device=device, dtype=torch.float32)
+    return t
+
+
+def parts_bytes(C):
+    """Capacity in bytes of a partial-sum buffer for C channels (abl_parts_bytes)."""
+    return int(_native.load().abl_parts_bytes(int(C)))
+
+
+def parts_buffer(C, device):
+    return torch.zeros(parts_bytes(C) // 4, device=device, dtype=torch.float32)
+
+
+def parts_reduce(parts, out, accumulate=False):
+    """out[c] (+)= sum of the rows a producer left in `parts`, fixed order (abl_parts_reduce)."""
+    _chk(parts, torch.float32, "parts"); _chk(out, torch.float32, "out")
+    _native.call("abl_parts_reduce", _ptr(parts), _ptr(out), out.numel(), int(bool(accumulate)), _stream())
+
+
+def _parts_args(final, parts, C, device, key):
+    """(parts tensor or None, bytes) for a producer: the caller's parts buffer, or scratch when only the finished
+    [C] vector was asked for (then the caller of this helper reduces into it)."""
+    if parts is not None:
+        _chk(parts, torch.float32, "parts")
+        return parts, parts.numel() * 4
+    if final is None:
+        return None, 0
+    _chk(final, torch.float32, key)
+    t = _scratch(device, ("parts", key), parts_bytes(C))
+    return t, t.numel() * 4
+
+
 def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool=None, flags=0, colsum=None,
-                  pool_code=None):
-    """x bf16 [B,H,W,Cin]; w_kmajor bf16 [9,Cout,Cin]; see include/abl_b200.h abl_conv3x3_igemm."""
-    _chk(colsum, torch.float32, "colsum"); _chk(pool_code, torch.int16, "pool_code")
+                  pool_code=None, colsum_parts=None):
+    """x bf16 [B,H,W,Cin]; w_kmajor bf16 [9,Cout,Cin]; see include/abl_b200.h abl_conv3x3_igemm.
+    colsum_parts: parts buffer receiving the per-CTA column sums; colsum (fp32 [Cout]): the finished sums, OVERWRITTEN
+    (this wrapper adds an abl_parts_reduce launch)."""
+    _chk(pool_code, torch.int16, "pool_code")
     for t, n in ((x, "x"), (w_kmajor, "w"), (mask_src, "mask_src"), (out_full, "out_full"), (out_pool, "out_pool")):
         _chk(t, torch.bfloat16, n)
     _chk(bias, torch.float32, "bias")
@@ -52,8 +97,11 @@ def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool
         assert out_pool.shape == (B, H // 2, W // 2, Cout)
     if mask_src is not None:
         assert mask_src.shape == (B, H, W, Cout)
+    parts, pbytes = _parts_args(colsum, colsum_parts, Cout, x.device, "colsum")
     _native.call("abl_conv3x3_igemm", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(mask_src), _ptr(out_full),
-                 _ptr(out_pool), _ptr(pool_code), _ptr(colsum), B, H, W, Cin, Cout, flags, _stream())
+                 _ptr(out_pool), _ptr(pool_code), _ptr(parts), pbytes, B, H, W, Cin, Cout, flags, _stream())
+    if colsum is not None and colsum_parts is None:
+        parts_reduce(parts, colsum)
 
 
 def igemm_gap_supported(H, W, Cout):
@@ -83,17 +131,21 @@ def dgrad_unpool_supported(H, W, Cout):
     return W % 16 == 0 and H % 16 == 0 and Cout % 64 == 0 and Cout <= 128
 
 
-def conv3x3_dgrad_unpool(dz, w_dgrad, pooled, pool_code, dz_out, db=None):
-    """dgrad + relu'(pooled) + MaxPoolGrad (+ BiasAddGrad) in one kernel; see abl_conv3x3_dgrad_unpool."""
+def conv3x3_dgrad_unpool(dz, w_dgrad, pooled, pool_code, dz_out, db=None, db_parts=None):
+    """dgrad + relu'(pooled) + MaxPoolGrad (+ BiasAddGrad) in one kernel; see abl_conv3x3_dgrad_unpool.
+    db_parts: parts buffer for the bias partial sums; db: the finished fp32 [Cout] vector (overwritten, extra launch)."""
     for t, n in ((dz, "dz"), (w_dgrad, "w_dgrad"), (pooled, "pooled"), (dz_out, "dz_out")):
         _chk(t, torch.bfloat16, n)
-    _chk(pool_code, torch.int16, "pool_code"); _chk(db, torch.float32, "db")
+    _chk(pool_code, torch.int16, "pool_code")
     B, H, W, Cin = dz.shape
     Cout = w_dgrad.shape[1]
     assert w_dgrad.shape == (9, Cout, Cin) and pooled.shape == (B, H, W, Cout)
     assert dz_out.shape == (B, 2 * H, 2 * W, Cout) and pool_code.shape == (B, H, W, Cout // 8)
+    parts, pbytes = _parts_args(db, db_parts, Cout, dz.device, "db")
     _native.call("abl_conv3x3_dgrad_unpool", _ptr(dz), _ptr(w_dgrad), _ptr(pooled), _ptr(pool_code), _ptr(dz_out),
-                 _ptr(db), B, H, W, Cin, Cout, _stream())
+                 _ptr(parts), pbytes, B, H, W, Cin, Cout, _stream())
+    if db is not None and db_parts is None:
+        parts_reduce(parts, db)
 
 
 def wgrad_workspace_bytes(B, H, W, Cin, Cout):
@@ -103,17 +155,18 @@ def wgrad_workspace_bytes(B, H, W, Cin, Cout):
     return n
 
 
-def conv3x3_wgrad(x, dz, dw, db, workspace, accumulate=False):
-    """dw fp32 [3,3,Cin,Cout] (+)= x (*) dz; db fp32 [Cout] += sum dz (if given)."""
+def conv3x3_wgrad(x, dz, dw, db, workspace, accumulate=False, db_parts=None):
+    """dw fp32 [3,3,Cin,Cout] (+)= x (*) dz; db fp32 [Cout] = sum dz (if given; overwritten).  db_parts: the parts buffer
+    the producer of dz filled -- then dz is not read again for db."""
     _chk(x, torch.bfloat16, "x"); _chk(dz, torch.bfloat16, "dz")
-    _chk(dw, torch.float32, "dw"); _chk(db, torch.float32, "db")
+    _chk(dw, torch.float32, "dw"); _chk(db, torch.float32, "db"); _chk(db_parts, torch.float32, "db_parts")
     B, H, W, Cin = x.shape
     Cout = dz.shape[3]
     assert dz.shape == (B, H, W, Cout) and dw.numel() == 9 * Cin * Cout
-    _native.call("abl_conv3x3_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), _ptr(workspace),
+    _native.call("abl_conv3x3_wgrad", _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), _ptr(db_parts), _ptr(workspace),
                  workspace.numel() * workspace.element_size(), int(bool(accumulate)), B, H, W, Cin, Cout, _stream())
-    if db is None or wgrad_fuses_bias(Cin):
-        _native.launch_count -= 1      # GEMM + slice reduction only (no separate bias-grad kernel)
+    if db is not None and db_parts is None and not wgrad_fuses_bias(Cin):
+        _native.launch_count += 1      # stand-alone column-sum pass over dz
 
 
 def wgrad_fuses_bias(cin):
@@ -123,9 +176,12 @@ def wgrad_fuses_bias(cin):
 
 
 def bias_grad(dz, db):
+    """db[c] = sum over all leading dims of dz[..., c] (partial rows + fixed-order reduction; overwrites db)."""
     _chk(dz, torch.bfloat16, "dz"); _chk(db, torch.float32, "db")
     C = dz.shape[-1]
-    _native.call("abl_bias_grad", _ptr(dz), _ptr(db), dz.numel() // C, C, _stream())
+    parts, pbytes = _parts_args(db, None, C, dz.device, "bias_grad")
+    _native.call("abl_bias_grad", _ptr(dz), _ptr(parts), pbytes, dz.numel() // C, C, _stream())
+    parts_reduce(parts, db)
 
 
 def _first_suffix(x):
@@ -144,12 +200,19 @@ def conv_first_fwd(x, w_hwio, bias, out):
                  out.shape[3], _stream())
 
 
-def conv_first_wgrad(x, dz, dw, db):
-    _chk(dz, torch.bfloat16, "dz"); _chk(dw, torch.float32, "dw")
+def conv_first_wgrad_workspace_bytes():
+    return int(_native.load().abl_conv_first_wgrad_workspace_bytes())
+
+
+def conv_first_wgrad(x, dz, dw, db, workspace=None):
+    """dw fp32 [3,3,3,64], db fp32 [64] (both overwritten); workspace: >= conv_first_wgrad_workspace_bytes() bytes."""
+    _chk(dz, torch.bfloat16, "dz"); _chk(dw, torch.float32, "dw"); _chk(db, torch.float32, "db")
     B, H, W, c = x.shape
     assert c == 3
-    _native.call("abl_conv_first_wgrad" + _first_suffix(x), _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), B, H, W,
-                 dz.shape[3], _stream())
+    if workspace is None:
+        workspace = _scratch(x.device, "first_wgrad", conv_first_wgrad_workspace_bytes())
+    _native.call("abl_conv_first_wgrad" + _first_suffix(x), _ptr(x), _ptr(dz), _ptr(dw), _ptr(db), _ptr(workspace),
+                 workspace.numel() * workspace.element_size(), B, H, W, dz.shape[3], _stream())
 
 
 def prep_conv_weights(w_hwio, w_fwd=None, w_dgrad=None):
@@ -173,20 +236,26 @@ def prep_conv_weights_multi(layers):
                  C.cast(cin, C.c_void_p), C.cast(cout, C.c_void_p), n, _stream())
 
 
-def maxpool_bwd_relu(dp, a, pooled, dz, db=None):
+def maxpool_bwd_relu(dp, a, pooled, dz, db=None, db_parts=None):
+    """db_parts: parts buffer for the fused bias partial sums; db: finished fp32 [C] (overwritten, extra launch)."""
     for t in (dp, a, pooled, dz):
         _chk(t, torch.bfloat16, "tensor")
-    _chk(db, torch.float32, "db")
     B, H, W, Cc = a.shape
-    _native.call("abl_maxpool_bwd_relu", _ptr(dp), _ptr(a), _ptr(pooled), _ptr(dz), _ptr(db), B, H, W, Cc, _stream())
+    parts, pbytes = _parts_args(db, db_parts, Cc, a.device, "db")
+    _native.call("abl_maxpool_bwd_relu", _ptr(dp), _ptr(a), _ptr(pooled), _ptr(dz), _ptr(parts), pbytes, B, H, W, Cc,
+                 _stream())
+    if db is not None and db_parts is None:
+        parts_reduce(parts, db)
 
 
-def maxpool_bwd_code(dp, pool_code, dz, db=None):
+def maxpool_bwd_code(dp, pool_code, dz, db=None, db_parts=None):
     """dz from the forward's 2-bit routing codes; dp must already carry relu'(pooled) (abl_maxpool_bwd_code)."""
     _chk(dp, torch.bfloat16, "dp"); _chk(dz, torch.bfloat16, "dz"); _chk(pool_code, torch.int16, "pool_code")
-    _chk(db, torch.float32, "db")
     B, H, W, Cc = dz.shape
-    _native.call("abl_maxpool_bwd_code", _ptr(dp), _ptr(pool_code), _ptr(dz), _ptr(db), B, H, W, Cc, _stream())
+    parts, pbytes = _parts_args(db, db_parts, Cc, dz.device, "db")
+    _native.call("abl_maxpool_bwd_code", _ptr(dp), _ptr(pool_code), _ptr(dz), _ptr(parts), pbytes, B, H, W, Cc, _stream())
+    if db is not None and db_parts is None:
+        parts_reduce(parts, db)
 
 
 def gap_fwd(a, gap):
@@ -195,30 +264,43 @@ def gap_fwd(a, gap):
     _native.call("abl_gap_fwd", _ptr(a), _ptr(gap), B, H * W, Cc, _stream())
 
 
-def gap_bwd_relu(dgap, a, dz, db=None):
+def gap_bwd_relu(dgap, a, dz, db=None, db_parts=None):
     _chk(dgap, torch.float32, "dgap"); _chk(a, torch.bfloat16, "a"); _chk(dz, torch.bfloat16, "dz")
-    _chk(db, torch.float32, "db")
     B, H, W, Cc = a.shape
-    _native.call("abl_gap_bwd_relu", _ptr(dgap), _ptr(a), _ptr(dz), _ptr(db), B, H * W, Cc, _stream())
+    parts, pbytes = _parts_args(db, db_parts, Cc, a.device, "db")
+    _native.call("abl_gap_bwd_relu", _ptr(dgap), _ptr(a), _ptr(dz), _ptr(parts), pbytes, B, H * W, Cc, _stream())
+    if db is not None and db_parts is None:
+        parts_reduce(parts, db)
+
+
+def head_loss_ws(B, device):
+    """Zeroed workspace for the deterministic batch-loss sum of head_fwd (abl_head_loss_ws_bytes)."""
+    return torch.zeros(int(_native.load().abl_head_loss_ws_bytes(int(B))) // 4, device=device, dtype=torch.float32)
 
 
 def head_fwd(gap, w, b, logits, probs, y=None, class_weight=None, inv_batch=1.0, loss_sum=None, dlogits=None,
-             keep_mask=None, keep_mask_in=False, training=False, dropout=0.0, seed=0, step=0, rank=0, step_dev=None):
-    for t in (gap, w, b, logits, probs, y, class_weight, loss_sum, dlogits):
+             keep_mask=None, keep_mask_in=False, training=False, dropout=0.0, seed=0, step=0, rank=0, step_dev=None,
+             loss_ws=None, loss_accumulate=True):
+    """loss_sum (+)= batch loss (loss_accumulate False: overwritten).  step_dev: int32[2] device counters {dropout step,
+    optimizer step}, both advanced by the kernel (CUDA-graph replays)."""
+    for t in (gap, w, b, logits, probs, y, class_weight, loss_sum, dlogits, loss_ws):
         _chk(t, torch.float32, "tensor")
     _chk(keep_mask, torch.uint8, "keep_mask")
     B, Cc = gap.shape
     n = w.shape[1]
+    if loss_ws is None and loss_sum is not None and y is not None:
+        loss_ws = _scratch(gap.device, "loss_ws", int(_native.load().abl_head_loss_ws_bytes(B)))
     if step_dev is not None:       # dropout counter in device memory (CUDA-graph replays)
         _chk(step_dev, torch.int32, "step_dev")
         _native.call("abl_head_fwd_stepdev", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
                      _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
-                     int(bool(training)), float(dropout), int(seed), _ptr(step_dev), int(rank), B, Cc, n, _stream())
+                     int(bool(training)), float(dropout), int(seed), _ptr(step_dev), int(rank), B, Cc, n,
+                     int(bool(loss_accumulate)), _ptr(loss_ws), _stream())
         return
     _native.call("abl_head_fwd", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
                  _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
                  int(bool(keep_mask_in)), int(bool(training)), float(dropout), int(seed), int(step), int(rank),
-                 B, Cc, n, _stream())
+                 B, Cc, n, int(bool(loss_accumulate)), _ptr(loss_ws), _stream())
 
 
 def head_bwd(gap, w, dlogits, keep_mask, dropout, dw, db, dgap):

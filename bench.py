@@ -319,12 +319,12 @@ def main():
             k = kernels.setdefault(name, {"calls": 0, "ms": 0.0, "gflop": 0.0})
             k["calls"] += 1
             k["ms"] += t
-            if name == "abl_conv3x3_igemm":        # (x, w, bias, mask, full, pool, code, colsum, B, H, W, Cin, Cout, ...)
+            if name == "abl_conv3x3_igemm":        # (x, w, bias, mask, full, pool, code, parts, bytes, B, H, W, Cin, Cout, ...)
+                fl = 2.0 * a[9] * a[10] * a[11] * 9 * a[12] * a[13]
+            elif name == "abl_conv3x3_wgrad":      # (x, dz, dw, db, db_parts, ws, ws_bytes, acc, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
-            elif name == "abl_conv3x3_wgrad":      # (x, dz, dw, db, ws, ws_bytes, acc, B, H, W, Cin, Cout, stream)
+            elif name == "abl_conv3x3_dgrad_unpool":   # (dz, w, pooled, code, out, parts, bytes, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
-            elif name == "abl_conv3x3_dgrad_unpool":   # (dz, w, pooled, code, out, db, B, H, W, Cin, Cout, stream)
-                fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
             elif name == "abl_conv3x3_igemm_gap":      # (x, w, bias, out, gap_part, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]
             else:

@@ -14,6 +14,9 @@
  *   - Return value: 0 on success, negative ABL_ERR_* otherwise; abl_last_error() (thread-local)
  *     describes the failure.  No exceptions cross this boundary.
  *   - Re-entrant; no global mutable state besides per-device one-time kernel attributes.
+ *   - Deterministic: no floating-point atomics anywhere.  Every sum across CTAs goes through per-CTA partial sums
+ *     that a later kernel adds in a fixed order, so two runs on the same inputs give the same bits (gradients, loss,
+ *     weights after any number of steps).
  */
 #ifndef ABL_B200_H_
 #define ABL_B200_H_
@@ -22,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 6
+#define ABL_ABI_VERSION 7
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -38,6 +41,18 @@ extern "C" {
 int abl_abi_version(void);
 const char* abl_last_error(void);
 
+/* Partial-sum ("parts") buffers -- how a bias gradient travels from the kernel that produces a dZ tensor to the kernel
+ * that finishes it, without atomics and without re-reading dZ.  A parts buffer is caller-owned fp32 device memory,
+ * 16-byte aligned, of at least abl_parts_bytes(C) bytes:
+ *   word 0                           int32 R = number of rows the producer wrote (one per CTA)
+ *   floats [ABL_PARTS_HEADER + r*C .. +C)   row r: that CTA's partial sums of the C channels
+ * Producers (the *_parts arguments below) overwrite the buffer; consumers (abl_conv3x3_wgrad's db_parts,
+ * abl_parts_reduce) add rows 0..R-1 in a fixed order. */
+#define ABL_PARTS_HEADER 64
+long long abl_parts_bytes(int C);
+/* out[c] (+)= sum_r row_r[c]  (accumulate != 0 adds to out, else overwrites it); C % 4 == 0. */
+int abl_parts_reduce(const float* parts, float* out, int C, int accumulate, void* stream);
+
 /* Conv2D 3x3/s1/SAME as a tcgen05 implicit GEMM.  Replaces Keras Conv2D+BiasAdd+Relu(+MaxPool2D)
  * of the VGG16 layers reused at src/models/models.py:409-413 (forward) and, with the tap-flipped
  * transposed filter and ABL_EPI_RELU_MASK, TF's Conv2DBackpropInput+ReluGrad that model.fit's
@@ -51,12 +66,13 @@ const char* abl_last_error(void);
  *   pool_code uint16 [B,H/2,W/2,Cout/8] or NULL (needs out_pool): per pooled element the 2-bit index (window scan
  *            order) of the FIRST maximum, channel k of an 8-channel chunk in bits [2k,2k+1] -- what MaxPoolGrad needs,
  *            so training keeps neither the full-resolution activation nor re-reads it (abl_maxpool_bwd_code)
- *   colsum   fp32 [Cout] or NULL: colsum[c] += sum_{n,h,w} out_full[n,h,w,c] -- with the dgrad epilogue this is
- *            TF's BiasAddGrad of the layer below, fused so its dZ is not read a second time (needs out_full)
+ *   colsum_parts  parts buffer (see above) or NULL: partial sums over (n,h,w) of out_full[n,h,w,c] -- with the dgrad
+ *            epilogue this is TF's BiasAddGrad of the layer below, fused so its dZ is not read a second time (needs
+ *            out_full); colsum_parts_bytes = its capacity
  * Requires Cin, Cout multiples of 64 (<= 512), H*W tileable into 128-pixel rectangles. */
 int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
-                      void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, int B, int H, int W,
-                      int Cin, int Cout, int flags, void* stream);
+                      void* out_full, void* out_pool, unsigned short* pool_code, float* colsum_parts,
+                      long long colsum_parts_bytes, int B, int H, int W, int Cin, int Cout, int flags, void* stream);
 
 /* Forward conv + bias + ReLU (as abl_conv3x3_igemm with ABL_EPI_BIAS_RELU) of the LAST conv layer with Keras'
  * GlobalAveragePooling2D (models.py:414) fused in: the epilogue also writes the per-channel sums of every 8x16-pixel
@@ -74,32 +90,41 @@ int abl_gap_reduce(const float* gap_part, float* gap, int B, int parts, int C, i
  * gradient never reaches HBM and no separate MaxPoolGrad pass runs.
  *   dz bf16 [B,H,W,Cin_gemm] (gradient of this conv's output); w_dgrad bf16 [9][Cout][Cin_gemm] (abl_prep_conv_weights);
  *   pooled bf16 [B,H,W,Cout], pool_code uint16 [B,H,W,Cout/8] (both from the forward abl_conv3x3_igemm of the layer
- *   below); dz_out bf16 [B,2H,2W,Cout]; db fp32 [Cout] or NULL: += sum of the routed gradients (BiasAddGrad of the
- *   layer below).  Requires Cout <= 128, W % 16 == 0, H % 16 == 0. */
+ *   below); dz_out bf16 [B,2H,2W,Cout]; db_parts: parts buffer or NULL receiving the partial sums of the routed
+ *   gradients (BiasAddGrad of the layer below).  Requires Cout <= 128, W % 16 == 0, H % 16 == 0. */
 int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, const void* pooled, const unsigned short* pool_code,
-                             void* dz_out, float* db, int B, int H, int W, int Cin, int Cout, void* stream);
+                             void* dz_out, float* db_parts, long long db_parts_bytes, int B, int H, int W, int Cin,
+                             int Cout, void* stream);
 
 /* Conv2DBackpropFilter (+BiasAddGrad) of model.fit's tape (models.py:427,432) as a tcgen05 GEMM with
  * MN-major operands read straight from the NHWC tensors, split over pixel slices into `workspace`
  * and reduced in a fixed order (deterministic), fp32 accumulation:
  *   dw[kh][kw][ci][co] (+)= sum_{n,h,w} x[n,h+kh-1,w+kw-1,ci] * dz[n,h,w,co]   (HWIO fp32)
- *   db[co]              += sum_{n,h,w} dz[n,h,w,co]                            (if db != NULL; always accumulates)
+ *   db[co]               = sum_{n,h,w} dz[n,h,w,co]                            (if db != NULL; overwrites)
  * x bf16 [B,H,W,Cin], dz bf16 [B,H,W,Cout]; accumulate != 0 adds to dw, else overwrites it.
+ * db_parts: the parts buffer that the kernel which PRODUCED dz filled (abl_conv3x3_igemm colsum_parts,
+ *   abl_conv3x3_dgrad_unpool, abl_gap_bwd_relu, abl_maxpool_bwd_*): the slice-reduction kernel of this call adds its rows
+ *   into db.  NULL with db != NULL: the column sums come from this call itself (Cin == 64: a ones row of the GEMM; else a
+ *   pass over dz).
  * workspace: >= abl_conv3x3_wgrad_workspace_bytes(...) bytes, 16-byte aligned, caller-owned. */
 long long abl_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
-int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float* db, void* workspace,
+int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float* db, const float* db_parts, void* workspace,
                       long long workspace_bytes, int accumulate, int B, int H, int W, int Cin, int Cout,
                       void* stream);
-/* BiasAddGrad alone: db[c] += sum_r dz[r][c], dz bf16 [rows][C]. */
-int abl_bias_grad(const void* dz, float* db, long long rows, int C, void* stream);
+/* BiasAddGrad alone, first half: db_parts rows = per-block sums over rows of dz bf16 [rows][C] (finish with
+ * abl_parts_reduce or abl_conv3x3_wgrad's db_parts). */
+int abl_bias_grad(const void* dz, float* db_parts, long long db_parts_bytes, long long rows, int C, void* stream);
 
 /* block1_conv1 (Cin=3, K=27: HBM-bound, not tensor-core shaped).  Forward reads the caller's fp32
  * NHWC frame (already BGR / mean-subtracted, preprocessor.py:60-63) and writes bf16 relu(conv+b). */
 int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H, int W,
                        int Cout, void* stream);
-/* dw[3][3][3][Cout] += ..., db[Cout] += ... for block1_conv1 (x fp32 [B,H,W,3], dz bf16 [B,H,W,Cout]). */
-int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, int B, int H, int W, int Cout,
-                         void* stream);
+/* dw[3][3][3][Cout] = ..., db[Cout] = ... (overwritten; db may be NULL) for block1_conv1 (x fp32 [B,H,W,3], dz bf16
+ * [B,H,W,Cout]): per-CTA sums go to `workspace` (abl_conv_first_wgrad_workspace_bytes() bytes) and a second kernel adds
+ * them in a fixed order. */
+long long abl_conv_first_wgrad_workspace_bytes(void);
+int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, void* workspace,
+                         long long workspace_bytes, int B, int H, int W, int Cout, void* stream);
 
 /* Same two kernels fed by the RAW uint8 RGB frame [B,H,W,3] (what decode_jpeg + nearest resize leave,
  * reference preprocessor.py:76-80): Keras vgg16 preprocess_input (RGB->BGR, subtract 103.939/116.779/123.68;
@@ -107,8 +132,8 @@ int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, i
  * host->device copy is 4x smaller. */
 int abl_conv_first_fwd_u8(const unsigned char* frames_rgb, const float* w_hwio, const float* bias, void* out, int B,
                           int H, int W, int Cout, void* stream);
-int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db, int B, int H,
-                            int W, int Cout, void* stream);
+int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db, void* workspace,
+                            long long workspace_bytes, int B, int H, int W, int Cout, void* stream);
 
 /* fp32 HWIO master kernel -> the two bf16 GEMM operand layouts, taps indexed kw-major (t' = kw*3 + kh):
  *   w_fwd  [kw*3+kh][co][ci]         = w[kh][kw][ci][co]
@@ -121,21 +146,22 @@ int abl_prep_conv_weights_multi(const float* const* w_hwio, void* const* w_fwd, 
 
 /* MaxPoolGrad + ReluGrad: dz[n,h,w,c] = dp[n,h/2,w/2,c] if a[n,h,w,c] is the first maximum of its 2x2
  * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16.
- * db fp32 [C] or NULL: db[c] += sum dz[..., c] (BiasAddGrad of the conv above the pool, fused). */
-int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db, int B, int H,
-                         int W, int C, void* stream);
+ * db_parts: parts buffer or NULL receiving the partial sums of dz[..., c] (BiasAddGrad of the conv above the pool). */
+int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db_parts,
+                         long long db_parts_bytes, int B, int H, int W, int C, void* stream);
 
 /* MaxPoolGrad from the routing codes of abl_conv3x3_igemm (pool_code): dz[n,h,w,c] = dp[n,h/2,w/2,c] for the window
  * element the code names, else 0.  dp must already be masked by relu'(pooled) (run the dgrad that produces it with
- * ABL_EPI_RELU_MASK and mask_src = the pooled activation).  db as in abl_maxpool_bwd_relu. */
-int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db, int B, int H, int W,
-                         int C, void* stream);
+ * ABL_EPI_RELU_MASK and mask_src = the pooled activation).  db_parts as in abl_maxpool_bwd_relu. */
+int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db_parts,
+                         long long db_parts_bytes, int B, int H, int W, int C, void* stream);
 
 /* GlobalAveragePooling2D (models.py:414): gap[n][c] = mean_{hw} a[n,hw,c]; a bf16, gap fp32. */
 int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream);
 /* its gradient fused with ReluGrad of the last conv: dz = a > 0 ? dgap[n][c] / HW : 0 (bf16);
- * db fp32 [C] or NULL: db[c] += sum dz[..., c] (BiasAddGrad of the last conv, fused). */
-int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db, int B, int HW, int C, void* stream);
+ * db_parts: parts buffer or NULL receiving the partial sums of dz[..., c] (BiasAddGrad of the last conv, fused). */
+int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db_parts, long long db_parts_bytes, int B, int HW,
+                     int C, void* stream);
 
 /* Dropout -> Dense(n_classes) -> softmax (models.py:415-416) [+ categorical_crossentropy with
  * class_weight, models.py:426 / train.py:135-136].
@@ -144,21 +170,29 @@ int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db, int 
  *     P(drop) = dropout, kept values scaled 1/(1-dropout); mask bytes written to keep_mask [B,C]
  *     (if keep_mask_in != 0 the mask is READ from keep_mask instead -- test hook).
  *   y_onehot fp32 [B,n] or NULL (no loss).  class_weight fp32 [n] or NULL.
- *   loss_sum += sum_i w_i * (logsumexp(z_i) - z_i[y_i]) * inv_batch     (fp32 scalar, ACCUMULATES)
- *   dlogits[i][j] = w_i * inv_batch * (p_ij - y_ij)                      (if dlogits != NULL) */
+ *   loss_sum (+)= sum_i w_i * (logsumexp(z_i) - z_i[y_i]) * inv_batch   (fp32 scalar; loss_accumulate != 0 adds to it --
+ *            Keras evaluate over many batches -- else overwrites it)
+ *   dlogits[i][j] = w_i * inv_batch * (p_ij - y_ij)                      (if dlogits != NULL)
+ *   loss_ws  abl_head_loss_ws_bytes(B) bytes, ZEROED ONCE by the caller (needed when loss_sum and y_onehot are given):
+ *            per-block loss sums + an integer ticket; the last block to finish adds them in block order, so the batch
+ *            loss is one deterministic sum and a single read-modify-write of *loss_sum (the ticket resets itself). */
+long long abl_head_loss_ws_bytes(int B);
 int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
                  const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                  float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                  unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                 void* stream);
-/* abl_head_fwd with the dropout step counter read from DEVICE memory (*step_dev) instead of passed by value, so the
- * launch can be replayed from a CUDA graph while the counter advances on the device (mask always generated). */
+                 int loss_accumulate, float* loss_ws, void* stream);
+/* abl_head_fwd with the dropout step counter read from DEVICE memory instead of passed by value, so the launch can be
+ * replayed from a CUDA graph (mask always generated; y_onehot and loss_sum required).  step_dev: uint32[2] = {dropout
+ * step, optimizer step}; the kernel's last block increments BOTH after every block has read the dropout step, so a
+ * captured train step needs no separate counter kernels (abl_adam_flat_tab reads step_dev[1] later in the step). */
 int abl_head_fwd_stepdev(const float* gap, const float* w, const float* b, float* logits, float* probs,
                          const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                          float* dlogits, unsigned char* keep_mask, int training, float dropout, unsigned long long seed,
-                         const unsigned int* step_dev, unsigned int rank, int B, int C, int n, void* stream);
-/* dw[C][n] += h^T dlogits, db[n] += sum_i dlogits, dgap[i][c] = scale_ic * sum_j dlogits[i][j] w[c][j]
- * with h = gap * scale, scale_ic = keep_mask ? mask/(1-dropout) : 1. */
+                         unsigned int* step_dev, unsigned int rank, int B, int C, int n, int loss_accumulate,
+                         float* loss_ws, void* stream);
+/* dw[C][n] = h^T dlogits, db[n] = sum_i dlogits (both OVERWRITTEN; fixed summation order),
+ * dgap[i][c] = scale_ic * sum_j dlogits[i][j] w[c][j] with h = gap * scale, scale_ic = keep_mask ? mask/(1-dropout) : 1. */
 int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,
                  float dropout, float* dw, float* db, float* dgap, int B, int C, int n, void* stream);
 

@@ -55,13 +55,13 @@ eng = CutoffVGG16Engine(rank=rank, world_size=world)
 tr = set(eng.layer_names())
 mark("engine built")
 sl = slice(rank * Bl, (rank + 1) * Bl)
-loss = eng.train_step(x[sl], y[sl], tr, keep_mask=keep[sl], apply_update=False, global_batch=G)
+loss = eng.train_step(x[sl], y[sl], tr, keep_mask=keep[sl], apply_update=False, global_batch=G).clone()
 torch.cuda.synchronize()
 g_dp = eng.grad.clone()
 mark(f"DP step done, local loss {loss.item():.5f}")
 # single-device reference on the concatenated batch (every rank computes it; world_size forced to 1)
 eng.world_size = 1
-loss1 = eng.train_step(x, y, tr, keep_mask=keep, apply_update=False, global_batch=G)
+loss1 = eng.train_step(x, y, tr, keep_mask=keep, apply_update=False, global_batch=G).clone()
 torch.cuda.synchronize()
 g_1 = eng.grad.clone()
 eng.world_size = world
@@ -69,63 +69,76 @@ ls = loss.clone()
 dist.all_reduce(ls)
 err = float((g_dp - g_1).abs().max() / g_1.abs().max())
 mark(f"single-device step done: loss {loss1.item():.5f} vs DP sum {ls.item():.5f}; max|dg|/max|g| = {err:.3e}")
-assert err < 2e-2, err                      # bf16 inter-layer gradients: batch split changes nothing but fp32 order
-assert abs(ls.item() - loss1.item()) < 1e-4
+# every frame's dZ is independent of how the batch is split (per-frame bf16 roundings are the same); only the fp32
+# summation order of the weight / bias gradient sums differs between the sharded and the concatenated batch
+assert err < 1e-4, err
+assert abs(ls.item() - loss1.item()) < 1e-5
+# the DP gradient itself is bit-reproducible: no float atomics in any kernel, NCCL's reduction order is fixed
+loss_b = eng.train_step(x[sl], y[sl], tr, keep_mask=keep[sl], apply_update=False, global_batch=G).clone()
+torch.cuda.synchronize()
+assert torch.equal(eng.grad, g_dp) and torch.equal(loss_b, loss), "two DP steps on the same inputs differ"
+mark("DP step repeated: gradient and loss bit-identical")
 # ---- training: the fused peer-memory optimizer (reduce-scatter + Adam/RMSprop + all-gather in one kernel) must keep
-# every rank's weights bit-identical and track single-device training on the concatenated batch.
+# every rank's weights bit-identical, repeat exactly, and equal NCCL all-reduce + the local optimizer kernel.
 w0 = eng.get_weights()
 steps = 4
-for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
+
+
+def run_steps(opt, lr, xs, ys, ks, gb):
     eng.set_weights(w0)
-    eng.opt_state.clear(); eng.opt_steps.clear()
-    th_steps = []
+    eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+    out = []
     for i in range(steps):
-        eng.train_step(x[sl], y[sl], tr, opt, lr, keep_mask=keep[sl], global_batch=G)
+        eng.train_step(xs, ys, tr, opt, lr, keep_mask=ks, global_batch=gb)
         torch.cuda.synchronize()
-        th_steps.append(eng.theta.clone())
+        out.append(eng.theta.clone())
+    return out
+
+
+for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
+    th_steps = run_steps(opt, lr, x[sl], y[sl], keep[sl], G)
     th_dp = th_steps[-1]
     ths = [torch.empty_like(th_dp) for _ in range(world)]
     dist.all_gather(ths, th_dp)
     assert all(torch.equal(ths[0], t) for t in ths), f"{opt}: weights diverged across ranks"
-    # (a) same DP training through NCCL all-reduce + the local optimizer kernel.  After ONE step the two paths must agree
-    #     to fp32 rounding (same per-rank gradients up to float-atomic order; only the cross-rank summation differs).
-    #     Over several steps ANY two runs drift apart -- a 1e-8 weight difference flips a few ReLU masks, and the
-    #     normalised Adam / RMSprop steps amplify that (two NCCL-path runs differ by 6e-4 max / 1 % of the weights after
-    #     four RMSprop steps) -- so the multi-step comparison is statistical.
-    th_dp_1 = th_steps[0]
+    again = run_steps(opt, lr, x[sl], y[sl], keep[sl], G)
+    assert all(torch.equal(a, b) for a, b in zip(th_steps, again)), f"{opt}: two fused-DP runs differ"
+    # (a) same DP training through NCCL all-reduce + the local optimizer kernel (same update arithmetic, shared device
+    #     function).  Two ranks: a + b is commutative, so the two paths must agree BIT FOR BIT after every step.  More
+    #     ranks: NCCL's ring/tree order differs from the fused kernel's rank order by fp32 rounding of the gradient sum;
+    #     one step must agree to that noise, later steps are reported (a 1e-9 weight difference can flip a bf16 weight
+    #     rounding, hence a few ReLU masks, and the normalised optimizer steps amplify that).
     symm_saved, eng._symm = eng._symm, None
-    eng.set_weights(w0)
-    eng.opt_state.clear(); eng.opt_steps.clear()
-    th_nccl_steps = []
-    for i in range(steps):
-        eng.train_step(x[sl], y[sl], tr, opt, lr, keep_mask=keep[sl], global_batch=G)
-        torch.cuda.synchronize()
-        th_nccl_steps.append(eng.theta.clone())
-    th_nccl = th_nccl_steps[-1]
-    d1 = (th_dp_1 - th_nccl_steps[0]).abs()
-    d = (th_dp - th_nccl).abs()
-    mark(f"{opt}: fused={symm_saved is not None}; vs NCCL all-reduce + local optimizer: after 1 step max diff "
-         f"{float(d1.max()):.3e}; after {steps} steps max {float(d.max()):.3e}, "
+    th_nccl_steps = run_steps(opt, lr, x[sl], y[sl], keep[sl], G)
+    again = run_steps(opt, lr, x[sl], y[sl], keep[sl], G)
+    assert all(torch.equal(a, b) for a, b in zip(th_nccl_steps, again)), f"{opt}: two NCCL-path runs differ"
+    d1 = (th_steps[0] - th_nccl_steps[0]).abs()
+    d = (th_dp - th_nccl_steps[-1]).abs()
+    exact = all(torch.equal(a, b) for a, b in zip(th_steps, th_nccl_steps))
+    mark(f"{opt}: fused={symm_saved is not None}; vs NCCL all-reduce + local optimizer: bit-identical over {steps} steps: "
+         f"{exact}; after 1 step max diff {float(d1.max()):.3e}; after {steps} steps max {float(d.max()):.3e}, "
          f"{float((d > 2e-5).float().mean()):.2e} of the weights differ by > 2e-5")
+    if world == 2 and symm_saved is not None:
+        assert exact, "2 ranks: fused peer-memory optimizer != NCCL all-reduce + optimizer"
     assert float(d1.max()) < 1e-7, "fused peer-memory optimizer != NCCL all-reduce + optimizer after one step"
     assert float((d > 2e-5).float().mean()) < 5e-2 and float(d.median()) < 1e-6
-    # (b) single-device training on the concatenated batch (world_size forced to 1).  Adam / RMSprop normalise the
-    #     step, so an element whose gradient is at fp32-summation-noise level may step differently: bound the typical
-    #     difference and the FRACTION of such elements, not the maximum.
+    # (b) single-device training on the concatenated batch (world_size forced to 1): differs from DP only by the fp32
+    #     order of the gradient sums -> one step within that noise; several steps as in (a).
     eng.world_size = 1
-    eng.set_weights(w0)
-    eng.opt_state.clear(); eng.opt_steps.clear()
-    for i in range(steps):
-        eng.train_step(x, y, tr, opt, lr, keep_mask=keep, global_batch=G)
-    torch.cuda.synchronize()
-    th_1 = eng.theta.clone()
+    th_1_steps = run_steps(opt, lr, x, y, keep, G)
     eng.world_size, eng._symm = world, symm_saved
+    th_1 = th_1_steps[-1]
     moved = float((th_1 - torch.from_numpy(np.concatenate([np.pad(w0[k].ravel(), (0, (-w0[k].size) % 4))
                                                               for k in eng.segments])).cuda()).abs().max())
+    d1 = (th_steps[0] - th_1_steps[0]).abs()
     d = (th_dp - th_1).abs()
     diff, frac_off = float(d.max()), float((d > 2e-5).float().mean())
-    mark(f"{opt}: {steps} DP steps vs 1 GPU on the concatenated batch: max diff {diff:.3e}, median {float(d.median()):.1e}, "
-         f"{frac_off:.2e} of the weights differ by > 2e-5 (weights moved {moved:.3e})")
+    mark(f"{opt}: DP vs 1 GPU on the concatenated batch: after 1 step max diff {float(d1.max()):.3e} "
+         f"({float((d1 > 1e-7).float().mean()):.2e} of the weights > 1e-7); after {steps} steps max {diff:.3e}, median "
+         f"{float(d.median()):.1e}, {frac_off:.2e} of the weights differ by > 2e-5 (weights moved {moved:.3e})")
+    # one step: Adam's first step is lr * g / (|g| + 3.2e-6): an element whose gradient is at summation-noise level
+    # (|g| ~ 1e-9) may move differently by a fraction of lr; everything else agrees to fp32 rounding
+    assert float((d1 > 1e-7).float().mean()) < 1e-3 and float(d1.max()) <= 2.1 * lr
     assert frac_off < 5e-2 and float(d.median()) < 1e-6 and moved > 1e-4, (opt, diff, frac_off, moved)
 eng.set_weights(w0)
 eng.opt_state.clear(); eng.opt_steps.clear()

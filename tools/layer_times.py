@@ -27,13 +27,13 @@ for r in range(reps):
     recs, _native.timing = _native.timing, None
     for i, (name, a, e0, e1) in enumerate(recs):
         if name == "abl_conv3x3_igemm":
-            shape = (a[8], a[9], a[10], a[11], a[12], a[13]); fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
+            shape = (a[9], a[10], a[11], a[12], a[13], a[14]); fl = 2.0 * a[9] * a[10] * a[11] * 9 * a[12] * a[13]
         elif name == "abl_conv3x3_igemm_gap":
             shape = (a[5], a[6], a[7], a[8], a[9], "gap"); fl = 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]
         elif name == "abl_conv3x3_dgrad_unpool":
-            shape = (a[6], a[7], a[8], a[9], a[10], "unpool"); fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
+            shape = (a[7], a[8], a[9], a[10], a[11], "unpool"); fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
         elif name == "abl_conv3x3_wgrad":
-            shape = (a[7], a[8], a[9], a[10], a[11]); fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
+            shape = (a[8], a[9], a[10], a[11], a[12]); fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
         else:
             shape, fl = (), 0.0
         key = (i, name, shape)

@@ -12,13 +12,17 @@ sms = torch.cuda.get_device_properties(0).multi_processor_count
 iters = 2000
 st = torch.cuda.current_stream().cuda_stream
 print(f"{'N':>4} {'mode':>22} {'clk/MMA 1 CTA':>14} {'clk/MMA all SMs':>16} {'math clk':>9}")
-for mode, name in ((0, "plain SS"), (1, "weight-stationary pair"), (2, "rotating filter window")):
+MODES = ((0, "plain SS", 4), (1, "weight-stationary pair", 8), (2, "rotating filter window", 4),
+         (4, "2 accumulators plain", 8), (3, "4 accumulators plain", 16), (5, "ws quad fill-use-use-last", 16))
+for mode, name, per_it in MODES:
     for n in (64, 128, 192, 256):
+        if mode in (1, 5) and n == 192 or mode in (3, 5) and n > 128:
+            continue
         res = []
         for ctas in (1, sms):
             out = torch.zeros(ctas, 2, device="cuda", dtype=torch.int64)
             _native.call("abl_dev_mma_rate_probe", n, mode, iters, ctas, out.data_ptr(), st)
             torch.cuda.synchronize()
-            per = (8 if mode == 1 else 4) * iters
+            per = per_it * iters
             res.append(float(out[:, 1].double().mean()) / per)
         print(f"{n:>4} {name:>22} {res[0]:>14.1f} {res[1]:>16.1f} {n / 2:>9.0f}")
