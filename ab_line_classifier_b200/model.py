@@ -310,14 +310,19 @@ class B200Model:
         self.stop_training = False
         for cb in callbacks:
             cb.on_train_begin() if hasattr(cb, "on_train_begin") else None
+        # per-step losses: written by the step into a device ring and copied to pinned host memory right behind it
+        # (4 bytes, asynchronous), so the host never waits for a step inside the epoch
         ring = torch.zeros(1024, device=eng.device, dtype=torch.float32)
+        on_gpu = torch.device(eng.device).type == "cuda"
+        ring_host = torch.zeros(1024, dtype=torch.float32)
+        if on_gpu:
+            ring_host = ring_host.pin_memory()
         for epoch in range(initial_epoch, epochs):
             for cb in callbacks:
                 cb.on_epoch_begin(epoch) if hasattr(cb, "on_epoch_begin") else None
             opt = self.optimizer
             tot_loss, n_seen, slot_i = 0.0, 0, 0
             sizes, probs, ys = [], [], []
-            ring.zero_()
             plan = M.device_plan(self.metric_objs, self.n_classes) if self.metric_objs else None
             if plan is not None:
                 eng.metrics_begin(*plan)
@@ -325,9 +330,10 @@ class B200Model:
             def drain():
                 nonlocal tot_loss, slot_i
                 if slot_i:
-                    vals = ring[:slot_i].cpu().numpy()
+                    if on_gpu:
+                        torch.cuda.current_stream().synchronize()
+                    vals = ring_host[:slot_i].numpy()
                     tot_loss += float(np.dot(vals, np.asarray(sizes[-slot_i:], np.float64)))
-                    ring.zero_()
                     slot_i = 0
 
             kw = ({"beta_1": opt.beta_1, "beta_2": opt.beta_2, "eps": opt.epsilon} if opt.kind == "adam"
@@ -335,18 +341,22 @@ class B200Model:
             # software pipeline: the H2D copy of batch i+1 (copy stream) overlaps the kernels of batch i
             batches = _iter_batches(train_data)
             nxt = next(batches, None)
-            if nxt is not None:
-                eng.reserve(len(nxt[0]), True)
-                nslot = eng.stage(nxt[0], nxt[1])
+            nslot = None
             while nxt is not None:
-                (x, y), slot = nxt, nslot
+                (x, y) = nxt
                 B = len(x)
+                if nslot is None:                                  # nothing staged ahead (first batch, or the buffers grew)
+                    eng.reserve(B, True)
+                    nslot = eng.stage(x, y)
+                slot, nslot = nslot, None
                 nxt = next(batches, None)
-                if nxt is not None:
-                    eng.reserve(len(nxt[0]), True)
+                if nxt is not None and len(nxt[0]) <= eng._cap:
+                    # a LARGER next batch would re-allocate the input slots under the staged one: it is staged after
+                    # this step instead (reserve + stage at the top of the loop)
                     nslot = eng.stage(nxt[0], nxt[1], slot=slot ^ 1)
                 eng.fit_step(trainable, opt.kind, opt.learning_rate, slot, B, B * eng.world_size,
                              loss_out=ring[slot_i:slot_i + 1], **kw)
+                ring_host[slot_i:slot_i + 1].copy_(ring[slot_i:slot_i + 1], non_blocking=True)
                 if plan is not None:
                     eng.metrics_update(B)      # training-batch outputs (dropout on), as Keras reports them
                 elif self.metric_objs:

@@ -97,7 +97,7 @@ class FakeEngine:
         self._buf["probs"], self._last_y = torch.from_numpy(fwd["probs"]), y
         t = torch.tensor([loss], dtype=torch.float32)
         if loss_out is not None:
-            loss_out += t
+            loss_out.copy_(t)          # the step's loss overwrites its destination (engine.forward_device)
             return loss_out
         return t
 
