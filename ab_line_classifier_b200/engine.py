@@ -79,6 +79,15 @@ class CutoffVGG16Engine:
             raise RuntimeError("ab_line_classifier_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         ops._native.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("ab_line_classifier_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if self.device.index != torch.cuda.current_device():
+            # the launch shims use the CURRENT device's stream and per-device kernel attributes: an engine on another
+            # device would launch on the wrong stream (one process per GPU is the intended layout)
+            raise RuntimeError(f"make {self.device} the current device first (torch.cuda.set_device({self.device.index})): "
+                               "the engine launches on the current device's stream")
         self.input_shape = tuple(int(v) for v in input_shape)
         self.n_classes = int(n_classes)
         if not 1 <= self.n_classes <= 8:

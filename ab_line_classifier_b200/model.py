@@ -396,43 +396,213 @@ class B200Model:
             cb.on_train_end() if hasattr(cb, "on_train_end") else None
         return hist
 
-    # ---- checkpoint interchange (Keras names and layouts; .npz because h5py is absent here)
-    def save(self, path):
-        save_model(self, path)
+    # ---- checkpoint interchange (Keras names and layouts: .npz, or Keras' legacy HDF5 layout through h5lite)
+    def save(self, path, include_optimizer=True):
+        save_model(self, path, include_optimizer=include_optimizer)
 
 
-def save_model(model, path):
-    """Counterpart of ``tf.keras.models.save_model(model.model, path)`` (train.py:139-144): weights under
-    Keras names/layouts + the architecture config, as .npz."""
-    inner = model.model if hasattr(model, "model") and not isinstance(model, B200Model) else model
+def _is_hdf5(path):
+    with open(path, "rb") as fh:
+        return fh.read(8) == b"\x89HDF\r\n\x1a\n"
+
+
+def _inner(model):
+    return model.model if hasattr(model, "model") and not isinstance(model, B200Model) else model
+
+
+def _keras_model_config(inner):
+    """model_config JSON in the shape Keras' functional API writes (class names, layer names, the arguments that define
+    the architecture).  Enough for load_model() here to rebuild the engine; not a byte-for-byte Keras config."""
+    H, W, C = (int(v) for v in inner.input_shape_)
+    layers = [{"class_name": "InputLayer", "name": "input",
+               "config": {"name": "input", "batch_input_shape": [None, H, W, C], "dtype": "float32"}}]
+    for l in inner.layers[1:]:
+        if l.kind == "conv":
+            spec = next(s for s in inner.engine.specs if s.name == l.name)
+            cfg = {"name": l.name, "filters": spec.cout, "kernel_size": [3, 3], "strides": [1, 1], "padding": "same",
+                   "activation": "relu", "use_bias": True, "trainable": bool(l.trainable)}
+            layers.append({"class_name": "Conv2D", "name": l.name, "config": cfg})
+        elif l.kind == "pool":
+            layers.append({"class_name": "MaxPooling2D", "name": l.name,
+                           "config": {"name": l.name, "pool_size": [2, 2], "strides": [2, 2], "padding": "valid"}})
+        elif l.kind == "gap":
+            layers.append({"class_name": "GlobalAveragePooling2D", "name": l.name, "config": {"name": l.name}})
+        elif l.kind == "dropout":
+            layers.append({"class_name": "Dropout", "name": l.name, "config": {"name": l.name, "rate": float(inner.dropout)}})
+        elif l.kind == "dense":
+            layers.append({"class_name": "Dense", "name": l.name,
+                           "config": {"name": l.name, "units": int(inner.n_classes), "activation": "softmax",
+                                      "use_bias": True, "trainable": bool(l.trainable)}})
+    return {"class_name": "Functional", "config": {"name": "model", "layers": layers,
+                                                    "input_layers": [["input", 0, 0]], "output_layers": [["output", 0, 0]]}}
+
+
+def _optimizer_state(eng):
+    """Everything a resumed run needs besides the weights: optimizer slots (flat, engine layout), their step counts and
+    the dropout step counter.  (The reference saves no optimizer state at all -- train.py:139-144 -- so a resumed Keras
+    run restarts Adam's moments; here resume is exact.)"""
+    st = {"step_count": np.asarray(eng.step_count, np.int64)}
+    for k, v in getattr(eng, "opt_state", {}).items():
+        st["slot_" + k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    for k, v in getattr(eng, "opt_steps", {}).items():
+        st["steps_" + k] = np.asarray(v, np.int64)
+    return st
+
+
+def _restore_optimizer_state(eng, st):
+    eng.step_count = int(st.get("step_count", 0))
+    for k, v in st.items():
+        if k.startswith("slot_"):
+            t = torch.from_numpy(np.ascontiguousarray(v, np.float32))
+            eng.opt_state[k[5:]] = t.to(eng.device) if torch.device(eng.device).type == "cuda" else t
+        elif k.startswith("steps_"):
+            eng.opt_steps[k[6:]] = int(v)
+
+
+def save_model(model, path, include_optimizer=True):
+    """Counterpart of ``tf.keras.models.save_model(model.model, path)`` (train.py:139-144): weights under Keras
+    names/layouts + the architecture config [+ optimizer state, as Keras' include_optimizer=True].
+    ``*.h5`` / ``*.hdf5``: Keras' legacy HDF5 layout (``model_weights/<layer>/<layer>/kernel:0`` datasets, ``layer_names``
+    / ``weight_names`` attributes, ``model_config``), written by h5lite; anything else: ``.npz``."""
+    inner = _inner(model)
     w = inner.get_weights()
+    eng = inner.engine
+    opt = _optimizer_state(eng) if include_optimizer else {}
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    if str(path).endswith((".h5", ".hdf5")):
+        import json
+        from .h5lite import H5Writer
+        wr = H5Writer()
+        wr.attr(wr.root, "backend", b"ab_line_classifier_b200")
+        wr.attr(wr.root, "keras_version", b"2.9.0")
+        wr.attr(wr.root, "model_config", json.dumps(_keras_model_config(inner)).encode("utf8"))
+        mw = wr.group(wr.root, "model_weights")
+        names = [l.name for l in inner.layers]
+        wr.attr(mw, "layer_names", np.array([n.encode("utf8") for n in names]))
+        wr.attr(mw, "backend", b"ab_line_classifier_b200")
+        wr.attr(mw, "keras_version", b"2.9.0")
+        for l in inner.layers:
+            g = wr.group(mw, l.name)
+            mine = [k for k in w if k.split("/")[0] == l.name]
+            if mine:
+                wr.attr(g, "weight_names", np.array([(k + ":0").encode("utf8") for k in mine]))
+                for k in mine:       # Keras nests by the '/' in the variable name: <layer>/<layer>/kernel:0
+                    sub = wr.group(g, l.name)
+                    wr.dataset(sub, k.split("/", 1)[1] + ":0", w[k])
+        if opt:
+            og = wr.group(wr.root, "b200_optimizer_state")
+            for k, v in opt.items():
+                wr.dataset(og, k, np.atleast_1d(v))
+        wr.save(path)
+        return path
     cfg = dict(input_shape=np.asarray(inner.input_shape_), n_classes=inner.n_classes, dropout=inner.dropout,
-               cutoff_layer=inner.engine.cutoff_layer)
+               cutoff_layer=eng.cutoff_layer)
     if not str(path).endswith(".npz"):
         path = str(path) + ".npz"
-    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    np.savez(path, **{"weights/" + k: v for k, v in w.items()}, **{"config/" + k: v for k, v in cfg.items()})
+    np.savez(path, **{"weights/" + k: v for k, v in w.items()}, **{"config/" + k: v for k, v in cfg.items()},
+             **{"optimizer/" + k: v for k, v in opt.items()})
     return path
 
 
-def load_model(path, compile=False, device=None):
-    """Counterpart of ``load_model(model_path, compile=False)`` (predict.py:50) for files written by save_model."""
+def read_keras_h5(path):
+    """(weights dict, model_config dict or None, optimizer-state dict) from a Keras HDF5 file: a full model
+    (``save_model``: weights below ``model_weights``) or a weights file (``save_weights`` / the keras-applications
+    ``vgg16_weights_tf_dim_ordering_tf_kernels_notop.h5``: layer groups at the root).  Variables are keyed
+    ``<layer>/kernel`` / ``<layer>/bias`` whatever the file calls them (``kernel:0``, legacy ``block1_conv1_W_1:0``):
+    within a layer the array with more than one axis is the kernel, the vector is the bias."""
+    import json
+    from .h5lite import H5File
+    f = H5File(path)
+    g = f["model_weights"] if "model_weights" in f else f
+    layer_names = g.attrs.get("layer_names")
+    layers = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.asarray(layer_names).ravel()] \
+        if layer_names is not None else g.keys()
+    weights = {}
+    for ln in layers:
+        if ln not in g:
+            continue
+        lg = g[ln]
+        if not lg.is_group:
+            continue
+        wn = lg.attrs.get("weight_names")
+        if wn is not None:
+            paths = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.asarray(wn).ravel()]
+            arrays = [lg[p].read() for p in paths]
+        else:
+            arrays = [d.read() for _, d in lg.visit_datasets()]
+        for a in arrays:
+            key = ln + ("/kernel" if a.ndim > 1 else "/bias")
+            if key in weights:
+                raise ValueError(f"{path}: layer {ln} holds more than one {key.split('/')[1]} (not a Conv2D / Dense layer)")
+            weights[key] = np.asarray(a, np.float32)
+    cfg = f.attrs.get("model_config")
+    if cfg is not None:
+        cfg = json.loads(cfg.decode("utf8") if isinstance(cfg, bytes) else cfg)
+    opt = {}
+    if "b200_optimizer_state" in f:
+        for k, d in f["b200_optimizer_state"].visit_datasets():
+            v = d.read()
+            opt[k] = v if k.startswith("slot_") else v.reshape(-1)[0]
+    return weights, cfg, opt
+
+
+def _arch_from_keras(weights, cfg, input_shape=None):
+    """(input_shape, n_classes, cutoff_layer, dropout) of a cutoffvgg16 model from its Keras config / weight shapes."""
+    from .engine import VGG16_LAYERS
+    names = [n for n, _, _ in VGG16_LAYERS]
+    dropout, layer_list = 0.45, None
+    if cfg is not None:
+        layer_list = [l.get("name", l.get("config", {}).get("name")) for l in cfg.get("config", {}).get("layers", [])]
+        for l in cfg.get("config", {}).get("layers", []):
+            c = l.get("config", {})
+            if l.get("class_name") == "Dropout":
+                dropout = float(c.get("rate", dropout))
+            if l.get("class_name") == "InputLayer" and c.get("batch_input_shape") and input_shape is None:
+                input_shape = tuple(int(v) for v in c["batch_input_shape"][1:])
+    present = layer_list if layer_list is not None else [k.split("/")[0] for k in weights]
+    kept = [i for i, n in enumerate(names) if n in present]
+    if not kept or "output/kernel" not in weights:
+        raise ValueError("not a cutoffvgg16 model: no VGG16 block layers / no 'output' Dense layer in the file")
+    cutoff = max(kept) + 2            # vgg16.layers[1:cutoff] keeps VGG16_LAYERS[:cutoff - 1]
+    if input_shape is None:
+        input_shape = (128, 128, 3)   # config.yml DATA.IMG_DIM default of the reference
+    return tuple(input_shape), int(weights["output/kernel"].shape[1]), cutoff, dropout
+
+
+def load_model(path, compile=False, device=None, input_shape=None):
+    """Counterpart of ``load_model(model_path, compile=False)`` (predict.py:50): ``.npz`` files written by save_model, or
+    a Keras HDF5 model / weights file (the format the reference's train.py writes)."""
     if not os.path.exists(path):
         raise FileNotFoundError(f"Could not find model weights at file path: {path}")
-    z = np.load(path)
-    cfg = {k[len("config/"):]: z[k] for k in z.files if k.startswith("config/")}
-    eng = CutoffVGG16Engine(tuple(int(v) for v in cfg["input_shape"]), int(cfg["n_classes"]), int(cfg["cutoff_layer"]),
-                            float(cfg["dropout"]), device=device)
+    if _is_hdf5(path):
+        weights, cfg, opt = read_keras_h5(path)
+        ishape, n_classes, cutoff, dropout = _arch_from_keras(weights, cfg, input_shape)
+    else:
+        z = np.load(path)
+        cfg = {k[len("config/"):]: z[k] for k in z.files if k.startswith("config/")}
+        ishape, n_classes = tuple(int(v) for v in cfg["input_shape"]), int(cfg["n_classes"])
+        cutoff, dropout = int(cfg["cutoff_layer"]), float(cfg["dropout"])
+        weights = {k[len("weights/"):]: z[k] for k in z.files if k.startswith("weights/")}
+        opt = {k[len("optimizer/"):]: z[k] for k in z.files if k.startswith("optimizer/")}
+    eng = CutoffVGG16Engine(ishape, n_classes, cutoff, dropout, device=device)
     model = B200Model(eng, eng.input_shape, eng.n_classes, eng.dropout)
-    model.set_weights({k[len("weights/"):]: z[k] for k in z.files if k.startswith("weights/")})
+    model.set_weights(weights)
+    if opt:
+        _restore_optimizer_state(eng, opt)     # resume: Adam / RMSprop slots, step counts, dropout counter
     return model
 
 
-def initialize_with_pretrained_weights(model, weights_path):
-    """model_utils.py:6-23: copy weights by layer name from a saved model into ``model``."""
-    assert os.path.exists(weights_path), f"Could not find model weights at file path: {weights_path}"
+def _stored_weights(weights_path):
+    if _is_hdf5(weights_path):
+        return read_keras_h5(weights_path)[0]
     z = np.load(weights_path)
-    have = {k[len("weights/"):]: z[k] for k in z.files if k.startswith("weights/")}
+    return {k[len("weights/"):]: z[k] for k in z.files if k.startswith("weights/")}
+
+
+def initialize_with_pretrained_weights(model, weights_path):
+    """model_utils.py:6-23: copy weights by layer name from a saved model (.npz or Keras .h5) into ``model``."""
+    assert os.path.exists(weights_path), f"Could not find model weights at file path: {weights_path}"
+    have = {(k[:-2] if k.endswith(":0") else k): v for k, v in _stored_weights(weights_path).items()}
     cur = model.get_weights()
     for k, v in have.items():
         if k in cur and cur[k].shape == v.shape:
@@ -447,7 +617,8 @@ class CutoffVGG16:
     """Drop-in for the reference class of the same name (src/models/models.py:387-444)."""
 
     def __init__(self, model_config, input_shape, metrics, n_classes, mixed_precision=False, output_bias=None,
-                 weights_path=None, device=None, seed=10001, rank=0, world_size=1, process_group=None):
+                 weights_path=None, device=None, seed=10001, rank=0, world_size=1, process_group=None,
+                 vgg16_weights=None):
         self.lr_extract = model_config['LR_EXTRACT']
         self.lr_finetune = model_config['LR_FINETUNE']
         self.dropout = model_config['DROPOUT']
@@ -465,6 +636,9 @@ class CutoffVGG16:
         self.mixed_precision = mixed_precision     # stored and unused, as in the reference (models.py:403)
         self.weights_path = weights_path
         self._engine_kw = dict(device=device, seed=seed, rank=rank, world_size=world_size, process_group=process_group)
+        # the reference builds on VGG16(weights='imagenet') (models.py:409, a download); offline, point this at the
+        # keras-applications file vgg16_weights_tf_dim_ordering_tf_kernels_notop.h5 (or its .npz conversion)
+        self.vgg16_weights = vgg16_weights if vgg16_weights is not None else os.environ.get("ABL_VGG16_WEIGHTS")
         self.model = self.define_model()
 
     def define_model(self):
@@ -473,6 +647,21 @@ class CutoffVGG16:
         model = B200Model(eng, self.input_shape, self.n_classes, self.dropout)
         # vgg16.layers[1:cutoff_layer] (models.py:410): conv AND pool layers, in Keras order
         self.vgg16_layers = [l for l in model.layers if l.kind in ("conv", "pool")]
+        if self.vgg16_weights:
+            # VGG16(weights='imagenet'): the convolutional base starts from the published filters (by layer name)
+            have = _stored_weights(self.vgg16_weights)
+            cur = model.get_weights()
+            missing = [k for k in cur if k.split("/")[0] != "output" and (k not in have or have[k].shape != cur[k].shape)]
+            if missing:
+                raise ValueError(f"{self.vgg16_weights}: no weights of the right shape for {missing}")
+            cur.update({k: have[k] for k in cur if k.split("/")[0] != "output"})
+            model.set_weights(cur)
+        elif self.weights_path is None:
+            import warnings
+            warnings.warn("CutoffVGG16: no pretrained VGG16 weights supplied (ABL_VGG16_WEIGHTS / vgg16_weights=...): the "
+                          "convolutional base is Glorot-initialised, whereas the reference starts from "
+                          "VGG16(weights='imagenet') (models.py:409).  Phase 1 then trains the head on random features.",
+                          stacklevel=3)
         if self.weights_path is not None:
             model = initialize_with_pretrained_weights(model, self.weights_path)
         return model

@@ -8,6 +8,12 @@ logits / probabilities / one training-step loss with oracle/oracle.py on the com
 the brightness constant, the projective-transform resampling and the metric definitions (section 8 f4).
 
     python oracle/keras_check.py            # prints PINNED ok / UNPINNED (TensorFlow missing) / mismatch
+    python oracle/keras_check.py --emit     # additionally writes tests/golden/keras_pinned_seed1234.npz (+ a real Keras
+                                            # .h5 of the same model): REAL Keras outputs on the committed golden frames --
+                                            # probabilities, logits, class-weighted loss, two weight gradients, one Adam and
+                                            # one RMSprop step.  Commit them: tests/test_oracle.py then checks the oracle
+                                            # against Keras itself in every environment, and the parity claim is pinned
+                                            # without TensorFlow in the image.
 """
 import os
 import sys
@@ -59,9 +65,42 @@ def main():
     loss_ref, _, _ = oracle.loss_and_grads(params, x, y, None, np.ones((len(x), 256), np.float32), dropout=0.0)
     print(f"categorical_crossentropy: Keras {loss_keras:.6f}  oracle {float(loss_ref):.6f}")
     ok = ok and dp < 1e-4 and abs(loss_keras - float(loss_ref)) < 1e-4
+    if "--emit" in sys.argv:
+        emit_golden(tf, model, layers, params, x, y)
     ok = pin_input_pipeline_and_metrics(tf) and ok
     print("PINNED ok" if ok else "MISMATCH between Keras and the oracle")
     return 0 if ok else 1
+
+
+def emit_golden(tf, model, layers, params, x, y):
+    """Real-Keras golden vectors for tests/test_oracle.py::test_oracle_matches_keras_golden_vectors (consumed when the
+    file exists).  Everything is computed by Keras/TF ops only; the oracle is not involved."""
+    cw = np.array([0.75, 1.5], np.float32)
+    xs = tf.constant(x)
+    with tf.GradientTape() as tape:
+        p = model(xs, training=False)
+        # Keras: loss = sum_i w_i * CCE_i / batch (class_weight -> sample weights, SUM_OVER_BATCH_SIZE; train.py:135-136)
+        li = tf.keras.losses.categorical_crossentropy(y, p)
+        loss = tf.reduce_sum(li * tf.reduce_sum(y * cw, axis=-1)) / float(len(x))
+    out_layer, c33 = model.get_layer("output"), [l for l in layers if l.name == "block3_conv3"][0]
+    g_out, g_c33k, g_c33b = tape.gradient(loss, [out_layer.kernel, c33.kernel, c33.bias])
+    logits = tf.keras.Model(model.inputs, out_layer.input)(xs, training=False).numpy() @ params["output/kernel"] + params["output/bias"]
+    # one optimizer step each on a small tensor (Keras 2.9 Adam / RMSprop defaults as models.py:397-398 builds them)
+    rng = np.random.default_rng(5)
+    th0, gr = rng.normal(size=64).astype(np.float32), (rng.normal(size=64) * 0.01).astype(np.float32)
+    steps = {}
+    for name, opt in (("adam", tf.keras.optimizers.Adam(learning_rate=3e-4)), ("rmsprop", tf.keras.optimizers.RMSprop(learning_rate=9.3e-6))):
+        v = tf.Variable(th0)
+        for _ in range(3):
+            opt.apply_gradients([(tf.constant(gr), v)])
+        steps[name] = v.numpy()
+    path = os.path.join(ROOT, "tests", "golden", "keras_pinned_seed1234.npz")
+    np.savez(path, probs=p.numpy(), logits=logits, loss_class_weighted=np.float32(loss.numpy()),
+             grad_output_kernel=g_out.numpy(), grad_block3_conv3_kernel=g_c33k.numpy(), grad_block3_conv3_bias=g_c33b.numpy(),
+             opt_theta0=th0, opt_grad=gr, adam_3_steps=steps["adam"], rmsprop_3_steps=steps["rmsprop"],
+             tf_version=np.array(tf.__version__), keras_version=np.array(tf.keras.__version__))
+    model.save(os.path.join(ROOT, "tests", "golden", "keras_cutoffvgg16_seed10001.h5"))     # a REAL Keras .h5 for the f3 reader
+    print("wrote", path, "and tests/golden/keras_cutoffvgg16_seed10001.h5")
 
 
 def pin_input_pipeline_and_metrics(tf):

@@ -87,14 +87,20 @@ def predict_with_contiguity_threshold(pred_probs, contiguity_threshold, classifi
     return np.array([1 - clip_pred, clip_pred])
 
 
-def highest_avg_contiguous_pred_prob(pred_probs, window):
-    '''Highest mean B-line probability over any `window` consecutive frames (predict.py:365-376); like the
-    reference's loop it is 0 when the clip has fewer than `window` frames.'''
-    pred_probs = np.asarray(pred_probs, np.float64)
-    if window <= 0 or len(pred_probs) < window:
-        return 0.0
-    c = np.concatenate([[0.0], np.cumsum(pred_probs)])
-    return float(max(0.0, np.max((c[window:] - c[:-window]) / window)))
+def highest_avg_contiguous_pred_prob(pred_probs, window_length):
+    '''
+    Highest mean B-line probability over any `window_length` consecutive frames (reference predict.py:365-376).
+    :param pred_probs [N, C]: framewise predictions for each class (column 1 = B-lines, as in the reference); a 1-D
+                              vector of B-line probabilities is accepted as an extension
+    :return: np.array([1 - m, m]) like the reference; m = 0 when the clip has fewer than `window_length` frames
+    '''
+    p = np.asarray(pred_probs, np.float64)
+    b = p[:, 1] if p.ndim == 2 else p
+    m = 0.0
+    if window_length > 0 and len(b) >= window_length:
+        c = np.concatenate([[0.0], np.cumsum(b)])
+        m = float(max(0.0, np.max((c[window_length:] - c[:-window_length]) / window_length)))
+    return np.array([1. - m, m])
 
 
 def compute_clip_predictions(model, preprocessing_func, clips, class_thresh=0.5, clip_algorithm='contiguous'):

@@ -60,13 +60,22 @@ def train_classifier(model_def, train_set, val_set, hparams, output_bias, class_
     model = model_def(hparams, input_shape, metrics, cfg['TRAIN']['N_CLASSES'],
                       mixed_precision=cfg['TRAIN']['MIXED_PRECISION'], output_bias=output_bias,
                       weights_path=pretrained_path)
-    callbacks = define_callbacks(cfg['TRAIN']['LOG_FREQ']) + list(extra_callbacks or [])
+    callbacks = define_callbacks(cfg['TRAIN'].get('LOG_FREQ')) + list(extra_callbacks or [])
     model.fit(train_set, epochs=cfg['TRAIN']['EPOCHS'] if epochs is None else epochs, validation_data=val_set,
               callbacks=callbacks, verbose=verbose, class_weight=class_weight)
     if save_weights:
         model_path = cfg['PATHS']['MODEL_WEIGHTS'] + 'model' + datetime.datetime.now().strftime("%Y%m%d-%H%M%S") + '.npz'
         save_model(model.model, model_path)
     return model
+
+
+def b200_options(config):
+    """(synthetic train frames, synthetic val frames, augment) from the optional B200 section of config.yml.  The section
+    is ours; the reference's own config.yml has none and gets these defaults (train set augmented, as train_utils.py:85
+    always does)."""
+    b200 = config.get('B200') or {}
+    return (int(b200.get('SYNTH_TRAIN_FRAMES', 2048)), int(b200.get('SYNTH_VAL_FRAMES', 256)),
+            bool(b200.get('AUGMENT', True)))
 
 
 def synthetic_datasets(n_train, n_val, preprocessing_fn, seed=1234):
@@ -77,7 +86,7 @@ def synthetic_datasets(n_train, n_val, preprocessing_fn, seed=1234):
     xtr, ltr = synth_frames(n_train, seed=seed)
     xva, lva = synth_frames(n_val, seed=seed + 1)
     preprocessor = Preprocessor(preprocessing_fn)
-    train = preprocessor.prepare((xtr, ltr), shuffle=True, augment=bool(cfg.get('B200', {}).get('AUGMENT', False)))
+    train = preprocessor.prepare((xtr, ltr), shuffle=True, augment=b200_options(cfg)[2])
     return train, preprocessor.prepare((xva, lva), shuffle=False, augment=False), ltr
 
 
@@ -87,8 +96,8 @@ def train_experiment(experiment='single_train', save_weights=False, epochs=None)
                                   "(cross_validation / hparam_search are W&B control plane)")
     model_def, preprocessing_fn = get_model(cfg['TRAIN']['MODEL_DEF'])
     hparams = cfg['HPARAMS'][cfg['TRAIN']['MODEL_DEF'].upper()]
-    train_set, val_set, labels = synthetic_datasets(cfg['B200']['SYNTH_TRAIN_FRAMES'], cfg['B200']['SYNTH_VAL_FRAMES'],
-                                                    preprocessing_fn)
+    n_train, n_val, _ = b200_options(cfg)
+    train_set, val_set, labels = synthetic_datasets(n_train, n_val, preprocessing_fn)
     model = train_classifier(model_def, train_set, val_set, hparams, compute_output_bias(labels),
                              compute_class_weight(labels), save_weights=save_weights, epochs=epochs)
     print(dict(zip(model.metrics_names, model.evaluate(val_set, verbose=0))))

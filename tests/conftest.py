@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+    # tests build random-init models on purpose; the product warns about that (the reference starts from ImageNet weights)
+    config.addinivalue_line("filterwarnings", "ignore:CutoffVGG16. no pretrained VGG16 weights supplied")
 
 
 @pytest.fixture(scope="session", autouse=True)

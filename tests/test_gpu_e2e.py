@@ -273,6 +273,34 @@ def test_gradcam_heatmaps_512_frame_clip_property_and_oracle(setup):
     assert (probs.cpu().numpy()[:3].argmax(-1) == ref_probs.argmax(-1)).all()
 
 
+def test_batch_256_logits_and_weight_gradients_against_the_oracle(setup):
+    """BASELINE configs[1] size, against the oracle rather than against the device itself: forward logits of all 256
+    frames and the weight / bias gradients of three layers (one per kernel family: the Cin = 64 wgrad with its ones-row
+    bias gradient, the generic wgrad fed by the dgrad epilogue's partial sums, the Dense head) from one training step
+    (bf16-faithful oracle on the host cores: ~30 s)."""
+    eng, params = setup
+    eng.set_weights(params)
+    x, y, _ = _frames(256, seed=31)
+    ref = oracle.forward(params, x, bf16=True, keep=("logits", "probs"))
+    eng.predict_batch(x)
+    logits = eng._buf["logits"][:256].cpu().numpy()
+    assert np.abs(logits - ref["logits"]).max() < TOL_BF16
+    margin = np.abs(ref["logits"][:, 0] - ref["logits"][:, 1])
+    sure = margin > 2 * TOL_BF16
+    assert (logits.argmax(-1)[sure] == ref["logits"].argmax(-1)[sure]).all() and sure.sum() > 128
+    mask = synth.dropout_mask(256, 256, 0.45)
+    tr = {"block2_conv1", "block3_conv2", "output"}
+    loss = eng.train_step(x, y, tr, keep_mask=mask, apply_update=False)
+    l_ref, g_ref, _ = oracle.loss_and_grads(params, x, y, None, mask, trainable=tr, bf16=True)
+    assert abs(float(loss.item()) - l_ref) < 2e-3
+    for layer in tr:
+        for part in ("kernel", "bias"):
+            name = f"{layer}/{part}"
+            got = eng.view(name, eng.grad).cpu().numpy()
+            assert np.abs(got - g_ref[name]).max() <= 3e-2 * np.abs(g_ref[name]).max(), name
+    eng.set_weights(params)
+
+
 def test_full_size_batches_size_independent_properties(setup):
     """BASELINE.json sizes (batch 256 training, batch 1024 inference) are beyond what the CPU oracle finishes in
     seconds, so they are checked through properties that do not need it:
@@ -299,27 +327,36 @@ def test_full_size_batches_size_independent_properties(setup):
     eng.set_weights(params)
 
 
-@pytest.mark.parametrize("H,W,cutoff", [(64, 64, 10), (256, 128, 10), (128, 128, 7), (96, 96, 10)])
+def test_img_dims_the_kernels_cannot_tile_raise_a_clear_error():
+    """96x96 frames give 24x24 block-3 maps, which the 8x16-pixel tiles of the tcgen05 kernels do not divide: the engine
+    must refuse the configuration up front, naming the config key, instead of mis-computing or failing inside a launch."""
+    from ab_line_classifier_b200.engine import CutoffVGG16Engine
+    from ab_line_classifier_b200.model import CutoffVGG16
+    with pytest.raises(NotImplementedError, match="DATA.IMG_DIM.*block3_conv1"):
+        CutoffVGG16Engine(input_shape=(96, 96, 3), cutoff_layer=10)
+    hp = {"LR_EXTRACT": 3e-4, "LR_FINETUNE": 9.3e-6, "DROPOUT": 0.45, "CUTOFF_LAYER": 10, "FINETUNE_LAYER": 7,
+          "EXTRACT_EPOCHS": 1}
+    with pytest.raises(NotImplementedError, match="DATA.IMG_DIM"):
+        CutoffVGG16(hp, [96, 96, 3], ["accuracy"], 2)
+    CutoffVGG16Engine(input_shape=(96, 96, 3), cutoff_layer=7)        # block-2 maps (48x48) tile fine: accepted
+
+
+@pytest.mark.parametrize("H,W,cutoff", [(64, 64, 10), (256, 128, 10), (128, 128, 7), (96, 96, 7), (128, 128, 14),
+                                        (64, 128, 13)])
 def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
     """config.yml DATA.IMG_DIM / HPARAMS.CUTOFFVGG16.CUTOFF_LAYER other than the graded 128x128 / 10: forward logits and
-    one training step's loss + gradients against the bf16-faithful oracle (96x96 exercises the v1 conv kernel and the
-    per-pixel gather of block1_conv1: its block-3 maps are 24x24, which 16-pixel-wide tiles do not divide)."""
+    one training step's loss + gradients against the bf16-faithful oracle.  96x96 / cutoff 7 exercises the v1 conv
+    kernel and non-power-of-two rows in block1_conv1; cutoff 13 / 14 reach the Cin = Cout = 512 layers of block 4 (two
+    N tiles per pixel tile, stand-alone bias-gradient pass, un-fused MaxPoolGrad for the 256-channel pool)."""
     from ab_line_classifier_b200.engine import CutoffVGG16Engine
     params = synth.randomize_biases(synth.glorot_weights(10001, cutoff_layer=cutoff))
-    try:
-        eng = CutoffVGG16Engine(input_shape=(H, W, 3), cutoff_layer=cutoff)
-    except NotImplementedError as e:
-        pytest.skip(str(e))
+    eng = CutoffVGG16Engine(input_shape=(H, W, 3), cutoff_layer=cutoff)
     eng.set_weights(params)
     rng = np.random.default_rng(H + W + cutoff)
     B = 4
     x = synth.vgg16_preprocess(rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8))
     y = synth.one_hot(np.arange(B) % 2)
-    try:
-        eng.predict_batch(x, use_graph=False)
-    except RuntimeError as e:          # shapes the kernels cannot tile are reported, never silently mis-computed
-        assert "abl_" in str(e)
-        pytest.skip(f"unsupported by the kernels: {e}")
+    eng.predict_batch(x, use_graph=False)
     logits = eng._buf["logits"][:B].cpu().numpy()
     ref = oracle.forward(params, x, cutoff_layer=cutoff, bf16=True)
     assert np.abs(logits - ref["logits"]).max() < TOL_BF16

@@ -149,9 +149,15 @@ def test_clip_aggregation_rules():
         probs = np.stack([1 - pb, pb], 1)
         np.testing.assert_array_equal(predict_with_contiguity_threshold(probs, 3, 0.5),
                                       clip_rules.contiguity_rule(probs, 3, 0.5))
-        assert highest_avg_contiguous_pred_prob(pb, 4) == pytest.approx(clip_rules.sliding_window_rule(probs, 4)[1])
-    assert highest_avg_contiguous_pred_prob([.1, .9, .8, .7, .6, .1], 4) == pytest.approx(0.75)
-    assert highest_avg_contiguous_pred_prob([.2, .4], 4) == 0.0        # no full window: the reference's loop never runs
+        # the reference contract (predict.py:365-376): [N, C] frame probabilities in, np.array([1 - m, m]) out
+        got = highest_avg_contiguous_pred_prob(probs, 4)
+        assert isinstance(got, np.ndarray) and got.shape == (2,)
+        np.testing.assert_allclose(got, clip_rules.sliding_window_rule(probs, 4), atol=1e-12)
+        np.testing.assert_allclose(highest_avg_contiguous_pred_prob(pb, 4), got, atol=1e-12)   # 1-D extension
+    two_d = np.array([[.9, .1], [.1, .9], [.2, .8], [.3, .7], [.4, .6], [.9, .1]])
+    np.testing.assert_allclose(highest_avg_contiguous_pred_prob(two_d, 4), [0.25, 0.75])
+    # no full window: the reference's loop never runs
+    np.testing.assert_array_equal(highest_avg_contiguous_pred_prob(np.array([[.8, .2], [.6, .4]]), 4), [1.0, 0.0])
 
 
 def test_engine_plan_and_unsupported_configs():
@@ -245,3 +251,201 @@ def test_array_dataset_data_parallel_shards_partition_every_global_batch():
         ArrayDataset(x, y, 6, world_size=4)
     with pytest.raises(ValueError):
         ArrayDataset(x, y, 8, rank=4, world_size=4)
+
+
+def _keras_style_h5(path, weights, legacy_names=False, as_weights_file=False, model_config=None):
+    """A file laid out like the ones Keras writes (save_model / save_weights / the keras-applications VGG16 notop file)."""
+    from ab_line_classifier_b200.h5lite import H5Writer
+    w = H5Writer()
+    g = w.root if as_weights_file else w.group(w.root, "model_weights")
+    layers = []
+    for k in weights:
+        if k.split("/")[0] not in layers:
+            layers.append(k.split("/")[0])
+    w.attr(g, "layer_names", np.array([n.encode() for n in layers + ["global_avgpool"]]))
+    w.attr(g, "backend", b"tensorflow")
+    if model_config is not None:
+        w.attr(w.root, "model_config", model_config.encode())
+    for ln in layers:
+        lg = w.group(g, ln)
+        names = []
+        for part in ("kernel", "bias"):
+            var = f"{ln}_{'W' if part == 'kernel' else 'b'}_1:0" if legacy_names else f"{ln}/{part}:0"
+            names.append(var)
+            parts = var.split("/")
+            node = lg
+            for p in parts[:-1]:
+                node = w.group(node, p)
+            w.dataset(node, parts[-1], weights[f"{ln}/{part}"])
+        w.attr(lg, "weight_names", np.array([n.encode() for n in names]))
+    w.group(g, "global_avgpool")        # a layer without weights, as Keras writes it
+    w.save(path)
+
+
+def test_h5lite_reads_what_it_writes_incl_many_links_and_attributes(tmp_path):
+    from ab_line_classifier_b200.h5lite import H5File, H5Writer
+    rng = np.random.default_rng(0)
+    w = H5Writer()
+    w.attr(w.root, "keras_version", b"2.9.0")
+    w.attr(w.root, "an_int", np.int64(7))
+    w.attr(w.root, "floats", np.arange(3, dtype=np.float64))
+    ref = {}
+    for i in range(37):                               # more links than one symbol-table node holds (8): several SNODs
+        a = rng.normal(size=(i % 4 + 1, 3)).astype(np.float32 if i % 2 else np.float64)
+        ref[f"g/d{i:02d}"] = a
+        w.create_path(f"g/d{i:02d}", a)
+    w.create_path("ints", np.arange(10, dtype=np.int32))
+    w.create_path("empty", np.zeros((0, 4), np.float32))
+    p = str(tmp_path / "t.h5")
+    w.save(p)
+    f = H5File(p)
+    assert f.keys() == ["empty", "g", "ints"] and f.attrs["keras_version"] == b"2.9.0" and int(f.attrs["an_int"]) == 7
+    np.testing.assert_array_equal(f.attrs["floats"], [0.0, 1.0, 2.0])
+    assert len(f["g"].keys()) == 37 and not f["g/d00"].is_group and "g/nope" not in f
+    for k, a in ref.items():
+        got = f[k].read()
+        assert got.dtype == a.dtype and np.array_equal(got, a)
+    np.testing.assert_array_equal(f["ints"].read(), np.arange(10))
+    assert f["empty"].read().shape == (0, 4)
+    assert [k for k, _ in f.visit_datasets()][:2] == ["empty", "g/d00"]
+    with pytest.raises(ValueError):
+        H5File(data=b"not an hdf5 file at all" * 40)
+
+
+def test_h5lite_reads_structures_the_writer_never_emits():
+    """Hand-assembled HDF5 structures the HDF5 C library produces but H5Writer does not: an object-header continuation
+    block, a version-3 attribute, a variable-length string through the global heap, a compact dataset and a chunked
+    dataset behind a version-1 chunk B-tree (all per the HDF5 file format specification)."""
+    import struct
+    from ab_line_classifier_b200 import h5lite as H
+    buf = bytearray(b"\0" * 96)
+
+    def alloc(b):
+        b = H._pad8(bytes(b))
+        a = len(buf)
+        buf.extend(b)
+        return a
+
+    # global heap collection holding the string b"hello world" as object 1
+    s = b"hello world"
+    gcol_body = struct.pack("<HHIQ", 1, 1, 0, len(s)) + H._pad8(s) + struct.pack("<HHIQ", 0, 0, 0, 0)
+    gcol = alloc(b"GCOL" + struct.pack("<B3xQ", 1, 16 + len(gcol_body)) + gcol_body)
+    # vlen-string attribute, message version 3 (no padding, charset byte)
+    vl_dt = struct.pack("<BBBBI", 0x19, 0x01, 0, 0, 16) + struct.pack("<BBBBI", 0x13, 0, 0, 0, 1)
+    ds_scalar = struct.pack("<BBBB", 2, 0, 0, 0)                       # dataspace v2, scalar
+    attr3 = struct.pack("<BBHHHB", 3, 0, 5, len(vl_dt), len(ds_scalar), 0) + b"note\0" + vl_dt + ds_scalar + \
+        struct.pack("<IQI", len(s), gcol, 1)
+    # chunked float32 dataset [5, 4] in chunks of [2, 4]: three chunks, the last one partial
+    data = np.arange(20, dtype=np.float32).reshape(5, 4)
+    chunks = []
+    for r0 in (0, 2, 4):
+        c = np.zeros((2, 4), np.float32)
+        c[: min(2, 5 - r0)] = data[r0:r0 + 2]
+        chunks.append((r0, alloc(c.tobytes())))
+    tree = b"TREE" + struct.pack("<BBHQQ", 1, 0, 3, H.UNDEF, H.UNDEF)
+    for r0, addr in chunks:
+        tree += struct.pack("<II", 32, 0) + struct.pack("<QQQ", r0, 0, 0) + struct.pack("<Q", addr)
+    tree += struct.pack("<II", 0, 0) + struct.pack("<QQQ", 6, 0, 0)
+    btree = alloc(tree)
+    layout = struct.pack("<BBB", 3, 2, 3) + struct.pack("<Q", btree) + struct.pack("<III", 2, 4, 4)
+    cont = alloc(H._msg(0x08, layout) + H._msg(0x0C, attr3))             # continuation block: layout + attribute
+    msgs = [H._msg(0x01, H._ds_bytes((5, 4))), H._msg(0x03, H._dt_bytes(np.float32)),
+            H._msg(0x10, struct.pack("<QQ", cont, len(buf) - cont))]
+    body = b"".join(msgs)
+    chunked = alloc(struct.pack("<BBHII4x", 1, 0, 5, 1, len(body)) + body)
+    # compact int16 dataset
+    small = np.array([3, -4, 5], np.int16)
+    lay_c = struct.pack("<BBH", 3, 0, small.nbytes) + small.tobytes()
+    body = b"".join([H._msg(0x01, H._ds_bytes((3,))), H._msg(0x03, H._dt_bytes(np.int16)), H._msg(0x08, lay_c)])
+    compact = alloc(struct.pack("<BBHII4x", 1, 0, 3, 1, len(body)) + body)
+    # root group: symbol table with the two datasets
+    heap = bytearray(b"\0" * 8)
+    offs = {}
+    for n in ("chunked", "compact"):
+        offs[n] = len(heap)
+        heap += H._pad8(n.encode() + b"\0")
+    heap_data = alloc(heap)
+    heap_addr = alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), H.UNDEF, heap_data))
+    ent = struct.pack("<QQII16x", offs["chunked"], chunked, 0, 0) + struct.pack("<QQII16x", offs["compact"], compact, 0, 0)
+    snod = alloc(b"SNOD" + struct.pack("<BBH", 1, 0, 2) + ent + b"\0" * (40 * 6))
+    gtree = alloc(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, H.UNDEF, H.UNDEF) + struct.pack("<QQQ", 0, snod, offs["compact"]))
+    body = H._msg(0x11, struct.pack("<QQ", gtree, heap_addr))
+    root = alloc(struct.pack("<BBHII4x", 1, 0, 1, 1, len(body)) + body)
+    sb = H.SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0) + \
+        struct.pack("<QQQQ", 0, H.UNDEF, len(buf), H.UNDEF) + struct.pack("<QQII", 0, root, 0, 0) + b"\0" * 16
+    buf[:len(sb)] = sb
+    f = H.H5File(data=bytes(buf))
+    assert f.keys() == ["chunked", "compact"]
+    np.testing.assert_array_equal(f["chunked"].read(), data)
+    assert f["chunked"].attrs["note"] == "hello world"
+    np.testing.assert_array_equal(f["compact"].read(), small)
+
+
+def test_keras_h5_checkpoints_load_by_layer_name(fake, tmp_path):
+    """f3: a model saved the way the reference saves it (Keras HDF5: model_weights/<layer>/<layer>/kernel:0, names with
+    ':0', layer_names / weight_names attributes) loads into the B200 path; so does a weights-only file with the legacy
+    variable names of the keras-applications VGG16 file; and save_model('...h5') writes that layout back."""
+    import json
+    src = model_mod.CutoffVGG16(HP, [8, 8, 3], [], 2, seed=3)
+    w = src.model.get_weights()
+    cfg = json.dumps(model_mod._keras_model_config(src.model))
+    full = str(tmp_path / "model.h5")
+    _keras_style_h5(full, w, model_config=cfg)
+    got, parsed, opt = model_mod.read_keras_h5(full)
+    assert sorted(got) == sorted(w) and opt == {} and parsed["class_name"] == "Functional"
+    for k in w:
+        np.testing.assert_array_equal(got[k], w[k])
+    m = model_mod.load_model(full)                       # architecture from model_config: 8x8 input, cutoff 4
+    assert m.engine.input_shape == (8, 8, 3) and m.engine.cutoff_layer == 4 and m.n_classes == 2
+    for k in w:
+        np.testing.assert_array_equal(m.get_weights()[k], w[k])
+    # weights-only file, legacy names (block1_conv1_W_1:0 / _b_1:0), layer groups at the root: by-name transplant
+    notop = str(tmp_path / "vgg16_notop.h5")
+    conv_only = {k: v + 1.0 for k, v in w.items() if not k.startswith("output")}
+    _keras_style_h5(notop, conv_only, legacy_names=True, as_weights_file=True)
+    m2 = model_mod.CutoffVGG16(HP, [8, 8, 3], [], 2, seed=9, vgg16_weights=notop)          # VGG16(weights='imagenet')
+    for k in conv_only:
+        np.testing.assert_array_equal(m2.model.get_weights()[k], conv_only[k])
+    m3 = model_mod.CutoffVGG16(HP, [8, 8, 3], [], 2, seed=9, weights_path=full)            # model_utils.py:6-23
+    for k in w:
+        np.testing.assert_array_equal(m3.model.get_weights()[k], w[k])
+    with pytest.warns(UserWarning, match="imagenet"):
+        model_mod.CutoffVGG16(HP, [8, 8, 3], [], 2)
+    # and back: save_model(..., '.h5') writes the Keras layout
+    out = model_mod.save_model(src.model, str(tmp_path / "saved.h5"))
+    from ab_line_classifier_b200.h5lite import H5File
+    f = H5File(out)
+    assert [n.decode() for n in f["model_weights"].attrs["layer_names"]][:2] == ["input", "block1_conv1"]
+    assert [n.decode() for n in f["model_weights/block1_conv1"].attrs["weight_names"]] == \
+        ["block1_conv1/kernel:0", "block1_conv1/bias:0"]
+    np.testing.assert_array_equal(f["model_weights/block1_conv1/block1_conv1/kernel:0"].read(), w["block1_conv1/kernel"])
+    m4 = model_mod.load_model(out)
+    for k in w:
+        np.testing.assert_array_equal(m4.get_weights()[k], w[k])
+
+
+def test_keras_fixture_file_converts_to_npz(tmp_path):
+    """tests/golden/keras_layout_cutoffvgg16_8x8.h5 (tests/golden/make_keras_layout_fixture.py) through the offline
+    converter tools/keras_h5_to_npz.py."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fix = os.path.join(root, "tests", "golden", "keras_layout_cutoffvgg16_8x8.h5")
+    dst = str(tmp_path / "conv.npz")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "keras_h5_to_npz.py"), fix, dst],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    z = np.load(dst)
+    assert int(z["config/cutoff_layer"]) == 4 and tuple(z["config/input_shape"]) == (8, 8, 3)
+    assert z["weights/block1_conv2/kernel"].shape == (3, 3, 64, 64) and z["weights/output/kernel"].shape == (64, 2)
+    exp = np.load(os.path.join(root, "tests", "golden", "keras_layout_cutoffvgg16_8x8_expected.npz"))
+    for k in exp.files:
+        np.testing.assert_array_equal(z["weights/" + k], exp[k])
+
+
+def test_b200_config_section_is_optional():
+    """src/train.py must run on the reference's own config.yml, which has no B200 section."""
+    from src.train import b200_options
+    assert b200_options({"TRAIN": {}, "B200": {"SYNTH_TRAIN_FRAMES": 64, "SYNTH_VAL_FRAMES": 8, "AUGMENT": False}}) == (64, 8, False)
+    assert b200_options({"TRAIN": {}}) == (2048, 256, True)
+    assert b200_options({"TRAIN": {}, "B200": None}) == (2048, 256, True)

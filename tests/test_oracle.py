@@ -3,6 +3,7 @@ The reference has no tests; these pin the restatement of Appendix A.
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import np_direct, oracle, synth
@@ -163,3 +164,35 @@ def test_keras_pinning_script_runs_and_reports_status():
                          text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert ("UNPINNED" in out.stdout) or ("PINNED ok" in out.stdout)
+
+
+KERAS_PIN = os.path.join(os.path.dirname(__file__), "golden", "keras_pinned_seed1234.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(KERAS_PIN), reason="parity UNPINNED: tests/golden/keras_pinned_seed1234.npz has not been "
+                    "emitted yet (run `python oracle/keras_check.py --emit` where TensorFlow 2.9 is installed and commit it)")
+def test_oracle_matches_keras_golden_vectors():
+    """Pins the oracle against REAL Keras outputs (emitted by oracle/keras_check.py --emit on a machine with TensorFlow):
+    probabilities, logits, class-weighted loss, gradients of block3_conv3 and the Dense head, and three Adam / RMSprop
+    steps.  fp32 against fp32: 1e-4 on probabilities / logits (different conv summation orders), 1e-6 on optimizers."""
+    k = np.load(KERAS_PIN)
+    g = np.load(GOLD)
+    x = synth.vgg16_preprocess(g["frames_u8"])
+    y = synth.one_hot(np.arange(len(x)) % 2)
+    params = synth.randomize_biases(synth.glorot_weights(10001))
+    fwd = oracle.forward(params, x)
+    assert np.abs(fwd["probs"] - k["probs"]).max() < 1e-4
+    assert np.abs(fwd["logits"] - k["logits"]).max() < 1e-3
+    assert (fwd["probs"].argmax(-1) == k["probs"].argmax(-1)).all()
+    loss, grads, _ = oracle.loss_and_grads(params, x, y, {0: 0.75, 1: 1.5}, np.ones((len(x), 256), np.float32), dropout=0.0)
+    assert abs(loss - float(k["loss_class_weighted"])) < 1e-4
+    for name, key in (("output/kernel", "grad_output_kernel"), ("block3_conv3/kernel", "grad_block3_conv3_kernel"),
+                      ("block3_conv3/bias", "grad_block3_conv3_bias")):
+        assert np.abs(grads[name] - k[key]).max() <= 1e-3 * np.abs(k[key]).max() + 1e-7, name
+    th_a, th_r = k["opt_theta0"].copy(), k["opt_theta0"].copy()
+    m = v = r = 0.0
+    for t in (1, 2, 3):
+        th_a, m, v = oracle.adam_step(th_a, k["opt_grad"], m, v, t)
+        th_r, r = oracle.rmsprop_step(th_r, k["opt_grad"], r)
+    np.testing.assert_allclose(th_a, k["adam_3_steps"], atol=1e-6)
+    np.testing.assert_allclose(th_r, k["rmsprop_3_steps"], atol=1e-7)

@@ -120,7 +120,9 @@ for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
          f"{float((d > 2e-5).float().mean()):.2e} of the weights differ by > 2e-5")
     if world == 2 and symm_saved is not None:
         assert exact, "2 ranks: fused peer-memory optimizer != NCCL all-reduce + optimizer"
-    assert float(d1.max()) < 1e-7, "fused peer-memory optimizer != NCCL all-reduce + optimizer after one step"
+    # more than two ranks: NCCL adds the ranks in ring/tree order, the fused kernel in rank order -- fp32 rounding of the
+    # gradient sum (~1e-7 relative), which the first normalised step turns into at most ~lr * 1e-9 / 3e-6 per weight
+    assert float(d1.max()) < (1e-7 if world == 2 else 1e-6), "fused peer-memory optimizer != NCCL all-reduce + optimizer after one step"
     assert float((d > 2e-5).float().mean()) < 5e-2 and float(d.median()) < 1e-6
     # (b) single-device training on the concatenated batch (world_size forced to 1): differs from DP only by the fp32
     #     order of the gradient sums -> one step within that noise; several steps as in (a).
