@@ -441,7 +441,8 @@ def _optimizer_state(eng):
     """Everything a resumed run needs besides the weights: optimizer slots (flat, engine layout), their step counts and
     the dropout step counter.  (The reference saves no optimizer state at all -- train.py:139-144 -- so a resumed Keras
     run restarts Adam's moments; here resume is exact.)"""
-    st = {"step_count": np.asarray(eng.step_count, np.int64)}
+    # dropout masks are a counter hash of (seed, step, rank, frame, channel): the seed belongs to the resumable state
+    st = {"step_count": np.asarray(eng.step_count, np.int64), "seed": np.asarray(getattr(eng, "seed", 0), np.int64)}
     for k, v in getattr(eng, "opt_state", {}).items():
         st["slot_" + k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
     for k, v in getattr(eng, "opt_steps", {}).items():
@@ -451,6 +452,8 @@ def _optimizer_state(eng):
 
 def _restore_optimizer_state(eng, st):
     eng.step_count = int(st.get("step_count", 0))
+    if "seed" in st:
+        eng.seed = int(st["seed"])
     for k, v in st.items():
         if k.startswith("slot_"):
             t = torch.from_numpy(np.ascontiguousarray(v, np.float32))
@@ -542,7 +545,7 @@ def read_keras_h5(path):
     if "b200_optimizer_state" in f:
         for k, d in f["b200_optimizer_state"].visit_datasets():
             v = d.read()
-            opt[k] = v if k.startswith("slot_") else v.reshape(-1)[0]
+            opt[k] = v if k.startswith("slot_") else v.reshape(-1)[0]      # scalars were stored as 1-element arrays
     return weights, cfg, opt
 
 

@@ -367,11 +367,16 @@ def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
     tr = set(eng.layer_names())
     loss = float(eng.train_step(x, y, tr, keep_mask=keep, apply_update=False).item())
     l_ref, g_ref, _ = oracle.loss_and_grads(params, x, y, None, keep, cutoff_layer=cutoff, bf16=True)
+    _, g_32, _ = oracle.loss_and_grads(params, x, y, None, keep, cutoff_layer=cutoff, bf16=False)
     assert abs(loss - float(l_ref)) < 1e-3 * max(1.0, abs(float(l_ref)))
     g = eng.grad.cpu().numpy()
     for name, (off, n, shape) in eng.segments.items():
         got, want = g[off:off + n].reshape(shape), g_ref[name]
-        assert np.abs(got - want).max() <= 3e-2 * (np.abs(want).max() + 1e-12), name
+        # 3 % of the tensor's largest gradient -- or, for the 10-conv prefixes (cutoff 13 / 14: bf16 rounding noise grows
+        # with every layer the gradient passes, 6-12 % at block1_conv1 with four frames), no further from the bf16-faithful
+        # oracle than bf16 rounding itself moves that oracle away from the fp32 one
+        bf16_noise = np.abs(g_32[name] - want).max()
+        assert np.abs(got - want).max() <= max(3e-2 * (np.abs(want).max() + 1e-12), 1.25 * bf16_noise), name
 
 
 def test_ragged_single_and_empty_batches(setup):
