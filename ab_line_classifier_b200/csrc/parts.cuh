@@ -9,7 +9,7 @@ namespace abl {
 
 // rows a producer of this library may write: pointwise kernels launch at most kPartWaves blocks per SM when they
 // produce partial sums (conv / wgrad kernels: one CTA per SM)
-constexpr int kPartWaves = 4;
+constexpr int kPartWaves = 8;
 
 // out[c] (+)= sum_r parts[HEADER + r*C + c], r in a fixed order: block = 4 float4 columns x 64 row groups; thread
 // (col, g) adds rows g, g+64, ... and the 64 group sums are combined in group order through shared memory.
