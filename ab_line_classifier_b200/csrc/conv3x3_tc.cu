@@ -213,27 +213,44 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
             tc_fence_before();
             mbar_arrive(arrive_bar);   // TMEM buffer may be overwritten by the next tile
         }
+        const int cbase = n0 + pass * kEpiN;
+        // un-pool: request this thread's routing codes of the pass now, so that the 2-byte loads overlap the barrier
+        // instead of sitting one by one on the critical path of the loop below (ncu: its first use was the kernel's top
+        // stall).  Slot k: q = et + 256 k -> tile row q / kCh16, chunk q % kCh16; two 16-bit codes per register.
+        constexpr int kUnpoolSlots = kTileM * (kEpiN / 8) / kEpiThreads;      // 4 (kEpiN 64) or 8 (kEpiN 128)
+        constexpr bool kCanUnpool = NTILE <= 128;         // the host never routes a 256-column tile through un-pool
+        uint32_t ucd[kUnpoolSlots / 2];
+        if (kCanUnpool && p.out_unpool != nullptr) {
+#pragma unroll
+            for (int k = 0; k < kUnpoolSlots; ++k) {
+                const int q = et + kEpiThreads * k;
+                const int r = q / (kEpiN / 8), cc = q - r * (kEpiN / 8);
+                const int ph = r / box_w, pw = r - ph * box_w;
+                const size_t pix = (static_cast<size_t>(img) * p.H + h0 + ph) * p.W + w0 + pw;
+                const uint32_t c16 = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((cbase >> 3) + cc));
+                ucd[k >> 1] = (k & 1) ? (ucd[k >> 1] | (c16 << 16)) : c16;
+            }
+        }
         fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
         named_bar_sync(1, kEpiThreads);     // staging filled
 
-        const int cbase = n0 + pass * kEpiN;
         if (p.out_full != nullptr && et == 0) {
 #pragma unroll
             for (int j = 0; j < kEpiN / 64; ++j)
                 tma_store_4d(map_out, stg + j * kABytes, cbase + j * 64, w0, h0, img);
             tma_store_commit();
         }
-        if (p.out_unpool != nullptr) {
+        if (kCanUnpool && p.out_unpool != nullptr) {
             // thread = (tile pixel, 8-channel chunk): consecutive threads cover one pixel's channels -> coalesced
             constexpr int kCh16 = kEpiN / 8;
             const size_t right = p.Cout, down = static_cast<size_t>(2 * p.W) * p.Cout;
-#pragma unroll 2
-            for (int q = et; q < kTileM * kCh16; q += kEpiThreads) {
+#pragma unroll
+            for (int k = 0; k < kUnpoolSlots; ++k) {
+                const int q = et + kEpiThreads * k;
                 const int r = q / kCh16, cc = q - r * kCh16;
                 const int ph = r / box_w, pw = r - ph * box_w;
                 const uint4 g = *reinterpret_cast<const uint4*>(stg + (cc >> 3) * kABytes + r * 128 + (((cc & 7) ^ (r & 7)) << 4));
-                const size_t pix = (static_cast<size_t>(img) * p.H + h0 + ph) * p.W + w0 + pw;
-                const uint32_t cd = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((cbase >> 3) + cc));
+                const uint32_t cd = (ucd[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
                 __nv_bfloat16* dst = p.out_unpool +
                     ((static_cast<size_t>(img) * 2 * p.H + 2 * (h0 + ph)) * (2 * p.W) + 2 * (w0 + pw)) * p.Cout + cbase + cc * 8;
                 unpool8_store(g, cd, dst, right, down);
@@ -682,24 +699,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ------------------------------------------------------------ epilogue (8 warps, 256 threads)
         const int et = threadIdx.x - 128;
         if constexpr (NTILE == 64 && MSUB == 2) {
-            // N = 64 is epilogue-latency-bound (1152 MMA clocks per sub-tile): the two sub-tiles of a tile are
-            // drained CONCURRENTLY by two independent groups of 4 warps (own staging buffer, own named barrier,
-            // own TMA-store thread), and the ReLU mask of the NEXT tile is prefetched while this one is processed.
+            // N = 64 is epilogue-bound (1152 MMA clocks per sub-tile; ncu round 2: 23 % of the dgrad kernel's stall
+            // samples sat on the two per-tile named barriers + proxy fence of a 4-warp group, 24 % of the un-pool
+            // kernel's on the dependent 2-byte routing-code loads).  So every WARP drains its own 32 accumulator rows
+            // = 2 image rows x 16 pixels of a sub-tile on its own: private 4 KiB staging slice, its own TMA store
+            // (box of 2 image rows), warp-level synchronisation only -- a 2x2 pooling window and an un-pool target
+            // never leave those two rows.  Warps 0-3 take sub-tile 0, warps 4-7 sub-tile 1.  The ReLU mask of the
+            // NEXT tile is prefetched while this one is processed; the routing codes of a tile are all requested
+            // before the first one is used.
             const int grp = et >> 7, gt = et & 127;
-            uint8_t* stg = staging + grp * Cfg::kStagingBytes;
+            const int lane = et & 31, wq = gt >> 5;              // warp within the group = image-row pair of the sub-tile
+            uint8_t* stg = staging + grp * Cfg::kStagingBytes + wq * 4096;      // this warp's 32 rows x 128 B
             uint4 mk[8];
             auto tile_origin = [&](int tile, int& img, int& h0, int& w0, int& n0) {
                 n0 = (tile % p.num_n_tiles) * NTILE;
                 int m_tile = tile / p.num_n_tiles;
                 w0 = (m_tile % p.tiles_w) * Cfg::kTileW;
                 m_tile /= p.tiles_w;
-                h0 = (m_tile % p.tiles_h) * kTileH + grp * Cfg::kSubH;
+                h0 = (m_tile % p.tiles_h) * kTileH + grp * Cfg::kSubH + 2 * wq;     // first image row of this WARP
                 img = m_tile / p.tiles_h;
             };
             auto load_mask = [&](int tile) {
                 int img, h0, w0, n0;
                 tile_origin(tile, img, h0, w0, n0);
-                const size_t off = ((static_cast<size_t>(img) * p.H + h0 + (gt >> 4)) * p.W + w0 + (gt & 15)) * p.Cout + n0;
+                const size_t off = ((static_cast<size_t>(img) * p.H + h0 + (lane >> 4)) * p.W + w0 + (lane & 15)) * p.Cout + n0;
                 const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
@@ -714,8 +737,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int as = it & 1;
                 mbar_wait(&tfull_bar[as], (it >> 1) & 1);
                 tc_fence_after();
-                if (gt == 0) tma_store_wait_read<0>();      // this group's previous store has finished reading stg
-                named_bar_sync(1 + grp, 128);
+                if (lane == 0) tma_store_wait_read<0>();    // this warp's previous store has finished reading its slice
+                __syncwarp();                               // ... and every lane is done with the previous tile's slice
                 const uint32_t tacc = tmem_base + (as * MSUB + grp) * NTILE + (static_cast<uint32_t>(gt & ~31) << 16);
                 uint32_t packed[2][16];
 #pragma unroll
@@ -755,27 +778,39 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                     if (tile + static_cast<int>(gridDim.x) < num_tiles) load_mask(tile + gridDim.x);   // next tile's mask
                 }
-                uint8_t* row = stg + gt * 128;
+                uint8_t* row = stg + lane * 128;            // slice row = lane: pixel (lane >> 4, lane & 15) of the row pair
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(row + ((j ^ (gt & 7)) << 4)) =
+                    *reinterpret_cast<uint4*>(row + ((j ^ (lane & 7)) << 4)) =
                         make_uint4(packed[j >> 2][(j & 3) * 4], packed[j >> 2][(j & 3) * 4 + 1],
                                    packed[j >> 2][(j & 3) * 4 + 2], packed[j >> 2][(j & 3) * 4 + 3]);
+                // un-pool: request all 8 routing codes of this lane now (`packed` is dead: no extra register pressure)
+                // -- slot k: slice row r = (lane >> 3) + 4 k, chunk cc = lane & 7 (the lane's chunk for the whole kernel)
+                uint32_t ucd[4] = {0u, 0u, 0u, 0u};
+                if (p.out_unpool != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = (lane >> 3) + 4 * k;
+                        const size_t pix = (static_cast<size_t>(img) * p.H + h0 + (r >> 4)) * p.W + w0 + (r & 15);
+                        const uint32_t c16 = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((n0 >> 3) + (lane & 7)));
+                        ucd[k >> 1] |= c16 << (16 * (k & 1));
+                    }
+                }
                 fence_proxy_async_smem();
-                named_bar_sync(1 + grp, 128);
-                if (p.out_full != nullptr && gt == 0) {
-                    tma_store_4d(&map_out, stg, n0, w0, h0, img);
+                __syncwarp();
+                if (p.out_full != nullptr && lane == 0) {
+                    tma_store_4d(&map_out, stg, n0, w0, h0, img);      // box = 64 channels x 16 pixels x 2 rows
                     tma_store_commit();
                 }
                 if (p.out_unpool != nullptr) {
                     const size_t right = p.Cout, down = static_cast<size_t>(2 * p.W) * p.Cout;
 #pragma unroll 2
-                    for (int q = gt; q < 128 * 8; q += 128) {        // q & 7 = this thread's chunk for the whole kernel
-                        const int r = q >> 3, cc = q & 7;
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = (lane >> 3) + 4 * k, cc = lane & 7;
                         const uint4 g = *reinterpret_cast<const uint4*>(stg + r * 128 + ((cc ^ (r & 7)) << 4));
                         const int hh = h0 + (r >> 4), ww = w0 + (r & 15);
-                        const size_t pix = (static_cast<size_t>(img) * p.H + hh) * p.W + ww;
-                        const uint32_t cd = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((n0 >> 3) + cc));
+                        const uint32_t cw = k < 4 ? (k < 2 ? ucd[0] : ucd[1]) : (k < 6 ? ucd[2] : ucd[3]);
+                        const uint32_t cd = (cw >> (16 * (k & 1))) & 0xFFFFu;
                         __nv_bfloat16* dst = p.out_unpool +
                             ((static_cast<size_t>(img) * 2 * p.H + 2 * hh) * (2 * p.W) + 2 * ww) * p.Cout + n0 + cc * 8;
                         unpool8_store(g, cd, dst, right, down);
@@ -788,11 +823,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                 }
                 if (p.out_pool != nullptr) {
+                    // the warp's two image rows hold 8 complete 2x2 windows: (window, chunk) = 64 items, 2 per lane
 #pragma unroll
-                    for (int q = gt; q < 32 * 8; q += 128) {
-                        const int prow = q >> 3, c8 = q & 7;
-                        const int ph = prow >> 3, pw = prow & 7;
-                        const int r00 = (2 * ph) * 16 + 2 * pw;
+                    for (int k = 0; k < 2; ++k) {
+                        const int q = lane + 32 * k;
+                        const int pw = q >> 3, c8 = q & 7;
+                        const int r00 = 2 * pw;
                         const int r01 = r00 + 1, r10 = r00 + 16, r11 = r10 + 1;
                         const uint4 a = *reinterpret_cast<const uint4*>(stg + r00 * 128 + ((c8 ^ (r00 & 7)) << 4));
                         const uint4 b = *reinterpret_cast<const uint4*>(stg + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
@@ -800,14 +836,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint4 d = *reinterpret_cast<const uint4*>(stg + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
                         uint32_t o[4], code;
                         pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
-                        const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1) + ph) * (p.W >> 1) +
+                        const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1)) * (p.W >> 1) +
                                             (w0 >> 1) + pw) * p.Cout + n0 + c8 * 8;
                         *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
                         if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
                     }
                 }
             }
-            if (gt == 0) tma_store_wait_all();
+            if (lane == 0) tma_store_wait_all();
             if (p.colsum != nullptr) {
                 // chunk sums of all 256 threads -> this CTA's row of the parts buffer, in a FIXED order: thread t parks
                 // its 8 sums in the (now idle) staging area, then channel c adds the 32 threads t with (t & 7) == c / 8
@@ -1349,7 +1385,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         if (out_full) {
             const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
             const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-            const uint32_t box[4] = {64, 16u, 8u, 1};
+            // N = 64: every epilogue warp stores its own 2 image rows (see the kernel); else one 8 x 16 sub-tile per store
+            const uint32_t box[4] = {64, 16u, ntile == 64 ? 2u : 8u, 1};
             int r = encode_tiled(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out_full, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (r != ABL_OK) return r;
         }
