@@ -50,7 +50,7 @@ SIGNATURES = {
     "abl_rmsprop_flat": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
     "abl_resize_nearest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_clip_aggregate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
-    "abl_opt_flat_dp": (_i, [_i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _f, _f, _f, _f, _vp]),
+    "abl_opt_flat_dp": (_i, [_i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _f, _f, _f, _f, _vp, _vp, _i, _vp]),
     "abl_augment_workspace_bytes": (_ll, [_i, _i, _i]),
     "abl_augment_frames": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "abl_metrics_counter_count": (_i, [_i, _i]),

@@ -603,7 +603,10 @@ struct PeerBufs {
 template <int kKind>   // 0 = Adam (p0 = alpha_t, p1 = beta1, p2 = beta2), 1 = RMSprop (p0 = lr, p1 = rho)
 __global__ void opt_flat_dp_kernel(const __grid_constant__ PeerBufs pb, float4* __restrict__ m, float4* __restrict__ v,
                                    long long lo4, long long hi4, int world, int rank, float p0, float p1, float p2,
-                                   float eps) {
+                                   float eps, const float* __restrict__ alpha_tab, const int* __restrict__ t_dev,
+                                   int tab_len) {
+    // CUDA-graph replays (Adam): alpha_t from the host-computed table, indexed by the device-side step count
+    if (kKind == 0 && alpha_tab != nullptr) p0 = alpha_tab[min(max(*t_dev, 1), tab_len) - 1];
     for (long long i = lo4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi4;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -960,7 +963,9 @@ extern "C" int abl_clip_aggregate(const float* probs, const long long* clip_offs
 
 extern "C" int abl_opt_flat_dp(int kind, float* const* theta_peers, const float* const* grad_peers, float* m_or_rms,
                                float* v, long long offset, long long n, int rank, int world, float lr_or_alpha,
-                               float b1_or_rho, float b2, float eps, void* stream) {
+                               float b1_or_rho, float b2, float eps, const float* alpha_tab, const int* t_dev,
+                               int tab_len, void* stream) {
+    if (alpha_tab && (!t_dev || tab_len <= 0)) { set_error("abl_opt_flat_dp: alpha_tab needs t_dev and tab_len"); return ABL_ERR_NULL; }
     if (!theta_peers || !grad_peers || !m_or_rms || (kind == 0 && !v)) { set_error("abl_opt_flat_dp: null pointer"); return ABL_ERR_NULL; }
     if (kind != 0 && kind != 1) { set_error("abl_opt_flat_dp: kind must be 0 (Adam) or 1 (RMSprop)"); return ABL_ERR_SHAPE; }
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("abl_opt_flat_dp: need 1 <= world <= 8"); return ABL_ERR_SHAPE; }
@@ -983,9 +988,11 @@ extern "C" int abl_opt_flat_dp(int kind, float* const* theta_peers, const float*
     const int grid = grid_for(hi4 - lo4, 256, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kind == 0)
-        opt_flat_dp_kernel<0><<<grid, 256, 0, st>>>(pb, m4, v4, lo4, hi4, world, rank, lr_or_alpha, b1_or_rho, b2, eps);
+        opt_flat_dp_kernel<0><<<grid, 256, 0, st>>>(pb, m4, v4, lo4, hi4, world, rank, lr_or_alpha, b1_or_rho, b2, eps,
+                                                    alpha_tab, t_dev, tab_len);
     else
-        opt_flat_dp_kernel<1><<<grid, 256, 0, st>>>(pb, m4, v4, lo4, hi4, world, rank, lr_or_alpha, b1_or_rho, b2, eps);
+        opt_flat_dp_kernel<1><<<grid, 256, 0, st>>>(pb, m4, v4, lo4, hi4, world, rank, lr_or_alpha, b1_or_rho, b2, eps,
+                                                    nullptr, nullptr, 0);
     return check_launch();
 }
 

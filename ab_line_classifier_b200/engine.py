@@ -118,6 +118,7 @@ class CutoffVGG16Engine:
         self._step_dev = self._t_dev = None
         self._dev_counters = None
         self.train_graphs = os.environ.get("ABL_TRAIN_GRAPHS", "1") != "0"
+        self.dp_graphs = os.environ.get("ABL_DP_GRAPHS", "1") != "0"      # whole-step graphs under data parallel
         # data parallel: all-reduce gradient buckets while backward still runs (True) or once after it (False).
         # Measured at 4 x B200, batch 256/GPU: 4.91 ms/step overlapped vs 4.68 ms after backward -- the persistent
         # conv kernels own every SM (1 CTA of ~220 KB shared memory each, static tile assignment), so a CTA whose SM
@@ -590,7 +591,8 @@ class CutoffVGG16Engine:
             for s, e in self._runs(trainable):
                 if fused:
                     ops.opt_flat_dp("adam", self._theta_peers, self._grad_peers, self.opt_state["m"],
-                                    self.opt_state["v"], s, e - s, self.rank, self.world_size, alpha, beta_1, beta_2, eps)
+                                    self.opt_state["v"], s, e - s, self.rank, self.world_size, alpha, beta_1, beta_2, eps,
+                                    alpha_tab=alpha_tab, t_dev=self._t_dev if alpha_tab is not None else None)
                 elif alpha_tab is not None:
                     ops.adam_flat_tab(self.theta[s:e], self.grad[s:e], self.opt_state["m"][s:e], self.opt_state["v"][s:e],
                                       alpha_tab, self._t_dev, beta_1, beta_2, eps)
@@ -723,12 +725,14 @@ class CutoffVGG16Engine:
     ALPHA_TABLE_LEN = 32768       # Adam alpha_t for t = 1..T (beyond T it equals lr to fp32 precision)
 
     def fit_step(self, trainable, optimizer, lr, slot, batch, global_batch, loss_out=None, **kw):
-        """What fit() does per batch: train_step on a staged slot + apply_optimizer.  For small batches on one GPU the
-        ~36 launches (forward, loss, backward, optimizer, operand re-cast) are captured ONCE per configuration into a
-        CUDA graph and replayed; the dropout step and the Adam step count advance in device memory."""
+        """What fit() does per batch: train_step on a staged slot + apply_optimizer.  For small batches the ~33
+        launches (forward, loss, backward, optimizer, operand re-cast) are captured ONCE per configuration into a CUDA
+        graph and replayed; the dropout step and the Adam step count advance in device memory.  Data parallel: the
+        captured step contains the two device-side barriers and the fused peer-memory optimizer kernel, so every
+        rank replays the same graph (all ranks see the same batch sizes, hence capture on the same step)."""
         trainable = frozenset(trainable)
-        eligible = (self.train_graphs and self.world_size == 1 and batch <= self.TRAIN_GRAPH_MAX_BATCH
-                    and batch <= self._cap and self._cap_train)
+        eligible = (self.train_graphs and (self.world_size == 1 or (self._symm is not None and self.dp_graphs))
+                    and batch <= self.TRAIN_GRAPH_MAX_BATCH and batch <= self._cap and self._cap_train)
         key = (batch, trainable, optimizer, float(lr), tuple(sorted(kw.items())), slot, self._slot_u8[slot],
                id(self._buf), float(global_batch)) if eligible else None
         if eligible:
@@ -768,8 +772,14 @@ class CutoffVGG16Engine:
                 self.forward_device(batch, training=True, y=b["y"][slot][:batch], inv_batch=1.0 / float(global_batch),
                                     loss_out=b["loss"], step_dev=self._step_dev)
                 self.backward_device(batch, trainable)
+                if self._symm is not None:
+                    self._grad_unreduced = True          # the fused optimizer sums the ranks' gradients itself
                 if optimizer == "adam":
                     self.apply_optimizer(optimizer, lr, trainable, alpha_tab=alpha_tab, **kw)
+                elif self._symm is not None:
+                    t_keep = self.opt_steps.get("rmsprop", 0)
+                    self.apply_optimizer(optimizer, lr, trainable, **kw)      # no step-dependent scalar in RMSprop
+                    self.opt_steps["rmsprop"] = t_keep                        # (the replay bookkeeping counts the step)
                 else:
                     self._apply_rmsprop_captured(lr, trainable, **kw)
             self._tgraphs = {k: v for k, v in self._tgraphs.items() if k[7] == id(self._buf)}

@@ -390,16 +390,18 @@ def clip_aggregate(probs, clip_offsets, b_idx, threshold, window):
 
 
 def opt_flat_dp(kind, theta_ptrs, grad_ptrs, m_or_rms, v, offset, n, rank, world, lr_or_alpha, b1_or_rho, b2=0.0,
-                eps=1e-7):
+                eps=1e-7, alpha_tab=None, t_dev=None):
     """Fused reduce-scatter(grad) -> Adam/RMSprop(shard) -> all-gather(theta) over peer pointers (abl_opt_flat_dp).
     theta_ptrs / grad_ptrs: lists of `world` device addresses (int) of every rank's flat buffers in this process."""
     import ctypes as C
     tp = (C.c_void_p * world)(*theta_ptrs)
     gp = (C.c_void_p * world)(*grad_ptrs)
     _chk(m_or_rms, torch.float32, "m_or_rms"); _chk(v, torch.float32, "v")
+    _chk(alpha_tab, torch.float32, "alpha_tab"); _chk(t_dev, torch.int32, "t_dev")
     _native.call("abl_opt_flat_dp", {"adam": 0, "rmsprop": 1}[kind], C.cast(tp, C.c_void_p), C.cast(gp, C.c_void_p),
                  _ptr(m_or_rms), _ptr(v), int(offset), int(n), int(rank), int(world), float(lr_or_alpha),
-                 float(b1_or_rho), float(b2), float(eps), _stream())
+                 float(b1_or_rho), float(b2), float(eps), _ptr(alpha_tab), _ptr(t_dev),
+                 0 if alpha_tab is None else alpha_tab.numel(), _stream())
 
 
 def gradcam(a, probs, w, heat):

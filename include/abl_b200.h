@@ -268,11 +268,12 @@ int abl_clip_aggregate(const float* probs, const long long* clip_offsets, int n_
  *   [offset, offset + n) of every buffer is processed (multiples of 4 floats).
  *   g = sum_r grad_r[i] in fixed rank order; theta updated with the local m_or_rms / v state (same offset); the new
  *   value is stored into every rank's theta.  Arguments as abl_adam_flat (lr_or_alpha = alpha_t, b1_or_rho = beta1)
- *   or abl_rmsprop_flat (lr, rho; b2 and v unused).
+ *   or abl_rmsprop_flat (lr, rho; b2 and v unused).  alpha_tab / t_dev / tab_len (Adam, may be NULL / 0): as in
+ *   abl_adam_flat_tab -- alpha_t read on the device, so the step can be replayed from a CUDA graph on every rank.
  * The caller must place a cross-rank barrier before (all gradients final) and after (all weights delivered). */
 int abl_opt_flat_dp(int kind, float* const* theta_peers, const float* const* grad_peers, float* m_or_rms, float* v,
                     long long offset, long long n, int rank, int world, float lr_or_alpha, float b1_or_rho, float b2,
-                    float eps, void* stream);
+                    float eps, const float* alpha_tab, const int* t_dev, int tab_len, void* stream);
 
 /* Grad-CAM of the predicted class for a GAP->Dense->softmax head (src/explainability/gradcam.py:68-81),
  * per frame: alpha_k = (1/HW) sum_j p_c (delta_cj - p_j) w[k][j]; heat = relu(mean_k alpha_k a[h,w,k]);

@@ -142,8 +142,34 @@ for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
     # (|g| ~ 1e-9) may move differently by a fraction of lr; everything else agrees to fp32 rounding
     assert float((d1 > 1e-7).float().mean()) < 1e-3 and float(d1.max()) <= 2.1 * lr
     assert frac_off < 5e-2 and float(d.median()) < 1e-6 and moved > 1e-4, (opt, diff, frac_off, moved)
+# ---- fit()'s per-batch step under data parallel replays a whole-step CUDA graph (forward, loss, backward, the two
+# device barriers, the fused peer-memory optimizer, operand re-cast): it must reproduce the eager steps bit for bit.
+if eng._symm is not None:
+    for opt, lr in (("adam", 3e-4), ("rmsprop", 1e-4)):
+        kw = {"beta_1": 0.9, "beta_2": 0.999, "eps": 1e-7} if opt == "adam" else {"rho": 0.9, "eps": 1e-7}
+        res = []
+        for use_graph in (False, True):
+            eng.set_weights(w0)
+            eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+            eng._tg_seen.clear(); eng._tgraphs.clear(); eng._dev_counters = None
+            eng.train_graphs = use_graph
+            eng.reserve(Bl, True)
+            losses = torch.zeros(6, device="cuda")
+            for i in range(6):
+                slot = eng.stage(x[sl], y[sl], slot=i & 1)
+                eng.fit_step(frozenset(tr), opt, lr, slot, Bl, G, loss_out=losses[i:i + 1], **kw)
+            torch.cuda.synchronize()
+            res.append((eng.theta.clone(), losses.clone(), len(eng._tgraphs)))
+        eng.train_graphs = True
+        same = torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        mark(f"{opt}: whole-step CUDA graph under DP ({res[1][2]} graphs captured) == eager steps bit for bit: {same}")
+        assert res[1][2] == 2 and res[0][2] == 0 and same
+        ths = [torch.empty_like(res[1][0]) for _ in range(world)]
+        dist.all_gather(ths, res[1][0])
+        assert all(torch.equal(ths[0], t) for t in ths), f"{opt}: graph replays diverged across ranks"
 eng.set_weights(w0)
-eng.opt_state.clear(); eng.opt_steps.clear()
+eng.opt_state.clear(); eng.opt_steps.clear(); eng.step_count = 0
+eng._tg_seen.clear(); eng._tgraphs.clear(); eng._dev_counters = None
 # ---- metric counters and epoch bookkeeping are summed over the ranks (every Keras metric is a ratio of counts)
 from ab_line_classifier_b200 import metrics as M  # noqa: E402
 plan = (M.auc_thresholds(200), np.full(2, 0.5, np.float32))
