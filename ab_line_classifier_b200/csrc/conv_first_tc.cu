@@ -42,6 +42,7 @@ struct FirstArgs {
     // staged-patch geometry (0 = tile shape not rectangular: per-thread global gather instead)
     int wt_log2;           // tile width = min(W, 128) = 1 << wt_log2 (tile = 128/wt rows x wt pixels)
     int patch_ok;
+    int w_log2, h_log2;    // log2(W), log2(H) when both are powers of two, else -1: shifts instead of per-tile divisions
 };
 
 constexpr int kF_PartRows = 55;                                // hi rows 0..26, lo rows 27..53, ones row 54
@@ -75,8 +76,14 @@ template <bool kU8>
 __device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t, const int (&code)[kF_PatchRegs],
                                             float (&r)[kF_PatchRegs]) {
     const long long pix0 = static_cast<long long>(tile) * kF_TileM;
-    const int c0 = static_cast<int>(pix0 % p.W);
-    const int h0 = static_cast<int>((pix0 / p.W) % p.H);
+    int c0, h0;
+    if (p.w_log2 >= 0) {       // ncu: the two 64-bit divisions per tile and thread were ~10 % of the kernel's instructions
+        c0 = static_cast<int>(pix0 & (p.W - 1));
+        h0 = static_cast<int>((pix0 >> p.w_log2) & (p.H - 1));
+    } else {
+        c0 = static_cast<int>(pix0 % p.W);
+        h0 = static_cast<int>((pix0 / p.W) % p.H);
+    }
     const int wt = 1 << p.wt_log2;
     // which borders of the frame this tile touches: an element on the matching patch border is zero padding
     const int edge = (h0 == 0 ? 8 : 0) | (h0 + (kF_TileM >> p.wt_log2) == p.H ? 16 : 0) | (c0 == 0 ? 32 : 0) |
@@ -166,9 +173,11 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
 // hi | lo << 16 of one input value: converted ONCE per input element when the patch is parked in shared memory
 // (the v1 gather converted every element 9 times, once per tap that touches it: 54 F2F per pixel).
 __device__ __forceinline__ uint32_t split_hi_lo(float v) {
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    return static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+    // the two-operand pack (F2FP.BF16.F32.PACK_AB) runs on the ALU pipe; the scalar F2F.BF16.F32 conversion it replaces
+    // was the kernel's top stall in the round-2 ncu source view.  Same round-to-nearest-even result.
+    const uint32_t hi = pack_bf16x2(v, 0.f) & 0xFFFFu;
+    const uint32_t lo = pack_bf16x2(v - __uint_as_float(hi << 16), 0.f) & 0xFFFFu;
+    return hi | (lo << 16);
 }
 
 // Same A rows as im2col_row, gathered from the packed shared-memory patch: 27 LDS + 27 byte-permutes per pixel.
@@ -207,20 +216,25 @@ __device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_
         if (blockIdx.x + static_cast<long long>(grp) * gridDim.x < p.num_tiles)
             patch_fetch<kU8>(p, blockIdx.x + grp * gridDim.x, row, code, nxt);
     }
+    int pbuf = 0;
     for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int stage = it % kF_Stages;
+        uint32_t* pcur = reinterpret_cast<uint32_t*>(patch) + pbuf * kF_PatchFloats;
         if (p.patch_ok) {
-            named_bar_sync(2 + grp, 128);                 // the previous tile's gather has finished reading the patch
+            // the patch is double buffered: this tile's values go to the buffer the tile BEFORE the previous one used
+            // (every thread passed the previous tile's barrier only after all threads had finished that older gather),
+            // so ONE named barrier per tile is enough (ncu round 2: 25 % of the stall samples were barrier waits)
 #pragma unroll
-            for (int k = 0; k < kF_PatchRegs; ++k) reinterpret_cast<uint32_t*>(patch)[row + 128 * k] = split_hi_lo(nxt[k]);
+            for (int k = 0; k < kF_PatchRegs; ++k) pcur[row + 128 * k] = split_hi_lo(nxt[k]);
             if (blockIdx.x + static_cast<long long>(it + kF_ProdGroups) * gridDim.x < p.num_tiles)
                 patch_fetch<kU8>(p, tile + kF_ProdGroups * gridDim.x, row, code, nxt);     // next tile: in flight
             named_bar_sync(2 + grp, 128);                 // patch complete
+            pbuf ^= 1;
         }
         mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
         if (p.patch_ok)
-            im2col_row_patch<kFwd>(reinterpret_cast<const uint32_t*>(patch), p.wt_log2, row, smem_a + stage * kStageBytes);
+            im2col_row_patch<kFwd>(pcur, p.wt_log2, row, smem_a + stage * kStageBytes);
         else
             im2col_row<kFwd, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kStageBytes);
         fence_proxy_async_smem();
@@ -316,13 +330,18 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
         const int row = (threadIdx.x - 128) & 127;       // tile row == TMEM lane (group base warp is a multiple of 4)
         const int grp = (threadIdx.x - 128) >> 7;
         uint8_t* stg = staging + grp * kF_ABlock;
+        // Every warp drains its own 32 accumulator rows = 32 consecutive raster pixels: private 4 KiB staging slice, its own
+        // TMA store (box of 32 pixels), warp-level synchronisation only (the group-wide named barriers of the first
+        // version showed up as the kernel's largest stall class).
+        const int lane = threadIdx.x & 31, wq = row >> 5;
+        uint8_t* stg_w = stg + wq * 4096;
         auto epilogue = [&](int it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int as = it % kF_AccBufs;
             mbar_wait(&tfull[as], (it / kF_AccBufs) & 1);
             tc_fence_after();
-            if (row == 0) tma_store_wait_read<0>();      // this group's previous store has finished reading stg
-            named_bar_sync(2 + grp, 128);
+            if (lane == 0) tma_store_wait_read<0>();     // this warp's previous store has finished reading its slice
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
@@ -334,24 +353,24 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
                     packed[j] = pack_bf16x2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(stg + row * 128 + (((c * 4 + j) ^ (row & 7)) << 4)) =
+                    *reinterpret_cast<uint4*>(stg_w + lane * 128 + (((c * 4 + j) ^ (lane & 7)) << 4)) =
                         make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);
             fence_proxy_async_smem();
-            named_bar_sync(2 + grp, 128);
-            if (row == 0) {
-                tma_store_2d(&map_out, stg, 0, tile * kF_TileM);
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&map_out, stg_w, 0, tile * kF_TileM + wq * 32);
                 tma_store_commit();
             }
         };
-        producer_loop<true, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp, epilogue);
+        producer_loop<true, kU8>(p, smem_a, patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, epilogue);
         // the last tile of this group has not been drained yet
         int n_here = 0;
         for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) ++n_here;
         if (n_here > 0) epilogue(grp + (n_here - 1) * kF_ProdGroups);
-        if (row == 0) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -433,7 +452,7 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
         {
             const int row = (threadIdx.x - 128) & 127;
             const int grp = (threadIdx.x - 128) >> 7;
-            producer_loop<false, kU8>(p, smem_a, patches + grp * kF_PatchFloats, afull, aempty, row, grp, [](int) {});
+            producer_loop<false, kU8>(p, smem_a, patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, [](int) {});
         }
         // D rows 0..63 live in TMEM lanes 0..63: warps 4 and 5 (lane quarters 0 and 1) drain them at the end
         const int row = threadIdx.x - 128;
@@ -518,13 +537,19 @@ static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W,
                    getenv("ABL_FIRST_GATHER") == nullptr) ? 1 : 0;
     a->wt_log2 = 0;
     while ((1 << a->wt_log2) < wt) ++a->wt_log2;
+    a->w_log2 = a->h_log2 = -1;
+    if ((W & (W - 1)) == 0 && (H & (H - 1)) == 0) {
+        a->w_log2 = a->h_log2 = 0;
+        while ((1 << a->w_log2) < W) ++a->w_log2;
+        while ((1 << a->h_log2) < H) ++a->h_log2;
+    }
     return ABL_OK;
 }
 
-static int pixel_map(CUtensorMap* m, const void* base, long long total_pix) {
+static int pixel_map(CUtensorMap* m, const void* base, long long total_pix, int box_rows) {
     const uint64_t dims[2] = {64, (uint64_t)total_pix};
     const uint64_t strides[1] = {128};
-    const uint32_t box[2] = {64, (uint32_t)kF_TileM};
+    const uint32_t box[2] = {64, (uint32_t)box_rows};
     return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -540,9 +565,9 @@ static int first_fwd(const void* x, const float* w_hwio, const float* bias, void
     if (r != ABL_OK) return r;
     a.w = w_hwio; a.bias = bias;
     CUtensorMap mo;
-    r = pixel_map(&mo, out, a.total_pix);
+    r = pixel_map(&mo, out, a.total_pix, 32);           // one store per epilogue warp: 32 pixels x 64 channels
     if (r != ABL_OK) return r;
-    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + kF_ProdGroups * kF_ABlock + 256 + kF_ProdGroups * kF_PatchFloats * 4;
+    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + kF_ProdGroups * kF_ABlock + 256 + kF_ProdGroups * 2 * kF_PatchFloats * 4;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -573,9 +598,9 @@ static int first_wgrad(const void* x, const void* dz, float* dw, float* db, void
     }
     a.part = static_cast<float*>(workspace);
     CUtensorMap mz;
-    r = pixel_map(&mz, dz, a.total_pix);
+    r = pixel_map(&mz, dz, a.total_pix, kF_TileM);
     if (r != ABL_OK) return r;
-    constexpr int smem_bytes = (2 * kF_Stages + 1) * kF_ABlock + 256 + kF_ProdGroups * kF_PatchFloats * 4;
+    constexpr int smem_bytes = (2 * kF_Stages + 1) * kF_ABlock + 256 + kF_ProdGroups * 2 * kF_PatchFloats * 4;
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
