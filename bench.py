@@ -134,8 +134,8 @@ def run_reference(args):
     t_all0 = time.perf_counter()
     # warm-up + timed "steps": each step is one B=32 train step (bounded sample of the B=256 workload)
     fps_list = []
-    n_iter = max(1, min(args.steps, 8))          # bounded sample: the whole arm ends within a few minutes
-    n_warm = max(1, min(args.warmup, 2))
+    n_iter = max(1, min(args.steps, 30))         # bounded sample (~0.35 s per step): the whole arm ends within a minute
+    n_warm = max(1, min(args.warmup, 5))
     fps, sec = cpu_train_frames_per_s(batch, n_iter, threads, n_warm)
     line = {
         "impl": "reference", "metric": "cutoffvgg16 train frames/sec", "value": fps, "unit": "frames/s",

@@ -618,4 +618,32 @@ def test_kernels_do_not_write_outside_their_output_buffers():
         rs, c15 = _guarded((B, 128, 128, 3), torch.uint8)
         ops.resize_nearest_u8(torch.randint(0, 256, (B, 77, 91, 3), generator=g, dtype=torch.uint8).cuda(), rs)
         c15("resize")
+        # partial-sum buffers sized EXACTLY abl_parts_bytes(C): the producers' per-CTA rows and the header must fit
+        for C, make in ((256, lambda pb: ops.conv3x3_igemm(x3, wd3, None, a3, dx3, None, ops.EPI_RELU_MASK, colsum_parts=pb)),
+                        (64, lambda pb: ops.conv3x3_dgrad_unpool(dz, wd2, pool, code, up, db_parts=pb)),
+                        (256, lambda pb: ops.gap_bwd_relu(torch.ones(B, 256, device="cuda"), a3, dx3, db_parts=pb)),
+                        (64, lambda pb: ops.maxpool_bwd_code(pool, code, dzf, db_parts=pb))):
+            pb, cp = _guarded((ops.parts_bytes(C) // 4,), torch.float32)
+            make(pb)
+            cp(f"parts buffer ({C} channels)")
+            rows = int(pb[:1].view(torch.int32).item())
+            assert 1 <= rows <= (ops.parts_bytes(C) // 4 - ops.PARTS_HEADER) // C
+            out = torch.empty(C, device="cuda")
+            ops.parts_reduce(pb, out)
+            _close(out, pb[ops.PARTS_HEADER:ops.PARTS_HEADER + rows * C].view(rows, C).double().sum(0).float(), 1e-5,
+                   "parts_reduce")
+        # block1_conv1 filter gradient: per-CTA workspace + fixed-order reduction
+        wsf, c16 = _guarded((ops.conv_first_wgrad_workspace_bytes(),), torch.uint8)
+        dw1, c17 = _guarded((3, 3, 3, 64), torch.float32); db1, c18 = _guarded((64,), torch.float32)
+        ops.conv_first_wgrad(frames, a1, dw1, db1, wsf)
+        c16("conv_first wgrad workspace"); c17("conv_first dw"); c18("conv_first db")
+        # head: loss workspace sized exactly abl_head_loss_ws_bytes(B)
+        lws, c19 = _guarded((int(ops._native.load().abl_head_loss_ws_bytes(B)) // 4,), torch.float32)
+        logits, c20 = _guarded((B, 2), torch.float32); probs, c21 = _guarded((B, 2), torch.float32)
+        loss, c22 = _guarded((1,), torch.float32)
+        yy = torch.zeros(B, 2, device="cuda"); yy[:, 0] = 1
+        ops.head_fwd(torch.rand(B, 256, device="cuda"), torch.randn(256, 2, device="cuda"), torch.zeros(2, device="cuda"),
+                     logits, probs, yy, None, 1.0 / B, loss, loss_ws=lws)
+        c19("head loss workspace"); c20("logits"); c21("probs"); c22("loss")
+        assert float(lws[0].view(torch.int32).item()) == 0        # the ticket reset itself for the next launch
     torch.cuda.synchronize()
