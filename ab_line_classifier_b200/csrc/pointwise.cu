@@ -35,27 +35,42 @@ struct PrepMulti {
     __nv_bfloat16* w_fwd[kMaxPrepLayers];
     __nv_bfloat16* w_dgrad[kMaxPrepLayers];
     int cin[kMaxPrepLayers], cout[kMaxPrepLayers];
+    int tile_end[kMaxPrepLayers];      // running total of 32x32 tiles (9 taps x Cin/32 x Cout/32 per layer)
+    int n_layers;
 };
-__global__ void prep_conv_weights_multi_kernel(const __grid_constant__ PrepMulti m) {
-    const int l = blockIdx.y;
-    const float* __restrict__ w = m.w[l];
+__global__ void __launch_bounds__(256)
+prep_conv_weights_multi_kernel(const __grid_constant__ PrepMulti m) {
+    // One block = one 32 (ci) x 32 (co) tile of one tap of one layer, transposed through shared memory: the fp32 source
+    // rows (co fastest) are read coalesced once, the dgrad copy (same orientation) and the forward copy (transposed) are
+    // both written coalesced.  (The first version indexed by output element and read the source with a stride of Cout
+    // floats: 21-25 us for 3.5 MB; this one is bound by launch latency.)
+    __shared__ float tile[32][33];
+    int l = 0, t = blockIdx.x;
+    while (l + 1 < m.n_layers && t >= m.tile_end[l]) ++l;
+    if (l > 0) t -= m.tile_end[l - 1];
+    const int Cin = m.cin[l], Cout = m.cout[l];
+    const int tiles_co = Cout >> 5, tiles_ci = Cin >> 5;
+    const int tap = t / (tiles_ci * tiles_co);
+    t -= tap * tiles_ci * tiles_co;
+    const int ci0 = (t / tiles_co) << 5, co0 = (t % tiles_co) << 5;
+    const int kh = tap / 3, kw = tap - kh * 3;
+    const float* __restrict__ w = m.w[l] + static_cast<size_t>(tap) * Cin * Cout;      // HWIO: tap = kh*3 + kw
     __nv_bfloat16* __restrict__ w_fwd = m.w_fwd[l];
     __nv_bfloat16* __restrict__ w_dgrad = m.w_dgrad[l];
-    const int Cin = m.cin[l], Cout = m.cout[l];
-    const int total = 9 * Cin * Cout;
-    // indexed by the OUTPUT element so that the 2-byte writes are coalesced (the strided fp32 reads hit L2):
-    // the per-layer kernel above scatters 2-byte writes Cin elements apart, which made this pass 25 us for 3.5 MB
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        if (w_dgrad) {      // w_dgrad[t'][ci][co], t' = (2-kw)*3 + (2-kh): same inner order as the HWIO source
-            const int co = i % Cout, ci = (i / Cout) % Cin, tp = i / (Cout * Cin);
-            const int kw = 2 - tp / 3, kh = 2 - (tp - (tp / 3) * 3);
-            w_dgrad[i] = __float2bfloat16_rn(w[(static_cast<size_t>(kh * 3 + kw) * Cin + ci) * Cout + co]);
-        }
-        if (w_fwd) {        // w_fwd[t'][co][ci], t' = kw*3 + kh
-            const int ci = i % Cin, co = (i / Cin) % Cout, tp = i / (Cout * Cin);
-            const int kw = tp / 3, kh = tp - kw * 3;
-            w_fwd[i] = __float2bfloat16_rn(w[(static_cast<size_t>(kh * 3 + kw) * Cin + ci) * Cout + co]);
-        }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const float v = w[static_cast<size_t>(ci0 + r) * Cout + co0 + tx];
+        tile[r][tx] = v;
+        // w_dgrad[t'][ci][co], t' = (2-kw)*3 + (2-kh): same inner order as the source
+        if (w_dgrad)
+            w_dgrad[(static_cast<size_t>((2 - kw) * 3 + (2 - kh)) * Cin + ci0 + r) * Cout + co0 + tx] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    if (w_fwd) {        // w_fwd[t'][co][ci], t' = kw*3 + kh
+#pragma unroll
+        for (int r = ty; r < 32; r += 8)
+            w_fwd[(static_cast<size_t>(kw * 3 + kh) * Cout + co0 + r) * Cin + ci0 + tx] = __float2bfloat16_rn(tile[tx][r]);
     }
 }
 
@@ -744,19 +759,20 @@ extern "C" int abl_prep_conv_weights_multi(const float* const* w_hwio, void* con
     if (!w_hwio || !w_fwd || !w_dgrad || !cin || !cout) { set_error("abl_prep_conv_weights_multi: null pointer"); return ABL_ERR_NULL; }
     if (n_layers <= 0 || n_layers > kMaxPrepLayers) { set_error("abl_prep_conv_weights_multi: 1..16 layers"); return ABL_ERR_SHAPE; }
     PrepMulti m;
-    int max_total = 0;
+    int tiles = 0;
     for (int l = 0; l < n_layers; ++l) {
-        if (!w_hwio[l] || (!w_fwd[l] && !w_dgrad[l]) || cin[l] <= 0 || cout[l] <= 0) {
-            set_error("abl_prep_conv_weights_multi: bad layer entry"); return ABL_ERR_NULL;
+        if (!w_hwio[l] || (!w_fwd[l] && !w_dgrad[l]) || cin[l] <= 0 || cout[l] <= 0 || (cin[l] & 31) || (cout[l] & 31)) {
+            set_error("abl_prep_conv_weights_multi: bad layer entry (Cin, Cout multiples of 32)"); return ABL_ERR_SHAPE;
         }
         m.w[l] = w_hwio[l];
         m.w_fwd[l] = static_cast<__nv_bfloat16*>(w_fwd[l]);
         m.w_dgrad[l] = static_cast<__nv_bfloat16*>(w_dgrad[l]);
         m.cin[l] = cin[l]; m.cout[l] = cout[l];
-        if (9 * cin[l] * cout[l] > max_total) max_total = 9 * cin[l] * cout[l];
+        tiles += 9 * (cin[l] >> 5) * (cout[l] >> 5);
+        m.tile_end[l] = tiles;
     }
-    const int bx = grid_for(max_total, 256, 4);
-    prep_conv_weights_multi_kernel<<<dim3(bx, n_layers), 256, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    m.n_layers = n_layers;
+    prep_conv_weights_multi_kernel<<<tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(m);
     return check_launch();
 }
 

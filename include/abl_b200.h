@@ -140,7 +140,8 @@ int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, flo
  *   w_dgrad[(2-kw)*3+(2-kh)][ci][co] = w[kh][kw][ci][co]   (180-degree rotated)      (either may be NULL) */
 int abl_prep_conv_weights(const float* w_hwio, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
 /* The same for n_layers (<= 16) layers in ONE launch (after each optimizer step); the five arrays are HOST
- * arrays of n_layers entries (device pointers / channel counts). */
+ * arrays of n_layers entries (device pointers / channel counts).  Cin and Cout must be multiples of 32 (32x32 tiles
+ * are transposed through shared memory so that the source and both copies are accessed coalesced). */
 int abl_prep_conv_weights_multi(const float* const* w_hwio, void* const* w_fwd, void* const* w_dgrad,
                                 const int* cin, const int* cout, int n_layers, void* stream);
 
