@@ -161,7 +161,7 @@ def main():
             by = next(pools)
         if by is None:
             continue
-        key = nme if nme != "abl_maxpool_bwd_relu" else f"{nme}[{a[6]}x{a[7]}x{a[8]}]"
+        key = nme if nme != "abl_maxpool_bwd_relu" else f"{nme}[{a[7]}x{a[8]}x{a[9]}]"
         hb[key] = {"ms": round(ms, 4), "alg_mbytes": round(by / 1e6, 1), "gbs": round(by / ms / 1e6, 1),
                    "frac_of_hbm_peak": round(by / ms / 1e6 / PEAKS["hbm_gbs"], 3)}
     out["hbm_bound_kernels_b256"] = hb
