@@ -322,6 +322,175 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-local epilogue of ONE 8 x 16-pixel sub-tile (128 accumulator rows x NTILE columns) for the haloed kernels with
+// N = 128 / 256.  Warp e of the 8 epilogue warps owns TMEM lanes 32*(e%4).. = two image rows of the sub-tile, and the
+// 64-column half e/4 of each 128-column pass: a 32-row x 128-byte slice of the swizzled staging area (4 KiB, exactly the
+// layout of a TMA box {64 channels, 16 pixels, 2 rows}).  The warp packs its slice, issues ITS OWN TMA store and does
+// the 2x2 max-pool / the un-pool scatter / the column sums of those two rows by itself -- a pooling window or an
+// un-pool target never leaves two image rows -- so the two 256-thread named barriers per pass of epilogue_tile (ncu
+// round 2: 17-22 % of the stall samples of the N = 128 kernels) become warp-level synchronisation.
+//   wsum   : this lane's running column sums (channels 2*lane, 2*lane+1 of the warp's 64 columns, per pass) for the
+//            fused bias gradient; the caller combines the four row-pair warps of a column in fixed order at the end
+//   gsum   : shared fp32 [4][128] exchange for the fused GlobalAveragePooling sums (the only cross-warp step: one
+//            named barrier pair per pass, in the last conv's forward only)
+template <int NTILE>
+__device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtensorMap* map_out, uint8_t* staging,
+                                                 uint32_t tmem_acc, int img, int h0, int w0, int n0, int et,
+                                                 uint64_t* wait_bar, uint32_t wait_phase, uint64_t* arrive_bar,
+                                                 float (&wsum)[NTILE / 128][2], long long next_origin, float* gap_row,
+                                                 float* gsum) {
+    constexpr int kEpiN = 128, kPasses = NTILE / kEpiN, kBoxW = 16;
+    const int lane = et & 31, quarter = (et >> 5) & 3, hsel = et >> 7;
+    const int lane_row = quarter * 32 + lane;                 // tile row == TMEM lane
+    const int ph_row = lane_row >> 4, pw_col = lane_row & 15;
+    const int hw0 = h0 + 2 * quarter;                         // first image row of this warp
+    const size_t pix_off = ((static_cast<size_t>(img) * p.H + h0 + ph_row) * p.W + w0 + pw_col) * p.Cout;
+    uint8_t* stg_w = staging + hsel * kABytes + quarter * 4096;       // this warp's 32 rows of 64-channel box `hsel`
+
+#pragma unroll 1
+    for (int pass = 0; pass < kPasses; ++pass) {
+        const int cw0 = n0 + pass * kEpiN + hsel * 64;        // first output channel of this warp in this pass
+        uint4 mk[8];
+        if (p.flags & ABL_EPI_RELU_MASK) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix_off + cw0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
+            const __nv_bfloat16* nx = nullptr;       // next pass: same pixel, next column block; then the next rectangle
+            if (pass + 1 < kPasses) nx = p.mask_src + pix_off + cw0 + kEpiN;
+            else if (next_origin >= 0)
+                nx = p.mask_src + next_origin + (static_cast<size_t>(ph_row) * p.W + pw_col) * p.Cout + n0 + hsel * 64;
+            if (nx != nullptr) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+            }
+        }
+        if (pass == 0 && wait_bar != nullptr) {
+            mbar_wait(wait_bar, wait_phase);
+            tc_fence_after();
+        }
+        if (lane == 0) tma_store_wait_read<0>();     // this warp's previous store has finished reading its slice
+        __syncwarp();                                // ... and every lane is done with the slice
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(lane_row & ~31) << 16) + pass * kEpiN + hsel * 64 + c * 32, r);
+            tmem_ld_wait();
+            uint32_t packed[16];
+            if (p.flags & ABL_EPI_BIAS_RELU) {
+                const float4* bs = reinterpret_cast<const float4*>(p.bias + cw0 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(bs + j);
+                    packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
+                                                fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
+                    packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
+                                                    fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    packed[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            }
+            if (p.flags & ABL_EPI_RELU_MASK) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t mm[4] = {mk[c * 4 + j].x, mk[c * 4 + j].y, mk[c * 4 + j].z, mk[c * 4 + j].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t lo_on = ((mm[k] & 0x7FFFu) != 0 && !(mm[k] & 0x8000u)) ? 0xFFFFu : 0u;
+                        const uint32_t hi_on =
+                            ((mm[k] & 0x7FFF0000u) != 0 && !(mm[k] & 0x80000000u)) ? 0xFFFF0000u : 0u;
+                        packed[4 * j + k] &= (lo_on | hi_on);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(stg_w + lane * 128 + (((c * 4 + j) ^ (lane & 7)) << 4)) =
+                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (pass == kPasses - 1 && arrive_bar != nullptr) {
+            tc_fence_before();
+            mbar_arrive(arrive_bar);   // TMEM buffer may be overwritten by the next tile
+        }
+        // un-pool: all 8 routing codes of this lane requested before the first is used (slot k: slice row
+        // r = (lane >> 3) + 4 k, 8-channel chunk cc = lane & 7 of the warp's 64 columns)
+        uint32_t ucd[4] = {0u, 0u, 0u, 0u};
+        if (NTILE <= 128 && p.out_unpool != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int r = (lane >> 3) + 4 * k;
+                const size_t pix = (static_cast<size_t>(img) * p.H + hw0 + (r >> 4)) * p.W + w0 + (r & 15);
+                const uint32_t c16 = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((cw0 >> 3) + (lane & 7)));
+                ucd[k >> 1] |= c16 << (16 * (k & 1));
+            }
+        }
+        fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA store
+        __syncwarp();                       // slice filled
+        if (p.out_full != nullptr && lane == 0) {
+            tma_store_4d(map_out, stg_w, cw0, w0, hw0, img);       // box = 64 channels x 16 pixels x 2 rows
+            tma_store_commit();
+        }
+        if (NTILE <= 128 && p.out_unpool != nullptr) {
+            const size_t right = p.Cout, down = static_cast<size_t>(2 * p.W) * p.Cout;
+#pragma unroll 2
+            for (int k = 0; k < 8; ++k) {
+                const int r = (lane >> 3) + 4 * k, cc = lane & 7;
+                const uint4 g = *reinterpret_cast<const uint4*>(stg_w + r * 128 + ((cc ^ (r & 7)) << 4));
+                const int hh = hw0 + (r >> 4), ww = w0 + (r & 15);
+                const uint32_t cw = k < 4 ? (k < 2 ? ucd[0] : ucd[1]) : (k < 6 ? ucd[2] : ucd[3]);
+                const uint32_t cd = (cw >> (16 * (k & 1))) & 0xFFFFu;
+                __nv_bfloat16* dst = p.out_unpool +
+                    ((static_cast<size_t>(img) * 2 * p.H + 2 * hh) * (2 * p.W) + 2 * ww) * p.Cout + cw0 + cc * 8;
+                unpool8_store(g, cd, dst, right, down);
+            }
+        }
+        if (p.colsum != nullptr || gap_row != nullptr) {
+            // column sums of this warp's 32 rows: lane = one packed word (2 channels) of every row (conflict-free: the
+            // 32 lanes read the 32 words of one 128-byte row)
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(stg_w + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                s0 += __uint_as_float(v << 16);
+                s1 += __uint_as_float(v & 0xFFFF0000u);
+            }
+            if (p.colsum != nullptr) { wsum[pass][0] += s0; wsum[pass][1] += s1; }
+            if (gap_row != nullptr) {
+                // GlobalAveragePooling partial sums of the whole 8 x 16 rectangle: the four row-pair warps of a column
+                // meet in shared memory and are added in fixed order (one writer per value -> deterministic)
+                gsum[quarter * 128 + hsel * 64 + 2 * lane] = s0;
+                gsum[quarter * 128 + hsel * 64 + 2 * lane + 1] = s1;
+                named_bar_sync(1, kEpiThreads);
+                if (et < kEpiN)
+                    gap_row[n0 + pass * kEpiN + et] = (gsum[et] + gsum[128 + et]) + (gsum[256 + et] + gsum[384 + et]);
+                named_bar_sync(1, kEpiThreads);
+            }
+        }
+        if (p.out_pool != nullptr) {
+            // the warp's two image rows hold 8 complete 2x2 windows x 8 chunks of 8 channels: 2 items per lane
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int q = lane + 32 * k;
+                const int pw = q >> 3, c8 = q & 7;
+                const int r00 = 2 * pw;
+                const int r01 = r00 + 1, r10 = r00 + kBoxW, r11 = r10 + 1;
+                const uint4 a = *reinterpret_cast<const uint4*>(stg_w + r00 * 128 + ((c8 ^ (r00 & 7)) << 4));
+                const uint4 b = *reinterpret_cast<const uint4*>(stg_w + r01 * 128 + ((c8 ^ (r01 & 7)) << 4));
+                const uint4 c2 = *reinterpret_cast<const uint4*>(stg_w + r10 * 128 + ((c8 ^ (r10 & 7)) << 4));
+                const uint4 d = *reinterpret_cast<const uint4*>(stg_w + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
+                uint32_t o[4], code;
+                pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
+                const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (hw0 >> 1)) * (p.W >> 1) + (w0 >> 1) + pw) * p.Cout +
+                                   cw0 + c8 * 8;
+                *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
+            }
+        }
+    }
+}
+
 // TAPS = taps consumed per pipeline stage.  TAPS == 1: stage = one tap x 64 channels (A 16 KiB + B).
 // TAPS == 3 (used for NTILE == 64, where 4 MMAs per stage cannot amortise the issuing thread's barrier wait
 // and the TMA instruction rate): tile = 4 x 32 pixels, stage = one kw x 64 channels; A is the tile plus one
@@ -507,7 +676,7 @@ struct HaloCfg {
     static constexpr int kStagingBytes = (kEpiN / 64) * kABytes;
     static constexpr int kStgBufs = NTILE == 64 ? 2 : 1;
     static constexpr int kAStages = 3;
-    static constexpr int kBarBytes = 2048;     // barriers (first 512 B) + fp32 column sums [NTILE] (fused bias grad)
+    static constexpr int kBarBytes = 4096;     // barriers (first 512 B) + fp32 [4][128] exchange of the fused GAP sums
     static constexpr int kBRoom = (227 * 1024 - kBarBytes - kStgBufs * kStagingBytes - kAStages * kAStage) / kBStage;
     static constexpr int kBStages = BRES ? 3 : (kBRoom > 8 ? 8 : kBRoom);     // BRES: 3 "stages" = the 3 kw groups
     static_assert(!BRES || (NTILE == 64 && kBRoom >= 3), "resident filter needs N = 64");
@@ -539,8 +708,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int kwkc = 3 * p.kchunks;                 // A stages per tile: (kw, 64-channel chunk)
-    if (p.colsum != nullptr)
-        for (int i = threadIdx.x; i < NTILE; i += blockDim.x) csum[i] = 0.f;
     constexpr int kTileH = Cfg::kSubH * MSUB;
 
     if (warp == 0 && elect_one()) {
@@ -862,7 +1029,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         } else {
         int it = 0;
-        uint32_t pass_ctr = 0;
+        float wsum[NTILE / 128][2];
+#pragma unroll
+        for (int q = 0; q < NTILE / 128; ++q) { wsum[q][0] = 0.f; wsum[q][1] = 0.f; }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int n_tile = tile % p.num_n_tiles;
             int m_tile = tile / p.num_n_tiles;
@@ -886,21 +1055,33 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         next_origin = ((static_cast<long long>(img2) * p.H + th2 * kTileH) * p.W + tw2 * Cfg::kTileW) * p.Cout;
                     }
                 }
-                epilogue_tile<NTILE, Cfg::kEpiN, Cfg::kStgBufs>(
+                epilogue_tile_wl<NTILE>(
                     p, &map_out, staging, tmem_base + (as * MSUB + sub) * NTILE, img, th * kTileH + sub * Cfg::kSubH,
-                    tw * Cfg::kTileW, n_tile * NTILE, Cfg::kTileW, et, pass_ctr, sub == 0 ? &tfull_bar[as] : nullptr,
-                    (it >> 1) & 1, sub == MSUB - 1 ? &tempty_bar[as] : nullptr, p.colsum != nullptr ? csum : nullptr,
-                    next_origin,
+                    tw * Cfg::kTileW, n_tile * NTILE, et, sub == 0 ? &tfull_bar[as] : nullptr, (it >> 1) & 1,
+                    sub == MSUB - 1 ? &tempty_bar[as] : nullptr, wsum, next_origin,
                     p.gap_part != nullptr
                         ? p.gap_part + ((static_cast<size_t>(img) * (p.H >> 3) + (th * kTileH >> 3) + sub) * p.tiles_w + tw) * p.Cout
-                        : nullptr);
+                        : nullptr,
+                    csum);
             }
         }
-        if (et == 0) tma_store_wait_all();   // all output tiles written before the CTA exits
-        if (p.colsum != nullptr) {           // one row per CTA (host guarantees a single N tile); no atomics
+        if ((et & 31) == 0) tma_store_wait_all();   // every warp's stores have been written before the CTA exits
+        if (p.colsum != nullptr) {
+            // one row per CTA (host guarantees a single N tile).  Each warp holds the sums of its row pair: they are
+            // parked in the (now idle) staging area and the four row-pair warps of a column are added in fixed order.
             named_bar_sync(1, kEpiThreads);
-            for (int i = et; i < NTILE; i += kEpiThreads)
-                p.colsum[ABL_PARTS_HEADER + static_cast<size_t>(blockIdx.x) * NTILE + i] = csum[i];
+            float* park = reinterpret_cast<float*>(staging);          // [pass][quarter][128 columns of the pass]
+            const int lane = et & 31, quarter = (et >> 5) & 3, hsel = et >> 7;
+#pragma unroll
+            for (int q = 0; q < NTILE / 128; ++q) {
+                park[(q * 4 + quarter) * 128 + hsel * 64 + 2 * lane] = wsum[q][0];
+                park[(q * 4 + quarter) * 128 + hsel * 64 + 2 * lane + 1] = wsum[q][1];
+            }
+            named_bar_sync(1, kEpiThreads);
+            for (int i = et; i < NTILE; i += kEpiThreads) {
+                const float* c4 = park + (i >> 7) * 512 + (i & 127);
+                p.colsum[ABL_PARTS_HEADER + static_cast<size_t>(blockIdx.x) * NTILE + i] = (c4[0] + c4[128]) + (c4[256] + c4[384]);
+            }
             if (blockIdx.x == 0 && et == 0) *reinterpret_cast<int*>(p.colsum) = static_cast<int>(gridDim.x);
         }
         }
@@ -1385,8 +1566,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         if (out_full) {
             const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
             const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-            // N = 64: every epilogue warp stores its own 2 image rows (see the kernel); else one 8 x 16 sub-tile per store
-            const uint32_t box[4] = {64, 16u, ntile == 64 ? 2u : 8u, 1};
+            // every epilogue warp stores its own 2 image rows x 16 pixels x 64 channels (see the kernels)
+            const uint32_t box[4] = {64, 16u, 2u, 1};
             int r = encode_tiled(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out_full, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (r != ABL_OK) return r;
         }
