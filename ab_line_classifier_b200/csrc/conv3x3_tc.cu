@@ -1325,13 +1325,19 @@ conv3x3_blk64_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             make_uint4(hm[4 * cc], hm[4 * cc + 1], hm[4 * cc + 2], hm[4 * cc + 3]);
                     hbits[(hsel * 128 + lane_row) * 2 + c] = bits;
                 }
-                named_bar_sync(1, kEpiThreads);                     // h-pooled rows and bits of the tile are in shared memory
-                const int npos = (kTileM / 2) * 2 * 8;              // (row pairs x blocks) x pixel pair x 8-channel chunks
-                for (int q = et; q < npos; q += kEpiThreads) {
-                    const int c8 = q & 7, pp = (q >> 3) & 1, pos = q >> 4;
-                    const int xb = pos % wb, rp = pos / wb;
+                // The vertical half of the pool pairs GEMM rows m and m + wb: only the 2*wb threads that hold one pair of
+                // image rows of one pixel-pair half have to meet (two warps at W = 128, one at W = 64) -- eight small
+                // named barriers instead of one over all 256 epilogue threads (ncu: 20 % barrier stalls).
+                const int gthreads = 2 * wb;                        // 64 or 32
+                const int gq = lane_row / gthreads, tg = lane_row - gq * gthreads;
+                const uint32_t bar_id = 1 + hsel * 4 + gq;
+                named_bar_sync(bar_id, gthreads);                   // h-pooled rows and bits of this row pair are in shared memory
+                const uint8_t* hb = staging + hsel * kABytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                       // (block, 8-channel chunk) of row pair gq: wb * 8 items
+                    const int q = tg + gthreads * k;
+                    const int c8 = q & 7, xb = q >> 3, rp = gq, pp = hsel;
                     const int m0 = (2 * rp) * wb + xb, m1 = m0 + wb;
-                    const uint8_t* hb = staging + pp * kABytes;
                     const uint4 t4 = *reinterpret_cast<const uint4*>(hb + m0 * 128 + ((c8 ^ (m0 & 7)) << 4));
                     const uint4 b4 = *reinterpret_cast<const uint4*>(hb + m1 * 128 + ((c8 ^ (m1 & 7)) << 4));
                     const uint32_t tb = (hbits[(pp * 128 + m0) * 2 + (c8 >> 2)] >> ((c8 & 3) * 8)) & 0xFFu;
@@ -1351,7 +1357,7 @@ conv3x3_blk64_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
                     if (p.pool_code != nullptr) p.pool_code[off >> 3] = static_cast<uint16_t>(code);
                 }
-                named_bar_sync(1, kEpiThreads);                     // the exchange buffers may be overwritten by the next tile
+                named_bar_sync(bar_id, gthreads);                   // the exchange rows may be overwritten by the next tile
             }
         }
     }
