@@ -53,7 +53,10 @@ struct ConvArgs {
     const uint16_t* unpool_code;    // [B,H,W,Cout/8]
     // fused GlobalAveragePooling partial sums: row (8x16-pixel rectangle index) x Cout fp32, plain stores (each value
     // has exactly one writer -> deterministic); abl_gap_reduce adds the rectangles of a frame in fixed order
-    float* gap_part;                // [B * (H/8) * (W/16)][Cout] or null
+    float* gap_part;                // [B * tiles_h * MSUB * tiles_w][Cout] or null (tiles rounded UP)
+    // the frame is not a whole number of tiles (haloed kernels): TMA zero-fills the loads and clips the stores; the
+    // epilogue zeroes accumulator rows that lie outside the frame and guards its non-TMA loads / stores
+    int partial;
 };
 
 // 2x2 max-pool of 8 channels (four packed bf16x2 words per window element) + optional routing code: for every
@@ -347,6 +350,7 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
     const int hw0 = h0 + 2 * quarter;                         // first image row of this warp
     const size_t pix_off = ((static_cast<size_t>(img) * p.H + h0 + ph_row) * p.W + w0 + pw_col) * p.Cout;
     uint8_t* stg_w = staging + hsel * kABytes + quarter * 4096;       // this warp's 32 rows of 64-channel box `hsel`
+    const bool valid = !p.partial || (h0 + ph_row < p.H && w0 + pw_col < p.W);      // this lane's pixel lies in the frame
 
 #pragma unroll 1
     for (int pass = 0; pass < kPasses; ++pass) {
@@ -355,12 +359,12 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
         if (p.flags & ABL_EPI_RELU_MASK) {
             const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + pix_off + cw0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
+            for (int j = 0; j < 8; ++j) mk[j] = valid ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u);
             const __nv_bfloat16* nx = nullptr;       // next pass: same pixel, next column block; then the next rectangle
             if (pass + 1 < kPasses) nx = p.mask_src + pix_off + cw0 + kEpiN;
             else if (next_origin >= 0)
                 nx = p.mask_src + next_origin + (static_cast<size_t>(ph_row) * p.W + pw_col) * p.Cout + n0 + hsel * 64;
-            if (nx != nullptr) {
+            if (nx != nullptr && !p.partial) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
             }
@@ -404,6 +408,11 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
                         packed[4 * j + k] &= (lo_on | hi_on);
                     }
                 }
+            } else if (!valid) {
+                // a row outside the frame holds sums over real neighbours: zero it, so that pooling, column sums and the
+                // GAP sums see nothing (the TMA store clips it anyway)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) packed[j] = 0u;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -421,6 +430,7 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int r = (lane >> 3) + 4 * k;
+                if (p.partial && (hw0 + (r >> 4) >= p.H || w0 + (r & 15) >= p.W)) continue;
                 const size_t pix = (static_cast<size_t>(img) * p.H + hw0 + (r >> 4)) * p.W + w0 + (r & 15);
                 const uint32_t c16 = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((cw0 >> 3) + (lane & 7)));
                 ucd[k >> 1] |= c16 << (16 * (k & 1));
@@ -439,6 +449,7 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
                 const int r = (lane >> 3) + 4 * k, cc = lane & 7;
                 const uint4 g = *reinterpret_cast<const uint4*>(stg_w + r * 128 + ((cc ^ (r & 7)) << 4));
                 const int hh = hw0 + (r >> 4), ww = w0 + (r & 15);
+                if (p.partial && (hh >= p.H || ww >= p.W)) continue;
                 const uint32_t cw = k < 4 ? (k < 2 ? ucd[0] : ucd[1]) : (k < 6 ? ucd[2] : ucd[3]);
                 const uint32_t cd = (cw >> (16 * (k & 1))) & 0xFFFFu;
                 __nv_bfloat16* dst = p.out_unpool +
@@ -482,6 +493,7 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
                 const uint4 d = *reinterpret_cast<const uint4*>(stg_w + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
                 uint32_t o[4], code;
                 pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
+                if (p.partial && (hw0 >= p.H || w0 + 2 * pw >= p.W)) continue;      // H, W even: a window is in or out as a whole
                 const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (hw0 >> 1)) * (p.W >> 1) + (w0 >> 1) + pw) * p.Cout +
                                    cw0 + c8 * 8;
                 *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -889,10 +901,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             auto load_mask = [&](int tile) {
                 int img, h0, w0, n0;
                 tile_origin(tile, img, h0, w0, n0);
+                const bool ok = !p.partial || (h0 + (lane >> 4) < p.H && w0 + (lane & 15) < p.W);
                 const size_t off = ((static_cast<size_t>(img) * p.H + h0 + (lane >> 4)) * p.W + w0 + (lane & 15)) * p.Cout + n0;
                 const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
+                for (int j = 0; j < 8; ++j) mk[j] = ok ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u);
             };
             const bool masked = (p.flags & ABL_EPI_RELU_MASK) != 0;
             float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // fused bias gradient of the un-pooled tensor
@@ -944,6 +957,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                     }
                     if (tile + static_cast<int>(gridDim.x) < num_tiles) load_mask(tile + gridDim.x);   // next tile's mask
+                } else if (p.partial && !(h0 + (lane >> 4) < p.H && w0 + (lane & 15) < p.W)) {
+                    // a row outside the frame: zero it for the pooling below (the TMA store clips it anyway)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { packed[0][j] = 0u; packed[1][j] = 0u; }
                 }
                 uint8_t* row = stg + lane * 128;            // slice row = lane: pixel (lane >> 4, lane & 15) of the row pair
 #pragma unroll
@@ -958,6 +975,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int r = (lane >> 3) + 4 * k;
+                        if (p.partial && (h0 + (r >> 4) >= p.H || w0 + (r & 15) >= p.W)) continue;
                         const size_t pix = (static_cast<size_t>(img) * p.H + h0 + (r >> 4)) * p.W + w0 + (r & 15);
                         const uint32_t c16 = __ldg(p.unpool_code + pix * (p.Cout >> 3) + ((n0 >> 3) + (lane & 7)));
                         ucd[k >> 1] |= c16 << (16 * (k & 1));
@@ -976,6 +994,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const int r = (lane >> 3) + 4 * k, cc = lane & 7;
                         const uint4 g = *reinterpret_cast<const uint4*>(stg + r * 128 + ((cc ^ (r & 7)) << 4));
                         const int hh = h0 + (r >> 4), ww = w0 + (r & 15);
+                        if (p.partial && (hh >= p.H || ww >= p.W)) continue;
                         const uint32_t cw = k < 4 ? (k < 2 ? ucd[0] : ucd[1]) : (k < 6 ? ucd[2] : ucd[3]);
                         const uint32_t cd = (cw >> (16 * (k & 1))) & 0xFFFFu;
                         __nv_bfloat16* dst = p.out_unpool +
@@ -1003,6 +1022,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint4 d = *reinterpret_cast<const uint4*>(stg + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
                         uint32_t o[4], code;
                         pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
+                        if (p.partial && (h0 >= p.H || w0 + 2 * pw >= p.W)) continue;      // H, W even: a window is in or out as a whole
                         const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1)) * (p.W >> 1) +
                                             (w0 >> 1) + pw) * p.Cout + n0 + c8 * 8;
                         *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1060,7 +1080,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     tw * Cfg::kTileW, n_tile * NTILE, et, sub == 0 ? &tfull_bar[as] : nullptr, (it >> 1) & 1,
                     sub == MSUB - 1 ? &tempty_bar[as] : nullptr, wsum, next_origin,
                     p.gap_part != nullptr
-                        ? p.gap_part + ((static_cast<size_t>(img) * (p.H >> 3) + (th * kTileH >> 3) + sub) * p.tiles_w + tw) * p.Cout
+                        ? p.gap_part + ((static_cast<size_t>(img) * (p.tiles_h * MSUB) + th * MSUB + sub) * p.tiles_w + tw) * p.Cout
                         : nullptr,
                     csum);
             }
@@ -1459,11 +1479,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
     }
     ConvArgs a;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
-    if (pick_box(H, W, &a.box_h, &a.box_w) != ABL_OK) {
-        set_error("abl_conv3x3_igemm: H x W cannot be tiled into 128-pixel rectangles (need W % 8 == 0 etc.)");
-        return ABL_ERR_SHAPE;
-    }
-    if (out_pool && (a.box_h & 1)) { set_error("abl_conv3x3_igemm: pooled output needs an even tile height"); return ABL_ERR_SHAPE; }
+    // v1 / blocked kernels need an exact tiling into 128-pixel rectangles; the haloed kernels below take any frame
+    const bool boxed = pick_box(H, W, &a.box_h, &a.box_w) == ABL_OK && !(out_pool && (a.box_h & 1));
     {
         // Blocked main loop (four pixels per GEMM row) for the pooled-only forward of a Cin = Cout = 64 layer
         // (block1_conv2 in training and inference).  ABL_BLOCKED64=0 falls back to the haloed kernel (A/B runs, tests).
@@ -1482,7 +1499,7 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
             a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
             a.pool_code = pool_code;
             a.colsum = nullptr;
-            a.out_unpool = nullptr; a.unpool_code = nullptr; a.gap_part = nullptr;
+            a.out_unpool = nullptr; a.unpool_code = nullptr; a.gap_part = nullptr; a.partial = 0;
             CUtensorMap ma, mb;
             {
                 const uint64_t dims[5] = {64, 4, (uint64_t)wb, (uint64_t)H, (uint64_t)B};
@@ -1522,9 +1539,16 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
     // -- without a ReLU-mask epilogue only: with one, the haloed kernel's next-tile mask prefetch wins (150 vs 157 us)
     const bool v1_better = ntile == 64 && Cin != 64 && !(flags & ABL_EPI_RELU_MASK) && (W % 32 == 0) && (H % 4 == 0) &&
                            !out_unpool && !gap_part && !(force_v1 && force_v1[0] == '0');
-    if (W % 16 == 0 && H % (8 * msub) == 0 && (!(force_v1 && force_v1[0] == '1') || out_unpool || gap_part) && !v1_better) {
+    // The haloed kernels take ANY frame size: tiles are counted rounding up, TMA zero-fills loads and clips stores beyond
+    // the frame, and the epilogue guards everything else (ConvArgs::partial).  Pooled / un-pooled outputs need even H, W.
+    // Frames v1 tiles exactly keep using it when the haloed tile does not fit (same kernels as before).
+    const bool exact = W % 16 == 0 && H % (8 * msub) == 0;
+    const bool want_halo = exact ? ((!(force_v1 && force_v1[0] == '1') || out_unpool || gap_part) && !v1_better)
+                                 : (out_unpool || gap_part || !boxed || (force_v1 && force_v1[0] == '0'));
+    if (want_halo) {
         a.box_w = 16; a.box_h = 8 * msub;
-        a.tiles_h = H / a.box_h; a.tiles_w = W / 16;
+        a.tiles_h = (H + a.box_h - 1) / a.box_h; a.tiles_w = (W + 15) / 16;
+        a.partial = exact ? 0 : 1;
         a.num_m_tiles = B * a.tiles_h * a.tiles_w;
         a.num_n_tiles = Cout / ntile;
         a.kchunks = Cin / kBlockK;
@@ -1594,8 +1618,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
             r = abl_bias_grad(out_full, colsum, colsum_bytes, static_cast<long long>(B) * H * W, Cout, stream);
         return r;
     }
-    if (out_unpool) { set_error("abl_conv3x3_dgrad_unpool: needs W % 16 == 0 and H % 16 == 0"); return ABL_ERR_SHAPE; }
-    if (gap_part) { set_error("abl_conv3x3_igemm_gap: needs W % 16 == 0 and H % 16 == 0 (H % 8 for Cout % 256 == 0)"); return ABL_ERR_SHAPE; }
+    if (!boxed) { set_error("abl_conv3x3_igemm: internal: the exact-tile kernel was chosen for a frame it cannot tile"); return ABL_ERR_SHAPE; }
+    a.partial = 0;
     a.colsum = nullptr;
     a.out_unpool = nullptr;
     a.unpool_code = nullptr;

@@ -38,7 +38,7 @@ struct FirstArgs {
     float* part;           // wgrad: per-CTA partial sums [gridDim.x][55][64] (rows 0..26 hi, 27..53 lo, 54 = bias)
     int H, W;
     long long total_pix;   // B*H*W
-    int num_tiles;         // total_pix / 128
+    int num_tiles;         // ceil(total_pix / 128)
     // staged-patch geometry (0 = tile shape not rectangular: per-thread global gather instead)
     int wt_log2;           // tile width = min(W, 128) = 1 << wt_log2 (tile = 128/wt rows x wt pixels)
     int patch_ok;
@@ -135,7 +135,7 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
     float v[27];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-        const bool hok = (hq + kh - 1) >= 0 && (hq + kh - 1) < p.H;
+        const bool hok = pix < p.total_pix && (hq + kh - 1) >= 0 && (hq + kh - 1) < p.H;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
             const bool ok = hok && (wq + kw - 1) >= 0 && (wq + kw - 1) < p.W;
@@ -518,9 +518,9 @@ conv_first_wgrad_reduce_kernel(const float4* __restrict__ part, int n_cta, float
 }
 
 static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W, int Cout, const char* who) {
-    if (B <= 0 || H <= 0 || W <= 0 || Cout != kF_Cout || (static_cast<long long>(B) * H * W) % kF_TileM != 0) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cout != kF_Cout) {
         char buf[160];
-        snprintf(buf, sizeof(buf), "%s: need Cout == 64 and B*H*W a multiple of 128", who);
+        snprintf(buf, sizeof(buf), "%s: need B, H, W > 0 and Cout == 64", who);
         set_error(buf);
         return ABL_ERR_SHAPE;
     }
@@ -528,7 +528,9 @@ static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W,
     a->x8 = u8 ? static_cast<const uint8_t*>(x) : nullptr;
     a->H = H; a->W = W;
     a->total_pix = static_cast<long long>(B) * H * W;
-    a->num_tiles = static_cast<int>(a->total_pix / kF_TileM);
+    // the last tile may be short (gather path only): its missing pixels read as zeros, TMA zero-fills dz rows beyond
+    // total_pix and clips the forward store
+    a->num_tiles = static_cast<int>((a->total_pix + kF_TileM - 1) / kF_TileM);
     a->w = nullptr; a->bias = nullptr; a->part = nullptr;
     // staged patch: a tile (128 raster pixels) must be a rectangle inside one frame
     const int wt = W < kF_TileM ? W : kF_TileM;

@@ -431,10 +431,12 @@ bias_grad_kernel(const uint4* __restrict__ dz, float* __restrict__ parts, long l
 static int wgrad_plan(int B, int H, int W, int Cin, int Cout, WgradArgs* a, int* nt_out) {
     if (B <= 0 || Cin % 64 != 0 || Cout % 64 != 0 || Cin > 512 || Cout > 512) return ABL_ERR_SHAPE;
     if (Cin != 64 && Cin % 128 != 0) return ABL_ERR_SHAPE;
-    if (W % kWgBw != 0 || H % kWgBh != 0) return ABL_ERR_SHAPE;
+    if (H <= 0 || W <= 0) return ABL_ERR_SHAPE;
     a->B = B; a->H = H; a->W = W; a->Cin = Cin; a->Cout = Cout;
     const int nt = (Cout % 128 == 0) ? 128 : 64;            // 3 accumulators x NT <= 512 TMEM columns
-    a->tiles_h = H / kWgBh; a->tiles_w = W / kWgBw;
+    // any frame size: tiles are counted rounding up; TMA zero-fills the pixels of x and dz beyond the frame, and a zero
+    // pixel adds nothing to either sum
+    a->tiles_h = (H + kWgBh - 1) / kWgBh; a->tiles_w = (W + kWgBw - 1) / kWgBw;
     a->num_ptiles = B * a->tiles_h * a->tiles_w;
     a->mode = Cin == 64 ? 1 : 0;
     a->ci_blocks = Cin == 64 ? 1 : Cin / 128;
@@ -524,8 +526,7 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
     WgradArgs a;
     int nt = 0;
     if (wgrad_plan(B, H, W, Cin, Cout, &a, &nt) != ABL_OK) {
-        set_error("abl_conv3x3_wgrad: unsupported shape (Cin 64 or a multiple of 128, Cout a multiple of 64, both <= 512; "
-                  "W % 16 == 0, H % 4 == 0)");
+        set_error("abl_conv3x3_wgrad: unsupported shape (Cin 64 or a multiple of 128, Cout a multiple of 64, both <= 512)");
         return ABL_ERR_SHAPE;
     }
     const long long need = wgrad_ws_dw_bytes(a) + wgrad_ws_rows_bytes(a) + abl_parts_bytes(Cout);

@@ -46,7 +46,8 @@ class ConvSpec:
 
 def build_plan(input_shape, cutoff_layer, check_tiling=False):
     """Conv specs for ``vgg16.layers[1:cutoff_layer]`` (models.py:410); a pool folds into the conv above it.
-    check_tiling: also require feature-map sizes the device kernels can tile (the engine sets it)."""
+    check_tiling: kept for callers of round 1; the device kernels now take any feature-map size (frames that are not a
+    whole number of 8 x 16-pixel tiles run with zero-padded partial tiles), so nothing extra is checked."""
     h, w, c = input_shape
     if c != 3:
         raise NotImplementedError("DATA.IMG_DIM must give 3-channel frames (VGG16 input)")
@@ -56,12 +57,6 @@ def build_plan(input_shape, cutoff_layer, check_tiling=False):
     specs = []
     for i, (name, kind, cout) in enumerate(kept):
         if kind == "conv":
-            if check_tiling and i > 0 and (w % 16 or h % 8):
-                # the tcgen05 kernels tile feature maps into 8 x 16 pixel rectangles (TMA boxes); other sizes would
-                # need partial tiles
-                raise NotImplementedError(
-                    f"DATA.IMG_DIM: the {h}x{w} input of {name} is not a multiple of 8x16 pixels "
-                    "(use image sides that are multiples of 64 for CUTOFF_LAYER 10)")
             specs.append(ConvSpec(name, c, cout, h, w, i))
             c = cout
         else:
@@ -281,7 +276,7 @@ class CutoffVGG16Engine:
         b["gap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
         last = self.specs[-1]
         if self.fuse_gap and not last.pool and ops.igemm_gap_supported(last.h, last.w, last.cout):
-            self._gap_parts = (last.h // 8) * (last.w // 16)
+            self._gap_parts = ops.igemm_gap_parts(last.h, last.w, last.cout)
             b["gap_part"] = torch.empty(cap * self._gap_parts, C, device=dev, dtype=torch.float32)
         b["logits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["probs"] = torch.empty(cap, n, device=dev, dtype=torch.float32)

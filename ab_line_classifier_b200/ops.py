@@ -105,8 +105,15 @@ def conv3x3_igemm(x, w_kmajor, bias=None, mask_src=None, out_full=None, out_pool
 
 
 def igemm_gap_supported(H, W, Cout):
-    """Shapes abl_conv3x3_igemm_gap handles."""
-    return W % 16 == 0 and Cout % 128 == 0 and (H % 8 == 0 if Cout % 256 == 0 else H % 16 == 0)
+    """Shapes abl_conv3x3_igemm_gap handles: any frame size (partial tiles are zero-padded), Cout % 128 == 0."""
+    return H > 0 and W > 0 and Cout % 128 == 0
+
+
+def igemm_gap_parts(H, W, Cout):
+    """8 x 16-pixel rectangles per frame in abl_conv3x3_igemm_gap's partial sums (tiles counted rounding up: the
+    kernel's tile is 8 rows for Cout % 256 == 0, else 16 rows = two rectangles)."""
+    msub = 1 if Cout % 256 == 0 else 2
+    return -(-H // (8 * msub)) * msub * -(-W // 16)
 
 
 def conv3x3_igemm_gap(x, w_kmajor, bias, out_full, gap_part):
@@ -115,7 +122,7 @@ def conv3x3_igemm_gap(x, w_kmajor, bias, out_full, gap_part):
     _chk(out_full, torch.bfloat16, "out_full"); _chk(gap_part, torch.float32, "gap_part")
     B, H, W, Cin = x.shape
     Cout = w_kmajor.shape[1]
-    assert gap_part.numel() >= B * (H // 8) * (W // 16) * Cout
+    assert gap_part.numel() >= B * igemm_gap_parts(H, W, Cout) * Cout
     _native.call("abl_conv3x3_igemm_gap", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(out_full), _ptr(gap_part), B, H, W,
                  Cin, Cout, _stream())
 
@@ -128,7 +135,7 @@ def gap_reduce(gap_part, gap, parts, hw):
 
 def dgrad_unpool_supported(H, W, Cout):
     """Shapes abl_conv3x3_dgrad_unpool handles (H, W = pooled resolution, Cout = channels of the pooled tensor)."""
-    return W % 16 == 0 and H % 16 == 0 and Cout % 64 == 0 and Cout <= 128
+    return H > 0 and W > 0 and Cout % 64 == 0 and Cout <= 128
 
 
 def conv3x3_dgrad_unpool(dz, w_dgrad, pooled, pool_code, dz_out, db=None, db_parts=None):

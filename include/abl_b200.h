@@ -69,19 +69,23 @@ int abl_parts_reduce(const float* parts, float* out, int C, int accumulate, void
  *   colsum_parts  parts buffer (see above) or NULL: partial sums over (n,h,w) of out_full[n,h,w,c] -- with the dgrad
  *            epilogue this is TF's BiasAddGrad of the layer below, fused so its dZ is not read a second time (needs
  *            out_full); colsum_parts_bytes = its capacity
- * Requires Cin, Cout multiples of 64 (<= 512), H*W tileable into 128-pixel rectangles. */
+ * Requires Cin, Cout multiples of 64 (<= 512); even H, W for out_pool.  ANY H x W: the kernels tile a frame into 8 x 16
+ * (or 16 x 16) pixel rectangles counted rounding up -- TMA zero-fills loads beyond the frame (= SAME padding) and clips
+ * the stores, and the epilogue keeps rows outside the frame out of the pooled output, the routing codes and every sum. */
 int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
                       void* out_full, void* out_pool, unsigned short* pool_code, float* colsum_parts,
                       long long colsum_parts_bytes, int B, int H, int W, int Cin, int Cout, int flags, void* stream);
 
 /* Forward conv + bias + ReLU (as abl_conv3x3_igemm with ABL_EPI_BIAS_RELU) of the LAST conv layer with Keras'
  * GlobalAveragePooling2D (models.py:414) fused in: the epilogue also writes the per-channel sums of every 8x16-pixel
- * rectangle it produces, gap_part fp32 [B * (H/8) * (W/16)][Cout] (one writer per value: deterministic), and
- * abl_gap_reduce adds a frame's rectangles in fixed order.  out_full may be NULL (inference without Grad-CAM: the
- * activation never reaches HBM).  Requires Cout % 128 == 0, W % 16 == 0, H % 16 == 0 (H % 8 if Cout % 256 == 0). */
+ * rectangle it produces, gap_part fp32 [B * parts][Cout] (one writer per value: deterministic), and abl_gap_reduce adds
+ * a frame's rectangles in fixed order.  parts = rectangles per frame, tiles counted rounding up:
+ *   Cout % 256 == 0: ceil(H/8) * ceil(W/16);   otherwise (16-row tiles): 2 * ceil(H/16) * ceil(W/16)
+ * (pixels outside the frame add 0).  out_full may be NULL (inference without Grad-CAM: the activation never reaches
+ * HBM).  Requires Cout % 128 == 0; any H, W. */
 int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full, float* gap_part, int B,
                           int H, int W, int Cin, int Cout, void* stream);
-/* gap[n][c] = (1/HW) * sum_{p < parts} gap_part[n*parts + p][c]   (parts = (H/8) * (W/16)) */
+/* gap[n][c] = (1/HW) * sum_{p < parts} gap_part[n*parts + p][c]   (parts as defined above) */
 int abl_gap_reduce(const float* gap_part, float* gap, int B, int parts, int C, int HW, void* stream);
 
 /* Conv2DBackpropInput + ReluGrad + MaxPoolGrad (+ BiasAddGrad) in ONE kernel, for a conv whose input is the output of a
@@ -91,7 +95,7 @@ int abl_gap_reduce(const float* gap_part, float* gap, int B, int parts, int C, i
  *   dz bf16 [B,H,W,Cin_gemm] (gradient of this conv's output); w_dgrad bf16 [9][Cout][Cin_gemm] (abl_prep_conv_weights);
  *   pooled bf16 [B,H,W,Cout], pool_code uint16 [B,H,W,Cout/8] (both from the forward abl_conv3x3_igemm of the layer
  *   below); dz_out bf16 [B,2H,2W,Cout]; db_parts: parts buffer or NULL receiving the partial sums of the routed
- *   gradients (BiasAddGrad of the layer below).  Requires Cout <= 128, W % 16 == 0, H % 16 == 0. */
+ *   gradients (BiasAddGrad of the layer below).  Requires Cout <= 128 (one N tile); any H, W. */
 int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, const void* pooled, const unsigned short* pool_code,
                              void* dz_out, float* db_parts, long long db_parts_bytes, int B, int H, int W, int Cin,
                              int Cout, void* stream);
@@ -101,7 +105,8 @@ int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, const void* po
  * and reduced in a fixed order (deterministic), fp32 accumulation:
  *   dw[kh][kw][ci][co] (+)= sum_{n,h,w} x[n,h+kh-1,w+kw-1,ci] * dz[n,h,w,co]   (HWIO fp32)
  *   db[co]               = sum_{n,h,w} dz[n,h,w,co]                            (if db != NULL; overwrites)
- * x bf16 [B,H,W,Cin], dz bf16 [B,H,W,Cout]; accumulate != 0 adds to dw, else overwrites it.
+ * x bf16 [B,H,W,Cin], dz bf16 [B,H,W,Cout]; accumulate != 0 adds to dw, else overwrites it.  Cin = 64 or a multiple
+ * of 128, Cout a multiple of 64, both <= 512; any H, W (4 x 16-pixel tiles counted rounding up, zero-filled by TMA).
  * db_parts: the parts buffer that the kernel which PRODUCED dz filled (abl_conv3x3_igemm colsum_parts,
  *   abl_conv3x3_dgrad_unpool, abl_gap_bwd_relu, abl_maxpool_bwd_*): the slice-reduction kernel of this call adds its rows
  *   into db.  NULL with db != NULL: the column sums come from this call itself (Cin == 64: a ones row of the GEMM; else a
@@ -116,7 +121,8 @@ int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float* db, const
 int abl_bias_grad(const void* dz, float* db_parts, long long db_parts_bytes, long long rows, int C, void* stream);
 
 /* block1_conv1 (Cin=3, K=27: HBM-bound, not tensor-core shaped).  Forward reads the caller's fp32
- * NHWC frame (already BGR / mean-subtracted, preprocessor.py:60-63) and writes bf16 relu(conv+b). */
+ * NHWC frame (already BGR / mean-subtracted, preprocessor.py:60-63) and writes bf16 relu(conv+b).  Any B, H, W (tiles
+ * are 128 raster pixels; the last one may be short). */
 int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H, int W,
                        int Cout, void* stream);
 /* dw[3][3][3][Cout] = ..., db[Cout] = ... (overwritten; db may be NULL) for block1_conv1 (x fp32 [B,H,W,3], dz bf16

@@ -46,7 +46,11 @@ def igemm_variant(request, monkeypatch):
 
 
 LAYERS = [(64, 64, 128, 128, True), (64, 128, 64, 64, False), (128, 128, 64, 64, True),
-          (128, 256, 32, 32, False), (256, 256, 32, 32, False)]
+          (128, 256, 32, 32, False), (256, 256, 32, 32, False),
+          # frames that are not a whole number of 8 x 16-pixel tiles (IMG_DIM 96, 100, 160, 224 ... give such block-2 / 3
+          # maps): partial tiles, zero-filled by TMA on load, clipped on store, guarded in the epilogue
+          (64, 64, 24, 40, True), (64, 128, 20, 20, False), (128, 128, 12, 24, True), (128, 256, 25, 25, False),
+          (256, 256, 24, 24, False), (256, 512, 10, 6, False), (128, 128, 56, 56, True)]
 
 
 @pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
@@ -218,7 +222,8 @@ def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B):
     assert torch.equal(dw, dw3), "wgrad must be deterministic (fixed-order slice reduction)"
 
 
-@pytest.mark.parametrize("B,H,W", [(3, 128, 128), (2, 64, 64), (1, 32, 256), (4, 16, 32), (2, 48, 96)])
+@pytest.mark.parametrize("B,H,W", [(3, 128, 128), (2, 64, 64), (1, 32, 256), (4, 16, 32), (2, 48, 96),
+                                   (3, 100, 100), (1, 25, 25), (2, 224, 224)])     # the last tile may be short
 @pytest.mark.parametrize("gather", ["patch", "global"])
 def test_conv_first_forward_and_wgrad_fp32(B, H, W, gather, monkeypatch):
     """Both im2col sources: the shared-memory patch prefetched one tile ahead (tiles that are rectangles of one frame:
@@ -325,7 +330,8 @@ def test_pool_routing_codes_reproduce_maxpool_backward_bit_exactly(cin, cout, H,
     assert torch.equal(code, code2)
 
 
-@pytest.mark.parametrize("cin,cout,H,W", [(64, 128, 64, 64), (128, 256, 32, 32)])
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 128, 64, 64), (128, 256, 32, 32), (64, 128, 12, 20), (128, 256, 24, 24),
+                                          (128, 256, 25, 25), (64, 64, 56, 56)])
 def test_dgrad_unpool_equals_dgrad_then_maxpool_backward(cin, cout, H, W):
     """abl_conv3x3_dgrad_unpool (dgrad + relu'(pooled) + MaxPoolGrad + BiasAddGrad in one kernel) vs the two-kernel
     path through the routing codes: bit-identical dZ, bias gradient equal up to fp32 order.  (cin = channels of the
@@ -351,7 +357,8 @@ def test_dgrad_unpool_equals_dgrad_then_maxpool_backward(cin, cout, H, W):
     _close(db, db_ref, 1e-4, "fused bias grad (dgrad + unpool)")
 
 
-@pytest.mark.parametrize("cin,cout,H,W", [(256, 256, 32, 32), (128, 128, 32, 64)])
+@pytest.mark.parametrize("cin,cout,H,W", [(256, 256, 32, 32), (128, 128, 32, 64), (256, 256, 24, 24), (128, 128, 20, 24),
+                                          (256, 256, 25, 25), (256, 256, 56, 56)])
 def test_conv_with_fused_gap_partial_sums(cin, cout, H, W):
     """abl_conv3x3_igemm_gap: same activation as the plain forward conv, and the epilogue's per-rectangle sums reduce
     to the GlobalAveragePooling of that (bf16) activation; with out_full = NULL the sums are unchanged (inference)."""
@@ -365,7 +372,7 @@ def test_conv_with_fused_gap_partial_sums(cin, cout, H, W):
     ops.prep_conv_weights(w.cuda(), wf, None)
     ref = torch.empty(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
     ops.conv3x3_igemm(x, wf, b, None, ref, None, ops.EPI_BIAS_RELU)
-    parts = (H // 8) * (W // 16)
+    parts = ops.igemm_gap_parts(H, W, cout)
     out = torch.full_like(ref, float("nan"))
     part = torch.full((B * parts, cout), float("nan"), device="cuda")
     ops.conv3x3_igemm_gap(x, wf, b, out, part)
@@ -537,11 +544,11 @@ def test_clip_aggregate_matches_reference_rules_bit_exactly_on_runs():
 
 def test_error_behaviour_bad_shapes_and_alignment():
     ops = _ops()
-    x = torch.zeros(1, 20, 20, 64, device="cuda", dtype=torch.bfloat16)       # 20x20 cannot be tiled
+    x = torch.zeros(1, 21, 20, 64, device="cuda", dtype=torch.bfloat16)       # a 2x2 pool needs even H and W
     w = torch.zeros(9, 64, 64, device="cuda", dtype=torch.bfloat16)
-    out = torch.zeros(1, 20, 20, 64, device="cuda", dtype=torch.bfloat16)
-    with pytest.raises(RuntimeError, match="abl_conv3x3_igemm"):
-        ops.conv3x3_igemm(x, w, None, None, out, None, 0)
+    pl = torch.zeros(1, 10, 10, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="even H, W"):
+        ops.conv3x3_igemm(x, w, torch.zeros(64, device="cuda"), None, None, pl, ops.EPI_BIAS_RELU)
     x = torch.zeros(1, 32, 32, 48, device="cuda", dtype=torch.bfloat16)       # Cin not a multiple of 64
     w = torch.zeros(9, 64, 48, device="cuda", dtype=torch.bfloat16)
     out = torch.zeros(1, 32, 32, 64, device="cuda", dtype=torch.bfloat16)
@@ -646,4 +653,40 @@ def test_kernels_do_not_write_outside_their_output_buffers():
                      logits, probs, yy, None, 1.0 / B, loss, loss_ws=lws)
         c19("head loss workspace"); c20("logits"); c21("probs"); c22("loss")
         assert int(lws[:1].view(torch.int32).item()) == 0        # the ticket reset itself for the next launch
+    # partial tiles: every output of a frame that is not a whole number of tiles stays inside its tensor
+    B = 2
+    x = (torch.randn(B, 24, 40, 64, generator=g) * 0.5).to(bf).cuda()
+    w = torch.randn(3, 3, 64, 64, generator=g) * 0.05
+    wf = torch.empty(9, 64, 64, device="cuda", dtype=bf); wd = torch.empty(9, 64, 64, device="cuda", dtype=bf)
+    ops.prep_conv_weights(w.cuda(), wf, wd)
+    full, c1 = _guarded((B, 24, 40, 64), bf); pool, c2 = _guarded((B, 12, 20, 64), bf)
+    code, c3 = _guarded((B, 12, 20, 8), torch.int16)
+    ops.conv3x3_igemm(x, wf, torch.zeros(64, device="cuda"), None, full, pool, ops.EPI_BIAS_RELU, pool_code=code)
+    c1("partial conv fwd full"); c2("partial conv fwd pooled"); c3("partial routing codes")
+    w2 = torch.randn(3, 3, 64, 128, generator=g) * 0.05
+    wd2 = torch.empty(9, 64, 128, device="cuda", dtype=bf)
+    ops.prep_conv_weights(w2.cuda(), None, wd2)
+    dz = (torch.randn(B, 12, 20, 128, generator=g) * 0.1).to(bf).cuda()
+    up, c4 = _guarded((B, 24, 40, 64), bf, fill=1); db, c5 = _guarded((64,), torch.float32)
+    ops.conv3x3_dgrad_unpool(dz, wd2, pool, code, up, db)
+    c4("partial dgrad unpool"); c5("partial fused bias grad")
+    x3 = (torch.randn(B, 25, 25, 256, generator=g) * 0.5).to(bf).cuda()
+    w3 = torch.randn(3, 3, 256, 256, generator=g) * 0.03
+    wf3 = torch.empty(9, 256, 256, device="cuda", dtype=bf); wd3 = torch.empty(9, 256, 256, device="cuda", dtype=bf)
+    ops.prep_conv_weights(w3.cuda(), wf3, wd3)
+    a3, c7 = _guarded((B, 25, 25, 256), bf)
+    part, c8 = _guarded((B * ops.igemm_gap_parts(25, 25, 256), 256), torch.float32)
+    ops.conv3x3_igemm_gap(x3, wf3, torch.zeros(256, device="cuda"), a3, part)
+    c7("partial igemm_gap activation"); c8("partial gap sums")
+    dx3, c9 = _guarded((B, 25, 25, 256), bf); cs, c10 = _guarded((256,), torch.float32)
+    ops.conv3x3_igemm(x3, wd3, None, a3, dx3, None, ops.EPI_RELU_MASK, colsum=cs)
+    c9("partial masked dgrad"); c10("partial column sums")
+    ws, c11 = _guarded((ops.wgrad_workspace_bytes(B, 25, 25, 256, 256),), torch.uint8)
+    dw, c12 = _guarded((3, 3, 256, 256), torch.float32)
+    ops.conv3x3_wgrad(x3, dx3, dw, None, ws)
+    c11("partial wgrad workspace"); c12("partial wgrad dw")
+    frames = (torch.rand(3, 25, 25, 3, generator=g) * 255 - 110).cuda()          # 1875 pixels: a short last tile
+    a1, c14 = _guarded((3, 25, 25, 64), bf)
+    ops.conv_first_fwd(frames, (torch.randn(3, 3, 3, 64, generator=g) * 0.1).cuda(), torch.zeros(64, device="cuda"), a1)
+    c14("short-tile conv_first fwd")
     torch.cuda.synchronize()

@@ -162,8 +162,13 @@ def test_clip_aggregation_rules():
 
 def test_engine_plan_and_unsupported_configs():
     from ab_line_classifier_b200.engine import build_plan
-    with pytest.raises(NotImplementedError, match="IMG_DIM"):
-        build_plan((96, 96, 3), 10, check_tiling=True)           # block3 maps would be 24x24: not tileable into 8x16 rectangles
+    with pytest.raises(NotImplementedError, match="IMG_DIM.*block2_pool"):
+        build_plan((90, 90, 3), 10)                              # 45x45 block-2 maps: the 2x2 pool would drop a row
+    specs, feat = build_plan((96, 96, 3), 10, check_tiling=True)     # 24x24 block-3 maps: partial 8x16-pixel tiles
+    assert feat == (24, 24, 256)
+    from ab_line_classifier_b200.ops import igemm_gap_parts
+    assert igemm_gap_parts(32, 32, 256) == 8 and igemm_gap_parts(24, 24, 256) == 6 and igemm_gap_parts(25, 25, 256) == 8
+    assert igemm_gap_parts(32, 64, 128) == 16 and igemm_gap_parts(20, 24, 128) == 8      # 16-row tiles = 2 rectangles
     specs, feat = build_plan((128, 128, 3), 10)
     assert [s.name for s in specs] == ["block1_conv1", "block1_conv2", "block2_conv1", "block2_conv2",
                                        "block3_conv1", "block3_conv2", "block3_conv3"]
