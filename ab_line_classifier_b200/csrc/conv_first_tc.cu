@@ -310,10 +310,11 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
                 mbar_wait(&afull[stage], phase);
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + stage * ((2 * kF_ABlock) >> 4);
+                // k-block 0 holds 55 slots (4 K = 16 steps), k-block 1 only 28 (2 steps): its upper half is all zeros
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < (kb == 0 ? 4 : 2); ++k)
                         umma_bf16_lohi(tmem_base + as * 64, a_lo + kb * (kF_ABlock >> 4) + k * 2, dhi,
                                        b_lo0 + kb * ((64 * 128) >> 4) + k * 2, dhi, idesc, (kb | k) ? 1u : 0u);
                 umma_commit(&aempty[stage]);
