@@ -28,6 +28,7 @@ constexpr int kF_Threads = 512;               // warps 0-3 control, 4-15 = 3 wor
 constexpr int kF_Stages = 4;
 constexpr int kF_ProdGroups = 3;              // worker group g owns the CTA's tiles g, g+3, g+6, ...: it builds the im2col
                                               // rows and (forward) drains the accumulator of its previous tile
+constexpr int kF_TsCols = 48;                // tensor-memory columns of one A stage (96 bf16 slots per row)
 constexpr int kF_AccBufs = 4;                 // forward TMEM accumulators (64 columns each)
 
 struct FirstArgs {
@@ -74,7 +75,7 @@ __device__ __forceinline__ int patch_code(const FirstArgs& p, int e) {
 // Issue this thread's loads of tile `tile`'s patch (values land in r[]; nothing waits here).
 template <bool kU8>
 __device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t, const int (&code)[kF_PatchRegs],
-                                            float (&r)[kF_PatchRegs]) {
+                                            uint32_t (&r)[kF_PatchRegs]) {
     const long long pix0 = static_cast<long long>(tile) * kF_TileM;
     int c0, h0;
     if (p.w_log2 >= 0) {       // ncu: the two 64-bit divisions per tile and thread were ~10 % of the kernel's instructions
@@ -94,21 +95,40 @@ __device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t,
         const int cd = code[k];
         const bool ok = (cd & 4) && !(cd & edge);
         const long long off = base + (cd >> 8);
-        if (kU8) {
-            const int ch = cd & 3;
-            const float mean = ch == 0 ? 103.939f : (ch == 1 ? 116.779f : 123.68f);      // BGR means
-            r[k] = ok ? static_cast<float>(__ldg(p.x8 + off)) - mean : 0.f;
-        } else {
-            r[k] = ok ? __ldg(p.x + off) : 0.f;
-        }
+        // uint8 frames: the RAW byte stays in the register (bit 8 = zero padding) and patch_value converts it when the
+        // patch is written -- a conversion here would make every load of the prefetch wait for its data at once
+        if (kU8) r[k] = ok ? static_cast<uint32_t>(__ldg(p.x8 + off)) : 0x100u;
+        else r[k] = ok ? __float_as_uint(__ldg(p.x + off)) : 0u;
     }
+}
+// The value patch_fetch left in a register, as the float the convolution sees.
+template <bool kU8>
+__device__ __forceinline__ float patch_value(uint32_t raw, int cd) {
+    if (!kU8) return __uint_as_float(raw);
+    const int ch = cd & 3;
+    const float mean = ch == 0 ? 103.939f : (ch == 1 ? 116.779f : 123.68f);      // BGR means
+    return (raw & 0x100u) ? 0.f : static_cast<float>(raw) - mean;
 }
 
 // Write one pixel's A row(s).  Only chunks that can hold data are stored: k-block 0 chunks 0..6 (slots 0..55) and, in
 // forward, k-block 1 chunks 0..3 (hi(x) in slots 0..26, the constant 1 of the bias row in slot 27); every other chunk
 // of the stage was zero-filled once at kernel start and is never written again.
-template <bool kFwd>
-__device__ __forceinline__ void store_a_row(const uint32_t (&s0)[32], int row, uint8_t* a_stage) {
+// kTS (forward only): the row goes to TENSOR memory instead -- lane = tile row, 48 columns = the 64 slots of k-block 0
+// followed by the 32 slots of k-block 1 -- and the MMA takes its A operand from there (tcgen05.mma [d], [a], b-desc):
+// no swizzled shared-memory A tile is written or read at all (it was 45 % of the kernel's shared-memory traffic).
+// a_tmem already carries the warp's lane base.
+template <bool kFwd, bool kTS>
+__device__ __forceinline__ void store_a_row(const uint32_t (&s0)[32], int row, uint8_t* a_stage, uint32_t a_tmem) {
+    if (kTS) {
+        tmem_st_32x32b_x32(a_tmem, s0);
+        uint32_t s1[16];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) s1[j] = s0[j];
+        s1[13] = (s0[13] & 0xFFFFu) | 0x3F800000u;       // hi(x[26]), 1.0 (pairs with lo(bias) in the B operand)
+        s1[14] = 0u; s1[15] = 0u;
+        tmem_st_32x32b_x16(a_tmem + 32, s1);
+        return;
+    }
     uint8_t* r0 = a_stage + row * 128;
     const int sw = row & 7;
 #pragma unroll
@@ -128,8 +148,8 @@ __device__ __forceinline__ void store_a_row(const uint32_t (&s0)[32], int row, u
 // kU8: the frame is raw uint8 RGB and Keras' vgg16 preprocess_input (caffe mode: RGB->BGR, subtract the
 // ImageNet BGR means; reference preprocessor.py:60-63 / models.py:13) is applied on the fly; the SAME zero
 // padding applies to the PREPROCESSED tensor, so out-of-frame taps stay exactly 0.
-template <bool kFwd, bool kU8>
-__device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, int row, uint8_t* a_stage) {
+template <bool kFwd, bool kU8, bool kTS>
+__device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, int row, uint8_t* a_stage, uint32_t a_tmem) {
     const int wq = static_cast<int>(pix % p.W);
     const int hq = static_cast<int>((pix / p.W) % p.H);
     float v[27];
@@ -167,7 +187,7 @@ __device__ __forceinline__ void im2col_row(const FirstArgs& p, long long pix, in
         const __nv_bfloat16 e1 = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : (k1 == 54 ? one : zero));
         s0[j] = static_cast<uint32_t>(__bfloat16_as_ushort(e0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(e1)) << 16);
     }
-    store_a_row<kFwd>(s0, row, a_stage);
+    store_a_row<kFwd, kTS>(s0, row, a_stage, a_tmem);
 }
 
 // hi | lo << 16 of one input value: converted ONCE per input element when the patch is parked in shared memory
@@ -181,8 +201,9 @@ __device__ __forceinline__ uint32_t split_hi_lo(float v) {
 }
 
 // Same A rows as im2col_row, gathered from the packed shared-memory patch: 27 LDS + 27 byte-permutes per pixel.
-template <bool kFwd>
-__device__ __forceinline__ void im2col_row_patch(const uint32_t* patch, int wt_log2, int row, uint8_t* a_stage) {
+template <bool kFwd, bool kTS>
+__device__ __forceinline__ void im2col_row_patch(const uint32_t* patch, int wt_log2, int row, uint8_t* a_stage,
+                                                 uint32_t a_tmem) {
     const int pcols = (1 << wt_log2) + 2;
     const uint32_t* base = patch + ((row >> wt_log2) * pcols + (row & ((1 << wt_log2) - 1))) * 3;
     uint32_t u[28];
@@ -199,17 +220,18 @@ __device__ __forceinline__ void im2col_row_patch(const uint32_t* patch, int wt_l
         else if (j <= 26) s0[j] = __byte_perm(u[2 * j - 27], u[2 * j - 26], 0x7632);        // lo[2j-27], lo[2j-26]
         else s0[j] = j == 27 ? 0x00003F80u : 0u;                                            // slot 54 = 1.0
     }
-    store_a_row<kFwd>(s0, row, a_stage);
+    store_a_row<kFwd, kTS>(s0, row, a_stage, a_tmem);
 }
 
 // im2col producer loop of one 128-thread group (group g builds the CTA's tiles g, g+2, ...): shared by forward and
 // wgrad.  kBlocks = 16 KiB k-blocks per A stage (2 forward, 1 wgrad).
-template <bool kFwd, bool kU8, typename AfterTile>
-__device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_a, float* patch, uint64_t* afull,
-                                              uint64_t* aempty, int row, int grp, AfterTile after_tile) {
+// kTS: the A rows go to tensor memory (a_tmem0 = stage 0, this warp's lanes; kF_TsCols columns per stage).
+template <bool kFwd, bool kU8, bool kTS, typename AfterTile>
+__device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_a, uint32_t a_tmem0, float* patch,
+                                              uint64_t* afull, uint64_t* aempty, int row, int grp, AfterTile after_tile) {
     constexpr int kStageBytes = (kFwd ? 2 : 1) * kF_ABlock;
     int code[kF_PatchRegs];
-    float nxt[kF_PatchRegs];
+    uint32_t nxt[kF_PatchRegs];
     if (p.patch_ok) {
 #pragma unroll
         for (int k = 0; k < kF_PatchRegs; ++k) code[k] = patch_code<kU8>(p, row + 128 * k);
@@ -226,30 +248,40 @@ __device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_
             // (every thread passed the previous tile's barrier only after all threads had finished that older gather),
             // so ONE named barrier per tile is enough (ncu round 2: 25 % of the stall samples were barrier waits)
 #pragma unroll
-            for (int k = 0; k < kF_PatchRegs; ++k) pcur[row + 128 * k] = split_hi_lo(nxt[k]);
+            for (int k = 0; k < kF_PatchRegs; ++k) pcur[row + 128 * k] = split_hi_lo(patch_value<kU8>(nxt[k], code[k]));
             if (blockIdx.x + static_cast<long long>(it + kF_ProdGroups) * gridDim.x < p.num_tiles)
                 patch_fetch<kU8>(p, tile + kF_ProdGroups * gridDim.x, row, code, nxt);     // next tile: in flight
             named_bar_sync(2 + grp, 128);                 // patch complete
             pbuf ^= 1;
         }
         mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
+        if (kTS) tc_fence_after();                        // the MMAs that read this stage's columns have completed
         if (p.patch_ok)
-            im2col_row_patch<kFwd>(pcur, p.wt_log2, row, smem_a + stage * kStageBytes);
+            im2col_row_patch<kFwd, kTS>(pcur, p.wt_log2, row, smem_a + stage * kStageBytes, a_tmem0 + stage * kF_TsCols);
         else
-            im2col_row<kFwd, kU8>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kStageBytes);
-        fence_proxy_async_smem();
+            im2col_row<kFwd, kU8, kTS>(p, static_cast<long long>(tile) * kF_TileM + row, row, smem_a + stage * kStageBytes,
+                                       a_tmem0 + stage * kF_TsCols);
+        if (kTS) {
+            tmem_st_wait();
+            tc_fence_before();
+        } else {
+            fence_proxy_async_smem();
+        }
         mbar_arrive(&afull[stage]);
         if (it >= kF_ProdGroups) after_tile(it - kF_ProdGroups);      // e.g. epilogue of this group's previous tile
     }
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <bool kU8>
+// kTS: A operand in tensor memory (store_a_row); ABL_FIRST_SMEM_A=1 selects the shared-memory form.
+template <bool kU8, bool kTS>
 __global__ void __launch_bounds__(kF_Threads, 1)
 conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const FirstArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* smem_a = smem;                                       // kF_Stages x 2 k-blocks x 16 KiB
-    uint8_t* smem_b = smem + kF_Stages * 2 * kF_ABlock;           // 2 k-blocks x [64 co][64 slots] = 16 KiB
+    constexpr int kASmem = kTS ? 0 : kF_Stages * 2 * kF_ABlock;
+    constexpr int kTmemCols = kTS ? 512 : kF_AccBufs * 64;        // accumulators [0, 256) + kF_Stages A stages from 256
+    uint8_t* smem_a = smem;                                       // kF_Stages x 2 k-blocks x 16 KiB (not kTS)
+    uint8_t* smem_b = smem + kASmem;                              // 2 k-blocks x [64 co][64 slots] = 16 KiB
     uint8_t* staging = smem_b + 2 * 64 * 128;                     // one 16 KiB swizzled output tile per worker group
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kF_ProdGroups * kF_ABlock);
     uint64_t* afull = bars;
@@ -266,8 +298,8 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
         fence_barrier_init();
         tma_prefetch_desc(&map_out);
     }
-    if (warp == 2) tmem_alloc<kF_AccBufs * 64>(tmem_slot);
-    for (int i = threadIdx.x; i < kF_Stages * 2 * kF_ABlock / 16; i += blockDim.x)
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    for (int i = threadIdx.x; i < kASmem / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);       // see store_a_row
     // B operand, built once per CTA: row = co (128 B, swizzled), slot k of block 0 = hi(W[k%27]) for k < 54,
     // block 1 = lo(W[k]) for k < 27.  The bias rides along: block 0 slot 54 (A holds 1.0 there) = hi(b[co]) and
@@ -314,9 +346,14 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int k = 0; k < (kb == 0 ? 4 : 2); ++k)
-                        umma_bf16_lohi(tmem_base + as * 64, a_lo + kb * (kF_ABlock >> 4) + k * 2, dhi,
-                                       b_lo0 + kb * ((64 * 128) >> 4) + k * 2, dhi, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < (kb == 0 ? 4 : 2); ++k) {
+                        if (kTS)      // 8 columns = 16 bf16 per K step; k-block 1 starts at column 32 of the stage
+                            umma_bf16_ts(tmem_base + as * 64, tmem_base + kF_AccBufs * 64 + stage * kF_TsCols + kb * 32 + k * 8,
+                                         b_lo0 + kb * ((64 * 128) >> 4) + k * 2, dhi, idesc, (kb | k) ? 1u : 0u);
+                        else
+                            umma_bf16_lohi(tmem_base + as * 64, a_lo + kb * (kF_ABlock >> 4) + k * 2, dhi,
+                                           b_lo0 + kb * ((64 * 128) >> 4) + k * 2, dhi, idesc, (kb | k) ? 1u : 0u);
+                    }
                 umma_commit(&aempty[stage]);
                 umma_commit(&tfull[as]);
                 if (++stage == kF_Stages) { stage = 0; phase ^= 1; }
@@ -366,7 +403,8 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
                 tma_store_commit();
             }
         };
-        producer_loop<true, kU8>(p, smem_a, patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, epilogue);
+        producer_loop<true, kU8, kTS>(p, smem_a, tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + kF_AccBufs * 64,
+                                      patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, epilogue);
         // the last tile of this group has not been drained yet
         int n_here = 0;
         for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) ++n_here;
@@ -377,7 +415,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<kF_AccBufs * 64>(tmem_base);
+        tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -453,7 +491,7 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
         {
             const int row = (threadIdx.x - 128) & 127;
             const int grp = (threadIdx.x - 128) >> 7;
-            producer_loop<false, kU8>(p, smem_a, patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, [](int) {});
+            producer_loop<false, kU8, false>(p, smem_a, 0u, patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, [](int) {});
         }
         // D rows 0..63 live in TMEM lanes 0..63: warps 4 and 5 (lane quarters 0 and 1) drain them at the end
         const int row = threadIdx.x - 128;
@@ -556,7 +594,7 @@ static int pixel_map(CUtensorMap* m, const void* base, long long total_pix, int 
     return encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <bool kU8>
+template <bool kU8, bool kTS>
 static int first_fwd(const void* x, const float* w_hwio, const float* bias, void* out, int B, int H, int W, int Cout,
                      void* stream, const char* who) {
     if (!x || !w_hwio || !bias || !out) { set_error("abl_conv_first_fwd: null pointer"); return ABL_ERR_NULL; }
@@ -570,17 +608,18 @@ static int first_fwd(const void* x, const float* w_hwio, const float* bias, void
     CUtensorMap mo;
     r = pixel_map(&mo, out, a.total_pix, 32);           // one store per epilogue warp: 32 pixels x 64 channels
     if (r != ABL_OK) return r;
-    constexpr int smem_bytes = kF_Stages * 2 * kF_ABlock + 2 * 64 * 128 + kF_ProdGroups * kF_ABlock + 256 + kF_ProdGroups * 2 * kF_PatchFloats * 4;
+    constexpr int smem_rest = 2 * 64 * 128 + kF_ProdGroups * kF_ABlock + 256 + kF_ProdGroups * 2 * kF_PatchFloats * 4;
+    constexpr int smem_bytes = smem_rest + (kTS ? 0 : kF_Stages * 2 * kF_ABlock);
     static bool attr_done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(conv_first_fwd_tc_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_first_fwd_tc_kernel<kU8, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
             return check_launch();
         attr_done[dev & 63] = true;
     }
     const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
-    conv_first_fwd_tc_kernel<kU8><<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mo, a);
+    conv_first_fwd_tc_kernel<kU8, kTS><<<grid, kF_Threads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(mo, a);
     return check_launch();
 }
 
@@ -628,11 +667,16 @@ using namespace abl;
 
 extern "C" int abl_conv_first_fwd(const float* x, const float* w_hwio, const float* bias, void* out, int B, int H,
                                   int W, int Cout, void* stream) {
-    return first_fwd<false>(x, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd");
+    const char* sa = getenv("ABL_FIRST_SMEM_A");       // A/B switch: the shared-memory A operand of round 1
+    if (sa && sa[0] == '1') return first_fwd<false, false>(x, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd");
+    return first_fwd<false, true>(x, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd");
 }
 extern "C" int abl_conv_first_fwd_u8(const unsigned char* frames_rgb, const float* w_hwio, const float* bias, void* out,
                                      int B, int H, int W, int Cout, void* stream) {
-    return first_fwd<true>(frames_rgb, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd_u8");
+    const char* sa = getenv("ABL_FIRST_SMEM_A");
+    if (sa && sa[0] == '1')
+        return first_fwd<true, false>(frames_rgb, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd_u8");
+    return first_fwd<true, true>(frames_rgb, w_hwio, bias, out, B, H, W, Cout, stream, "abl_conv_first_fwd_u8");
 }
 extern "C" long long abl_conv_first_wgrad_workspace_bytes(void) {
     return static_cast<long long>(sm_count()) * kF_PartRows * kF_Cout * 4;

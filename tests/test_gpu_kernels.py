@@ -224,14 +224,16 @@ def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B):
 
 @pytest.mark.parametrize("B,H,W", [(3, 128, 128), (2, 64, 64), (1, 32, 256), (4, 16, 32), (2, 48, 96),
                                    (3, 100, 100), (1, 25, 25), (2, 224, 224)])     # the last tile may be short
-@pytest.mark.parametrize("gather", ["patch", "global"])
+@pytest.mark.parametrize("gather", ["patch", "global", "patch-smem-a", "global-smem-a"])
 def test_conv_first_forward_and_wgrad_fp32(B, H, W, gather, monkeypatch):
     """Both im2col sources: the shared-memory patch prefetched one tile ahead (tiles that are rectangles of one frame:
-    W a power of two <= 128 or a multiple of 128) and the per-pixel global gather (any other shape, here 48x96)."""
-    if gather == "global":
+    W a power of two <= 128 or a multiple of 128) and the per-pixel global gather (any other shape, here 48x96); and both
+    homes of the forward's A operand: tensor memory (default) and the swizzled shared-memory tile (ABL_FIRST_SMEM_A=1)."""
+    if gather.startswith("global"):
         monkeypatch.setenv("ABL_FIRST_GATHER", "1")
     else:
         monkeypatch.delenv("ABL_FIRST_GATHER", raising=False)
+    monkeypatch.setenv("ABL_FIRST_SMEM_A", "1" if gather.endswith("smem-a") else "0")
     ops = _ops()
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(B, H, W, 3, generator=g) * 255 - 115).contiguous()
