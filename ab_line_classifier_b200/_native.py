@@ -56,6 +56,7 @@ SIGNATURES = {
     "abl_metrics_counter_count": (_i, [_i, _i]),
     "abl_metrics_accumulate": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "abl_dev_mma_rate_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
+    "abl_dev_write_probe": (_i, [_vp, _ll, _i, _i, _vp]),
     "abl_gradcam": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

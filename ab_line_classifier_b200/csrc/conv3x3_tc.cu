@@ -179,10 +179,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, const CUtensorM
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b4 = __ldg(bs + j);
-                    packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
-                                                fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
-                    packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
-                                                    fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                    packed[2 * j] = pack_bf16x2_relu(__uint_as_float(r[4 * j]) + b4.x,
+                                                __uint_as_float(r[4 * j + 1]) + b4.y);
+                    packed[2 * j + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * j + 2]) + b4.z,
+                                                    __uint_as_float(r[4 * j + 3]) + b4.w);
                 }
             } else {
 #pragma unroll
@@ -386,10 +386,10 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b4 = __ldg(bs + j);
-                    packed[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
-                                                fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
-                    packed[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
-                                                    fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                    packed[2 * j] = pack_bf16x2_relu(__uint_as_float(r[4 * j]) + b4.x,
+                                                __uint_as_float(r[4 * j + 1]) + b4.y);
+                    packed[2 * j + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * j + 2]) + b4.z,
+                                                    __uint_as_float(r[4 * j + 3]) + b4.w);
                 }
             } else {
 #pragma unroll
@@ -934,10 +934,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b4 = __ldg(bs + j);
-                            packed[c][2 * j] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j]) + b4.x, 0.f),
-                                                           fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
-                            packed[c][2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f),
-                                                               fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+                            packed[c][2 * j] = pack_bf16x2_relu(__uint_as_float(r[4 * j]) + b4.x,
+                                                           __uint_as_float(r[4 * j + 1]) + b4.y);
+                            packed[c][2 * j + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * j + 2]) + b4.z,
+                                                               __uint_as_float(r[4 * j + 3]) + b4.w);
                         }
                     } else {
 #pragma unroll
@@ -1323,14 +1323,14 @@ conv3x3_blk64_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 b4 = __ldg(bs + j);
-                        const uint32_t a0 = pack_bf16x2(fmaxf(__uint_as_float(ra[4 * j]) + b4.x, 0.f),
-                                                        fmaxf(__uint_as_float(ra[4 * j + 1]) + b4.y, 0.f));
-                        const uint32_t a1 = pack_bf16x2(fmaxf(__uint_as_float(ra[4 * j + 2]) + b4.z, 0.f),
-                                                        fmaxf(__uint_as_float(ra[4 * j + 3]) + b4.w, 0.f));
-                        const uint32_t c0 = pack_bf16x2(fmaxf(__uint_as_float(rb[4 * j]) + b4.x, 0.f),
-                                                        fmaxf(__uint_as_float(rb[4 * j + 1]) + b4.y, 0.f));
-                        const uint32_t c1 = pack_bf16x2(fmaxf(__uint_as_float(rb[4 * j + 2]) + b4.z, 0.f),
-                                                        fmaxf(__uint_as_float(rb[4 * j + 3]) + b4.w, 0.f));
+                        const uint32_t a0 = pack_bf16x2_relu(__uint_as_float(ra[4 * j]) + b4.x,
+                                                        __uint_as_float(ra[4 * j + 1]) + b4.y);
+                        const uint32_t a1 = pack_bf16x2_relu(__uint_as_float(ra[4 * j + 2]) + b4.z,
+                                                        __uint_as_float(ra[4 * j + 3]) + b4.w);
+                        const uint32_t c0 = pack_bf16x2_relu(__uint_as_float(rb[4 * j]) + b4.x,
+                                                        __uint_as_float(rb[4 * j + 1]) + b4.y);
+                        const uint32_t c1 = pack_bf16x2_relu(__uint_as_float(rb[4 * j + 2]) + b4.z,
+                                                        __uint_as_float(rb[4 * j + 3]) + b4.w);
                         hm[2 * j] = bf2_max(a0, c0);
                         hm[2 * j + 1] = bf2_max(a1, c1);
                         // post-ReLU values are >= +0: bit equality is value equality; the right pixel wins only if the

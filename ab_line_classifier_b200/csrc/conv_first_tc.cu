@@ -41,27 +41,32 @@ struct FirstArgs {
     long long total_pix;   // B*H*W
     int num_tiles;         // ceil(total_pix / 128)
     // staged-patch geometry (0 = tile shape not rectangular: per-thread global gather instead)
-    int wt_log2;           // tile width = min(W, 128) = 1 << wt_log2 (tile = 128/wt rows x wt pixels)
+    int wt_log2;           // a warp's 32 pixels = (32 >> wt_log2) rows x (1 << wt_log2) pixels (patch path)
     int patch_ok;
     int w_log2, h_log2;    // log2(W), log2(H) when both are powers of two, else -1: shifts instead of per-tile divisions
 };
 
 constexpr int kF_PartRows = 55;                                // hi rows 0..26, lo rows 27..53, ones row 54
-constexpr int kF_PatchRegs = 10;                               // ceil(3 * 130 * 3 / 128) elements per producer thread
-constexpr int kF_PatchFloats = kF_PatchRegs * 128;             // one group's haloed fp32 patch (5 KiB)
+constexpr int kF_PatchRegs = 10;                               // ceil(3 * 34 * 3 / 32) elements per producer thread
+constexpr int kF_WarpPatch = kF_PatchRegs * 32;                // one warp's haloed patch (1.25 KiB of packed hi|lo words)
+constexpr int kF_PatchFloats = 4 * kF_WarpPatch;               // the four warps of a group (5 KiB)
 
-// The input patch of a tile ((rows + 2) x (wt + 2) pixels x 3 channels, zero padded, already preprocessed) is
-// fetched with COALESCED loads one tile ahead into kF_PatchRegs registers per producer thread, parked in shared
-// memory, and the 27-tap gather then reads shared memory (lane stride 3 words: conflict-free).  The v1 gather
-// issued 27 dependent-latency global loads per pixel with only 8 producer warps per SM to hide them; ncu showed
-// the kernel at 30 % of HBM bandwidth with every pipe idle.
-// Per-thread, tile-invariant description of patch element e = t + 128 k, packed into one register:
+// The input patch of a WARP's 32 pixels ((rows + 2) x (wtw + 2) pixels x 3 channels, zero padded, already preprocessed;
+// wtw = min(tile width, 32), rows = 32 / wtw) is fetched with COALESCED loads one tile ahead into kF_PatchRegs registers
+// per producer thread, parked in shared memory, and the 27-tap gather then reads shared memory (lane stride 3 words:
+// conflict-free).  The v1 gather issued 27 dependent-latency global loads per pixel with only 8 producer warps per SM to
+// hide them; ncu showed the kernel at 30 % of HBM bandwidth with every pipe idle.  The patch belongs to the warp (not
+// to the 128-thread group, as in the first version: its named barrier per tile was the kernel's top stall, 1.7 stalled
+// warps per issue slot in the round-2 ncu capture), so a __syncwarp is all the synchronisation the gather needs; the
+// halo columns two neighbouring warps both load cost 5 % more (L1/L2-served) load instructions.
+// Per-thread, tile-invariant description of patch element e = lane + 32 k, packed into one register:
 //   bits 0-1 channel, bit 2 used, bit 3 first patch row, bit 4 last patch row, bit 5 first column, bit 6 last column,
-//   bits 8.. offset (in input elements) of the value relative to the tile's first pixel, biased by kF_RelBias.
+//   bits 8.. offset (in input elements) of the value relative to the warp's first pixel, biased by kF_RelBias.
 constexpr int kF_RelBias = 1 << 22;
 template <bool kU8>
 __device__ __forceinline__ int patch_code(const FirstArgs& p, int e) {
-    const int wt = 1 << p.wt_log2, pcols = wt + 2, nrows = (kF_TileM >> p.wt_log2) + 2;
+    const int wtw_log2 = p.wt_log2 < 5 ? p.wt_log2 : 5;
+    const int pcols = (1 << wtw_log2) + 2, nrows = (32 >> wtw_log2) + 2;
     const bool used = e < nrows * pcols * 3;
     const int prow = e / (pcols * 3);
     const int rem = e - prow * (pcols * 3);
@@ -72,11 +77,11 @@ __device__ __forceinline__ int patch_code(const FirstArgs& p, int e) {
            (pcol == pcols - 1 ? 64 : 0) | ((rel + kF_RelBias) << 8);
 }
 
-// Issue this thread's loads of tile `tile`'s patch (values land in r[]; nothing waits here).
+// Issue this lane's loads of the patch of warp `wq` of tile `tile` (values land in r[]; nothing waits here).
 template <bool kU8>
-__device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t, const int (&code)[kF_PatchRegs],
+__device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int wq, const int (&code)[kF_PatchRegs],
                                             uint32_t (&r)[kF_PatchRegs]) {
-    const long long pix0 = static_cast<long long>(tile) * kF_TileM;
+    const long long pix0 = static_cast<long long>(tile) * kF_TileM + 32 * wq;
     int c0, h0;
     if (p.w_log2 >= 0) {       // ncu: the two 64-bit divisions per tile and thread were ~10 % of the kernel's instructions
         c0 = static_cast<int>(pix0 & (p.W - 1));
@@ -85,15 +90,16 @@ __device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t,
         c0 = static_cast<int>(pix0 % p.W);
         h0 = static_cast<int>((pix0 / p.W) % p.H);
     }
-    const int wt = 1 << p.wt_log2;
-    // which borders of the frame this tile touches: an element on the matching patch border is zero padding
-    const int edge = (h0 == 0 ? 8 : 0) | (h0 + (kF_TileM >> p.wt_log2) == p.H ? 16 : 0) | (c0 == 0 ? 32 : 0) |
-                     (c0 + wt == p.W ? 64 : 0);
+    const int wtw_log2 = p.wt_log2 < 5 ? p.wt_log2 : 5;
+    // which borders of the frame this warp's rectangle touches: an element on the matching patch border is zero padding
+    // (bit 2 = "used" of every element: set for a warp beyond the last pixel of a short last tile -> all zeros)
+    const int edge = (h0 == 0 ? 8 : 0) | (h0 + (32 >> wtw_log2) == p.H ? 16 : 0) | (c0 == 0 ? 32 : 0) |
+                     (c0 + (1 << wtw_log2) == p.W ? 64 : 0) | (pix0 < p.total_pix ? 0 : 4);
     const long long base = pix0 * 3 - kF_RelBias;
 #pragma unroll
     for (int k = 0; k < kF_PatchRegs; ++k) {
         const int cd = code[k];
-        const bool ok = (cd & 4) && !(cd & edge);
+        const bool ok = (cd & 4) && !(cd & edge & ~4) && !(edge & 4);
         const long long off = base + (cd >> 8);
         // uint8 frames: the RAW byte stays in the register (bit 8 = zero padding) and patch_value converts it when the
         // patch is written -- a conversion here would make every load of the prefetch wait for its data at once
@@ -103,9 +109,8 @@ __device__ __forceinline__ void patch_fetch(const FirstArgs& p, int tile, int t,
 }
 // The value patch_fetch left in a register, as the float the convolution sees.
 template <bool kU8>
-__device__ __forceinline__ float patch_value(uint32_t raw, int cd) {
+__device__ __forceinline__ float patch_value(uint32_t raw, int ch) {
     if (!kU8) return __uint_as_float(raw);
-    const int ch = cd & 3;
     const float mean = ch == 0 ? 103.939f : (ch == 1 ? 116.779f : 123.68f);      // BGR means
     return (raw & 0x100u) ? 0.f : static_cast<float>(raw) - mean;
 }
@@ -204,8 +209,10 @@ __device__ __forceinline__ uint32_t split_hi_lo(float v) {
 template <bool kFwd, bool kTS>
 __device__ __forceinline__ void im2col_row_patch(const uint32_t* patch, int wt_log2, int row, uint8_t* a_stage,
                                                  uint32_t a_tmem) {
-    const int pcols = (1 << wt_log2) + 2;
-    const uint32_t* base = patch + ((row >> wt_log2) * pcols + (row & ((1 << wt_log2) - 1))) * 3;
+    // patch = this WARP's patch; the lane's pixel sits at (lane >> wtw_log2, lane & (wtw - 1)) of the warp's rectangle
+    const int wtw_log2 = wt_log2 < 5 ? wt_log2 : 5, lane = row & 31;
+    const int pcols = (1 << wtw_log2) + 2;
+    const uint32_t* base = patch + ((lane >> wtw_log2) * pcols + (lane & ((1 << wtw_log2) - 1))) * 3;
     uint32_t u[28];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
@@ -232,26 +239,29 @@ __device__ __forceinline__ void producer_loop(const FirstArgs& p, uint8_t* smem_
     constexpr int kStageBytes = (kFwd ? 2 : 1) * kF_ABlock;
     int code[kF_PatchRegs];
     uint32_t nxt[kF_PatchRegs];
+    const int lane = row & 31, wq = row >> 5;
+    const int ch0 = lane % 3;                 // channel of patch element e = lane + 32 k: e % 3 = (lane % 3 + 2 k) % 3
     if (p.patch_ok) {
 #pragma unroll
-        for (int k = 0; k < kF_PatchRegs; ++k) code[k] = patch_code<kU8>(p, row + 128 * k);
+        for (int k = 0; k < kF_PatchRegs; ++k) code[k] = patch_code<kU8>(p, lane + 32 * k);
         if (blockIdx.x + static_cast<long long>(grp) * gridDim.x < p.num_tiles)
-            patch_fetch<kU8>(p, blockIdx.x + grp * gridDim.x, row, code, nxt);
+            patch_fetch<kU8>(p, blockIdx.x + grp * gridDim.x, wq, code, nxt);
     }
     int pbuf = 0;
     for (int it = grp; blockIdx.x + static_cast<long long>(it) * gridDim.x < p.num_tiles; it += kF_ProdGroups) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int stage = it % kF_Stages;
-        uint32_t* pcur = reinterpret_cast<uint32_t*>(patch) + pbuf * kF_PatchFloats;
+        uint32_t* pcur = reinterpret_cast<uint32_t*>(patch) + pbuf * kF_PatchFloats + wq * kF_WarpPatch;
         if (p.patch_ok) {
-            // the patch is double buffered: this tile's values go to the buffer the tile BEFORE the previous one used
-            // (every thread passed the previous tile's barrier only after all threads had finished that older gather),
-            // so ONE named barrier per tile is enough (ncu round 2: 25 % of the stall samples were barrier waits)
+            // the warp's patch is double buffered: this tile's values go to the buffer the tile BEFORE the previous one
+            // used (every lane passed the previous tile's __syncwarp only after all lanes had finished that older
+            // gather), so one __syncwarp per tile is enough
 #pragma unroll
-            for (int k = 0; k < kF_PatchRegs; ++k) pcur[row + 128 * k] = split_hi_lo(patch_value<kU8>(nxt[k], code[k]));
+            for (int k = 0; k < kF_PatchRegs; ++k)
+                pcur[lane + 32 * k] = split_hi_lo(patch_value<kU8>(nxt[k], (ch0 + 2 * k) % 3));
             if (blockIdx.x + static_cast<long long>(it + kF_ProdGroups) * gridDim.x < p.num_tiles)
-                patch_fetch<kU8>(p, tile + kF_ProdGroups * gridDim.x, row, code, nxt);     // next tile: in flight
-            named_bar_sync(2 + grp, 128);                 // patch complete
+                patch_fetch<kU8>(p, tile + kF_ProdGroups * gridDim.x, wq, code, nxt);     // next tile: in flight
+            __syncwarp();                                 // patch complete
             pbuf ^= 1;
         }
         mbar_wait(&aempty[stage], ((it / kF_Stages) & 1) ^ 1);
@@ -388,7 +398,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
                 uint32_t packed[16];       // the accumulator already holds conv + bias (bias row of the B operand)
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    packed[j] = pack_bf16x2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
+                    packed[j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(stg_w + lane * 128 + (((c * 4 + j) ^ (lane & 7)) << 4)) =
@@ -571,13 +581,13 @@ static int first_args(FirstArgs* a, const void* x, bool u8, int B, int H, int W,
     // total_pix and clips the forward store
     a->num_tiles = static_cast<int>((a->total_pix + kF_TileM - 1) / kF_TileM);
     a->w = nullptr; a->bias = nullptr; a->part = nullptr;
-    // staged patch: a tile (128 raster pixels) must be a rectangle inside one frame
-    const int wt = W < kF_TileM ? W : kF_TileM;
-    const bool pow2 = (wt & (wt - 1)) == 0;
-    a->patch_ok = (pow2 && (W <= kF_TileM || W % kF_TileM == 0) && (static_cast<long long>(H) * W) % kF_TileM == 0 &&
-                   getenv("ABL_FIRST_GATHER") == nullptr) ? 1 : 0;
-    a->wt_log2 = 0;
-    while ((1 << a->wt_log2) < wt) ++a->wt_log2;
+    // staged patch: a WARP's 32 raster pixels must be a rectangle inside one frame -- a 32-pixel piece of one image row
+    // (W a multiple of 32: 96, 128, 160, 224 ...) or 32 / W whole rows of a narrow frame (W = 1, 2, ... 16)
+    const bool wide = W % 32 == 0;
+    const bool narrow = W < 32 && (W & (W - 1)) == 0 && (static_cast<long long>(H) * W) % 32 == 0;
+    a->patch_ok = ((wide || narrow) && getenv("ABL_FIRST_GATHER") == nullptr) ? 1 : 0;
+    a->wt_log2 = 5;            // log2 of the warp rectangle's width
+    if (!wide) { a->wt_log2 = 0; while ((1 << a->wt_log2) < W && a->wt_log2 < 5) ++a->wt_log2; }
     a->w_log2 = a->h_log2 = -1;
     if ((W & (W - 1)) == 0 && (H & (H - 1)) == 0) {
         a->w_log2 = a->h_log2 = 0;

@@ -87,6 +87,64 @@ mma_rate_probe_kernel(int n, int mode, int iters, unsigned long long* __restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- HBM write probe
+// How fast can SM-issued stores fill a buffer?  Every HBM-bound kernel of the path writes at least as much as it reads
+// (block1_conv1 forward: 92 % of its traffic), and the copy peak of MEASURED_PEAKS.json is half reads.  Modes:
+//   0 st.global.v4 (default policy)   1 st.global.cs.v4 (streaming)   2 st.global.wt.v4 (write-through)
+//   3 st.global.v4 + L2 evict_first policy   4 st.global.v8 (256-bit)   5 TMA bulk store, 4 KiB per warp from shared
+//   memory (what the conv epilogues do)   6 as 5 with an L2 evict_first hint
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__global__ void __launch_bounds__(512, 1) write_probe_kernel(uint4* __restrict__ dst, long long n16, int mode) {
+    extern __shared__ __align__(1024) uint8_t psm[];
+    const uint4 val = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (mode <= 3) {
+        const uint64_t pol = policy_evict_first();
+        for (long long i = tid; i < n16; i += nthreads) {
+            if (mode == 0) dst[i] = val;
+            else if (mode == 1) __stcs(dst + i, val);
+            else if (mode == 2) __stwt(dst + i, val);
+            else
+                asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst + i), "r"(val.x),
+                             "r"(val.y), "r"(val.z), "r"(val.w), "l"(pol)
+                             : "memory");
+        }
+    } else if (mode == 4) {
+        for (long long i = tid; 2 * i + 1 < n16; i += nthreads)
+            asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(dst + 2 * i), "r"(val.x) : "memory");
+    } else {
+        // every warp owns a 4 KiB shared-memory slice and streams it out with bulk stores, two in flight
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        uint4* slice = reinterpret_cast<uint4*>(psm + warp * 4096);
+        for (int j = lane; j < 256; j += 32) slice[j] = val;
+        fence_proxy_async_smem();
+        __syncwarp();
+        const uint64_t pol = policy_evict_first();
+        const long long nchunks = n16 / 256, nwarps = nthreads >> 5;
+        if (lane == 0) {
+            for (long long c = tid >> 5; c < nchunks; c += nwarps) {
+                if (mode == 5)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(dst + c * 256),
+                                 "r"(smem_u32(slice))
+                                 : "memory");
+                else
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], 4096, %2;" ::"l"(
+                                     dst + c * 256),
+                                 "r"(smem_u32(slice)), "l"(pol)
+                                 : "memory");
+                tma_store_commit();
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+            tma_store_wait_all();
+        }
+    }
+}
 }  // namespace abl
 
 using namespace abl;
@@ -102,5 +160,23 @@ extern "C" int abl_dev_mma_rate_probe(int n, int mode, int iters, int ctas, unsi
     if (cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmem) != cudaSuccess)
         return check_launch();
     mma_rate_probe_kernel<<<ctas, 128, kProbeSmem, static_cast<cudaStream_t>(stream)>>>(n, mode, iters, out_cycles);
+    return check_launch();
+}
+
+extern "C" int abl_dev_write_probe(void* dst, long long bytes, int mode, int ctas_per_sm, void* stream) {
+    if (!dst) { set_error("abl_dev_write_probe: null pointer"); return ABL_ERR_NULL; }
+    if (bytes <= 0 || (bytes & 4095) || mode < 0 || mode > 6 || ctas_per_sm < 1 || ctas_per_sm > 4 ||
+        (reinterpret_cast<uintptr_t>(dst) & 31)) {
+        set_error("abl_dev_write_probe: need bytes a multiple of 4096, mode 0..6, 1..4 CTAs per SM, 32-byte alignment");
+        return ABL_ERR_SHAPE;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem = mode >= 5 ? 16 * 4096 : 0;
+    if (cudaFuncSetAttribute(write_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4096) != cudaSuccess)
+        return check_launch();
+    write_probe_kernel<<<sms * ctas_per_sm, 512, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(dst),
+                                                                                           bytes / 16, mode);
     return check_launch();
 }

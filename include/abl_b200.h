@@ -257,6 +257,10 @@ int abl_metrics_accumulate(const float* probs, const float* y_true, int B, int n
  * MMA.  `ctas` CTAs (one per SM) each issue 4*iters MMAs (8*iters in mode 1) and write two uint64 to out_cycles
  * [ctas][2]: clocks of the issue loop and clocks until the last MMA retired.  tools/mma_rate.py prints the table. */
 int abl_dev_mma_rate_probe(int n, int mode, int iters, int ctas, unsigned long long* out_cycles, void* stream);
+/* Developer probe: fill `bytes` of device memory with SM-issued stores (mode 0 st.v4, 1 st.cs, 2 st.wt, 3 st + L2
+ * evict_first, 4 st.v8, 5 TMA bulk stores from shared memory, 6 as 5 with an L2 evict_first hint), ctas_per_sm x #SM CTAs
+ * of 512 threads.  tools/write_bw.py times it: the write-side roofline of the HBM-bound kernels. */
+int abl_dev_write_probe(void* dst, long long bytes, int mode, int ctas_per_sm, void* stream);
 
 /* Clip-level aggregation of frame probabilities (src/predict.py:159-166 with the helpers at 283-308 and 365-376),
  * all clips in one launch instead of the reference's per-clip Python loop.  probs fp32 [N_frames, n_classes] with the
