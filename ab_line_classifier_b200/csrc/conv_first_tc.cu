@@ -431,7 +431,11 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_out, const Firs
 
 // ------------------------------------------------------------------------------------------ wgrad
 // Persistent CTAs; each accumulates D[slot][co] over its tiles in TMEM, then stores rows 0..54 as its partial sums.
-template <bool kU8>
+// kM64: the MMA is M = 64 (the 64 slots) instead of M = 128 with a shared block of zeros as rows 64..127: the tensor
+// core's issue cost is the same, but each MMA reads 4 KiB instead of 6 KiB of shared memory, and this kernel is bound by
+// shared-memory bandwidth.  An M = 64 accumulator sits in 16 lanes of each 32-lane quarter (row r -> lane r % 16 + 32 *
+// (r / 16)).  ABL_FIRST_WGRAD_M128=1 selects the M = 128 form.
+template <bool kU8, bool kM64>
 __global__ void __launch_bounds__(kF_Threads, 1)
 conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const FirstArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -475,7 +479,7 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);      // both operands MN-major (K = pixels)
+            constexpr uint32_t idesc = make_idesc_bf16(kM64 ? 64 : 128, 64, 1, 1);      // both operands MN-major (K = pixels)
             constexpr uint32_t dhi = desc_hi_sw128(1024);
             int stage = 0;
             uint32_t phase = 0;
@@ -504,14 +508,16 @@ conv_first_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const Fir
             producer_loop<false, kU8, false>(p, smem_a, 0u, patches + grp * 2 * kF_PatchFloats, afull, aempty, row, grp, [](int) {});
         }
         // D rows 0..63 live in TMEM lanes 0..63: warps 4 and 5 (lane quarters 0 and 1) drain them at the end
-        const int row = threadIdx.x - 128;
-        if (warp < 6 && ntiles_here > 0) {
+        // (M = 64: in lanes 0..15 of all four quarters, warps 4..7)
+        const int tl = threadIdx.x - 128;                  // TMEM lane of this thread (first worker group only)
+        const int row = kM64 ? ((tl & 31) < 16 ? (tl >> 5) * 16 + (tl & 15) : kF_PartRows) : tl;
+        if (warp < (kM64 ? 8 : 6) && ntiles_here > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(row & ~31) << 16) + c * 32, r);
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(tl & ~31) << 16) + c * 32, r);
                 tmem_ld_wait();
                 if (row < kF_PartRows) {
                     // plain stores of this CTA's sums; conv_first_wgrad_reduce_kernel adds the CTAs in a fixed order
@@ -633,7 +639,7 @@ static int first_fwd(const void* x, const float* w_hwio, const float* bias, void
     return check_launch();
 }
 
-template <bool kU8>
+template <bool kU8, bool kM64>
 static int first_wgrad(const void* x, const void* dz, float* dw, float* db, void* workspace, long long workspace_bytes,
                        int B, int H, int W, int Cout, void* stream, const char* who) {
     if (!x || !dz || !dw || !workspace) { set_error("abl_conv_first_wgrad: null pointer"); return ABL_ERR_NULL; }
@@ -657,12 +663,12 @@ static int first_wgrad(const void* x, const void* dz, float* dw, float* db, void
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(conv_first_wgrad_tc_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_first_wgrad_tc_kernel<kU8, kM64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
             return check_launch();
         attr_done[dev & 63] = true;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    conv_first_wgrad_tc_kernel<kU8><<<grid, kF_Threads, smem_bytes, st>>>(mz, a);
+    conv_first_wgrad_tc_kernel<kU8, kM64><<<grid, kF_Threads, smem_bytes, st>>>(mz, a);
     r = check_launch();
     if (r != ABL_OK) return r;
     constexpr int kOut4 = 28 * (kF_Cout / 4);
@@ -693,11 +699,18 @@ extern "C" long long abl_conv_first_wgrad_workspace_bytes(void) {
 }
 extern "C" int abl_conv_first_wgrad(const float* x, const void* dz, float* dw, float* db, void* workspace,
                                     long long workspace_bytes, int B, int H, int W, int Cout, void* stream) {
-    return first_wgrad<false>(x, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream, "abl_conv_first_wgrad");
+    const char* m = getenv("ABL_FIRST_WGRAD_M128");
+    if (m && m[0] == '1')
+        return first_wgrad<false, false>(x, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream, "abl_conv_first_wgrad");
+    return first_wgrad<false, true>(x, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream, "abl_conv_first_wgrad");
 }
 extern "C" int abl_conv_first_wgrad_u8(const unsigned char* frames_rgb, const void* dz, float* dw, float* db,
                                        void* workspace, long long workspace_bytes, int B, int H, int W, int Cout,
                                        void* stream) {
-    return first_wgrad<true>(frames_rgb, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream,
-                             "abl_conv_first_wgrad_u8");
+    const char* m = getenv("ABL_FIRST_WGRAD_M128");
+    if (m && m[0] == '1')
+        return first_wgrad<true, false>(frames_rgb, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream,
+                                        "abl_conv_first_wgrad_u8");
+    return first_wgrad<true, true>(frames_rgb, dz, dw, db, workspace, workspace_bytes, B, H, W, Cout, stream,
+                                   "abl_conv_first_wgrad_u8");
 }

@@ -34,6 +34,29 @@ def run(B, H=128, W=128, reps=20):
             res[(mode, name)] = (us, out.clone())
             gb = (x.numel() * (4 if name == "fp32" else 1) + out.numel() * 2) / 1e9
             print(f"A in {'smem' if mode == '1' else 'tmem'}  {name:5s} {us:7.1f} us  {gb / us * 1e6:7.0f} GB/s")
+    dz = (torch.randn(B, H, W, 64, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    wres = {}
+    for mode in ("1", "0"):
+        os.environ["ABL_FIRST_WGRAD_M128"] = mode
+        dw, db = torch.empty(3, 3, 3, 64, device="cuda"), torch.empty(64, device="cuda")
+        for name, xin in (("fp32", x), ("u8", x8)):
+            fn = lambda: ops.conv_first_wgrad(xin, dz, dw, db)  # noqa: E731
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            wres[(mode, name)] = (dw.clone(), db.clone())
+            gb = (xin.numel() * xin.element_size() + dz.numel() * 2) / 1e9
+            print(f"wgrad M = {'128' if mode == '1' else ' 64'}  {name:5s} {us:7.1f} us  {gb / us * 1e6:7.0f} GB/s (incl. reduction kernel)")
+    for name in ("fp32", "u8"):
+        same = all(torch.equal(a, b) for a, b in zip(wres[("1", name)], wres[("0", name)]))
+        print(f"wgrad {name}: M64 == M128 bit for bit: {same}")
     # what a pure WRITE stream of the same size reaches on this board (the kernel's traffic is 92 % writes)
     import ctypes
     rt = ctypes.CDLL("libcudart.so.12")
