@@ -22,7 +22,7 @@ SIGNATURES = {
     "abl_parts_bytes": (_ll, [_i]),
     "abl_parts_reduce": (_i, [_vp, _vp, _i, _i, _vp]),
     "abl_conv3x3_igemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
-    "abl_conv3x3_igemm_gap": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "abl_conv3x3_igemm_gap": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "abl_gap_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_dgrad_unpool": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "abl_conv3x3_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
@@ -39,6 +39,7 @@ SIGNATURES = {
     "abl_maxpool_bwd_code": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "abl_gap_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "abl_gap_bwd_relu": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "abl_gap_bwd_bits": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "abl_head_loss_ws_bytes": (_ll, [_i]),
     "abl_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _ull, _u, _u,
                           _i, _i, _i, _i, _vp, _vp]),
@@ -82,7 +83,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abl_abi_version() != 7:
+    if lib.abl_abi_version() != 8:
         raise RuntimeError("libabl_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -54,6 +54,9 @@ struct ConvArgs {
     // fused GlobalAveragePooling partial sums: row (8x16-pixel rectangle index) x Cout fp32, plain stores (each value
     // has exactly one writer -> deterministic); abl_gap_reduce adds the rectangles of a frame in fixed order
     float* gap_part;                // [B * tiles_h * MSUB * tiles_w][Cout] or null (tiles rounded UP)
+    // 1-bit ReLU mask of the (bias + ReLU) output, [B,H,W,Cout/32] words, bit k of word g = channel 32 g + k is > 0; the
+    // last conv of a training step writes THIS instead of its activation (nothing but the mask of it is used afterwards)
+    uint32_t* relu_bits;            // or null (abl_conv3x3_igemm_gap only)
     // the frame is not a whole number of tiles (haloed kernels): TMA zero-fills the loads and clips the stores; the
     // epilogue zeroes accumulator rows that lie outside the frame and guards its non-TMA loads / stores
     int partial;
@@ -381,7 +384,26 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
             tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(lane_row & ~31) << 16) + pass * kEpiN + hsel * 64 + c * 32, r);
             tmem_ld_wait();
             uint32_t packed[16];
-            if (p.flags & ABL_EPI_BIAS_RELU) {
+            if (NTILE == 256 && (p.flags & ABL_EPI_BIAS_RELU) && p.relu_bits != nullptr) {      // (N = 256 kernels only)
+                // as below, and the signs are collected on the way: u | (u - 1) has its top bit set iff the float with
+                // bits u is <= 0 (either zero included); one funnel shift per channel appends it, channel 0 first
+                const float4* bs = reinterpret_cast<const float4*>(p.bias + cw0 + c * 32);
+                uint32_t off = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(bs + j);
+                    const float v[4] = {__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y,
+                                        __uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t u = __float_as_uint(v[k]);
+                        off = __funnelshift_l(u | (u - 1u), off, 1);
+                    }
+                    packed[2 * j] = pack_bf16x2_relu(v[0], v[1]);
+                    packed[2 * j + 1] = pack_bf16x2_relu(v[2], v[3]);
+                }
+                if (valid) p.relu_bits[(pix_off + cw0 + c * 32) >> 5] = ~__brev(off);
+            } else if (p.flags & ABL_EPI_BIAS_RELU) {
                 const float4* bs = reinterpret_cast<const float4*>(p.bias + cw0 + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -1462,7 +1484,8 @@ extern "C" int abl_bias_grad(const void* dz, float* db_parts, long long db_parts
 
 static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
                            void* out_full, void* out_pool, unsigned short* pool_code, float* colsum, long long colsum_bytes,
-                           void* out_unpool, const unsigned short* unpool_code, float* gap_part, int B, int H, int W,
+                           void* out_unpool, const unsigned short* unpool_code, float* gap_part,
+                           unsigned int* relu_bits, int B, int H, int W,
                            int Cin, int Cout, int flags, void* stream) {
     if (colsum && !out_full && !out_unpool) { set_error("abl_conv3x3_igemm: colsum needs out_full"); return ABL_ERR_NULL; }
     if (pool_code && !out_pool) { set_error("abl_conv3x3_igemm: pool_code needs out_pool"); return ABL_ERR_NULL; }
@@ -1509,7 +1532,7 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
             a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
             a.pool_code = pool_code;
             a.colsum = nullptr;
-            a.out_unpool = nullptr; a.unpool_code = nullptr; a.gap_part = nullptr; a.partial = 0;
+            a.out_unpool = nullptr; a.unpool_code = nullptr; a.gap_part = nullptr; a.partial = 0; a.relu_bits = nullptr;
             CUtensorMap ma, mb;
             {
                 const uint64_t dims[5] = {64, 4, (uint64_t)wb, (uint64_t)H, (uint64_t)B};
@@ -1583,6 +1606,8 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         a.out_unpool = static_cast<__nv_bfloat16*>(out_unpool);
         a.unpool_code = unpool_code;
         a.gap_part = gap_part;
+        a.relu_bits = relu_bits;
+        if (relu_bits && ntile != 256) { set_error("abl_conv3x3_igemm_gap: relu_bits needs Cout a multiple of 256"); return ABL_ERR_SHAPE; }
         if (gap_part && ntile == 64) { set_error("abl_conv3x3_igemm_gap: needs Cout a multiple of 128"); return ABL_ERR_SHAPE; }
         if (out_unpool && (ntile == 256 || !fuse_colsum && colsum != nullptr)) {
             set_error("abl_conv3x3_dgrad_unpool: supported for Cout <= 128 (single N tile)"); return ABL_ERR_SHAPE;
@@ -1634,6 +1659,7 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
     a.out_unpool = nullptr;
     a.unpool_code = nullptr;
     a.gap_part = nullptr;
+    a.relu_bits = nullptr;
     // 3-taps-per-stage main loop for the narrow tile: needs the 4 x 32 pixel rectangle
     const bool taps3 = ntile == 64 && (W % 32 == 0) && (H % 4 == 0);
     if (taps3) { a.box_w = 32; a.box_h = 4; }
@@ -1688,15 +1714,17 @@ extern "C" int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const floa
                                  long long colsum_parts_bytes, int B, int H, int W, int Cin, int Cout, int flags,
                                  void* stream) {
     return conv_igemm_impl(x, w_kmajor, bias, mask_src, out_full, out_pool, pool_code, colsum_parts, colsum_parts_bytes,
-                           nullptr, nullptr, nullptr, B, H, W, Cin, Cout, flags, stream);
+                           nullptr, nullptr, nullptr, nullptr, B, H, W, Cin, Cout, flags, stream);
 }
 
 // See include/abl_b200.h: forward conv + bias + ReLU with the GlobalAveragePooling partial sums fused in.
 extern "C" int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full,
-                                     float* gap_part, int B, int H, int W, int Cin, int Cout, void* stream) {
+                                     float* gap_part, unsigned int* relu_bits, int B, int H, int W, int Cin, int Cout,
+                                     void* stream) {
     if (!gap_part) { set_error("abl_conv3x3_igemm_gap: gap_part is null"); return ABL_ERR_NULL; }
+    if (reinterpret_cast<uintptr_t>(relu_bits) & 3) { set_error("abl_conv3x3_igemm_gap: relu_bits must be 4-byte aligned"); return ABL_ERR_ALIGN; }
     return conv_igemm_impl(x, w_kmajor, bias, nullptr, out_full, nullptr, nullptr, nullptr, 0, nullptr, nullptr, gap_part,
-                           B, H, W, Cin, Cout, ABL_EPI_BIAS_RELU, stream);
+                           relu_bits, B, H, W, Cin, Cout, ABL_EPI_BIAS_RELU, stream);
 }
 
 // See include/abl_b200.h: dgrad through a max-pool in one kernel.
@@ -1705,5 +1733,5 @@ extern "C" int abl_conv3x3_dgrad_unpool(const void* dz, const void* w_dgrad, con
                                         long long db_parts_bytes, int B, int H, int W, int Cin, int Cout, void* stream) {
     if (!pooled || !pool_code || !dz_out) { set_error("abl_conv3x3_dgrad_unpool: null pointer"); return ABL_ERR_NULL; }
     return conv_igemm_impl(dz, w_dgrad, nullptr, pooled, nullptr, nullptr, nullptr, db_parts, db_parts_bytes, dz_out,
-                           pool_code, nullptr, B, H, W, Cin, Cout, ABL_EPI_RELU_MASK, stream);
+                           pool_code, nullptr, nullptr, B, H, W, Cin, Cout, ABL_EPI_RELU_MASK, stream);
 }

@@ -243,31 +243,88 @@ __global__ void gap_reduce_kernel(const float4* __restrict__ part, float4* __res
     }
 }
 
+// Index arithmetic: the block's 256 threads cover 256 / C8 whole pixels per iteration, so a thread's channel chunk is
+// fixed and the frame index is one 32-bit division per pixel.
 __global__ void __launch_bounds__(256)
 gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4* __restrict__ a,
                                     uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw,
                                     float* __restrict__ db) {
     extern __shared__ float red[];
     float bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long total = static_cast<long long>(B) * HW * C8;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % C8);
-        const int n = static_cast<int>(i / (static_cast<long long>(HW) * C8));
-        const uint4 v = a[i];
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8) + 1);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const uint32_t av[4] = {v.x, v.y, v.z, v.w};
-        uint32_t o[4];
+    const unsigned rgs = 256u / C8, c = threadIdx.x % C8, npix = static_cast<unsigned>(B) * HW;
+    const unsigned stride = gridDim.x * rgs;
+    constexpr int kU = 4;       // four activation loads in flight per thread (see gap_bwd_bits_kernel)
+    // (C8 not dividing 256: the last 256 % C8 threads idle)
+    for (unsigned pix0 = threadIdx.x / C8 < rgs ? blockIdx.x * rgs + threadIdx.x / C8 : npix; pix0 < npix;
+         pix0 += kU * stride) {
+        uint4 av4[kU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float lo = bf16_lo(av[j]) > 0.f ? g[2 * j] * inv_hw : 0.f;
-            const float hi = bf16_hi(av[j]) > 0.f ? g[2 * j + 1] * inv_hw : 0.f;
-            o[j] = pack_bf16x2(lo, hi);
-            if (db != nullptr) { bacc[2 * j] += bf16_lo(o[j]); bacc[2 * j + 1] += bf16_hi(o[j]); }   // sum of the ROUNDED dz
+        for (int u = 0; u < kU; ++u) {
+            const unsigned pix = pix0 + u * stride;
+            av4[u] = pix < npix ? a[static_cast<size_t>(pix) * C8 + c] : make_uint4(0u, 0u, 0u, 0u);
         }
-        dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const unsigned pix = pix0 + u * stride;
+            if (pix >= npix) break;
+            const unsigned n = pix / static_cast<unsigned>(HW);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8) + 1);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const uint32_t av[4] = {av4[u].x, av4[u].y, av4[u].z, av4[u].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = bf16_lo(av[j]) > 0.f ? g[2 * j] * inv_hw : 0.f;
+                const float hi = bf16_hi(av[j]) > 0.f ? g[2 * j + 1] * inv_hw : 0.f;
+                o[j] = pack_bf16x2(lo, hi);
+                if (db != nullptr) { bacc[2 * j] += bf16_lo(o[j]); bacc[2 * j + 1] += bf16_hi(o[j]); }   // sum of the ROUNDED dz
+            }
+            dz[static_cast<size_t>(pix) * C8 + c] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
+}
+
+// The same dZ from the 1-bit ReLU mask the last conv wrote instead of its activation (abl_conv3x3_igemm_gap relu_bits):
+// 1 bit instead of 16 read per element, and the forward never wrote the activation.  One thread = 8 channels of a pixel.
+__global__ void __launch_bounds__(256)
+gap_bwd_bits_kernel(const float* __restrict__ dgap, const unsigned char* __restrict__ bits,
+                    uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw, float* __restrict__ db) {
+    extern __shared__ float red[];
+    float bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned rgs = 256u / C8, c = threadIdx.x % C8, npix = static_cast<unsigned>(B) * HW;
+    const unsigned stride = gridDim.x * rgs;
+    constexpr int kU = 4;       // mask bytes of four pixels in flight per thread (8 and 16 measured no faster: ~100 instructions
+                                // per 16-byte store make the kernel issue-bound at ~3.3 TB/s)
+    // (C8 not dividing 256: the last 256 % C8 threads idle)
+    for (unsigned pix0 = threadIdx.x / C8 < rgs ? blockIdx.x * rgs + threadIdx.x / C8 : npix; pix0 < npix;
+         pix0 += kU * stride) {
+        uint32_t on[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const unsigned pix = pix0 + u * stride;
+            // little-endian words: byte i = channels 8 i .. 8 i + 7 of the flattened [pixel][C/8] array
+            on[u] = pix < npix ? __ldg(bits + static_cast<size_t>(pix) * C8 + c) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const unsigned pix = pix0 + u * stride;
+            if (pix >= npix) break;
+            const unsigned n = pix / static_cast<unsigned>(HW);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8) + 1);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = (on[u] >> (2 * j)) & 1u ? g[2 * j] * inv_hw : 0.f;
+                const float hi = (on[u] >> (2 * j + 1)) & 1u ? g[2 * j + 1] * inv_hw : 0.f;
+                o[j] = pack_bf16x2(lo, hi);
+                if (db != nullptr) { bacc[2 * j] += bf16_lo(o[j]); bacc[2 * j + 1] += bf16_hi(o[j]); }   // sum of the ROUNDED dz
+            }
+            dz[static_cast<size_t>(pix) * C8 + c] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
     if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
 }
@@ -853,6 +910,23 @@ extern "C" int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, floa
     gap_bwd_relu_kernel<<<grid, 256, fuse ? 256 * 8 * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
         dgap, static_cast<const uint4*>(a), static_cast<uint4*>(dz), B, HW, C / 8, 1.f / static_cast<float>(HW),
         fuse ? db_parts : nullptr);
+    int r = check_launch();
+    if (r == ABL_OK && db_parts != nullptr && !fuse)
+        r = abl_bias_grad(dz, db_parts, db_parts_bytes, static_cast<long long>(B) * HW, C, stream);
+    return r;
+}
+
+extern "C" int abl_gap_bwd_bits(const float* dgap, const unsigned int* relu_bits, void* dz, float* db_parts,
+                                long long db_parts_bytes, int B, int HW, int C, void* stream) {
+    if (!dgap || !relu_bits || !dz) { set_error("abl_gap_bwd_bits: null pointer"); return ABL_ERR_NULL; }
+    if (B <= 0 || HW <= 0 || (C & 31)) { set_error("abl_gap_bwd_bits: need C % 32 == 0"); return ABL_ERR_SHAPE; }
+    const long long total = static_cast<long long>(B) * HW * (C / 8);
+    const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;
+    const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);
+    if (fuse) { int r = parts_check(db_parts, db_parts_bytes, grid, C, "abl_gap_bwd_bits"); if (r != ABL_OK) return r; }
+    gap_bwd_bits_kernel<<<grid, 256, fuse ? 256 * 8 * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
+        dgap, reinterpret_cast<const unsigned char*>(relu_bits), static_cast<uint4*>(dz), B, HW, C / 8,
+        1.f / static_cast<float>(HW), fuse ? db_parts : nullptr);
     int r = check_launch();
     if (r == ABL_OK && db_parts != nullptr && !fuse)
         r = abl_bias_grad(dz, db_parts, db_parts_bytes, static_cast<long long>(B) * HW, C, stream);

@@ -101,6 +101,8 @@ class CutoffVGG16Engine:
         self.pool_codes = os.environ.get("ABL_POOL_CODES", "1") != "0"
         self.fuse_unpool = os.environ.get("ABL_FUSE_UNPOOL", "1") != "0"    # MaxPoolGrad inside the dgrad epilogue
         self.fuse_gap = os.environ.get("ABL_FUSE_GAP", "1") != "0"          # GAP partial sums inside the last conv
+        # training keeps a 1-bit ReLU mask of the last conv's activation instead of the activation (needs fuse_gap)
+        self.relu_bits = os.environ.get("ABL_RELU_BITS", "1") != "0"
         self._gap_parts = 0
         self.step_count = 0           # dropout counter
         self.opt_steps = {}           # optimizer name -> steps taken (Adam bias correction)
@@ -278,6 +280,10 @@ class CutoffVGG16Engine:
         if self.fuse_gap and not last.pool and ops.igemm_gap_supported(last.h, last.w, last.cout):
             self._gap_parts = ops.igemm_gap_parts(last.h, last.w, last.cout)
             b["gap_part"] = torch.empty(cap * self._gap_parts, C, device=dev, dtype=torch.float32)
+            if training and self.relu_bits and last.cout % 256 == 0:       # (the N = 256 kernel writes the bits)
+                # after the GAP sums only the SIGN of the last activation is used (ReluGrad): the forward writes one bit
+                # per element here and never the activation; abl_gap_bwd_bits reads it back
+                b["bits_last"] = torch.empty(cap, last.h, last.w, last.cout // 32, device=dev, dtype=torch.int32)
         b["logits"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["probs"] = torch.empty(cap, n, device=dev, dtype=torch.float32)
         b["y"] = [torch.empty(cap, n, device=dev, dtype=torch.float32) for _ in range(2)]
@@ -330,8 +336,10 @@ class CutoffVGG16Engine:
             elif li == len(self.specs) - 1 and "gap_part" in b:
                 # last conv: GlobalAveragePooling partial sums come out of the epilogue; without Grad-CAM / training
                 # (need_last_act False) the activation itself is never written
+                bits = b["bits_last"][:B] if (training and "bits_last" in b) else None
                 ops.conv3x3_igemm_gap(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"),
-                                      full if (training or need_last_act) else None, b["gap_part"])
+                                      full if ((bits is None) if training else need_last_act) else None,
+                                      b["gap_part"], relu_bits=bits)
             else:
                 code = b.get("code_" + s.name)
                 ops.conv3x3_igemm(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"), None,
@@ -518,7 +526,10 @@ class CutoffVGG16Engine:
         def bias_parts_of(i):
             return b["bpart"] if (tr[i] and i > 0 and not wgrad_has_bias(i)) else None
 
-        ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, db_parts=bias_parts_of(nconv - 1))
+        if "bits_last" in b:
+            ops.gap_bwd_bits(b["dgap"][:B], b["bits_last"][:B], dz, db_parts=bias_parts_of(nconv - 1))
+        else:
+            ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, db_parts=bias_parts_of(nconv - 1))
         for li in range(nconv - 1, lowest - 1, -1):
             s = self.specs[li]
             if tr[li]:

@@ -116,15 +116,18 @@ def igemm_gap_parts(H, W, Cout):
     return -(-H // (8 * msub)) * msub * -(-W // 16)
 
 
-def conv3x3_igemm_gap(x, w_kmajor, bias, out_full, gap_part):
-    """Last conv forward (+bias+ReLU) with the GAP partial sums fused in; out_full may be None."""
+def conv3x3_igemm_gap(x, w_kmajor, bias, out_full, gap_part, relu_bits=None):
+    """Last conv forward (+bias+ReLU) with the GAP partial sums fused in; out_full may be None.  relu_bits: int32
+    [B,H,W,Cout/32] receiving the 1-bit ReLU mask of the activation (what a training step keeps instead of out_full)."""
     _chk(x, torch.bfloat16, "x"); _chk(w_kmajor, torch.bfloat16, "w"); _chk(bias, torch.float32, "bias")
     _chk(out_full, torch.bfloat16, "out_full"); _chk(gap_part, torch.float32, "gap_part")
+    _chk(relu_bits, torch.int32, "relu_bits")
     B, H, W, Cin = x.shape
     Cout = w_kmajor.shape[1]
     assert gap_part.numel() >= B * igemm_gap_parts(H, W, Cout) * Cout
-    _native.call("abl_conv3x3_igemm_gap", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(out_full), _ptr(gap_part), B, H, W,
-                 Cin, Cout, _stream())
+    assert relu_bits is None or relu_bits.numel() >= B * H * W * (Cout // 32)
+    _native.call("abl_conv3x3_igemm_gap", _ptr(x), _ptr(w_kmajor), _ptr(bias), _ptr(out_full), _ptr(gap_part),
+                 _ptr(relu_bits), B, H, W, Cin, Cout, _stream())
 
 
 def gap_reduce(gap_part, gap, parts, hw):
@@ -276,6 +279,17 @@ def gap_bwd_relu(dgap, a, dz, db=None, db_parts=None):
     B, H, W, Cc = a.shape
     parts, pbytes = _parts_args(db, db_parts, Cc, a.device, "db")
     _native.call("abl_gap_bwd_relu", _ptr(dgap), _ptr(a), _ptr(dz), _ptr(parts), pbytes, B, H * W, Cc, _stream())
+    if db is not None and db_parts is None:
+        parts_reduce(parts, db)
+
+
+def gap_bwd_bits(dgap, relu_bits, dz, db=None, db_parts=None):
+    """gap_bwd_relu from the 1-bit ReLU mask conv3x3_igemm_gap wrote (relu_bits int32 [B,H,W,C/32])."""
+    _chk(dgap, torch.float32, "dgap"); _chk(relu_bits, torch.int32, "relu_bits"); _chk(dz, torch.bfloat16, "dz")
+    B, H, W, Cc = dz.shape
+    assert relu_bits.numel() >= B * H * W * (Cc // 32)
+    parts, pbytes = _parts_args(db, db_parts, Cc, dz.device, "db")
+    _native.call("abl_gap_bwd_bits", _ptr(dgap), _ptr(relu_bits), _ptr(dz), _ptr(parts), pbytes, B, H * W, Cc, _stream())
     if db is not None and db_parts is None:
         parts_reduce(parts, db)
 

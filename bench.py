@@ -346,7 +346,8 @@ def main():
         npix = B * 128 * 128
         hbm_bytes = {   # algorithmic bytes per launch of the HBM-bound kernels
             "abl_conv_first_fwd": npix * (3 * 4 + 64 * 2), "abl_conv_first_wgrad": npix * (3 * 4 + 64 * 2),
-            "abl_gap_bwd_relu": B * 1024 * 256 * 4, "abl_adam_flat": 28 * eng.n_flat,
+            "abl_gap_bwd_relu": B * 1024 * 256 * 4, "abl_gap_bwd_bits": B * 1024 * 256 * 2 + B * 1024 * 256 // 8,
+            "abl_adam_flat": 28 * eng.n_flat,
             "abl_prep_conv_weights_multi": 8 * (eng.n_params - 514 - 1472)}
         for name, a, t in recs:
             k = kernels.setdefault(name, {"calls": 0, "ms": 0.0, "gflop": 0.0})
@@ -358,8 +359,8 @@ def main():
                 fl = 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]
             elif name == "abl_conv3x3_dgrad_unpool":   # (dz, w, pooled, code, out, parts, bytes, B, H, W, Cin, Cout, stream)
                 fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
-            elif name == "abl_conv3x3_igemm_gap":      # (x, w, bias, out, gap_part, B, H, W, Cin, Cout, stream)
-                fl = 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]
+            elif name == "abl_conv3x3_igemm_gap":      # (x, w, bias, out, gap_part, relu_bits, B, H, W, Cin, Cout, stream)
+                fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
             else:
                 fl = 0.0
             k["gflop"] += fl / 1e9

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ABL_ABI_VERSION 7
+#define ABL_ABI_VERSION 8
 
 #define ABL_OK 0
 #define ABL_ERR_SHAPE (-1)
@@ -82,9 +82,12 @@ int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, co
  * a frame's rectangles in fixed order.  parts = rectangles per frame, tiles counted rounding up:
  *   Cout % 256 == 0: ceil(H/8) * ceil(W/16);   otherwise (16-row tiles): 2 * ceil(H/16) * ceil(W/16)
  * (pixels outside the frame add 0).  out_full may be NULL (inference without Grad-CAM: the activation never reaches
- * HBM).  Requires Cout % 128 == 0; any H, W. */
-int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full, float* gap_part, int B,
-                          int H, int W, int Cin, int Cout, void* stream);
+ * HBM).  relu_bits (or NULL): uint32 [B,H,W,Cout/32], bit k of word g = (output channel 32 g + k is > 0) -- the 1-bit
+ * ReLU mask of the activation.  A training step passes relu_bits and out_full = NULL: after the GAP sums nothing but
+ * the sign of this layer's activation is used (ReluGrad in abl_gap_bwd_bits), so 16 bits per element are neither written
+ * nor read back.  Requires Cout % 128 == 0 (relu_bits: Cout % 256 == 0); any H, W. */
+int abl_conv3x3_igemm_gap(const void* x, const void* w_kmajor, const float* bias, void* out_full, float* gap_part,
+                          unsigned int* relu_bits, int B, int H, int W, int Cin, int Cout, void* stream);
 /* gap[n][c] = (1/HW) * sum_{p < parts} gap_part[n*parts + p][c]   (parts as defined above) */
 int abl_gap_reduce(const float* gap_part, float* gap, int B, int parts, int C, int HW, void* stream);
 
@@ -169,6 +172,9 @@ int abl_gap_fwd(const void* a, float* gap, int B, int HW, int C, void* stream);
  * db_parts: parts buffer or NULL receiving the partial sums of dz[..., c] (BiasAddGrad of the last conv, fused). */
 int abl_gap_bwd_relu(const float* dgap, const void* a, void* dz, float* db_parts, long long db_parts_bytes, int B, int HW,
                      int C, void* stream);
+/* the same dz from the 1-bit ReLU mask abl_conv3x3_igemm_gap wrote (relu_bits uint32 [B,HW,C/32]); C % 32 == 0. */
+int abl_gap_bwd_bits(const float* dgap, const unsigned int* relu_bits, void* dz, float* db_parts, long long db_parts_bytes,
+                     int B, int HW, int C, void* stream);
 
 /* Dropout -> Dense(n_classes) -> softmax (models.py:415-416) [+ categorical_crossentropy with
  * class_weight, models.py:426 / train.py:135-136].

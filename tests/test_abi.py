@@ -33,7 +33,7 @@ def test_ctypes_binding_covers_every_header_symbol():
 
 def test_loads_without_a_gpu_and_reports_version():
     lib = _native.load()
-    assert lib.abl_abi_version() == 7
+    assert lib.abl_abi_version() == 8
     assert lib.abl_last_error() is not None
 
 

@@ -385,6 +385,23 @@ def test_conv_with_fused_gap_partial_sums(cin, cout, H, W):
     part2 = torch.full_like(part, float("nan"))
     ops.conv3x3_igemm_gap(x, wf, b, None, part2)
     assert torch.equal(part, part2)                       # deterministic, independent of the activation store
+    # 1-bit ReLU mask instead of the activation (what a training step keeps), and the GAP gradient rebuilt from it
+    if cout % 256:
+        return
+    bits = torch.full((B, H, W, cout // 32), -1, device="cuda", dtype=torch.int32)
+    part3 = torch.full_like(part, float("nan"))
+    ops.conv3x3_igemm_gap(x, wf, b, None, part3, relu_bits=bits)
+    assert torch.equal(part, part3)
+    on = (ref.float() > 0).view(B, H, W, cout // 32, 32).to(torch.int64)
+    want = (on << torch.arange(32, device="cuda")).sum(-1)
+    want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).to(torch.int32)
+    assert torch.equal(bits, want)                        # bit k of word g <=> channel 32 g + k is > 0, exactly
+    dgap = torch.randn(B, cout, device="cuda")
+    dz_a, dz_b = torch.empty_like(ref), torch.full_like(ref, float("nan"))
+    db_a, db_b = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
+    ops.gap_bwd_relu(dgap, ref, dz_a, db=db_a)
+    ops.gap_bwd_bits(dgap, bits, dz_b, db=db_b)
+    assert torch.equal(dz_a, dz_b) and torch.equal(db_a, db_b)
 
 
 def test_gap_forward_backward():

@@ -29,7 +29,7 @@ for r in range(reps):
         if name == "abl_conv3x3_igemm":
             shape = (a[9], a[10], a[11], a[12], a[13], a[14]); fl = 2.0 * a[9] * a[10] * a[11] * 9 * a[12] * a[13]
         elif name == "abl_conv3x3_igemm_gap":
-            shape = (a[5], a[6], a[7], a[8], a[9], "gap"); fl = 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]
+            shape = (a[6], a[7], a[8], a[9], a[10], "gap"); fl = 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]
         elif name == "abl_conv3x3_dgrad_unpool":
             shape = (a[7], a[8], a[9], a[10], a[11], "unpool"); fl = 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]
         elif name == "abl_conv3x3_wgrad":
