@@ -63,8 +63,17 @@ SIGNATURES = {
 
 _lib = None
 
-# kernels launched per entry point (GEMM + fixed-order reduction of the per-CTA sums)
-LAUNCHES_PER_CALL = {"abl_conv3x3_wgrad": 2, "abl_conv_first_wgrad": 2, "abl_conv_first_wgrad_u8": 2}
+# kernels launched per entry point.  block1_conv1's wgrad = GEMM + fixed-order reduction of the per-CTA sums; the 3x3
+# wgrad GEMM reduces its pixel slices itself unless ABL_WGRAD_FUSED_REDUCE=0 brings the separate reduction kernel back.
+LAUNCHES_PER_CALL = {"abl_conv_first_wgrad": 2, "abl_conv_first_wgrad_u8": 2}
+
+
+def _wgrad_launches(args):
+    """abl_conv3x3_wgrad(x, dz, dw, db, db_parts, ws, ws_bytes, accumulate, B, H, W, Cin, Cout, stream): the Cin >= 128
+    GEMM reduces its pixel slices itself, the Cin = 64 one is followed by wgrad_reduce_kernel (see wgrad_tc.cu)."""
+    mode = os.environ.get("ABL_WGRAD_FUSED_REDUCE", "1")
+    fused = mode == "2" or (mode != "0" and int(args[11]) != 64)
+    return 1 if fused else 2
 launch_count = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
 timing = None             # set to a list to record (name, args, start_event, end_event) per call
 
@@ -102,7 +111,7 @@ def call(name, *args):
         timing.append((name, args, e0, e1))
     else:
         rc = getattr(lib, name)(*args)
-    launch_count += LAUNCHES_PER_CALL.get(name, 1)
+    launch_count += _wgrad_launches(args) if name == "abl_conv3x3_wgrad" else LAUNCHES_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.abl_last_error().decode(errors="replace")
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")

@@ -17,6 +17,8 @@
 // the slices in a fixed order (deterministic) into the fp32 HWIO gradient.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "host_util.h"
 #include "ptx.cuh"
 #include "parts.cuh"
@@ -39,7 +41,120 @@ struct WgradArgs {
     int units, splits, stages, stage_bytes;
     float* partial;      // [splits][9][Cin][Cout] fp32
     float* db_rows;      // wgrad64 only: bias-gradient partial rows [splits][Cout] (ones row of the GEMM) or null
+    // Slice reduction INSIDE the GEMM kernel (tickets != null; wgrad_unit_finish).  tickets: 2 * units zeroed words
+    // (arrivals, departures) that the kernel leaves zeroed again.
+    unsigned int* tickets;
+    float* dw;           // [9][Cin][Cout] fp32 result
+    int accumulate;      // dw += instead of dw =
+    float* db;           // bias gradient [Cout] or null
+    const float* db_src; // a parts buffer (db_nrows < 0: row count in its header) finished by the first db_blocks CTAs
+    int db_nrows, db_blocks;
 };
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned int* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Fixed-order sum of the pixel slices, done by the GEMM kernel itself (round 2 ran a separate reduction kernel after every
+// wgrad GEMM: 8-15 us each, six per step).  Called by ALL 256 threads of CTA (unit, split) after the __syncthreads that
+// follows the epilogue's stores of the CTA's slice sums into p.partial:
+//   1. arrive on the unit's ticket and wait until all `splits` CTAs of the unit have arrived -- they are all resident
+//      (grid <= #SM, one CTA per SM), so the wait cannot deadlock; a bounded spin traps instead of hanging;
+//   2. this CTA owns rows [split * R / splits, ...) of the unit's region of dw.  Every output float4 is the sum of its
+//      `splits` slice values; G = 256 / outputs threads share one output, thread g of them adds a contiguous range of
+//      slices in slice order (16 L2 loads in flight: __ldcg, other SMs wrote the data) and the G sums are added in g
+//      order -- the same order on every launch, so the result is bit-reproducible;
+//   3. the last CTA to leave zeroes the unit's two tickets for the next launch.
+// row_off(r): offset (floats) of row r of the unit's region inside a [9][Cin][Cout] image; ncol floats per row.
+template <typename RowOff>
+__device__ __forceinline__ void wgrad_unit_finish(const WgradArgs& p, int unit, int split, int nrows, int ncol,
+                                                  RowOff row_off) {
+    const int t = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    unsigned int* arrive = p.tickets + unit;
+    unsigned int* leave = p.tickets + p.units + unit;
+    if (t == 0) {
+        atomicAdd(arrive, 1u);
+        if (ld_acquire_u32(arrive) < static_cast<unsigned>(p.splits)) {
+            const uint64_t t0 = global_timer_ns();
+            uint32_t spins = 0;
+            while (ld_acquire_u32(arrive) < static_cast<unsigned>(p.splits))
+                if ((++spins & 0xFFF) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+        }
+    }
+    __syncthreads();
+    const int c4n = ncol >> 2;                       // float4 per row (16 or 32)
+    const int per = (nrows + p.splits - 1) / p.splits;
+    const int r0 = split * per, r1 = min(nrows, r0 + per);
+    const int n_out = max(r1 - r0, 0) * c4n;         // float4 outputs of this CTA
+    int G = 1;                                       // threads per output: a power of two, lanes of one warp
+    while (G < 32 && n_out * (G * 2) <= 256) G *= 2;
+    const int g = t & (G - 1);
+    const int kper = (p.splits + G - 1) / G;         // slices per thread
+    const int k0 = g * kper, k1 = min(p.splits, k0 + kper);
+    const size_t sstride4 = static_cast<size_t>(9) * p.Cin * p.Cout >> 2;
+    const int passes = (n_out * G + 255) / 256;
+    for (int pass = 0; pass < passes; ++pass) {      // (uniform trip count: the shuffles below need whole warps)
+        const int o = (pass * 256 + t) / G;
+        const bool live = o < n_out;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        size_t off = 0;
+        if (live) {
+            off = row_off(r0 + o / c4n) + static_cast<size_t>(o % c4n) * 4;
+            const float4* src = reinterpret_cast<const float4*>(p.partial + off);
+            for (int k = k0; k < k1; k += 16) {
+                float4 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = k + j < k1 ? __ldcg(src + static_cast<size_t>(k + j) * sstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+            }
+        }
+        float4 tot = acc;
+        for (int q = 1; q < G; ++q) {                // thread g == 0 collects the other groups' sums in g order
+            const int srcl = (t & 31 & ~(G - 1)) + q;
+            tot.x += __shfl_sync(0xffffffffu, acc.x, srcl);
+            tot.y += __shfl_sync(0xffffffffu, acc.y, srcl);
+            tot.z += __shfl_sync(0xffffffffu, acc.z, srcl);
+            tot.w += __shfl_sync(0xffffffffu, acc.w, srcl);
+        }
+        if (live && g == 0) {
+            float4* dst = reinterpret_cast<float4*>(p.dw + off);
+            if (p.accumulate) { const float4 d = *dst; tot.x += d.x; tot.y += d.y; tot.z += d.z; tot.w += d.w; }
+            *dst = tot;
+        }
+    }
+    // wgrad64: the ones row of every slice -> db of this unit's 64 output channels (slice order)
+    if (p.db_rows != nullptr && p.db != nullptr && split == 0 && t < 16) {
+        const float4* src = reinterpret_cast<const float4*>(p.db_rows + unit * 64) + t;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < p.splits; ++k) {
+            const float4 v = __ldcg(src + (static_cast<size_t>(k) * p.Cout >> 2));
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        }
+        reinterpret_cast<float4*>(p.db + unit * 64)[t] = s4;
+    }
+    if (t == 0 && atomicAdd(leave, 1u) == static_cast<unsigned>(p.splits) - 1u) {
+        *arrive = 0u;           // every CTA of the unit has passed its wait: safe to re-arm for the next launch
+        *leave = 0u;
+    }
+}
+
+// BiasAddGrad finish from a parts buffer inside the GEMM kernel: the first db_blocks CTAs each add the rows of 16 channels
+// (all 256 threads, after the CTA's own work; `red` = 4 KiB of the drained pipeline's shared memory).
+__device__ __forceinline__ void wgrad_bias_finish(const WgradArgs& p, uint8_t* smem) {
+    if (p.db_src == nullptr || static_cast<int>(blockIdx.x) >= p.db_blocks) return;
+    const float* rows = p.db_nrows < 0 ? p.db_src + ABL_PARTS_HEADER : p.db_src;
+    const int nrows = p.db_nrows < 0 ? parts_rows(p.db_src) : p.db_nrows;
+    for (int blk = blockIdx.x; blk < p.db_blocks; blk += gridDim.x) {       // (a tiny problem has fewer CTAs than blocks)
+        parts_reduce_block(rows, nrows, p.Cout, p.db, 0, blk, reinterpret_cast<float4(*)[4]>(smem));
+        __syncthreads();
+    }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -192,6 +307,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
+    if (p.tickets != nullptr) {
+        // the unit's region of dw: (kh, M half, 64 or 128 input channels) x NT output channels
+        const int rows_half = p.mode == 0 ? 128 : 64, halves = p.mode == 0 ? 1 : (kw1 >= 0 ? 2 : 1);
+        wgrad_unit_finish(p, unit, split, 3 * halves * rows_half, NT, [&](int r) {
+            const int hf = r / (3 * rows_half), rr = r - hf * 3 * rows_half;
+            const int kh_r = rr / rows_half, ci_r = ci0 + rr % rows_half;
+            return (static_cast<size_t>(kh_r * 3 + (hf == 0 ? kw0 : kw1)) * p.Cin + ci_r) * p.Cout + co0;
+        });
+    }
+    wgrad_bias_finish(p, smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -351,6 +476,9 @@ wgrad64_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
+    if (p.tickets != nullptr)      // the unit's region of dw: all 9 taps x 64 input channels x its 64 output channels
+        wgrad_unit_finish(p, unit, split, 9 * 64, 64, [&](int r) { return static_cast<size_t>(r) * p.Cout + co0; });
+    wgrad_bias_finish(p, smem);
 }
 
 // dw[i] (+)= sum_s partial[s][i], fixed summation order (deterministic).  Block = 32 float4 columns x 8 split groups:
@@ -488,6 +616,40 @@ static int nhwc_block_map(CUtensorMap* m, const void* base, int B, int H, int W,
 
 using namespace abl;
 
+// Tickets of the in-kernel slice reduction: zero-initialised module memory, one slot per (device, stream) that has
+// called abl_conv3x3_wgrad, so that wgrads on different streams never share counters (two launches on ONE stream are
+// ordered; a captured graph keeps the slot of the stream it was captured on).  No free slot -> null -> the caller
+// falls back to the separate reduction kernel.
+constexpr int kTicketSlots = 16, kTicketWords = 128;            // 2 * units <= 96 words used
+__device__ unsigned int g_wgrad_tickets[kTicketSlots][kTicketWords];
+static unsigned int* wgrad_ticket_slot(cudaStream_t st) {
+    struct Slot { int dev; cudaStream_t st; };
+    static Slot slots[kTicketSlots];
+    static int used = 0;
+    static unsigned int* base[64] = {nullptr};
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (base[dev & 63] == nullptr) {
+        void* ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_wgrad_tickets) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        base[dev & 63] = static_cast<unsigned int*>(ptr);
+    }
+    int idx = -1, per_dev = 0;
+    for (int i = 0; i < used; ++i) {
+        if (slots[i].dev != dev) continue;
+        if (slots[i].st == st) { idx = per_dev; break; }
+        ++per_dev;
+    }
+    if (idx < 0) {
+        if (used == kTicketSlots) return nullptr;
+        slots[used].dev = dev; slots[used].st = st; ++used;
+        idx = per_dev;
+    }
+    return base[dev & 63] + static_cast<size_t>(idx) * kTicketWords;
+}
+
 // workspace layout: [splits][9][Cin][Cout] fp32 slice sums | [splits][Cout] fp32 bias rows of the Cin == 64 kernel's ones
 // row | a parts buffer for the stand-alone bias pass (db requested, no db_parts given, Cin != 64)
 static long long wgrad_ws_dw_bytes(const WgradArgs& a) { return static_cast<long long>(a.splits) * 9 * a.Cin * a.Cout * 4; }
@@ -536,6 +698,17 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
         set_error("abl_conv3x3_wgrad: pointers must be 16-byte aligned"); return ABL_ERR_ALIGN;
     }
     a.partial = static_cast<float*>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // slice reduction inside the GEMM kernel (default) or by wgrad_reduce_kernel (ABL_WGRAD_FUSED_REDUCE=0, or no free
+    // ticket slot for this stream)
+    // Measured on B200 (batch 256, same box): the Cin >= 128 layers gain 1-4 us each (176 / 182 / 106 / 173 us against
+    // 179 / 186 / 108 / 175 us with the separate kernel) and lose a launch; the Cin = 64 kernel, whose 74-148 slices per
+    // unit leave every CTA only a few rows, was 3-9 us SLOWER, so it keeps the reduction kernel (ABL_WGRAD_FUSED_REDUCE=2
+    // forces the in-kernel form there too).
+    const char* fr = getenv("ABL_WGRAD_FUSED_REDUCE");
+    const bool fuse_reduce = fr ? (fr[0] == '2' || (fr[0] != '0' && a.mode != 2)) : a.mode != 2;
+    a.tickets = fuse_reduce ? wgrad_ticket_slot(st) : nullptr;
+    a.dw = dw; a.accumulate = accumulate; a.db = db; a.db_src = nullptr; a.db_nrows = 0; a.db_blocks = 0;
     float* ws_rows = reinterpret_cast<float*>(static_cast<char*>(workspace) + wgrad_ws_dw_bytes(a));
     float* ws_parts = reinterpret_cast<float*>(static_cast<char*>(workspace) + wgrad_ws_dw_bytes(a) + wgrad_ws_rows_bytes(a));
     // where db comes from: partial rows the producer of dz left (db_parts), the ones row of the Cin == 64 GEMM, or a
@@ -543,8 +716,21 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
     const bool own_rows = db != nullptr && db_parts == nullptr && a.mode == 2;
     a.db_rows = own_rows ? ws_rows : nullptr;
     CUtensorMap mx, mdz;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     int r;
+    const float* rows_src = nullptr;
+    int nrows = 0;
+    if (db != nullptr) {
+        if (db_parts != nullptr) { rows_src = db_parts; nrows = -1; }
+        else if (own_rows) { rows_src = ws_rows; nrows = a.splits; }
+        else {      // before the GEMM: with the fused reduction its first CTAs finish the bias gradient at their end
+            r = abl_bias_grad(dz, ws_parts, abl_parts_bytes(Cout), static_cast<long long>(B) * H * W, Cout, stream);
+            if (r != ABL_OK) return r;
+            rows_src = ws_parts; nrows = -1;
+        }
+    }
+    const int bias_blocks = db != nullptr ? (Cout / 4 + 3) / 4 : 0;
+    if (a.tickets != nullptr && db != nullptr && !own_rows) { a.db_src = rows_src; a.db_nrows = nrows; a.db_blocks = bias_blocks; }
+    if (a.tickets == nullptr) a.db = nullptr;            // (the kernels' own-rows finish belongs to the fused path)
     if (a.mode == 2) {
         r = nhwc_block_map(&mx, x, B, H, W, Cin, kWgBh, 1);              // plain 4 x 16 pixel tile per kw
         if (r != ABL_OK) return r;
@@ -568,23 +754,11 @@ extern "C" int abl_conv3x3_wgrad(const void* x, const void* dz, float* dw, float
         if (r != ABL_OK) return r;
         r = (nt == 128) ? launch_wgrad<128>(mx, mdz, a, st) : launch_wgrad<64>(mx, mdz, a, st);
     }
-    if (r != ABL_OK) return r;
-    const float* rows_src = nullptr;
-    int nrows = 0;
-    if (db != nullptr) {
-        if (db_parts != nullptr) { rows_src = db_parts; nrows = -1; }
-        else if (own_rows) { rows_src = ws_rows; nrows = a.splits; }
-        else {
-            r = abl_bias_grad(dz, ws_parts, abl_parts_bytes(Cout), static_cast<long long>(B) * H * W, Cout, stream);
-            if (r != ABL_OK) return r;
-            rows_src = ws_parts; nrows = -1;
-        }
-    }
+    if (r != ABL_OK || a.tickets != nullptr) return r;
     const long long n4 = 9LL * Cin * Cout / 4;
     long long blocks = (n4 + 31) / 32;
     const long long cap = static_cast<long long>(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
-    const int bias_blocks = db != nullptr ? (Cout / 4 + 3) / 4 : 0;
     wgrad_reduce_kernel<<<static_cast<int>(blocks) + bias_blocks, 256, 0, st>>>(
         static_cast<const float4*>(workspace), reinterpret_cast<float4*>(dw), n4, a.splits, accumulate,
         static_cast<int>(blocks), rows_src, nrows, db, Cout);

@@ -193,7 +193,11 @@ def test_conv3x3_dgrad_with_relu_mask(cin, cout, H, W, pool, igemm_variant):
 
 @pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
 @pytest.mark.parametrize("B", [1, 5])
-def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B):
+@pytest.mark.parametrize("reduce", ["in-kernel", "separate-kernel"])
+def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B, reduce, monkeypatch):
+    """reduce: the fixed-order sum of the pixel slices inside the GEMM kernel (default: arrive / wait tickets, every CTA
+    reduces its share of the unit) or by wgrad_reduce_kernel (ABL_WGRAD_FUSED_REDUCE=0)."""
+    monkeypatch.setenv("ABL_WGRAD_FUSED_REDUCE", "2" if reduce == "in-kernel" else "0")      # 2: also for Cin = 64
     ops = _ops()
     g = torch.Generator().manual_seed(cin * 3 + cout + B)
     x = _bf(torch.relu(torch.randn(B, H, W, cin, generator=g)))
@@ -220,6 +224,10 @@ def test_conv3x3_wgrad_and_bias_grad(cin, cout, H, W, pool, B):
     dw3 = torch.empty_like(dw)
     ops.conv3x3_wgrad(xg, dzg, dw3, None, ws, accumulate=False)
     assert torch.equal(dw, dw3), "wgrad must be deterministic (fixed-order slice reduction)"
+    for _ in range(3):          # back-to-back launches: the tickets re-arm themselves
+        ops.conv3x3_wgrad(xg, dzg, dw3, db_p, ws, accumulate=False, db_parts=parts)
+    assert torch.equal(dw, dw3)
+    _close(db_p, dz.sum(dim=(0, 1, 2)), 1e-5, "bias grad from producer parts (repeat)")
 
 
 @pytest.mark.parametrize("B,H,W", [(3, 128, 128), (2, 64, 64), (1, 32, 256), (4, 16, 32), (2, 48, 96),
