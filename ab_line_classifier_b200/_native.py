@@ -42,9 +42,9 @@ SIGNATURES = {
     "abl_gap_bwd_bits": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "abl_head_loss_ws_bytes": (_ll, [_i]),
     "abl_head_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _ull, _u, _u,
-                          _i, _i, _i, _i, _vp, _vp]),
+                          _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "abl_head_fwd_stepdev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _f, _ull, _vp, _u, _i, _i, _i,
-                                  _i, _vp, _vp]),
+                                  _i, _vp, _vp, _i, _i, _vp]),
     "abl_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "abl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "abl_adam_flat_tab": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _f, _f, _f, _vp]),

@@ -346,7 +346,8 @@ constexpr int kMaxClasses = 8;
 // last (integer ticket in loss_ws word 0, reset for the next launch) adds all partials in block order and does the
 // single read-modify-write of *loss_sum -> the loss is bit-reproducible (no floating-point atomics).
 __global__ void __launch_bounds__(128)
-head_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, const float* __restrict__ b,
+head_fwd_kernel(float* __restrict__ gap, const float* __restrict__ gap_part, int gap_parts, float gap_inv_hw,
+                const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ logits, float* __restrict__ probs, const float* __restrict__ y,
                 const float* __restrict__ cw, float inv_batch, float* __restrict__ loss_sum,
                 float* __restrict__ dlogits, unsigned char* __restrict__ keep_mask, int keep_mask_in, int training,
@@ -365,8 +366,20 @@ head_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w, cons
     float z[kMaxClasses];
 #pragma unroll
     for (int j = 0; j < kMaxClasses; ++j) z[j] = 0.f;
+#pragma unroll 2
     for (int c = lane; c < C; c += 32) {
-        float h = gap[static_cast<size_t>(frame) * C + c];
+        float h;
+        if (gap_part != nullptr) {
+            // GlobalAveragePooling finish folded in (abl_gap_reduce's arithmetic, rectangle order): the frame's mean is
+            // stored for head_bwd
+            float sum = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < gap_parts; ++q) sum += __ldg(gap_part + (static_cast<size_t>(frame) * gap_parts + q) * C + c);
+            h = sum * gap_inv_hw;
+            gap[static_cast<size_t>(frame) * C + c] = h;
+        } else {
+            h = gap[static_cast<size_t>(frame) * C + c];
+        }
         if (training) {
             unsigned char keep;
             const size_t mi = static_cast<size_t>(frame) * C + c;
@@ -933,7 +946,8 @@ extern "C" int abl_gap_bwd_bits(const float* dgap, const unsigned int* relu_bits
     return r;
 }
 
-static int head_fwd_impl(const float* gap, const float* w, const float* b, float* logits, float* probs,
+static int head_fwd_impl(float* gap, const float* gap_part, int gap_parts, int gap_hw, const float* w, const float* b,
+                         float* logits, float* probs,
                          const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                          float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                          unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
@@ -943,8 +957,9 @@ static int head_fwd_impl(const float* gap, const float* w, const float* b, float
     if (training && !keep_mask) { set_error("abl_head_fwd: training needs a keep_mask buffer"); return ABL_ERR_NULL; }
     if (B <= 0 || C <= 0 || n <= 0 || n > kMaxClasses) { set_error("abl_head_fwd: need 1 <= n <= 8"); return ABL_ERR_SHAPE; }
     if (training && !(dropout >= 0.f && dropout < 1.f)) { set_error("abl_head_fwd: dropout must be in [0,1)"); return ABL_ERR_SHAPE; }
+    if (gap_part && (gap_parts <= 0 || gap_hw <= 0)) { set_error("abl_head_fwd: gap_part needs gap_parts > 0 and gap_hw > 0"); return ABL_ERR_SHAPE; }
     head_fwd_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, keep_mask_in,
+        gap, gap_part, gap_parts, gap_part ? 1.f / static_cast<float>(gap_hw) : 0.f, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, keep_mask_in,
         training, training ? dropout : 0.f, seed, step, rank, B, C, n, step_dev, loss_ws, loss_accumulate);
     return check_launch();
 }
@@ -954,24 +969,27 @@ extern "C" long long abl_head_loss_ws_bytes(int B) {
     return (static_cast<long long>(ABL_PARTS_HEADER) + (B + 3) / 4) * 4;
 }
 
-extern "C" int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
+extern "C" int abl_head_fwd(float* gap, const float* w, const float* b, float* logits, float* probs,
                             const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                             float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                             unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                            int loss_accumulate, float* loss_ws, void* stream) {
-    return head_fwd_impl(gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask,
+                            int loss_accumulate, float* loss_ws, const float* gap_part, int gap_parts, int gap_hw,
+                            void* stream) {
+    return head_fwd_impl(gap, gap_part, gap_parts, gap_hw, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask,
                          keep_mask_in, training, dropout, seed, step, rank, B, C, n, nullptr, loss_accumulate, loss_ws, stream);
 }
 
-extern "C" int abl_head_fwd_stepdev(const float* gap, const float* w, const float* b, float* logits, float* probs,
+extern "C" int abl_head_fwd_stepdev(float* gap, const float* w, const float* b, float* logits, float* probs,
                                     const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                                     float* dlogits, unsigned char* keep_mask, int training, float dropout,
                                     unsigned long long seed, unsigned int* step_dev, unsigned int rank, int B,
-                                    int C, int n, int loss_accumulate, float* loss_ws, void* stream) {
+                                    int C, int n, int loss_accumulate, float* loss_ws, const float* gap_part,
+                                    int gap_parts, int gap_hw, void* stream) {
     if (!step_dev) { set_error("abl_head_fwd_stepdev: step_dev is null"); return ABL_ERR_NULL; }
     if (!loss_sum || !y_onehot) { set_error("abl_head_fwd_stepdev: needs y_onehot and loss_sum (the counters advance with the loss)"); return ABL_ERR_NULL; }
-    return head_fwd_impl(gap, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum, dlogits, keep_mask, 0,
-                         training, dropout, seed, 0u, rank, B, C, n, step_dev, loss_accumulate, loss_ws, stream);
+    return head_fwd_impl(gap, gap_part, gap_parts, gap_hw, w, b, logits, probs, y_onehot, class_weight, inv_batch, loss_sum,
+                         dlogits, keep_mask, 0, training, dropout, seed, 0u, rank, B, C, n, step_dev, loss_accumulate, loss_ws,
+                         stream);
 }
 
 extern "C" int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,

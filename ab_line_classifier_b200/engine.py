@@ -345,8 +345,10 @@ class CutoffVGG16Engine:
                 ops.conv3x3_igemm(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"), None,
                                   full, pooled, ops.EPI_BIAS_RELU, pool_code=code[:B] if code is not None else None)
         last = self.specs[-1]
+        gp = {}
         if "gap_part" in b:
-            ops.gap_reduce(b["gap_part"], b["gap"][:B], self._gap_parts, last.h * last.w)
+            # the per-rectangle sums are finished inside the head kernel (it writes b["gap"] for the backward pass)
+            gp = dict(gap_part=b["gap_part"], gap_parts=self._gap_parts, gap_hw=last.h * last.w)
         else:
             feat = b["pool_" + last.name][:B] if last.pool else b["act_" + last.name][:B]
             ops.gap_fwd(feat, b["gap"][:B])
@@ -359,13 +361,14 @@ class CutoffVGG16Engine:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
                          b["probs"][:B], y, self.class_weight, inv_batch, loss_out, b["dlogits"][:B],
                          b["keep"][:B], keep_mask_in, True, self.dropout, self.seed, self.step_count, self.rank,
-                         step_dev=step_dev, loss_ws=b["loss_ws"], loss_accumulate=False)
+                         step_dev=step_dev, loss_ws=b["loss_ws"], loss_accumulate=False, **gp)
         elif y is not None:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
-                         b["probs"][:B], y, None, inv_batch, loss_out, loss_ws=b["loss_ws"], loss_accumulate=accumulate)
+                         b["probs"][:B], y, None, inv_batch, loss_out, loss_ws=b["loss_ws"], loss_accumulate=accumulate,
+                         **gp)
         else:
             ops.head_fwd(b["gap"][:B], self.view("output/kernel"), self.view("output/bias"), b["logits"][:B],
-                         b["probs"][:B])
+                         b["probs"][:B], **gp)
         return b["probs"][:B]
 
     def reserve(self, batch, training=False):

@@ -301,10 +301,11 @@ def head_loss_ws(B, device):
 
 def head_fwd(gap, w, b, logits, probs, y=None, class_weight=None, inv_batch=1.0, loss_sum=None, dlogits=None,
              keep_mask=None, keep_mask_in=False, training=False, dropout=0.0, seed=0, step=0, rank=0, step_dev=None,
-             loss_ws=None, loss_accumulate=True):
+             loss_ws=None, loss_accumulate=True, gap_part=None, gap_parts=0, gap_hw=0):
     """loss_sum (+)= batch loss (loss_accumulate False: overwritten).  step_dev: int32[2] device counters {dropout step,
-    optimizer step}, both advanced by the kernel (CUDA-graph replays)."""
-    for t in (gap, w, b, logits, probs, y, class_weight, loss_sum, dlogits, loss_ws):
+    optimizer step}, both advanced by the kernel (CUDA-graph replays).  gap_part (+ gap_parts rectangles per frame of
+    gap_hw pixels in all): conv3x3_igemm_gap's partial sums -- the kernel finishes the pooling itself and WRITES gap."""
+    for t in (gap, w, b, logits, probs, y, class_weight, loss_sum, dlogits, loss_ws, gap_part):
         _chk(t, torch.float32, "tensor")
     _chk(keep_mask, torch.uint8, "keep_mask")
     B, Cc = gap.shape
@@ -316,12 +317,13 @@ def head_fwd(gap, w, b, logits, probs, y=None, class_weight=None, inv_batch=1.0,
         _native.call("abl_head_fwd_stepdev", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
                      _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
                      int(bool(training)), float(dropout), int(seed), _ptr(step_dev), int(rank), B, Cc, n,
-                     int(bool(loss_accumulate)), _ptr(loss_ws), _stream())
+                     int(bool(loss_accumulate)), _ptr(loss_ws), _ptr(gap_part), int(gap_parts), int(gap_hw), _stream())
         return
     _native.call("abl_head_fwd", _ptr(gap), _ptr(w), _ptr(b), _ptr(logits), _ptr(probs), _ptr(y),
                  _ptr(class_weight), float(inv_batch), _ptr(loss_sum), _ptr(dlogits), _ptr(keep_mask),
                  int(bool(keep_mask_in)), int(bool(training)), float(dropout), int(seed), int(step), int(rank),
-                 B, Cc, n, int(bool(loss_accumulate)), _ptr(loss_ws), _stream())
+                 B, Cc, n, int(bool(loss_accumulate)), _ptr(loss_ws), _ptr(gap_part), int(gap_parts), int(gap_hw),
+                 _stream())
 
 
 def head_bwd(gap, w, dlogits, keep_mask, dropout, dw, db, dgap):

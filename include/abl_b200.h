@@ -188,22 +188,26 @@ int abl_gap_bwd_bits(const float* dgap, const unsigned int* relu_bits, void* dz,
  *   dlogits[i][j] = w_i * inv_batch * (p_ij - y_ij)                      (if dlogits != NULL)
  *   loss_ws  abl_head_loss_ws_bytes(B) bytes, ZEROED ONCE by the caller (needed when loss_sum and y_onehot are given):
  *            per-block loss sums + an integer ticket; the last block to finish adds them in block order, so the batch
- *            loss is one deterministic sum and a single read-modify-write of *loss_sum (the ticket resets itself). */
+ *            loss is one deterministic sum and a single read-modify-write of *loss_sum (the ticket resets itself).
+ *   gap_part (or NULL), gap_parts, gap_hw: the GlobalAveragePooling finish folded in -- the per-rectangle sums that
+ *            abl_conv3x3_igemm_gap left (fp32 [B * gap_parts][C]); the kernel then WRITES gap[n][c] = (1 / gap_hw) *
+ *            sum_p gap_part[n * gap_parts + p][c] (abl_gap_reduce's arithmetic and order) before using it, and no
+ *            abl_gap_reduce launch is needed.  With gap_part == NULL, gap is an input. */
 long long abl_head_loss_ws_bytes(int B);
-int abl_head_fwd(const float* gap, const float* w, const float* b, float* logits, float* probs,
+int abl_head_fwd(float* gap, const float* w, const float* b, float* logits, float* probs,
                  const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                  float* dlogits, unsigned char* keep_mask, int keep_mask_in, int training, float dropout,
                  unsigned long long seed, unsigned int step, unsigned int rank, int B, int C, int n,
-                 int loss_accumulate, float* loss_ws, void* stream);
+                 int loss_accumulate, float* loss_ws, const float* gap_part, int gap_parts, int gap_hw, void* stream);
 /* abl_head_fwd with the dropout step counter read from DEVICE memory instead of passed by value, so the launch can be
  * replayed from a CUDA graph (mask always generated; y_onehot and loss_sum required).  step_dev: uint32[2] = {dropout
  * step, optimizer step}; the kernel's last block increments BOTH after every block has read the dropout step, so a
  * captured train step needs no separate counter kernels (abl_adam_flat_tab reads step_dev[1] later in the step). */
-int abl_head_fwd_stepdev(const float* gap, const float* w, const float* b, float* logits, float* probs,
+int abl_head_fwd_stepdev(float* gap, const float* w, const float* b, float* logits, float* probs,
                          const float* y_onehot, const float* class_weight, float inv_batch, float* loss_sum,
                          float* dlogits, unsigned char* keep_mask, int training, float dropout, unsigned long long seed,
                          unsigned int* step_dev, unsigned int rank, int B, int C, int n, int loss_accumulate,
-                         float* loss_ws, void* stream);
+                         float* loss_ws, const float* gap_part, int gap_parts, int gap_hw, void* stream);
 /* dw[C][n] = h^T dlogits, db[n] = sum_i dlogits (both OVERWRITTEN; fixed summation order),
  * dgap[i][c] = scale_ic * sum_j dlogits[i][j] w[c][j] with h = gap * scale, scale_ic = keep_mask ? mask/(1-dropout) : 1. */
 int abl_head_bwd(const float* gap, const float* w, const float* dlogits, const unsigned char* keep_mask,

@@ -393,6 +393,14 @@ def test_conv_with_fused_gap_partial_sums(cin, cout, H, W):
     part2 = torch.full_like(part, float("nan"))
     ops.conv3x3_igemm_gap(x, wf, b, None, part2)
     assert torch.equal(part, part2)                       # deterministic, independent of the activation store
+    # the head kernel finishes the pooling itself (no gap_reduce launch): same bits in gap, same logits
+    wh, bh = torch.randn(cout, 2, device="cuda") * 0.1, torch.randn(2, device="cuda") * 0.1
+    lg_a, pr_a = torch.empty(B, 2, device="cuda"), torch.empty(B, 2, device="cuda")
+    lg_b, pr_b = torch.empty(B, 2, device="cuda"), torch.empty(B, 2, device="cuda")
+    ops.head_fwd(gap, wh, bh, lg_a, pr_a)
+    gap_b = torch.full_like(gap, float("nan"))
+    ops.head_fwd(gap_b, wh, bh, lg_b, pr_b, gap_part=part, gap_parts=parts, gap_hw=H * W)
+    assert torch.equal(gap_b, gap) and torch.equal(lg_a, lg_b) and torch.equal(pr_a, pr_b)
     # 1-bit ReLU mask instead of the activation (what a training step keeps), and the GAP gradient rebuilt from it
     if cout % 256:
         return
