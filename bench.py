@@ -394,7 +394,7 @@ def main():
                     traffic = round(sum(r.get("dram_read_bytes", 0) + r.get("dram_write_bytes", 0) for r in fam) / 1e9, 3)
                     traffic_note = (f"GB per step: dram__bytes_read.sum + dram__bytes_write.sum over the {len(fam)} conv-family "
                                     f"launches of one step (profiles/{cap_name}); algorithmic activation+gradient bytes "
-                                    "of the same launches: 9.58 GB (DESIGN.md section 4)")
+                                    "of the same launches: 9.45 GB (DESIGN.md section 4)")
                     break
             except Exception:
                 continue
