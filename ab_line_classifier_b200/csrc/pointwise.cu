@@ -288,43 +288,73 @@ gap_bwd_relu_kernel(const float* __restrict__ dgap, const uint4* __restrict__ a,
 
 // The same dZ from the 1-bit ReLU mask the last conv wrote instead of its activation (abl_conv3x3_igemm_gap relu_bits):
 // 1 bit instead of 16 read per element, and the forward never wrote the activation.  One thread = 8 channels of a pixel.
+// A block works on `slice_px` pixels of ONE frame at a time (work items = frames x slices, strided over the grid), so
+// the eight rounded values dgap[n][c] / HW of a thread are loop-invariant: per pixel the thread loads one mask byte,
+// expands it to four bf16x2 AND-masks (multiply the nibble by 0x10204080: bit k lands on the top bit of byte k; PRMT
+// replicates a byte's top bit over a half word) and stores 16 bytes -- ~30 instructions instead of the ~100 of the
+// select / multiply / convert form.  The bias gradient is value x count: the
+// mask bits of a slice are counted in byte lanes (<= 255 pixels per thread and slice), and n * q is exact in fp32.
+// prmt.b32 in its default mode: a selector nibble 8 + k replicates the TOP BIT of source byte k over the result byte
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t selector) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(selector));
+    return d;
+}
 __global__ void __launch_bounds__(256)
 gap_bwd_bits_kernel(const float* __restrict__ dgap, const unsigned char* __restrict__ bits,
-                    uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw, float* __restrict__ db) {
+                    uint4* __restrict__ dz, int B, int HW, int C8, float inv_hw, int slices, int slice_px,
+                    float* __restrict__ db) {
     extern __shared__ float red[];
     float bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const unsigned rgs = 256u / C8, c = threadIdx.x % C8, npix = static_cast<unsigned>(B) * HW;
-    const unsigned stride = gridDim.x * rgs;
-    constexpr int kU = 4;       // mask bytes of four pixels in flight per thread (8 and 16 measured no faster: ~100 instructions
-                                // per 16-byte store make the kernel issue-bound at ~3.3 TB/s)
-    // (C8 not dividing 256: the last 256 % C8 threads idle)
-    for (unsigned pix0 = threadIdx.x / C8 < rgs ? blockIdx.x * rgs + threadIdx.x / C8 : npix; pix0 < npix;
-         pix0 += kU * stride) {
-        uint32_t on[kU];
+    const unsigned rgs = 256u / C8, c = threadIdx.x % C8, prow = threadIdx.x / C8;
+    const int items = B * slices;
+    constexpr int kPx = 8;                           // pixels per thread and item (the host sizes slice_px = kPx * rgs)
+    // the mask bytes of the NEXT item are in flight while this one is expanded and stored (ncu on the first form: the
+    // kernel waited on one 1-byte load per 16-byte store -- 22 stalled warps per issue on `long_scoreboard`)
+    auto fetch = [&](int item, uint32_t (&on)[kPx]) {
+        const int n = item / slices, sl = item - n * slices;
+        const int p0 = sl * slice_px, p1 = min(HW, p0 + slice_px);
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const unsigned pix = pix0 + u * stride;
+        for (int u = 0; u < kPx; ++u) {
+            const int px = p0 + static_cast<int>(prow + u * rgs);
             // little-endian words: byte i = channels 8 i .. 8 i + 7 of the flattened [pixel][C/8] array
-            on[u] = pix < npix ? __ldg(bits + static_cast<size_t>(pix) * C8 + c) : 0u;
+            on[u] = (item < items && prow < rgs && px < p1) ? __ldg(bits + (static_cast<size_t>(n) * HW + px) * C8 + c) : 0u;
         }
+    };
+    uint32_t cur[kPx], nxt[kPx];
+    fetch(blockIdx.x, cur);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        fetch(item + gridDim.x, nxt);
+        const int n = item / slices, sl = item - n * slices;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8) + 1);
+        const uint32_t q[4] = {pack_bf16x2(g0.x * inv_hw, g0.y * inv_hw), pack_bf16x2(g0.z * inv_hw, g0.w * inv_hw),
+                               pack_bf16x2(g1.x * inv_hw, g1.y * inv_hw), pack_bf16x2(g1.z * inv_hw, g1.w * inv_hw)};
+        uint32_t cnt_lo = 0u, cnt_hi = 0u;           // byte k: pixels of this slice whose channel k (4 + k) is on
+        const int p0 = sl * slice_px, p1 = min(HW, p0 + slice_px);
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const unsigned pix = pix0 + u * stride;
-            if (pix >= npix) break;
-            const unsigned n = pix / static_cast<unsigned>(HW);
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (static_cast<size_t>(n) * C8 + c) * 8) + 1);
-            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            uint32_t o[4];
+        for (int u = 0; u < kPx; ++u) {
+            const int px = p0 + static_cast<int>(prow + u * rgs);
+            if (prow < rgs && px < p1) {              // (C8 not dividing 256: the last 256 % C8 threads idle)
+                const uint32_t on = cur[u];
+                const uint32_t x = (on & 0xFu) * 0x10204080u, y = (on >> 4) * 0x10204080u;
+                dz[(static_cast<size_t>(n) * HW + px) * C8 + c] =
+                    make_uint4(q[0] & prmt_b32(x, 0x9988u), q[1] & prmt_b32(x, 0xBBAAu), q[2] & prmt_b32(y, 0x9988u),
+                               q[3] & prmt_b32(y, 0xBBAAu));
+                cnt_lo += (x >> 7) & 0x01010101u;
+                cnt_hi += (y >> 7) & 0x01010101u;
+            }
+        }
+        if (db != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float lo = (on[u] >> (2 * j)) & 1u ? g[2 * j] * inv_hw : 0.f;
-                const float hi = (on[u] >> (2 * j + 1)) & 1u ? g[2 * j + 1] * inv_hw : 0.f;
-                o[j] = pack_bf16x2(lo, hi);
-                if (db != nullptr) { bacc[2 * j] += bf16_lo(o[j]); bacc[2 * j + 1] += bf16_hi(o[j]); }   // sum of the ROUNDED dz
+                bacc[2 * j] += bf16_lo(q[j]) * static_cast<float>((j < 2 ? cnt_lo >> (16 * j) : cnt_hi >> (16 * (j - 2))) & 0xFFu);
+                bacc[2 * j + 1] += bf16_hi(q[j]) *
+                                   static_cast<float>((j < 2 ? cnt_lo >> (16 * j + 8) : cnt_hi >> (16 * (j - 2) + 8)) & 0xFFu);
             }
-            dz[static_cast<size_t>(pix) * C8 + c] = make_uint4(o[0], o[1], o[2], o[3]);
         }
+#pragma unroll
+        for (int u = 0; u < kPx; ++u) cur[u] = nxt[u];
     }
     if (db != nullptr) bias_partial_flush(bacc, db, C8, red);
 }
@@ -933,13 +963,33 @@ extern "C" int abl_gap_bwd_bits(const float* dgap, const unsigned int* relu_bits
                                 long long db_parts_bytes, int B, int HW, int C, void* stream) {
     if (!dgap || !relu_bits || !dz) { set_error("abl_gap_bwd_bits: null pointer"); return ABL_ERR_NULL; }
     if (B <= 0 || HW <= 0 || (C & 31)) { set_error("abl_gap_bwd_bits: need C % 32 == 0"); return ABL_ERR_SHAPE; }
-    const long long total = static_cast<long long>(B) * HW * (C / 8);
     const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;
-    const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);
+    // Work items = frames x 64-pixel slices of a frame (a thread sees <= 255 pixels of a slice: byte-lane counters),
+    // strided over a grid of exactly the blocks that are resident at once.  (The first version launched 8 blocks per SM
+    // regardless of the kernel's registers: 5-6 fit, so a second, mostly empty wave ran -- ncu: 1.6 waves.)
+    const int C8 = C / 8, rgs = 256 / C8 > 0 ? 256 / C8 : 1;
+    const size_t dyn_smem = fuse ? 256 * 8 * sizeof(float) : 0;
+    static int occ_cache[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_cache[dev & 63][fuse ? 1 : 0];
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gap_bwd_bits_kernel, 256, dyn_smem) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            occ = 1;
+        }
+        if (occ > kPartWaves) occ = kPartWaves;                   // (parts buffers hold kPartWaves rows per SM)
+    }
+    int slice_px = 8 * rgs;                                       // eight pixels per thread and item
+    if (slice_px > HW) slice_px = HW;
+    const int slices = (HW + slice_px - 1) / slice_px;
+    const long long items = static_cast<long long>(B) * slices;
+    const long long cap = static_cast<long long>(sm_count()) * occ;
+    const int grid = static_cast<int>(items < cap ? items : cap);
     if (fuse) { int r = parts_check(db_parts, db_parts_bytes, grid, C, "abl_gap_bwd_bits"); if (r != ABL_OK) return r; }
-    gap_bwd_bits_kernel<<<grid, 256, fuse ? 256 * 8 * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
-        dgap, reinterpret_cast<const unsigned char*>(relu_bits), static_cast<uint4*>(dz), B, HW, C / 8,
-        1.f / static_cast<float>(HW), fuse ? db_parts : nullptr);
+    gap_bwd_bits_kernel<<<grid, 256, dyn_smem, static_cast<cudaStream_t>(stream)>>>(
+        dgap, reinterpret_cast<const unsigned char*>(relu_bits), static_cast<uint4*>(dz), B, HW, C8,
+        1.f / static_cast<float>(HW), slices, slice_px, fuse ? db_parts : nullptr);
     int r = check_launch();
     if (r == ABL_OK && db_parts != nullptr && !fuse)
         r = abl_bias_grad(dz, db_parts, db_parts_bytes, static_cast<long long>(B) * HW, C, stream);
