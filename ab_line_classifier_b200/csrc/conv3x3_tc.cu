@@ -1592,7 +1592,11 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
             // Same-box A/B on B200 (batch 256): N = 64 +4 %; N = 128: block2_conv1 fwd 122 -> 114 us, block2_conv2 dgrad
             // 226 -> 210 us, but block2_conv2 fwd 200 -> 206 us, so N = 128 uses it for Cin = 64 and masked Cin = 128.
             const char* ws = getenv("ABL_N64_WS");
-            const bool ws_shape = ntile == 64 || (ntile == 128 && (Cin == 64 || (Cin == 128 && (flags & ABL_EPI_RELU_MASK))));
+            // (round 2, second A/B with ABL_N128_WS_ALL=1: the N = 128 dgrad + un-pool with K = 256 gains too, 130 -> 127 us;
+            // the un-masked Cin = 128 forward still loses, 201 -> 206 us)
+            const char* ws_all = getenv("ABL_N128_WS_ALL");
+            const bool ws_shape = ntile == 64 || (ntile == 128 && (Cin == 64 || (Cin == 128 && (flags & ABL_EPI_RELU_MASK)) ||
+                                                                   out_unpool != nullptr || (ws_all && ws_all[0] == '1')));
             if (ws_shape && !(ws && ws[0] == '0')) a.flags |= ABL_MAIN_WS_PAIRS;
         }
         a.bias = bias;
