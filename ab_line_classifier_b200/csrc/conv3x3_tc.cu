@@ -515,7 +515,7 @@ __device__ __forceinline__ void epilogue_tile_wl(const ConvArgs& p, const CUtens
                 const uint4 d = *reinterpret_cast<const uint4*>(stg_w + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
                 uint32_t o[4], code;
                 pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
-                if (PARTIAL && (hw0 >= p.H || w0 + 2 * pw >= p.W)) continue;      // H, W even: a window is in or out as a whole
+                if (PARTIAL && (hw0 + 1 >= p.H || w0 + 2 * pw + 1 >= p.W)) continue;      // only complete windows (Keras 'valid' pooling floors odd sides)
                 const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (hw0 >> 1)) * (p.W >> 1) + (w0 >> 1) + pw) * p.Cout +
                                    cw0 + c8 * 8;
                 *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1047,7 +1047,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint4 d = *reinterpret_cast<const uint4*>(stg + r11 * 128 + ((c8 ^ (r11 & 7)) << 4));
                         uint32_t o[4], code;
                         pool8(a, b, c2, d, o, code, p.pool_code != nullptr);
-                        if (PARTIAL && (h0 >= p.H || w0 + 2 * pw >= p.W)) continue;      // H, W even: a window is in or out as a whole
+                        if (PARTIAL && (h0 + 1 >= p.H || w0 + 2 * pw + 1 >= p.W)) continue;      // only complete windows
                         const size_t off = ((static_cast<size_t>(img) * (p.H >> 1) + (h0 >> 1)) * (p.W >> 1) +
                                             (w0 >> 1) + pw) * p.Cout + n0 + c8 * 8;
                         *reinterpret_cast<uint4*>(p.out_pool + off) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1503,7 +1503,7 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
         set_error("abl_conv3x3_igemm: need B>0, Cin and Cout multiples of 64 and <= 512");
         return ABL_ERR_SHAPE;
     }
-    if (out_pool && ((H & 1) || (W & 1))) { set_error("abl_conv3x3_igemm: pooled output needs even H, W"); return ABL_ERR_SHAPE; }
+    if (out_pool && (H < 2 || W < 2)) { set_error("abl_conv3x3_igemm: pooled output needs H, W >= 2"); return ABL_ERR_SHAPE; }
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_kmajor) |
          reinterpret_cast<uintptr_t>(out_full) | reinterpret_cast<uintptr_t>(out_pool) |
          reinterpret_cast<uintptr_t>(mask_src)) & 15) {
@@ -1513,7 +1513,7 @@ static int conv_igemm_impl(const void* x, const void* w_kmajor, const float* bia
     ConvArgs a;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
     // v1 / blocked kernels need an exact tiling into 128-pixel rectangles; the haloed kernels below take any frame
-    const bool boxed = pick_box(H, W, &a.box_h, &a.box_w) == ABL_OK && !(out_pool && (a.box_h & 1));
+    const bool boxed = pick_box(H, W, &a.box_h, &a.box_w) == ABL_OK && !(out_pool && ((a.box_h | H | W) & 1));
     {
         // Blocked main loop (four pixels per GEMM row) for the pooled-only forward of a Cin = Cout = 64 layer
         // (block1_conv2 in training and inference).  ABL_BLOCKED64=0 falls back to the haloed kernel (A/B runs, tests).

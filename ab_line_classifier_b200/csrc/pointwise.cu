@@ -895,7 +895,9 @@ extern "C" int abl_parts_reduce(const float* parts, float* out, int C, int accum
 extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db_parts,
                                     long long db_parts_bytes, int B, int H, int W, int C, void* stream) {
     if (!dp || !a || !pooled || !dz) { set_error("abl_maxpool_bwd_relu: null pointer"); return ABL_ERR_NULL; }
-    if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_relu: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
+    if (B <= 0 || H < 2 || W < 2 || (C & 7)) { set_error("abl_maxpool_bwd_relu: need H, W >= 2 and C % 8 == 0"); return ABL_ERR_SHAPE; }
+    if (((H | W) & 1) && cudaMemsetAsync(dz, 0, static_cast<size_t>(B) * H * W * C * 2, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+        return check_launch();      // (see abl_maxpool_bwd_code)
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
     const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;      // a thread keeps one channel chunk
     const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);
@@ -912,7 +914,11 @@ extern "C" int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* p
 extern "C" int abl_maxpool_bwd_code(const void* dp, const unsigned short* pool_code, void* dz, float* db_parts,
                                     long long db_parts_bytes, int B, int H, int W, int C, void* stream) {
     if (!dp || !pool_code || !dz) { set_error("abl_maxpool_bwd_code: null pointer"); return ABL_ERR_NULL; }
-    if (B <= 0 || (H & 1) || (W & 1) || (C & 7)) { set_error("abl_maxpool_bwd_code: need even H,W and C % 8 == 0"); return ABL_ERR_SHAPE; }
+    if (B <= 0 || H < 2 || W < 2 || (C & 7)) { set_error("abl_maxpool_bwd_code: need H, W >= 2 and C % 8 == 0"); return ABL_ERR_SHAPE; }
+    // odd H or W (Keras 'valid' pooling drops the last row / column): those elements belong to no window, their
+    // gradient is zero -- the kernel only writes whole windows, so the tensor is cleared first
+    if (((H | W) & 1) && cudaMemsetAsync(dz, 0, static_cast<size_t>(B) * H * W * C * 2, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+        return check_launch();
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
     const bool fuse = db_parts != nullptr && (256 % (C / 8)) == 0;
     const int grid = grid_for(total, 256, fuse ? kPartWaves : 16);

@@ -60,10 +60,10 @@ def build_plan(input_shape, cutoff_layer, check_tiling=False):
             specs.append(ConvSpec(name, c, cout, h, w, i))
             c = cout
         else:
-            if h % 2 or w % 2:
-                raise NotImplementedError(f"DATA.IMG_DIM not divisible for {name}")
+            if h < 2 or w < 2:
+                raise NotImplementedError(f"DATA.IMG_DIM is too small for {name} (its input would be {h}x{w})")
             specs[-1].pool = True
-            h, w = h // 2, w // 2
+            h, w = h // 2, w // 2          # Keras MaxPooling2D, padding 'valid': an odd side drops its last row / column
     return specs, (h, w, c)
 
 
@@ -550,7 +550,10 @@ class CutoffVGG16Engine:
                     dp = b["dp"][: B * s.h * s.w * s.cin].view(B, s.h, s.w, s.cin)
                     ndz = other[: B * prev.h * prev.w * prev.cout].view(B, prev.h, prev.w, prev.cout)
                     code = b.get("code_" + prev.name)
-                    if code is not None and self.fuse_unpool and ops.dgrad_unpool_supported(s.h, s.w, s.cin):
+                    # (an odd side before the pool: the un-pooled tensor has a row / column no window covers -- the
+                    # two-kernel path below zero-fills it)
+                    even = prev.h == 2 * s.h and prev.w == 2 * s.w
+                    if code is not None and self.fuse_unpool and even and ops.dgrad_unpool_supported(s.h, s.w, s.cin):
                         # dgrad + relu'(pooled) + MaxPoolGrad (+ BiasAddGrad) in one kernel
                         ops.conv3x3_dgrad_unpool(dz, self.w_dgrad[s.name], b["pool_" + prev.name][:B], code[:B], ndz,
                                                  db_parts=bias_parts_of(li - 1))

@@ -69,7 +69,8 @@ int abl_parts_reduce(const float* parts, float* out, int C, int accumulate, void
  *   colsum_parts  parts buffer (see above) or NULL: partial sums over (n,h,w) of out_full[n,h,w,c] -- with the dgrad
  *            epilogue this is TF's BiasAddGrad of the layer below, fused so its dZ is not read a second time (needs
  *            out_full); colsum_parts_bytes = its capacity
- * Requires Cin, Cout multiples of 64 (<= 512); even H, W for out_pool.  ANY H x W: the kernels tile a frame into 8 x 16
+ * Requires Cin, Cout multiples of 64 (<= 512).  out_pool is [B, H/2, W/2, Cout] with the divisions rounding DOWN (Keras
+ * MaxPooling2D, padding 'valid': an odd side loses its last row / column).  ANY H x W: the kernels tile a frame into 8 x 16
  * (or 16 x 16) pixel rectangles counted rounding up -- TMA zero-fills loads beyond the frame (= SAME padding) and clips
  * the stores, and the epilogue keeps rows outside the frame out of the pooled output, the routing codes and every sum. */
 int abl_conv3x3_igemm(const void* x, const void* w_kmajor, const float* bias, const void* mask_src,
@@ -155,7 +156,8 @@ int abl_prep_conv_weights_multi(const float* const* w_hwio, void* const* w_fwd, 
                                 const int* cin, const int* cout, int n_layers, void* stream);
 
 /* MaxPoolGrad + ReluGrad: dz[n,h,w,c] = dp[n,h/2,w/2,c] if a[n,h,w,c] is the first maximum of its 2x2
- * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16.
+ * window and a > 0, else 0.  a bf16 [B,H,W,C] (pre-pool, post-ReLU), pooled = maxpool(a), dp, dz bf16.  Odd H or W:
+ * dp / pooled are [B,H/2,W/2,C] rounding down, and the last row / column of dz (no window) is zero.
  * db_parts: parts buffer or NULL receiving the partial sums of dz[..., c] (BiasAddGrad of the conv above the pool). */
 int abl_maxpool_bwd_relu(const void* dp, const void* a, const void* pooled, void* dz, float* db_parts,
                          long long db_parts_bytes, int B, int H, int W, int C, void* stream);

@@ -327,31 +327,33 @@ def test_full_size_batches_size_independent_properties(setup):
     eng.set_weights(params)
 
 
-def test_img_dims_with_an_odd_pooled_side_raise_a_clear_error():
-    """Any IMG_DIM runs (maps that are not a whole number of 8x16-pixel tiles use partial tiles) as long as every pooled
-    side is even; 90x90 frames give a 45x45 block-2 map whose 2x2 pool would drop a row, which the engine refuses up
-    front, naming the config key.  100x100 (25x25 block-3 maps, no pool after them for CUTOFF_LAYER 10) is accepted."""
+def test_img_dims_too_small_for_the_pools_raise_a_clear_error():
+    """Any IMG_DIM runs: maps that are not a whole number of 8x16-pixel tiles use partial tiles, and an odd side under a
+    pool loses its last row / column as in Keras (padding 'valid').  Only a frame the pools shrink to nothing is refused,
+    up front, naming the config key."""
     from ab_line_classifier_b200.engine import CutoffVGG16Engine
     from ab_line_classifier_b200.model import CutoffVGG16
     with pytest.raises(NotImplementedError, match="DATA.IMG_DIM.*block2_pool"):
-        CutoffVGG16Engine(input_shape=(90, 90, 3), cutoff_layer=10)
+        CutoffVGG16Engine(input_shape=(3, 3, 3), cutoff_layer=10)
     hp = {"LR_EXTRACT": 3e-4, "LR_FINETUNE": 9.3e-6, "DROPOUT": 0.45, "CUTOFF_LAYER": 10, "FINETUNE_LAYER": 7,
           "EXTRACT_EPOCHS": 1}
     with pytest.raises(NotImplementedError, match="DATA.IMG_DIM"):
-        CutoffVGG16(hp, [90, 90, 3], ["accuracy"], 2)
-    CutoffVGG16Engine(input_shape=(100, 100, 3), cutoff_layer=10)
+        CutoffVGG16(hp, [3, 3, 3], ["accuracy"], 2)
+    assert CutoffVGG16Engine(input_shape=(90, 90, 3), cutoff_layer=10).feat_shape == (22, 22, 256)
 
 
 @pytest.mark.parametrize("H,W,cutoff", [(64, 64, 10), (256, 128, 10), (128, 128, 7), (96, 96, 7), (128, 128, 14),
                                         (64, 128, 13), (96, 96, 10), (100, 100, 10), (160, 160, 10), (72, 104, 10),
-                                        (224, 224, 10), (96, 96, 14)])
+                                        (224, 224, 10), (96, 96, 14), (90, 90, 10), (150, 150, 10), (50, 70, 10)])
 def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
     """config.yml DATA.IMG_DIM / HPARAMS.CUTOFFVGG16.CUTOFF_LAYER other than the graded 128x128 / 10: forward logits and
     one training step's loss + gradients against the bf16-faithful oracle.  96x96 / cutoff 7 exercises the v1 conv
     kernel and non-power-of-two rows in block1_conv1; cutoff 13 / 14 reach the Cin = Cout = 512 layers of block 4 (two
     N tiles per pixel tile, stand-alone bias-gradient pass, un-fused MaxPoolGrad for the 256-channel pool).  96 / 100 /
     160 / 224-pixel sides give block-2 / block-3 maps (24, 25, 40, 56 ...) that are not a whole number of 8x16-pixel
-    tiles: partial tiles in every conv kernel, and (100x100) a short last tile in block1_conv1."""
+    tiles: partial tiles in every conv kernel, and (100x100) a short last tile in block1_conv1.  90 / 150 / 50x70 put an
+    ODD side under a pool (45, 75, 25 / 35): the pooled map drops the last row / column as Keras does, and the un-pooled
+    gradient is zero there."""
     from ab_line_classifier_b200.engine import CutoffVGG16Engine
     params = synth.randomize_biases(synth.glorot_weights(10001, cutoff_layer=cutoff))
     eng = CutoffVGG16Engine(input_shape=(H, W, 3), cutoff_layer=cutoff)

@@ -50,7 +50,9 @@ LAYERS = [(64, 64, 128, 128, True), (64, 128, 64, 64, False), (128, 128, 64, 64,
           # frames that are not a whole number of 8 x 16-pixel tiles (IMG_DIM 96, 100, 160, 224 ... give such block-2 / 3
           # maps): partial tiles, zero-filled by TMA on load, clipped on store, guarded in the epilogue
           (64, 64, 24, 40, True), (64, 128, 20, 20, False), (128, 128, 12, 24, True), (128, 256, 25, 25, False),
-          (256, 256, 24, 24, False), (256, 512, 10, 6, False), (128, 128, 56, 56, True)]
+          (256, 256, 24, 24, False), (256, 512, 10, 6, False), (128, 128, 56, 56, True),
+          # odd sides under a pool: Keras' 'valid' MaxPooling2D drops the last row / column
+          (64, 64, 25, 41, True), (128, 128, 45, 45, True)]
 
 
 @pytest.mark.parametrize("cin,cout,H,W,pool", LAYERS)
@@ -306,7 +308,7 @@ def test_maxpool_backward_routes_to_first_max_and_relu_masks():
     _close(db, ref.sum(dim=(0, 1, 2)), 1e-5, "fused bias grad (maxpool bwd)")
 
 
-@pytest.mark.parametrize("cin,cout,H,W", [(64, 64, 128, 128), (128, 128, 64, 64)])
+@pytest.mark.parametrize("cin,cout,H,W", [(64, 64, 128, 128), (128, 128, 64, 64), (64, 64, 45, 45), (128, 128, 37, 22)])
 def test_pool_routing_codes_reproduce_maxpool_backward_bit_exactly(cin, cout, H, W, igemm_variant):
     """Training keeps 2-bit routing codes from the fused max-pool epilogue instead of the pre-pool activation:
     MaxPoolGrad + ReluGrad through the codes must equal the activation-based kernel bit for bit (first maximum wins,
@@ -334,6 +336,15 @@ def test_pool_routing_codes_reproduce_maxpool_backward_bit_exactly(cin, cout, H,
     ops.maxpool_bwd_code(dp_masked, code, dz, db)
     assert torch.equal(dz, dz_ref)
     _close(db, db_ref, 1e-5, "bias grad through routing codes")
+    # against autograd of the plain PyTorch ops (odd sides: the last row / column belongs to no window -> zero gradient)
+    a = full.float().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    F.max_pool2d(F.relu(a), 2, 2).backward(dp.float().cpu().permute(0, 3, 1, 2))
+    got, want = dz.float().cpu(), a.grad.permute(0, 2, 3, 1)
+    assert torch.equal(got, want)                         # same first-maximum rule (row-major scan of the window)
+    if H % 2:
+        assert not got[:, H - 1].any()
+    if W % 2:
+        assert not got[:, :, W - 1].any()
     # pooled-only (inference-style) launch writes the same codes
     code2 = torch.zeros_like(code)
     ops.conv3x3_igemm(x.cuda().to(torch.bfloat16), wf, b.cuda(), None, None, pooled, ops.EPI_BIAS_RELU, pool_code=code2)
@@ -583,11 +594,12 @@ def test_clip_aggregate_matches_reference_rules_bit_exactly_on_runs():
 
 def test_error_behaviour_bad_shapes_and_alignment():
     ops = _ops()
-    x = torch.zeros(1, 21, 20, 64, device="cuda", dtype=torch.bfloat16)       # a 2x2 pool needs even H and W
+    x = torch.zeros(1, 1, 20, 64, device="cuda", dtype=torch.bfloat16)        # a 2x2 pool needs two rows
     w = torch.zeros(9, 64, 64, device="cuda", dtype=torch.bfloat16)
-    pl = torch.zeros(1, 10, 10, 64, device="cuda", dtype=torch.bfloat16)
-    with pytest.raises(RuntimeError, match="even H, W"):
-        ops.conv3x3_igemm(x, w, torch.zeros(64, device="cuda"), None, None, pl, ops.EPI_BIAS_RELU)
+    pl = torch.zeros(1, 1, 10, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="H, W >= 2"):                       # (through the C ABI: the wrapper checks shapes)
+        ops._native.call("abl_conv3x3_igemm", x.data_ptr(), w.data_ptr(), torch.zeros(64, device="cuda").data_ptr(), None,
+                         None, pl.data_ptr(), None, None, 0, 1, 1, 20, 64, 64, ops.EPI_BIAS_RELU, ops._stream())
     x = torch.zeros(1, 32, 32, 48, device="cuda", dtype=torch.bfloat16)       # Cin not a multiple of 64
     w = torch.zeros(9, 64, 48, device="cuda", dtype=torch.bfloat16)
     out = torch.zeros(1, 32, 32, 64, device="cuda", dtype=torch.bfloat16)

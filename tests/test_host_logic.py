@@ -163,7 +163,8 @@ def test_clip_aggregation_rules():
 def test_engine_plan_and_unsupported_configs():
     from ab_line_classifier_b200.engine import build_plan
     with pytest.raises(NotImplementedError, match="IMG_DIM.*block2_pool"):
-        build_plan((90, 90, 3), 10)                              # 45x45 block-2 maps: the 2x2 pool would drop a row
+        build_plan((3, 3, 3), 10)                                # 1x1 block-2 maps: nothing left to pool
+    assert build_plan((90, 90, 3), 10)[1] == (22, 22, 256)       # 45x45 block-2 maps: the pool drops the last row / column
     specs, feat = build_plan((96, 96, 3), 10, check_tiling=True)     # 24x24 block-3 maps: partial 8x16-pixel tiles
     assert feat == (24, 24, 256)
     from ab_line_classifier_b200.ops import igemm_gap_parts
