@@ -514,8 +514,6 @@ class CutoffVGG16Engine:
         if lowest >= nconv:
             return
         last = self.specs[-1]
-        if last.pool:
-            raise NotImplementedError("training with a cutoff that ends in a pool layer")
         cur, other = b["dz_a"], b["dz_b"]
         dz = cur[: B * last.h * last.w * last.cout].view(B, last.h, last.w, last.cout)
         # BiasAddGrad of a layer is fused into whichever kernel PRODUCES that layer's dZ (GAP backward, max-pool
@@ -529,7 +527,20 @@ class CutoffVGG16Engine:
         def bias_parts_of(i):
             return b["bpart"] if (tr[i] and i > 0 and not wgrad_has_bias(i)) else None
 
-        if "bits_last" in b:
+        if last.pool:
+            # CUTOFF_LAYER ends in a pool (4, 7, 11 ...): the average runs over the POOLED map.  Its gradient, masked by
+            # relu'(pooled) (pooled = max of post-ReLU values: zero iff the whole window is), is routed back through the
+            # forward's codes; the bias gradient of the conv rides along as usual.
+            ph, pw = last.h // 2, last.w // 2
+            dp = b["dp"][: B * ph * pw * last.cout].view(B, ph, pw, last.cout)
+            ops.gap_bwd_relu(b["dgap"][:B], b["pool_" + last.name][:B], dp)
+            code = b.get("code_" + last.name)
+            if code is not None:
+                ops.maxpool_bwd_code(dp, code[:B], dz, db_parts=bias_parts_of(nconv - 1))
+            else:
+                ops.maxpool_bwd_relu(dp, b["act_" + last.name][:B], b["pool_" + last.name][:B], dz,
+                                     db_parts=bias_parts_of(nconv - 1))
+        elif "bits_last" in b:
             ops.gap_bwd_bits(b["dgap"][:B], b["bits_last"][:B], dz, db_parts=bias_parts_of(nconv - 1))
         else:
             ops.gap_bwd_relu(b["dgap"][:B], b["act_" + last.name][:B], dz, db_parts=bias_parts_of(nconv - 1))
