@@ -344,7 +344,8 @@ def test_img_dims_too_small_for_the_pools_raise_a_clear_error():
 
 @pytest.mark.parametrize("H,W,cutoff", [(64, 64, 10), (256, 128, 10), (128, 128, 7), (96, 96, 7), (128, 128, 14),
                                         (64, 128, 13), (96, 96, 10), (100, 100, 10), (160, 160, 10), (72, 104, 10),
-                                        (224, 224, 10), (96, 96, 14), (90, 90, 10), (150, 150, 10), (50, 70, 10)])
+                                        (224, 224, 10), (96, 96, 14), (90, 90, 10), (150, 150, 10), (50, 70, 10),
+                                        (64, 64, 18), (128, 96, 16)])
 def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
     """config.yml DATA.IMG_DIM / HPARAMS.CUTOFFVGG16.CUTOFF_LAYER other than the graded 128x128 / 10: forward logits and
     one training step's loss + gradients against the bf16-faithful oracle.  96x96 / cutoff 7 exercises the v1 conv
@@ -353,7 +354,8 @@ def test_other_img_dims_and_cutoff_layers_match_the_oracle(H, W, cutoff):
     160 / 224-pixel sides give block-2 / block-3 maps (24, 25, 40, 56 ...) that are not a whole number of 8x16-pixel
     tiles: partial tiles in every conv kernel, and (100x100) a short last tile in block1_conv1.  90 / 150 / 50x70 put an
     ODD side under a pool (45, 75, 25 / 35): the pooled map drops the last row / column as Keras does, and the un-pooled
-    gradient is zero there."""
+    gradient is zero there.  Cutoff 16 / 18 run all of VGG16's conv blocks 1-4 / 1-5 (block-5 maps of 4x4 pixels: one
+    partial tile per frame)."""
     from ab_line_classifier_b200.engine import CutoffVGG16Engine
     params = synth.randomize_biases(synth.glorot_weights(10001, cutoff_layer=cutoff))
     eng = CutoffVGG16Engine(input_shape=(H, W, 3), cutoff_layer=cutoff)
