@@ -109,6 +109,7 @@ class CutoffVGG16Engine:
         self._alloc_params(output_bias)
         self._cap = 0
         self._cap_train = False
+        self._keep_last_act = False     # Grad-CAM with a cutoff that ends in a pool: keep the last conv's pre-pool output
         self._buf = {}
         self._graphs = {}             # (batch, uint8 input, buffer generation) -> captured forward CUDA graph
         self._tgraphs, self._tg_seen, self._alpha_tabs = {}, {}, {}      # whole-train-step graphs (fit_step)
@@ -277,6 +278,8 @@ class CutoffVGG16Engine:
         n = self.n_classes
         b["gap"] = torch.empty(cap, C, device=dev, dtype=torch.float32)
         last = self.specs[-1]
+        if last.pool and self._keep_last_act:
+            b["gcam_act"] = torch.empty(cap, last.h, last.w, last.cout, device=dev, dtype=bf)
         if self.fuse_gap and not last.pool and ops.igemm_gap_supported(last.h, last.w, last.cout):
             self._gap_parts = ops.igemm_gap_parts(last.h, last.w, last.cout)
             b["gap_part"] = torch.empty(cap * self._gap_parts, C, device=dev, dtype=torch.float32)
@@ -342,6 +345,8 @@ class CutoffVGG16Engine:
                                       b["gap_part"], relu_bits=bits)
             else:
                 code = b.get("code_" + s.name)
+                if li == len(self.specs) - 1 and s.pool and need_last_act and not training and "gcam_act" in b:
+                    full = b["gcam_act"][:B]             # Grad-CAM wants the map BEFORE the trailing pool
                 ops.conv3x3_igemm(self._in_act(li, B), self.w_fwd[s.name], self.view(s.name + "/bias"), None,
                                   full, pooled, ops.EPI_BIAS_RELU, pool_code=code[:B] if code is not None else None)
         last = self.specs[-1]
@@ -828,11 +833,17 @@ class CutoffVGG16Engine:
     def gradcam_batch(self, x, out_hw=None):
         """Per-frame Grad-CAM heat-maps (gradcam.py:68-81) -> (device heat [B,oh,ow] fp32, device probs)."""
         last = self.specs[-1]
-        if last.pool:
-            raise NotImplementedError("Grad-CAM with a cutoff that ends in a pool layer")
+        if last.pool and not self._keep_last_act:
+            # The reference takes the LAST CONV layer's output (gradcam.py:33-37), i.e. the map before a trailing pool.
+            # The gradient of the class probability reaches it through MaxPool + GAP: every window hands
+            # dp/dgap_c / (H'W') to one of its elements, so the spatial mean is dp/dgap_c / (HW) -- the same alpha_c as
+            # without the pool, and the closed form applies to the pre-pool map unchanged.
+            self._keep_last_act = True
+            self._cap = 0                                   # re-allocate with the extra activation buffer
         probs = self.predict_batch(x, need_last_act=True)
         B = x.shape[0]
         oh, ow = out_hw if out_hw is not None else self.input_shape[:2]
         heat = torch.empty(B, oh, ow, device=self.device, dtype=torch.float32)
-        ops.gradcam(self._buf["act_" + last.name][:B], probs, self.view("output/kernel"), heat)
+        act = self._buf["gcam_act"] if last.pool else self._buf["act_" + last.name]
+        ops.gradcam(act[:B], probs, self.view("output/kernel"), heat)
         return heat, probs

@@ -273,6 +273,22 @@ def test_gradcam_heatmaps_512_frame_clip_property_and_oracle(setup):
     assert (probs.cpu().numpy()[:3].argmax(-1) == ref_probs.argmax(-1)).all()
 
 
+def test_gradcam_with_a_cutoff_that_ends_in_a_pool_layer():
+    """CUTOFF_LAYER 7 ends in block2_pool: the reference explains the last CONV layer (gradcam.py:33-37), whose gradient
+    comes through MaxPool + GAP; the closed form on the pre-pool map must equal autograd through the real pool."""
+    from ab_line_classifier_b200.engine import CutoffVGG16Engine
+    params = synth.randomize_biases(synth.glorot_weights(10001, cutoff_layer=7))
+    eng = CutoffVGG16Engine(input_shape=(64, 64, 3), cutoff_layer=7)
+    eng.set_weights(params)
+    rng = np.random.default_rng(7)
+    x = synth.vgg16_preprocess(rng.integers(0, 256, size=(3, 64, 64, 3), dtype=np.uint8))
+    heat, probs = eng.gradcam_batch(x)
+    ref_heat, ref_probs = oracle.gradcam_autograd(params, x, cutoff_layer=7, out_hw=(64, 64), bf16=True)
+    assert heat.shape == (3, 64, 64)
+    assert np.abs(heat.cpu().numpy() - ref_heat).max() < 3e-2
+    assert np.abs(probs.cpu().numpy() - ref_probs).max() < 5e-3
+
+
 def test_batch_256_logits_and_weight_gradients_against_the_oracle(setup):
     """BASELINE configs[1] size, against the oracle rather than against the device itself: forward logits of all 256
     frames and the weight / bias gradients of three layers (one per kernel family: the Cin = 64 wgrad with its ones-row
