@@ -455,3 +455,17 @@ def test_b200_config_section_is_optional():
     assert b200_options({"TRAIN": {}, "B200": {"SYNTH_TRAIN_FRAMES": 64, "SYNTH_VAL_FRAMES": 8, "AUGMENT": False}}) == (64, 8, False)
     assert b200_options({"TRAIN": {}}) == (2048, 256, True)
     assert b200_options({"TRAIN": {}, "B200": None}) == (2048, 256, True)
+
+
+def test_launch_accounting_of_the_wgrad_entry_point(monkeypatch):
+    """bench.py's gpu_launches comes from _native.launch_count: abl_conv3x3_wgrad is one kernel when the GEMM reduces its
+    own pixel slices (Cin >= 128, the default) and two when wgrad_reduce_kernel follows it (Cin = 64, or the switch)."""
+    from ab_line_classifier_b200 import _native
+    args128 = [0] * 11 + [128, 256, 0]        # (x, dz, dw, db, db_parts, ws, ws_bytes, accumulate, B, H, W, Cin, Cout, stream)
+    args64 = [0] * 11 + [64, 128, 0]
+    monkeypatch.delenv("ABL_WGRAD_FUSED_REDUCE", raising=False)
+    assert _native._wgrad_launches(args128) == 1 and _native._wgrad_launches(args64) == 2
+    monkeypatch.setenv("ABL_WGRAD_FUSED_REDUCE", "0")
+    assert _native._wgrad_launches(args128) == 2 and _native._wgrad_launches(args64) == 2
+    monkeypatch.setenv("ABL_WGRAD_FUSED_REDUCE", "2")
+    assert _native._wgrad_launches(args128) == 1 and _native._wgrad_launches(args64) == 1
